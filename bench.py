@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the many-chain sampling hot path (BASELINE.json metric:
+leapfrog grad-evals/sec at 65,536+ chains on 1/2/4/8 B200 next to the host CPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Default workload (config 4 of BASELINE.json, per-GPU shard): batched HMC on the 100-D Rosenbrock
+target, 65,536 chains per GPU, L = 32 leapfrog steps per transition, f32, fixed step size after a
+pooled dual-averaging warm-up.  A "step" is one HMC transition of every chain (L gradient
+evaluations per chain) including the [chains, samples, dim] sample write-out; `value` = chains x
+steps x L / device time, inputs resident in HBM.  `e2e` is the same metric through the host-buffer
+C-ABI call gmcmc_run (H2D of the initial positions + D2H of the samples inside the timed region).
+
+Other workloads (extra lines for the record, same JSON shape): mh_gauss2d (config 2).
+
+One process per GPU; under torchrun the ranks shard the chains (weak scaling: fixed chains per GPU),
+no data-path collective; timing = max over ranks of the CUDA-event time between two barriers.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHAINS_PER_GPU = 65536
+DIM = 100
+N_LEAPFROG = 32
+STEP_SIZE = 0.01
+TRANSITIONS_PER_LAUNCH = 100
+E2E_TRANSITIONS = 16
+FLOP_PER_GRAD_EVAL = 21 * DIM        # 15(d-1) target + 6d integrator, FMA = 2
+BYTES_PER_STEP_PER_CHAIN = DIM * 4   # sample write-out, f32
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        d["source"] = "measured (MEASURED_PEAKS.json)"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+            time.sleep(0.15)
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.1)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.05] or [l for (_, l) in self.lines[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in rows:
+            f = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except Exception:
+                continue
+            for k, name in enumerate(names):
+                if len(f) > 4 + k and f[4 + k].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def init_positions(rank, n_chains, dim, dtype=np.float32):
+    rng = np.random.default_rng(1234 + rank)
+    return (1.0 + 0.1 * rng.standard_normal((n_chains, dim))).astype(dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle "port": the C++ restatement of the reference algorithm, all host threads)
+# ------------------------------------------------------------------------------------------------
+def cpu_hmc_rate(target_seconds=12.0, chains=None):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    oracle_lib.build()
+    threads = oracle_lib.max_threads()
+    chains = chains or max(threads * 16, 512)
+    q0 = init_positions(0, chains, DIM)
+    secs, _, _ = oracle_lib.hmc_bench(oracle_lib.ROSENBROCK_ND, [], q0, STEP_SIZE, N_LEAPFROG, 1, seed=1)
+    rate1 = chains * N_LEAPFROG / max(secs, 1e-9)
+    n_steps = int(max(1, min(2000, target_seconds * rate1 / (chains * N_LEAPFROG))))
+    secs, _, _ = oracle_lib.hmc_bench(oracle_lib.ROSENBROCK_ND, [], q0, STEP_SIZE, N_LEAPFROG, n_steps, seed=2)
+    rate = chains * n_steps * N_LEAPFROG / secs
+    return rate, threads, "%d chains x %d transitions x L=%d, d=%d, f32 (%.1f s)" % (chains, n_steps, N_LEAPFROG, DIM, secs)
+
+
+def cpu_mh_rate(target_seconds=12.0):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    oracle_lib.build()
+    threads = oracle_lib.max_threads()
+    chains = max(threads * 256, 8192)
+    x0 = np.random.default_rng(0).standard_normal((chains, 2))
+    params = [0.0, 0.0, 1.0, 0.0, 0.0, 1.0]
+    secs, _, _ = oracle_lib.mh_bench(oracle_lib.GAUSS2D, params, x0, 1.0, 20, seed=1, keep_samples=True)
+    rate1 = chains * 20 / max(secs, 1e-9)
+    n_steps = int(max(1, min(1000, target_seconds * rate1 / chains)))
+    secs, _, _ = oracle_lib.mh_bench(oracle_lib.GAUSS2D, params, x0, 1.0, n_steps, seed=2, keep_samples=True)
+    return chains * n_steps / secs, threads, "%d chains x %d steps, f64, samples kept (%.1f s)" % (chains, n_steps, secs)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    if args.workload == "mh_gauss2d":
+        rate, threads, sample = cpu_mh_rate(30.0)
+        metric, unit = "mh_chain_steps_per_sec", "chain-steps/s"
+        cfg = {"workload": "cfg2: batched MH Gaussian2D, IsotropicGaussian proposal, f64 (CPU sample)"}
+        dtype = "f64"
+    else:
+        t0 = time.time()
+        # bounded: a sample of chains, K transitions capped by a time budget
+        rate, threads, sample = cpu_hmc_rate(min(60.0, max(5.0, 0.02 * args.steps)))
+        metric, unit = "leapfrog_grad_evals_per_sec", "grad-evals/s"
+        cfg = {"workload": "cfg4 shard: batched HMC RosenbrockND d=100 L=32 f32 (CPU sample)"}
+        dtype = "f32"
+        del t0
+    line = {"impl": "reference", "metric": metric, "value": rate, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": dtype, "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": rate, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the Rust reference cannot be built here (no cargo); this is the C++ restatement of its algorithm "
+                    "(oracle/, -O3, OpenMP over chains like rayon core.rs:221-225) on all host threads"}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def pinned_array(gm_lib, shape, dtype):
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    from general_mcmc_b200 import _lib as L
+    L.check(gm_lib.gmcmc_host_alloc(C.c_size_t(n), C.byref(p)))
+    buf = (C.c_char * n).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape), p
+
+
+def run_ours(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    import general_mcmc_b200 as gm
+    from general_mcmc_b200 import _lib as L
+
+    torch.cuda.set_device(local)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(gm.Context.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().tolist())
+    ctx = gm.Context(local, rank, world, nccl_id)
+    lib = L.lib()
+    pk = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    stream = torch.cuda.ExternalStream(ctx.stream())
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    if args.workload == "mh_gauss2d":
+        chains = args.chains or 1048576
+        per_launch = 1000
+        x0 = np.random.default_rng(100 + rank).standard_normal((chains, 2))
+        tgt = gm.Gaussian2D([0.0, 0.0], [[1.0, 0.0], [0.0, 1.0]])
+        s = gm.MetropolisHastings(tgt, gm.IsotropicGaussian(1.0), x0, ctx=ctx, chain_offset=rank * chains).seed(42)
+        unit_per_step = chains           # chain-steps per step
+        metric, unit, dtype = "mh_chain_steps_per_sec", "chain-steps/s", "f64"
+        bytes_per_step = chains * 16
+        workload = "cfg2: batched MH, Gaussian2D target, IsotropicGaussian proposal, %d chains/GPU, f64 state and output" % chains
+        e2e_T = 16
+    else:
+        chains = args.chains or CHAINS_PER_GPU
+        per_launch = TRANSITIONS_PER_LAUNCH
+        q0 = init_positions(rank, chains, DIM)
+        s = gm.HMC(gm.RosenbrockND(DIM), q0, STEP_SIZE, N_LEAPFROG, seed=42, ctx=ctx, chain_offset=rank * chains)
+        # warm-up with pooled dual averaging over all ranks (NCCL all-reduce of the acceptance statistic)
+        s.set_adaptation("pooled", 0.8)
+        s.run_device(0, 100)
+        unit_per_step = chains * N_LEAPFROG
+        metric, unit, dtype = "leapfrog_grad_evals_per_sec", "grad-evals/s", "f32"
+        bytes_per_step = chains * BYTES_PER_STEP_PER_CHAIN
+        workload = ("cfg4 shard: batched HMC, RosenbrockND d=%d, %d chains/GPU, L=%d, f32, pooled dual-averaging "
+                    "warm-up then fixed step" % (DIM, chains, N_LEAPFROG))
+        e2e_T = E2E_TRANSITIONS
+
+    def launches_for(k):
+        full, rem = divmod(k, per_launch)
+        return [per_launch] * full + ([rem] if rem else [])
+
+    # ---- warm-up
+    for n in launches_for(max(args.warmup, 3)):
+        s.run_device(n, 0)
+    barrier()
+    step_size = s.counters().step_size if args.workload != "mh_gauss2d" else None
+
+    # ---- timed region: exactly K steps
+    flush.fill_(1)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    plan = launches_for(args.steps)
+    t_wall0 = time.time()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for n in plan:
+            s.run_device(n, 0)
+        e1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
+    value = unit_per_step * args.steps * world / (ms * 1e-3)
+    kernel_ms_per_launch = ms / len(plan)
+
+    # ---- e2e: host buffers through gmcmc_set_positions + gmcmc_run (pinned host memory)
+    out_dtype = np.float64 if args.workload == "mh_gauss2d" else np.float32
+    dim = 2 if args.workload == "mh_gauss2d" else DIM
+    host_out, host_ptr = pinned_array(lib, (chains, e2e_T, dim), out_dtype)
+    init_host, init_ptr = pinned_array(lib, (chains, dim), s.dtype)
+    init_host[...] = s.positions()
+    e2e_calls = max(3, min(20, args.steps // e2e_T))
+    for _ in range(2):
+        s.set_positions(init_host)
+        s.run(e2e_T, 0, out=host_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_calls):
+        L.check(lib.gmcmc_set_positions(s._h, L.ptr(init_host)))
+        s.run(e2e_T, 0, out=host_out)
+    ctx.synchronize()
+    t1 = time.perf_counter()
+    e2e_s = max_over_ranks(t1 - t0)
+    e2e_value = unit_per_step * e2e_T * e2e_calls * world / e2e_s
+    h2d = init_host.nbytes / e2e_T
+    d2h = host_out.nbytes / e2e_T
+
+    # ---- roofline of the dominant kernel (per launch)
+    if args.workload == "mh_gauss2d":
+        ach = bytes_per_step * per_launch / (kernel_ms_per_launch * 1e-3) / 1e9 if len(plan) and plan[0] == per_launch else \
+            bytes_per_step * args.steps / (ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "mh_run_kernel<double,2>", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "algorithmic_bytes_per_unit": 16, "note": "co-bound by the FP64 pipe (f64 Box-Muller + log per chain-step)"}
+    else:
+        fp32_peak = C.c_double(0)
+        L.check(lib.gmcmc_measure_fp32_peak(ctx._h, C.byref(fp32_peak)))
+        tfl = value / world * FLOP_PER_GRAD_EVAL / 1e12
+        hbm = bytes_per_step * args.steps / (ms * 1e-3) / 1e9
+        roof = {"bound": "fp32", "kernel": "hmc_run_kernel<float,25,RosenbrockND>", "achieved": tfl, "peak": fp32_peak.value,
+                "unit": "TFLOP/s", "frac": tfl / fp32_peak.value if fp32_peak.value else None, "traffic": None,
+                "peak_source": "FFMA micro-benchmark in this run (gmcmc_measure_fp32_peak); nominal 148*128*2*%.3f GHz = %.1f"
+                               % (pk["sm_max_mhz"] / 1e3, 148 * 128 * 2 * pk["sm_max_mhz"] / 1e6),
+                "algorithmic_flop_per_unit": FLOP_PER_GRAD_EVAL,
+                "hbm": {"achieved": hbm, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm / pk["hbm_gbs"],
+                        "algorithmic_bytes_per_unit": BYTES_PER_STEP_PER_CHAIN / N_LEAPFROG,
+                        "note": "state is register-resident for all L steps; HBM carries only the sample write-out, so "
+                                "this kernel is FP32-pipe bound, not HBM bound (north_star: FP32-pipe utilisation)"}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        if args.workload == "mh_gauss2d":
+            r, th, sample = cpu_mh_rate(10.0)
+        else:
+            r, th, sample = cpu_hmc_rate(10.0)
+        cpu = {"value": r, "unit": unit, "cores": th, "kind": "port", "sample": sample}
+
+    c = s.counters()
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+                "config": {"workload": workload, "chains_per_gpu": chains, "transitions_per_launch": per_launch,
+                           "step_size": step_size, "accept_rate": c.accept_rate,
+                           "l2": "256 MB flush before the timed region; per-launch sample write-out (%.0f MB) exceeds "
+                                 "nothing on-chip is reused between launches" % (bytes_per_step * per_launch / 1e6)},
+                "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "calls": e2e_calls, "transitions_per_call": e2e_T, "host_memory": "pinned"},
+                "gpu_launches": len(plan), "roofline": roof, "cpu_baseline": cpu, "clocks": clk}
+        print(json.dumps(line), flush=True)
+    lib.gmcmc_host_free(host_ptr)
+    lib.gmcmc_host_free(init_ptr)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=400)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hmc_rosenbrock", choices=["hmc_rosenbrock", "mh_gauss2d"])
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank, world, local = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

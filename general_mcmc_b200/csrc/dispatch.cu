@@ -1,0 +1,71 @@
+// dispatch.cu — routes type-erased launch descriptors to the per-target translation units and
+// picks the (elements-per-lane, lanes-per-chain) decomposition.
+#include "kernels.h"
+
+#include <cstdlib>
+
+namespace gm {
+
+#define GM_DECL(fn)                                                        \
+  cudaError_t launch_hmc_##fn##_fast(const HmcLaunch&, cudaStream_t);      \
+  cudaError_t launch_hmc_##fn##_exact(const HmcLaunch&, cudaStream_t);     \
+  cudaError_t launch_eval_##fn##_fast(const EvalLaunch&, cudaStream_t);    \
+  cudaError_t launch_eval_##fn##_exact(const EvalLaunch&, cudaStream_t);
+GM_DECL(rosen) GM_DECL(iso) GM_DECL(dense) GM_DECL(mix) GM_DECL(rosen2d) GM_DECL(dgauss2d) GM_DECL(gauss2d)
+#undef GM_DECL
+
+#define GM_ROUTE(prefix, mode, L, st)                     \
+  switch ((L).tgt.kind) {                                 \
+    case 0: return prefix##iso_##mode(L, st);             \
+    case 1: return prefix##gauss2d_##mode(L, st);         \
+    case 2: return prefix##dgauss2d_##mode(L, st);        \
+    case 3: return prefix##dense_##mode(L, st);           \
+    case 4: return prefix##rosen2d_##mode(L, st);         \
+    case 5: return prefix##rosen_##mode(L, st);           \
+    case 6: return prefix##mix_##mode(L, st);             \
+  }                                                       \
+  return cudaErrorInvalidValue;
+
+cudaError_t launch_hmc_fast(const HmcLaunch& L, cudaStream_t st) { GM_ROUTE(launch_hmc_, fast, L, st) }
+cudaError_t launch_hmc_exact(const HmcLaunch& L, cudaStream_t st) { GM_ROUTE(launch_hmc_, exact, L, st) }
+cudaError_t launch_eval_fast(const EvalLaunch& E, cudaStream_t st) { GM_ROUTE(launch_eval_, fast, E, st) }
+cudaError_t launch_eval_exact(const EvalLaunch& E, cudaStream_t st) { GM_ROUTE(launch_eval_, exact, E, st) }
+
+// Decomposition: minimise padded slots (compute), penalising non exact fits (masking costs ~30 %);
+// ties go to more elements per lane (more ILP, fewer shuffles).  f64 is capped at 16 elements per lane
+// (4 live arrays x 16 x 2 registers).  GMCMC_EPL / GMCMC_LPC override for tuning.
+bool choose_decomposition(int dim, int dtype, int kind, int* epl, int* lpc) {
+  if (dim <= 0) return false;
+  if (kind == 1 || kind == 2 || kind == 4) {  // fixed 2-D targets: one lane per chain
+    if (dim != 2) return false;
+    *epl = 2; *lpc = 1;
+    return true;
+  }
+  static const int menu[] = {1, 2, 3, 4, 8, 13, 16, 25, 32};
+  const char* e_env = std::getenv("GMCMC_EPL");
+  const char* l_env = std::getenv("GMCMC_LPC");
+  if (e_env && l_env) {
+    int e = std::atoi(e_env), l = std::atoi(l_env);
+    bool ok = false;
+    for (int m : menu) ok = ok || (m == e);
+    if (ok && l >= 1 && l <= 32 && (l & (l - 1)) == 0 && e * l >= dim && !(dtype == 1 && e > 16)) {
+      *epl = e; *lpc = l;
+      return true;
+    }
+  }
+  double best = 1e30;
+  int be = 0, bl = 0;
+  for (int l = 1; l <= 32; l <<= 1)
+    for (int e : menu) {
+      if (dtype == 1 && e > 16) continue;
+      if (e * l < dim) continue;
+      if ((l - 1) * e >= dim) continue;  // last lane would own nothing
+      double cost = (double)e * l * ((e * l == dim) ? 1.0 : 1.3);
+      if (cost < best - 1e-9 || (cost < best + 1e-9 && e > be)) { best = cost; be = e; bl = l; }
+    }
+  if (!be) return false;
+  *epl = be; *lpc = bl;
+  return true;
+}
+
+}  // namespace gm

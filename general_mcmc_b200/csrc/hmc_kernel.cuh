@@ -1,0 +1,739 @@
+// hmc_kernel.cuh — K1: fused HMC trajectory kernel (sm_100a).
+//
+// Replaces, as ONE kernel per run segment, the ~40 allocating tensor passes per leapfrog of
+//   BatchedGenericHMC::step / leapfrog      /root/reference/src/batched_hmc.rs:129-190
+//   GenericHMC::step / leapfrog_chain       /root/reference/src/generic_hmc.rs:166-221
+//   BatchVector ops for Tensor<B,2>         /root/reference/src/euclidean.rs:447-534
+//   autodiff logp_and_grad adapter          /root/reference/src/hmc.rs:42-61
+//   HMC::run stack + permute                /root/reference/src/hmc.rs:164-181
+//
+// Mapping: a chain is spread over `lpc` adjacent lanes of one warp (lpc = 1,2,..,32); each lane owns
+// EPL contiguous coordinates in registers.  q, p and the gradient never leave registers during the L
+// leapfrog steps; cross-lane traffic is two shuffles per gradient (stencil halo) and one shuffle tree
+// per reduction (kinetic energy, log density).  A per-warp shared-memory row per chain stages (a) the
+// Philox normals (generated block-aligned by the chain's lanes, contract in include/gmcmc.h) and
+// (b) the accepted position, so the [chains, samples, dim] write-out is coalesced and vectorised.
+//
+// This header is compiled twice: GM_EXACT=0 (default flags: FMA contraction, merged half kicks,
+// log-density only where the Hamiltonian needs it) and GM_EXACT=1 with nvcc --fmad=false (reference
+// operation order, sequential left-to-right sums: bit-for-bit the CPU oracle).
+#pragma once
+#include "kernels.h"
+#include "philox.cuh"
+
+#include <cmath>
+
+#ifndef GM_EXACT
+#define GM_EXACT 0
+#endif
+#if GM_EXACT
+#define GM_NS exact
+#else
+#define GM_NS fast
+#endif
+
+namespace gm {
+namespace GM_NS {
+
+constexpr bool kExact = (GM_EXACT != 0);
+constexpr unsigned kFull = 0xffffffffu;
+
+struct Lane {
+  int part;       // which slice of the chain this lane owns
+  int lpc;        // lanes per chain
+  int gbase;      // warp lane index of part 0 of this chain
+  int lo;         // first coordinate owned
+  int d;          // chain dimension
+  int nvalid;     // number of owned coordinates that are < d
+  bool first;     // owns coordinate 0
+  bool last;      // owns coordinate d-1 as its LAST slot (exact-fit decompositions only)
+};
+
+template <int EPL>
+__device__ __forceinline__ Lane make_lane(int tid_in_grid, int lpc, int d) {
+  Lane ln;
+  ln.lpc = lpc;
+  ln.part = tid_in_grid & (lpc - 1);
+  ln.gbase = (threadIdx.x & 31) - ln.part;
+  ln.lo = ln.part * EPL;
+  ln.d = d;
+  int nv = d - ln.lo;
+  ln.nvalid = nv < 0 ? 0 : (nv > EPL ? EPL : nv);
+  ln.first = ln.part == 0;
+  ln.last = (ln.lo + EPL == d);
+  return ln;
+}
+
+// Sum of per-lane term arrays over the whole chain; every lane of the chain gets the result.
+// EXACT: strict left-to-right order over coordinates (lane k continues lane k-1's running sum).
+template <class T, int EPL>
+__device__ __forceinline__ T chain_sum(const T (&terms)[EPL], int n, const Lane& ln) {
+  if constexpr (kExact) {
+    T s = T(0);
+    for (int k = 0; k < ln.lpc; ++k) {
+      if (ln.part == k) {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j)
+          if (j < n) s = s + terms[j];
+      }
+      s = __shfl_sync(kFull, s, ln.gbase + k);
+    }
+    return s;
+  } else {
+    T s0 = T(0), s1 = T(0);
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      T v = (j < n) ? terms[j] : T(0);
+      if (j & 1) s1 += v; else s0 += v;
+    }
+    T s = s0 + s1;
+    for (int o = ln.lpc >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+    return s;
+  }
+}
+
+template <class T>
+__device__ __forceinline__ T chain_max(T v, const Lane& ln) {
+  for (int o = ln.lpc >> 1; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Targets.  eval<WANT_LOGP>(x, g, ...) writes the gradient slice and returns the chain's log
+// density (valid on every lane of the chain) when WANT_LOGP, else 0.
+// ----------------------------------------------------------------------------------------------
+template <class T>
+struct TParams {          // per-launch target parameters in T
+  T sp[kMaxScalarParams];
+  const T* dp;            // device block (dense Gaussian: mu[d], P[d*d], nc; mixture: w[K], mu[K*d])
+  int n_comp;
+  // derived for DiffableGaussian2D (distributions.rs:229-253)
+  T inv_cov[2][2];
+  T norm_const;
+};
+
+struct TagRosenbrockND {};
+struct TagIsoGauss {};
+struct TagDenseGauss {};
+struct TagMixture {};
+struct TagRosenbrock2D {};
+struct TagDiffGauss2D {};
+struct TagGauss2D {};
+
+// RosenbrockND — distributions.rs:544-554:  logp = -sum_{i<d-1} [100 (x_{i+1} - x_i^2)^2 + (1 - x_i)^2]
+// Gradient (the reference differentiates the same expression by autodiff):
+//   g_i = [i<d-1] (400 t_i x_i + 2 (1 - x_i)) + [i>0] (-200 t_{i-1}),  t_i = x_{i+1} - x_i^2
+template <class T, int EPL, bool PADDED, bool WANT_LOGP>
+__device__ __forceinline__ T eval_target(TagRosenbrockND, const T (&x)[EPL], T (&g)[EPL], const Lane& ln,
+                                         const TParams<T>&, T*) {
+  const T x_next_lane = __shfl_down_sync(kFull, x[0], 1);
+  T gt[EPL];     // fast: t_j ; exact: gt_j = -200 t_j
+  T terms[EPL];
+  bool low[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) {
+    const T xn = (j + 1 < EPL) ? x[j + 1] : x_next_lane;
+    bool has_low;
+    if constexpr (PADDED) has_low = (ln.lo + j) < (ln.d - 1);
+    else has_low = (j + 1 < EPL) ? true : !ln.last;
+    low[j] = has_low;
+    T t = xn - x[j] * x[j];
+    if (!has_low) t = T(0);
+    if constexpr (kExact) {
+      T u = (-x[j]) + T(1);
+      terms[j] = has_low ? ((t * t) * T(100) + u * u) : T(0);
+      gt[j] = T(-200) * t;
+    } else {
+      if constexpr (WANT_LOGP) {
+        T u = T(1) - x[j];
+        terms[j] = has_low ? (T(100) * t * t + u * u) : T(0);
+      }
+      gt[j] = t;
+    }
+  }
+  T prev = __shfl_up_sync(kFull, gt[EPL - 1], 1);
+  if (ln.first) prev = T(0);
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) {
+    const T gp = (j == 0) ? prev : gt[j - 1];
+    if constexpr (kExact) {
+      T u = (-x[j]) + T(1);
+      T gi;
+      if (low[j]) {
+        gi = (T(-2) * (gt[j] * x[j])) + T(2) * u;
+        if (ln.lo + j > 0) gi = gi + gp;
+      } else {
+        gi = (ln.lo + j > 0 && ln.lo + j < ln.d) ? gp : T(0);
+      }
+      g[j] = gi;
+    } else {
+      T a = T(400) * gt[j] - T(2);
+      T lowterm = x[j] * a + T(2);
+      if (!low[j]) lowterm = T(0);
+      T gi = T(-200) * gp + lowterm;
+      if constexpr (PADDED) { if (ln.lo + j >= ln.d) gi = T(0); }
+      g[j] = gi;
+    }
+  }
+  if constexpr (WANT_LOGP || kExact) {
+    if constexpr (!WANT_LOGP) return T(0);
+    // number of coordinates with a "low" term in this lane: i < d-1
+    int nl = ln.d - 1 - ln.lo;
+    nl = nl < 0 ? 0 : (nl > EPL ? EPL : nl);
+    return -chain_sum<T, EPL>(terms, nl, ln);
+  }
+  return T(0);
+}
+
+// IsotropicGaussian as a gradient target — distributions.rs:398-406 (nuts.rs:484-496 StandardNormal)
+template <class T, int EPL, bool PADDED, bool WANT_LOGP>
+__device__ __forceinline__ T eval_target(TagIsoGauss, const T (&x)[EPL], T (&g)[EPL], const Lane& ln,
+                                         const TParams<T>& tp, T*) {
+  const T var = tp.sp[0] * tp.sp[0];
+  T terms[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) {
+    terms[j] = x[j] * x[j];
+    g[j] = (j < ln.nvalid) ? (-x[j] / var) : T(0);
+  }
+  if constexpr (!WANT_LOGP) return T(0);
+  T sum = chain_sum<T, EPL>(terms, ln.nvalid, ln);
+  return -T(0.5) * sum / var;
+}
+
+// Dense-covariance Gaussian, generic-d register/shared path (the tensor-core path for large d is K3):
+//   delta = x - mu ; z = delta . P ; logp = nc - 0.5 sum(z * delta) ; grad = -z   (P symmetric)
+// N-D form of DiffableGaussian2D::unnorm_logp_batch, distributions.rs:265-291.
+template <class T, int EPL, bool PADDED, bool WANT_LOGP>
+__device__ __forceinline__ T eval_target(TagDenseGauss, const T (&x)[EPL], T (&g)[EPL], const Lane& ln,
+                                         const TParams<T>& tp, T* row) {
+  const int d = ln.d;
+  const T* mu = tp.dp;
+  const T* P = tp.dp + d;
+  T delta[EPL];
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) {
+    delta[j] = (j < ln.nvalid) ? (x[j] - mu[ln.lo + j]) : T(0);
+    if (j < ln.nvalid) row[ln.lo + j] = delta[j];
+  }
+  __syncwarp();
+  T z[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) z[j] = T(0);
+  for (int i = 0; i < d; ++i) {
+    const T di = row[i];
+    const T* Pi = P + (size_t)i * d + ln.lo;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j)
+      if (j < ln.nvalid) z[j] = z[j] + di * Pi[j];
+  }
+  __syncwarp();
+  T terms[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) {
+    g[j] = -z[j];
+    terms[j] = z[j] * delta[j];
+  }
+  if constexpr (!WANT_LOGP) return T(0);
+  T quad = chain_sum<T, EPL>(terms, ln.nvalid, ln);
+  const T nc = tp.dp[(size_t)d + (size_t)d * d];
+  return nc - quad * T(0.5);
+}
+
+// Isotropic Gaussian mixture (synthetic target of BASELINE cfg5):
+//   logp = logsumexp_k( ln w_k - |x - mu_k|^2 / (2 sigma^2) ),  grad = sum_k r_k (mu_k - x) / sigma^2
+constexpr int kMaxComp = 8;
+template <class T, int EPL, bool PADDED, bool WANT_LOGP>
+__device__ __forceinline__ T eval_target(TagMixture, const T (&x)[EPL], T (&g)[EPL], const Lane& ln,
+                                         const TParams<T>& tp, T*) {
+  const int K = tp.n_comp;
+  const int d = ln.d;
+  const T sigma = tp.sp[1];
+  const T inv_var = T(1) / (sigma * sigma);
+  const T* w = tp.dp;
+  const T* mu = tp.dp + K;
+  T a[kMaxComp];
+  T amax = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < kMaxComp; ++k) {
+    a[k] = -INFINITY;
+    if (k < K) {
+      T terms[EPL];
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) {
+        T df = (j < ln.nvalid) ? (x[j] - mu[(size_t)k * d + ln.lo + j]) : T(0);
+        terms[j] = df * df;
+      }
+      T sq = chain_sum<T, EPL>(terms, ln.nvalid, ln);
+      a[k] = log(w[k]) - T(0.5) * sq * inv_var;
+      amax = max(amax, a[k]);
+    }
+  }
+  T se = T(0);
+#pragma unroll
+  for (int k = 0; k < kMaxComp; ++k)
+    if (k < K) { a[k] = exp(a[k] - amax); se = se + a[k]; }
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) {
+    T acc = T(0);
+#pragma unroll
+    for (int k = 0; k < kMaxComp; ++k)
+      if (k < K && j < ln.nvalid) acc = acc + (a[k] / se) * (mu[(size_t)k * d + ln.lo + j] - x[j]);
+    g[j] = acc * inv_var;
+  }
+  return amax + log(se);
+}
+
+// Rosenbrock2D — distributions.rs:502-515 (one lane per chain, EPL == 2)
+template <class T, int EPL, bool PADDED, bool WANT_LOGP>
+__device__ __forceinline__ T eval_target(TagRosenbrock2D, const T (&x)[EPL], T (&g)[EPL], const Lane&,
+                                         const TParams<T>& tp, T*) {
+  static_assert(EPL == 2, "Rosenbrock2D is 2-D");
+  const T a = tp.sp[0], b = tp.sp[1];
+  T u = (-x[0]) + a;
+  T t = x[1] - x[0] * x[0];
+  T term1 = u * u;
+  T term2 = (t * t) * b;
+  T gt = -((T(2) * t) * b);
+  g[1] = gt;
+  g[0] = (T(2) * u) + (-(T(2) * (gt * x[0])));
+  return -(term1 + term2);
+}
+
+// DiffableGaussian2D — distributions.rs:265-291 (gradient in backward-pass order, see oracle)
+template <class T, int EPL, bool PADDED, bool WANT_LOGP>
+__device__ __forceinline__ T eval_target(TagDiffGauss2D, const T (&x)[EPL], T (&g)[EPL], const Lane&,
+                                         const TParams<T>& tp, T*) {
+  static_assert(EPL == 2, "DiffableGaussian2D is 2-D");
+  T d0 = x[0] - tp.sp[0], d1 = x[1] - tp.sp[1];
+  T z0 = d0 * tp.inv_cov[0][0] + d1 * tp.inv_cov[1][0];
+  T z1 = d0 * tp.inv_cov[0][1] + d1 * tp.inv_cov[1][1];
+  T quad = z0 * d0 + z1 * d1;
+  const T h = T(0.5);
+  T m0 = -(h * d0), m1 = -(h * d1);
+  g[0] = (-(h * z0)) + (m0 * tp.inv_cov[0][0] + m1 * tp.inv_cov[0][1]);
+  g[1] = (-(h * z1)) + (m0 * tp.inv_cov[1][0] + m1 * tp.inv_cov[1][1]);
+  return tp.norm_const - quad * h;
+}
+
+// Gaussian2D — distributions.rs:195-207 (+ gradient, which the reference does not define)
+template <class T, int EPL, bool PADDED, bool WANT_LOGP>
+__device__ __forceinline__ T eval_target(TagGauss2D, const T (&x)[EPL], T (&g)[EPL], const Lane&,
+                                         const TParams<T>& tp, T*) {
+  static_assert(EPL == 2, "Gaussian2D is 2-D");
+  T a = tp.sp[2], b = tp.sp[3], c = tp.sp[4], dd = tp.sp[5];
+  T det = a * dd - b * c;
+  T d0 = x[0] - tp.sp[0], d1 = x[1] - tp.sp[1];
+  T i00 = dd / det, i01 = (-b) / det, i10 = (-c) / det, i11 = a / det;
+  T v0 = d0 * i00 + d1 * i10;
+  T v1 = d0 * i01 + d1 * i11;
+  T w0 = i00 * d0 + i01 * d1;
+  T w1 = i10 * d0 + i11 * d1;
+  g[0] = -T(0.5) * (v0 + w0);
+  g[1] = -T(0.5) * (v1 + w1);
+  return -T(0.5) * (v0 * d0 + v1 * d1);
+}
+
+template <class T>
+__host__ inline TParams<T> make_tparams(const TargetDesc& td) {
+  TParams<T> tp;
+  for (int i = 0; i < kMaxScalarParams; ++i) tp.sp[i] = (T)td.sp[i];
+  tp.dp = (const T*)td.dparams;
+  tp.n_comp = td.n_comp;
+  tp.inv_cov[0][0] = tp.inv_cov[0][1] = tp.inv_cov[1][0] = tp.inv_cov[1][1] = T(0);
+  tp.norm_const = T(0);
+  if (td.kind == 2 /* DIFF_GAUSS2D */) {
+    // DiffableGaussian2D::new, distributions.rs:229-253, evaluated in T on the host (IEEE, same as oracle)
+    volatile T c00 = tp.sp[2], c01 = tp.sp[3], c10 = tp.sp[4], c11 = tp.sp[5];
+    volatile T m1 = c00 * c11;
+    volatile T m2 = c01 * c10;
+    volatile T det_cov = m1 - m2;
+    volatile T inv_det = T(1) / det_cov;
+    tp.inv_cov[0][0] = c11 * inv_det;
+    tp.inv_cov[0][1] = -c01 * inv_det;
+    tp.inv_cov[1][0] = -c10 * inv_det;
+    tp.inv_cov[1][1] = c00 * inv_det;
+    T logdet = std::log((T)det_cov);
+    T two = T(1) + T(1);
+    const T pi = (T)3.14159265358979323846264338327950288;
+    volatile T l2pi = std::log(two * pi);
+    volatile T tl = two * l2pi;
+    volatile T sum = tl + logdet;
+    tp.norm_const = -sum / two;
+  }
+  return tp;
+}
+
+// ----------------------------------------------------------------------------------------------
+// The trajectory kernel
+// ----------------------------------------------------------------------------------------------
+template <class T>
+struct HmcArgs {
+  TParams<T> tp;
+  size_t n_chains;
+  unsigned long long chain_offset;
+  PhiloxKey key;
+  uint32_t step_base;
+  T* positions;
+  const T* eps;
+  int eps_stride;
+  int d, d_pad, lpc;
+  uint32_t L, n_steps, n_skip;
+  T* out;
+  size_t out_n;
+  uint32_t out_t0;
+  unsigned long long* accept_total;
+  unsigned long long* diverge_total;
+  double* alpha_part;   // [warps of the grid] per-warp sum of min(1, exp(log_accept)) or null
+  T* da_eps; T* da_eps_bar; T* da_h_bar; T* da_mu;
+  uint32_t da_m_base, da_n_adapt;
+  T da_delta;
+  const T* inj_normals;
+  const T* inj_lnu;
+  T* diag_logacc;
+  uint8_t* diag_acc;
+  T* diag_pq;
+  T* diag_pp;
+};
+
+template <class T> struct VecOf;
+template <> struct VecOf<float> { using type = float4; static constexpr int n = 4; };
+template <> struct VecOf<double> { using type = double2; static constexpr int n = 2; };
+
+// Cooperative, coalesced copy of the warp's staged rows to [chain, slot, :] of the sample tensor.
+template <class T>
+__device__ __forceinline__ void store_rows(const T* warp_stage, int d, int d_pad, int chains_in_warp,
+                                           size_t first_chain, size_t n_chains, T* out, size_t out_n,
+                                           size_t slot) {
+  const int lane = threadIdx.x & 31;
+  using V = typename VecOf<T>::type;
+  constexpr int VN = VecOf<T>::n;
+  if ((d % VN) == 0) {
+    const int nv = d / VN;
+    for (int c = 0; c < chains_in_warp; ++c) {
+      size_t chain = first_chain + c;
+      if (chain >= n_chains) break;
+      const V* src = reinterpret_cast<const V*>(warp_stage + (size_t)c * d_pad);
+      V* dst = reinterpret_cast<V*>(out + (chain * out_n + slot) * (size_t)d);
+      for (int i = lane; i < nv; i += 32) __stcs(dst + i, src[i]);
+    }
+  } else {
+    for (int c = 0; c < chains_in_warp; ++c) {
+      size_t chain = first_chain + c;
+      if (chain >= n_chains) break;
+      const T* src = warp_stage + (size_t)c * d_pad;
+      T* dst = out + (chain * out_n + slot) * (size_t)d;
+      for (int i = lane; i < d; i += 32) __stcs(dst + i, src[i]);
+    }
+  }
+}
+
+template <class T, int EPL, class TAG, bool PADDED>
+__global__ void __launch_bounds__(kHmcBlock) hmc_run_kernel(const HmcArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* stage = reinterpret_cast<T*>(smem_raw);
+
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const Lane ln = make_lane<EPL>(tid, a.lpc, a.d);
+  const size_t chain = (size_t)(tid / a.lpc);
+  const bool active = chain < a.n_chains;
+  const int chains_in_warp = 32 / a.lpc;
+  const int warp_in_block = threadIdx.x >> 5;
+  const int chain_in_warp = (threadIdx.x & 31) / a.lpc;
+  T* warp_stage = stage + (size_t)warp_in_block * chains_in_warp * a.d_pad;
+  T* row = warp_stage + (size_t)chain_in_warp * a.d_pad;
+  const size_t warp_first_chain = (size_t)((tid & ~31) / a.lpc);
+  const unsigned long long gchain = a.chain_offset + chain;
+
+  // current position -> registers
+  T qc[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j)
+    qc[j] = (active && j < ln.nvalid) ? a.positions[chain * a.d + ln.lo + j] : T(1);
+
+  T eps = active ? a.eps[a.eps_stride ? chain : 0] : T(0.01);
+  // per-chain dual averaging state (GMCMC_ADAPT_PER_CHAIN; generic_nuts.rs:882-924)
+  T da_eps_bar = T(1), da_h_bar = T(0), da_mu = T(0);
+  const bool per_chain_da = a.da_eps != nullptr;
+  if (per_chain_da && active) {
+    eps = a.da_eps[chain]; da_eps_bar = a.da_eps_bar[chain]; da_h_bar = a.da_h_bar[chain]; da_mu = a.da_mu[chain];
+  }
+
+  unsigned int n_accept = 0, n_diverge = 0;
+  double alpha_acc = 0.0;
+
+  for (uint32_t s = 0; s < a.n_steps; ++s) {
+    const uint32_t step = a.step_base + s;
+    T q[EPL], p[EPL], g[EPL];
+
+    // ---- 1. momentum ~ N(0, I)   (batched_hmc.rs:131 / generic_hmc.rs:177)
+    if (a.inj_normals) {
+#pragma unroll
+      for (int j = 0; j < EPL; ++j)
+        p[j] = (active && j < ln.nvalid) ? a.inj_normals[((size_t)s * a.n_chains + chain) * a.d + ln.lo + j] : T(0);
+    } else {
+      constexpr int NPB = NormalsPerBlock<T>::value;
+      const int nblocks = (a.d + NPB - 1) / NPB;
+      __syncwarp();
+      for (int b = ln.part; b < nblocks; b += a.lpc) {
+        T z[NPB];
+        normals_from_block(philox4x32_10(philox_ctr(gchain, step, 0u, (uint32_t)b), a.key), z);
+#pragma unroll
+        for (int k = 0; k < NPB; ++k)
+          if (b * NPB + k < a.d_pad) row[b * NPB + k] = z[k];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) p[j] = (j < ln.nvalid) ? row[ln.lo + j] : T(0);
+      __syncwarp();
+    }
+
+    // ---- 2. kinetic energy, log density and gradient at the current point (batched_hmc.rs:134-138)
+    T terms[EPL];
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) { q[j] = qc[j]; terms[j] = p[j] * p[j]; }
+    const T ke0 = chain_sum<T, EPL>(terms, ln.nvalid, ln) * T(0.5);
+    const T logp0 = eval_target<T, EPL, PADDED, true>(TAG{}, q, g, ln, a.tp, row);
+
+    // ---- 3. L leapfrog steps (batched_hmc.rs:166-190 / generic_hmc.rs:204-221)
+    T logp1 = logp0;
+    if constexpr (kExact) {
+      const T half = T(0.5) * eps;
+      for (uint32_t l = 0; l < a.L; ++l) {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) p[j] = p[j] + g[j] * half;
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) q[j] = q[j] + p[j] * eps;
+        logp1 = eval_target<T, EPL, PADDED, true>(TAG{}, q, g, ln, a.tp, row);
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) p[j] = p[j] + g[j] * half;
+      }
+    } else {
+      // merged kicks: p += eps/2 g ; (q += eps p ; g = grad(q) ; p += eps g) x (L-1) ; last kick eps/2
+      const T half = T(0.5) * eps;
+      if (a.L > 0) {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) p[j] += half * g[j];
+        for (uint32_t l = 0; l + 1 < a.L; ++l) {
+#pragma unroll
+          for (int j = 0; j < EPL; ++j) q[j] += eps * p[j];
+          eval_target<T, EPL, PADDED, false>(TAG{}, q, g, ln, a.tp, row);
+#pragma unroll
+          for (int j = 0; j < EPL; ++j) p[j] += eps * g[j];
+        }
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) q[j] += eps * p[j];
+        logp1 = eval_target<T, EPL, PADDED, true>(TAG{}, q, g, ln, a.tp, row);
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) p[j] += half * g[j];
+      }
+    }
+
+    // ---- 4. Hamiltonian + Metropolis accept (batched_hmc.rs:148-162 / generic_hmc.rs:195-200)
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) terms[j] = p[j] * p[j];
+    const T ke1 = chain_sum<T, EPL>(terms, ln.nvalid, ln) * T(0.5);
+    const T log_accept = (logp1 - logp0) + (ke0 - ke1);
+    T ln_u;
+    if (a.inj_lnu) {
+      ln_u = active ? a.inj_lnu[(size_t)s * a.n_chains + chain] : T(0);
+    } else {
+      ln_u = log(accept_uniform<T>(philox4x32_10(philox_ctr(gchain, step, 1u, 0u), a.key)));
+    }
+    const bool accept = (ln_u <= log_accept);
+    if (accept) {
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) qc[j] = q[j];
+    }
+    const bool finite = (log_accept == log_accept) && (fabs(log_accept) < T(INFINITY));
+    const T alpha = finite ? min(T(1), exp(log_accept)) : (log_accept > T(0) ? T(1) : T(0));
+    if (active && ln.part == 0) {
+      n_accept += accept ? 1u : 0u;
+      n_diverge += finite ? 0u : 1u;
+      alpha_acc += (double)alpha;
+    }
+
+    if (a.diag_logacc && active) {
+      const size_t idx = (size_t)s * a.n_chains + chain;
+      if (ln.part == 0) { a.diag_logacc[idx] = log_accept; a.diag_acc[idx] = accept ? 1 : 0; }
+      if (a.diag_pq) {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j)
+          if (j < ln.nvalid) { a.diag_pq[idx * a.d + ln.lo + j] = q[j]; a.diag_pp[idx * a.d + ln.lo + j] = p[j]; }
+      }
+    }
+
+    // ---- 5. per-chain dual averaging (optional; constants generic_nuts.rs:638-641)
+    if (per_chain_da) {
+      const uint32_t m = a.da_m_base + s + 1;
+      if (m <= a.da_n_adapt) {
+        const T mm = (T)m;
+        T eta = T(1) / (T)(m + 10u);
+        da_h_bar = (T(1) - eta) * da_h_bar + eta * (a.da_delta - alpha);
+        eps = exp(da_mu - sqrt(mm) / T(0.05) * da_h_bar);
+        eta = pow(mm, -T(0.75));
+        da_eps_bar = exp((T(1) - eta) * log(da_eps_bar) + eta * log(eps));
+        if (m == a.da_n_adapt) eps = da_eps_bar;
+      }
+    }
+
+    // ---- 6. write-out [chain, slot, :]   (hmc.rs:173-180 stack+permute, fused)
+    if (s >= a.n_skip && a.out) {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < EPL; ++j)
+        if (j < ln.nvalid) row[ln.lo + j] = qc[j];
+      __syncwarp();
+      store_rows<T>(warp_stage, a.d, a.d_pad, chains_in_warp, warp_first_chain, a.n_chains, a.out, a.out_n,
+                    (size_t)a.out_t0 + (s - a.n_skip));
+      __syncwarp();
+    }
+  }
+
+  // ---- state back to HBM
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < EPL; ++j)
+      if (j < ln.nvalid) a.positions[chain * a.d + ln.lo + j] = qc[j];
+    if (per_chain_da && ln.part == 0) {
+      a.da_eps[chain] = eps; a.da_eps_bar[chain] = da_eps_bar; a.da_h_bar[chain] = da_h_bar;
+    }
+  }
+  // counters: warp reduce, one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) {
+    n_accept += __shfl_xor_sync(kFull, n_accept, o);
+    n_diverge += __shfl_xor_sync(kFull, n_diverge, o);
+    alpha_acc += __shfl_xor_sync(kFull, alpha_acc, o);   // xor tree: same value on every lane, fixed order
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (n_accept) atomicAdd(a.accept_total, (unsigned long long)n_accept);
+    if (n_diverge) atomicAdd(a.diverge_total, (unsigned long long)n_diverge);
+    if (a.alpha_part) a.alpha_part[(size_t)(blockIdx.x * blockDim.x + threadIdx.x) >> 5] = alpha_acc;
+  }
+}
+
+// logp / gradient of a batch of points through the same target code (gmcmc_target_logp_grad)
+template <class T, int EPL, class TAG, bool PADDED>
+__global__ void __launch_bounds__(kHmcBlock) eval_kernel(TParams<T> tp, size_t n, int d, int d_pad, int lpc,
+                                                         const T* x, T* logp, T* grad) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* stage = reinterpret_cast<T*>(smem_raw);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const Lane ln = make_lane<EPL>(tid, lpc, d);
+  const size_t pt = (size_t)(tid / lpc);
+  const bool active = pt < n;
+  T* row = stage + (size_t)(threadIdx.x / lpc) * d_pad;
+  T q[EPL], g[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) q[j] = (active && j < ln.nvalid) ? x[pt * d + ln.lo + j] : T(1);
+  T lp = eval_target<T, EPL, PADDED, true>(TAG{}, q, g, ln, tp, row);
+  if (active) {
+    if (ln.part == 0) logp[pt] = lp;
+    if (grad) {
+#pragma unroll
+      for (int j = 0; j < EPL; ++j)
+        if (j < ln.nvalid) grad[pt * d + ln.lo + j] = g[j];
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Host-side dispatch
+// ----------------------------------------------------------------------------------------------
+template <class T>
+inline HmcArgs<T> make_args(const HmcLaunch& L) {
+  HmcArgs<T> a;
+  a.tp = make_tparams<T>(L.tgt);
+  a.n_chains = L.n_chains;
+  a.chain_offset = L.chain_offset;
+  a.key = PhiloxKey{(uint32_t)L.seed, (uint32_t)(L.seed >> 32)};
+  a.step_base = L.step_base;
+  a.positions = (T*)L.positions;
+  a.eps = (const T*)L.eps;
+  a.eps_stride = L.eps_stride;
+  a.d = L.tgt.dim;
+  constexpr int VN = VecOf<T>::n;
+  a.d_pad = ((L.tgt.dim + 3) / 4) * 4;
+  (void)VN;
+  a.lpc = L.lpc;
+  a.L = L.n_leapfrog; a.n_steps = L.n_steps; a.n_skip = L.n_skip;
+  a.out = (T*)L.out; a.out_n = L.out_n; a.out_t0 = L.out_t0;
+  a.accept_total = L.accept_total; a.diverge_total = L.diverge_total; a.alpha_part = L.alpha_part;
+  a.da_eps = (T*)L.da_eps; a.da_eps_bar = (T*)L.da_eps_bar; a.da_h_bar = (T*)L.da_h_bar; a.da_mu = (T*)L.da_mu;
+  a.da_m_base = L.da_m_base; a.da_n_adapt = L.da_n_adapt; a.da_delta = (T)L.da_delta;
+  a.inj_normals = (const T*)L.inj_normals; a.inj_lnu = (const T*)L.inj_lnu;
+  a.diag_logacc = (T*)L.diag_logacc; a.diag_acc = L.diag_acc; a.diag_pq = (T*)L.diag_pq; a.diag_pp = (T*)L.diag_pp;
+  return a;
+}
+
+template <class T, int EPL, class TAG, bool PADDED>
+inline cudaError_t launch_one(const HmcLaunch& L, cudaStream_t st) {
+  HmcArgs<T> a = make_args<T>(L);
+  const size_t threads = L.n_chains * (size_t)L.lpc;
+  const unsigned blocks = (unsigned)((threads + kHmcBlock - 1) / kHmcBlock);
+  const size_t smem = (size_t)(kHmcBlock / L.lpc) * a.d_pad * sizeof(T);
+  auto kern = hmc_run_kernel<T, EPL, TAG, PADDED>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<blocks, kHmcBlock, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <class T, int EPL, class TAG, bool PADDED>
+inline cudaError_t eval_one(const EvalLaunch& E, cudaStream_t st) {
+  TParams<T> tp = make_tparams<T>(E.tgt);
+  const int d = E.tgt.dim, d_pad = ((d + 3) / 4) * 4;
+  const size_t threads = E.n * (size_t)E.lpc;
+  const unsigned blocks = (unsigned)((threads + kHmcBlock - 1) / kHmcBlock);
+  const size_t smem = (size_t)(kHmcBlock / E.lpc) * d_pad * sizeof(T);
+  auto kern = eval_kernel<T, EPL, TAG, PADDED>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<blocks, kHmcBlock, smem, st>>>(tp, E.n, d, d_pad, E.lpc, (const T*)E.x, (T*)E.logp, (T*)E.grad);
+  return cudaGetLastError();
+}
+
+// EPL menu of the register-resident kernels
+#define GM_FOR_EPL(X) X(1) X(2) X(3) X(4) X(8) X(13) X(16) X(25) X(32)
+
+template <class T, class TAG, bool ALLOW_EXACT_FIT>
+inline cudaError_t dispatch_epl(const HmcLaunch& L, cudaStream_t st) {
+  const bool padded = (L.epl * L.lpc != L.tgt.dim);
+  switch (L.epl) {
+#define GM_CASE(E)                                                                        \
+  case E:                                                                                 \
+    if constexpr (sizeof(T) == 8 && (E) > 16) return cudaErrorInvalidValue;               \
+    else {                                                                                \
+      if constexpr (ALLOW_EXACT_FIT) { if (!padded) return launch_one<T, E, TAG, false>(L, st); } \
+      return launch_one<T, E, TAG, true>(L, st);                                          \
+    }
+    GM_FOR_EPL(GM_CASE)
+#undef GM_CASE
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <class T, class TAG, bool ALLOW_EXACT_FIT>
+inline cudaError_t dispatch_eval_epl(const EvalLaunch& E, cudaStream_t st) {
+  const bool padded = (E.epl * E.lpc != E.tgt.dim);
+  switch (E.epl) {
+#define GM_CASE(EP)                                                                      \
+  case EP:                                                                                \
+    if constexpr (sizeof(T) == 8 && (EP) > 16) return cudaErrorInvalidValue;              \
+    else {                                                                                \
+      if constexpr (ALLOW_EXACT_FIT) { if (!padded) return eval_one<T, EP, TAG, false>(E, st); } \
+      return eval_one<T, EP, TAG, true>(E, st);                                           \
+    }
+    GM_FOR_EPL(GM_CASE)
+#undef GM_CASE
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace GM_NS
+}  // namespace gm

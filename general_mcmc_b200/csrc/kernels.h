@@ -1,0 +1,125 @@
+// kernels.h — type-erased launch descriptors shared by the host runtime (runtime.cu) and the
+// kernel translation units (hmc_*.cu, mh.cu, stats.cu, nuts.cu).  Internal; the public surface
+// is include/gmcmc.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace gm {
+
+constexpr int kMaxScalarParams = 8;
+constexpr int kHmcBlock = 128;  // threads per CTA of the trajectory kernels
+
+struct TargetDesc {
+  int kind;                          // gmcmc_target_kind
+  int dtype;                         // gmcmc_dtype
+  int dim;
+  double sp[kMaxScalarParams];       // small parameter block (cast to T in the kernel)
+  const void* dparams;               // device parameter block in T (dense Gaussian, mixture), or null
+  int n_comp;                        // mixture components
+};
+
+struct HmcLaunch {
+  TargetDesc tgt;
+  size_t n_chains;
+  uint64_t chain_offset;
+  uint64_t seed;
+  uint32_t step_base;    // transition index of the first transition of this launch
+  void* positions;       // [C, d] T, in/out
+  const void* eps;       // device step size(s), T
+  int eps_stride;        // 0: one shared scalar, 1: per chain
+  uint32_t n_leapfrog;
+  uint32_t n_steps;      // transitions in this launch
+  uint32_t n_skip;       // the first n_skip transitions are not recorded
+  void* out;             // samples base [C, out_n, d] T (may be null when n_steps == n_skip)
+  size_t out_n;          // samples per chain in `out`
+  uint32_t out_t0;       // sample slot of the first recorded transition of this launch
+  // statistics
+  unsigned long long* accept_total;  // [1]
+  unsigned long long* diverge_total; // [1]
+  double* alpha_part;                // [ceil(C*lpc/32)] per-warp sums of min(1, exp(log_accept)) over the launch, or null
+  // per-chain dual averaging (GMCMC_ADAPT_PER_CHAIN), all T [C]; null otherwise
+  void* da_eps; void* da_eps_bar; void* da_h_bar; void* da_mu;
+  uint32_t da_m_base;    // adaptation iteration of the first transition of this launch (1-based m = base + s + 1)
+  uint32_t da_n_adapt;   // adapt while m <= da_n_adapt
+  double da_delta;
+  // injection (parity mode) / diagnostics; null when unused
+  const void* inj_normals;  // [n, C, d]
+  const void* inj_lnu;      // [n, C]
+  void* diag_logacc;        // [n, C]
+  uint8_t* diag_acc;        // [n, C]
+  void* diag_pq;            // [n, C, d]
+  void* diag_pp;            // [n, C, d]
+  // decomposition: a chain is spread over `lpc` lanes (power of two <= 32), `epl` elements per lane
+  int epl, lpc;
+};
+
+struct EvalLaunch {  // logp + grad of a batch of points (gmcmc_target_logp_grad)
+  TargetDesc tgt;
+  size_t n;
+  const void* x;   // [n, d]
+  void* logp;      // [n]
+  void* grad;      // [n, d] or null
+  int epl, lpc;
+};
+
+struct MhLaunch {
+  TargetDesc tgt;
+  double prop_std;
+  size_t n_chains;
+  uint64_t chain_offset;
+  uint64_t seed;
+  uint32_t step_base;
+  void* state;        // [C, d] T in/out
+  uint32_t n_steps, n_skip;
+  double* out;        // [C, out_n, d] f64
+  size_t out_n;
+  uint32_t out_t0;
+  unsigned long long* accept_total;
+  const void* inj_normals;  // [n, C, d] T
+  const void* inj_lnu;      // [n, C] T
+  void* diag_logratio;      // [n, C] T
+  uint8_t* diag_acc;        // [n, C]
+};
+
+struct StatsLaunch {
+  const void* samples;   // [C, n, p] device, f32 (dtype 0) or f64 (dtype 1)
+  int dtype;
+  size_t C, n;
+  int p;
+  size_t N;              // padded FFT length (power of two >= 2*(n/2)-1)
+  int log2n;
+  int ppb;               // parameters per CTA of stats_accumulate
+  int n_groups;          // chain groups (grid.x of stats_accumulate)
+  const void* tw;        // [N/2] float2 twiddles
+  float* part_spec;      // [n_groups, p, N/2+1]
+  double* part_mom;      // [n_groups, p, 3]
+  float* spec;           // [p, N/2+1]   chain-summed power spectrum (all-reduced across ranks)
+  double* mom;           // [p, 3]       sum of split-chain means, of their squares, of within variances
+  float* rhat;           // [p] reference orientation sqrt(W / var_hat)
+  float* rhat_std;       // [p] sqrt(var_hat / W)
+  float* ess;            // [p]
+  float* acov;           // [p, n/2] mean autocovariance (optional, may be null)
+};
+
+size_t stats_npad(size_t n);
+int stats_ppb(size_t N);
+void stats_fill_twiddles(size_t N, float* host_tw);
+cudaError_t launch_stats_accumulate(const StatsLaunch&, cudaStream_t);
+cudaError_t launch_stats_reduce(const StatsLaunch&, cudaStream_t);
+cudaError_t launch_stats_finalize(const StatsLaunch&, double total_chains, cudaStream_t);
+
+// launchers (each returns the cudaError of the launch).  *_exact are compiled with --fmad=false.
+cudaError_t launch_hmc_fast(const HmcLaunch&, cudaStream_t);
+cudaError_t launch_hmc_exact(const HmcLaunch&, cudaStream_t);
+cudaError_t launch_eval_fast(const EvalLaunch&, cudaStream_t);
+cudaError_t launch_eval_exact(const EvalLaunch&, cudaStream_t);
+cudaError_t launch_mh_fast(const MhLaunch&, cudaStream_t);
+cudaError_t launch_mh_exact(const MhLaunch&, cudaStream_t);
+
+// picks (epl, lpc) for a dimension; returns false if unsupported by the register-resident kernels
+bool choose_decomposition(int dim, int dtype, int kind, int* epl, int* lpc);
+
+}  // namespace gm

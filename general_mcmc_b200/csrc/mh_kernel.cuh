@@ -1,0 +1,319 @@
+// mh_kernel.cuh — K2: fused multi-step Metropolis–Hastings kernel (sm_100a).
+//
+// Replaces, as ONE kernel per run, the per-chain host loop of
+//   MHMarkovChain::step                      /root/reference/src/metropolis_hastings.rs:306-318
+//   IsotropicGaussian::{sample, logp}        /root/reference/src/distributions.rs:368-390
+//   Gaussian2D / IsotropicGaussian targets   /root/reference/src/distributions.rs:195-207, 398-406
+//   run_chain + ChainRunner::run stack       /root/reference/src/core.rs:95-115, 219-229
+//
+// Mapping: one thread per chain; state, proposal and log densities live in registers for every
+// step of the launch.  The f64 [chains, samples, dim] write-out (Trace -> f64, core.rs:34-51) is
+// staged in shared memory for kStageDoubles/d steps and flushed row-by-row, so each chain writes
+// 256 contiguous, 256-byte aligned bytes per flush instead of d*8 bytes at a 8*n*d stride.
+//
+// Compiled twice like K1: GM_EXACT=0 (FMA contraction, log-ratio without the cancelling proposal
+// terms) and GM_EXACT=1 with --fmad=false (reference operation order: bit-for-bit the CPU oracle
+// given the same normals and ln u).  In both modes the current log density is carried over from
+// the previous step instead of being recomputed (metropolis_hastings.rs:308 recomputes it; the
+// value is the same function of the same state, hence bit-identical).
+#pragma once
+#include "kernels.h"
+#include "philox.cuh"
+
+#include <cmath>
+
+#ifndef GM_EXACT
+#define GM_EXACT 0
+#endif
+#if GM_EXACT
+#define GM_NS exact
+#else
+#define GM_NS fast
+#endif
+
+namespace gm {
+namespace GM_NS {
+
+constexpr bool kMhExact = (GM_EXACT != 0);
+constexpr int kMhBlock = 128;
+constexpr int kStageDoubles = 32;            // doubles staged per chain between flushes (256 B)
+constexpr int kStageStride = kStageDoubles + 1;  // +1: conflict-free column writes
+
+template <class T>
+struct MhArgs {
+  int kind;
+  int d;
+  T sp[kMaxScalarParams];
+  T inv_cov[2][2];
+  T norm_const;
+  T prop_std;
+  T prop_logq_const;   // -d * 0.5 * ln(var * pi * std * std), host-computed (distributions.rs:388)
+  size_t n_chains;
+  unsigned long long chain_offset;
+  PhiloxKey key;
+  uint32_t step_base, n_steps, n_skip;
+  T* state;
+  double* out;
+  size_t out_n;
+  uint32_t out_t0;
+  unsigned long long* accept_total;
+  const T* inj_normals;
+  const T* inj_lnu;
+  T* diag_logratio;
+  uint8_t* diag_acc;
+};
+
+// Target::unnorm_logp for the MH path (distributions.rs:107-110): log density only.
+template <class T, int MAXD>
+__device__ __forceinline__ T mh_logp(const MhArgs<T>& a, const T (&x)[MAXD]) {
+  const int d = a.d;
+  switch (a.kind) {
+    case 0: {  // IsotropicGaussian, distributions.rs:398-406
+      T sum = T(0);
+#pragma unroll
+      for (int i = 0; i < MAXD; ++i)
+        if (i < d) sum = sum + x[i] * x[i];
+      return -T(0.5) * sum / (a.sp[0] * a.sp[0]);
+    }
+    case 1: {  // Gaussian2D, distributions.rs:195-207
+      const T ca = a.sp[2], cb = a.sp[3], cc = a.sp[4], cd = a.sp[5];
+      const T det = ca * cd - cb * cc;
+      const T d0 = x[0] - a.sp[0], d1 = x[MAXD > 1 ? 1 : 0] - a.sp[1];
+      const T i00 = cd / det, i01 = (-cb) / det, i10 = (-cc) / det, i11 = ca / det;
+      const T v0 = d0 * i00 + d1 * i10;
+      const T v1 = d0 * i01 + d1 * i11;
+      return -T(0.5) * (v0 * d0 + v1 * d1);
+    }
+    case 2: {  // DiffableGaussian2D, distributions.rs:265-291
+      const T d0 = x[0] - a.sp[0], d1 = x[MAXD > 1 ? 1 : 0] - a.sp[1];
+      const T z0 = d0 * a.inv_cov[0][0] + d1 * a.inv_cov[1][0];
+      const T z1 = d0 * a.inv_cov[0][1] + d1 * a.inv_cov[1][1];
+      const T quad = z0 * d0 + z1 * d1;
+      return a.norm_const - quad * T(0.5);
+    }
+    case 4: {  // Rosenbrock2D, distributions.rs:502-515
+      const T u = (-x[0]) + a.sp[0];
+      const T t = x[MAXD > 1 ? 1 : 0] - x[0] * x[0];
+      return -(u * u + (t * t) * a.sp[1]);
+    }
+    case 5: {  // RosenbrockND, distributions.rs:544-554
+      T s = T(0);
+#pragma unroll
+      for (int i = 0; i < MAXD - 1; ++i) {
+        if (i < d - 1) {
+          const T t = x[i + 1] - x[i] * x[i];
+          const T u = (-x[i]) + T(1);
+          s = s + ((t * t) * T(100) + u * u);
+        }
+      }
+      return -s;
+    }
+  }
+  return T(0);
+}
+
+// IsotropicGaussian::logp(from, to), distributions.rs:378-390
+template <class T, int MAXD>
+__device__ __forceinline__ T mh_logq(const MhArgs<T>& a, const T (&from)[MAXD], const T (&to)[MAXD]) {
+  T lp = T(0);
+  const T var = a.prop_std * a.prop_std;
+#pragma unroll
+  for (int i = 0; i < MAXD; ++i) {
+    if (i < a.d) {
+      const T diff = to[i] - from[i];
+      const T exponent = -(diff * diff) / (T(2) * var);
+      lp = lp + exponent;
+    }
+  }
+  return lp + a.prop_logq_const;
+}
+
+template <class T, int MAXD>
+__global__ void __launch_bounds__(kMhBlock) mh_run_kernel(const MhArgs<T> a) {
+  __shared__ double stage[kMhBlock * kStageStride];
+
+  const size_t chain = (size_t)blockIdx.x * kMhBlock + threadIdx.x;
+  const bool active = chain < a.n_chains;
+  const unsigned long long gchain = a.chain_offset + chain;
+  const int d = a.d;
+  const int lane = threadIdx.x & 31;
+  const int warp_row0 = threadIdx.x & ~31;
+  const size_t warp_first_chain = (size_t)blockIdx.x * kMhBlock + warp_row0;
+  const int steps_per_flush = kStageDoubles / d;  // >= 1 (d <= kStageDoubles)
+
+  T x[MAXD];
+#pragma unroll
+  for (int i = 0; i < MAXD; ++i) x[i] = (active && i < d) ? a.state[chain * d + i] : T(0);
+  T lp_cur = mh_logp<T, MAXD>(a, x);
+
+  unsigned int n_accept = 0;
+  int staged = 0;                 // steps currently in the stage
+  size_t flush_slot = a.out_t0;   // sample slot of stage column 0
+
+  for (uint32_t s = 0; s < a.n_steps; ++s) {
+    const uint32_t step = a.step_base + s;
+    // ---- proposal noise (distributions.rs:368-376): stream 0 of the RNG contract
+    T z[MAXD];
+    if (a.inj_normals) {
+#pragma unroll
+      for (int i = 0; i < MAXD; ++i)
+        z[i] = (active && i < d) ? a.inj_normals[((size_t)s * a.n_chains + chain) * d + i] : T(0);
+    } else {
+      constexpr int NPB = NormalsPerBlock<T>::value;
+#pragma unroll
+      for (int b = 0; b < (MAXD + NPB - 1) / NPB; ++b) {
+        if (b * NPB < d) {
+          T zb[NPB];
+          normals_from_block(philox4x32_10(philox_ctr(gchain, step, 0u, (uint32_t)b), a.key), zb);
+#pragma unroll
+          for (int k = 0; k < NPB; ++k)
+            if (b * NPB + k < MAXD) z[b * NPB + k] = zb[k];
+        }
+      }
+    }
+    T xp[MAXD];
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i) xp[i] = (i < d) ? (x[i] + z[i] * a.prop_std) : T(0);
+
+    // ---- log acceptance ratio (metropolis_hastings.rs:308-312)
+    const T lp_prop = mh_logp<T, MAXD>(a, xp);
+    T log_ratio;
+    if constexpr (kMhExact) {
+      const T q_fwd = mh_logq<T, MAXD>(a, x, xp);
+      const T q_bwd = mh_logq<T, MAXD>(a, xp, x);
+      log_ratio = (lp_prop + q_bwd) - (lp_cur + q_fwd);
+    } else {
+      log_ratio = lp_prop - lp_cur;  // symmetric proposal: q_fwd == q_bwd bit-for-bit
+    }
+    // ---- accept iff log_ratio > ln u (strict; metropolis_hastings.rs:313-316): stream 1
+    T ln_u;
+    if (a.inj_lnu) ln_u = active ? a.inj_lnu[(size_t)s * a.n_chains + chain] : T(0);
+    else ln_u = log(accept_uniform<T>(philox4x32_10(philox_ctr(gchain, step, 1u, 0u), a.key)));
+    const bool accept = log_ratio > ln_u;
+    if (accept) {
+#pragma unroll
+      for (int i = 0; i < MAXD; ++i) x[i] = xp[i];
+      lp_cur = lp_prop;
+    }
+    if (active) n_accept += accept ? 1u : 0u;
+    if (a.diag_logratio && active) {
+      a.diag_logratio[(size_t)s * a.n_chains + chain] = log_ratio;
+      a.diag_acc[(size_t)s * a.n_chains + chain] = accept ? 1 : 0;
+    }
+
+    // ---- write-out: stage -> [chain, slot, :] in f64
+    if (s >= a.n_skip && a.out) {
+#pragma unroll
+      for (int i = 0; i < MAXD; ++i)
+        if (i < d) stage[threadIdx.x * kStageStride + staged * d + i] = (double)x[i];
+      ++staged;
+      const bool last = (s + 1 == a.n_steps);
+      if (staged == steps_per_flush || last) {
+        __syncwarp();
+        const int ncols = staged * d;
+        for (int r = 0; r < 32; ++r) {
+          const size_t c = warp_first_chain + r;
+          if (c >= a.n_chains) break;
+          if (lane < ncols)
+            __stcs(a.out + (c * a.out_n + flush_slot) * (size_t)d + lane, stage[(warp_row0 + r) * kStageStride + lane]);
+        }
+        __syncwarp();
+        flush_slot += staged;
+        staged = 0;
+      }
+    }
+  }
+
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i)
+      if (i < d) a.state[chain * d + i] = x[i];
+  }
+  for (int o = 16; o > 0; o >>= 1) n_accept += __shfl_xor_sync(0xffffffffu, n_accept, o);
+  if (lane == 0 && n_accept) atomicAdd(a.accept_total, (unsigned long long)n_accept);
+}
+
+template <class T>
+inline MhArgs<T> make_mh_args(const MhLaunch& L) {
+  MhArgs<T> a;
+  a.kind = L.tgt.kind;
+  a.d = L.tgt.dim;
+  for (int i = 0; i < kMaxScalarParams; ++i) a.sp[i] = (T)L.tgt.sp[i];
+  a.inv_cov[0][0] = a.inv_cov[0][1] = a.inv_cov[1][0] = a.inv_cov[1][1] = T(0);
+  a.norm_const = T(0);
+  if (L.tgt.kind == 2) {
+    // DiffableGaussian2D::new (distributions.rs:229-253), evaluated in T on the host
+    volatile T c00 = a.sp[2], c01 = a.sp[3], c10 = a.sp[4], c11 = a.sp[5];
+    volatile T m1 = c00 * c11;
+    volatile T m2 = c01 * c10;
+    volatile T det_cov = m1 - m2;
+    volatile T inv_det = T(1) / det_cov;
+    a.inv_cov[0][0] = c11 * inv_det;
+    a.inv_cov[0][1] = -c01 * inv_det;
+    a.inv_cov[1][0] = -c10 * inv_det;
+    a.inv_cov[1][1] = c00 * inv_det;
+    T logdet = std::log((T)det_cov);
+    T two = T(1) + T(1);
+    const T pi = (T)3.14159265358979323846264338327950288;
+    volatile T l2pi = std::log(two * pi);
+    volatile T tl = two * l2pi;
+    volatile T sum = tl + logdet;
+    a.norm_const = -sum / two;
+  }
+  a.prop_std = (T)L.prop_std;
+  {
+    // distributions.rs:388, in T with glibc log (same as the oracle)
+    const T pi = (T)3.14159265358979323846264338327950288;
+    volatile T var = a.prop_std * a.prop_std;
+    volatile T t1 = var * pi;
+    volatile T t2 = t1 * a.prop_std;
+    volatile T t3 = t2 * a.prop_std;
+    volatile T lg = std::log((T)t3);
+    volatile T nd = -(T)L.tgt.dim;
+    volatile T h = nd * T(0.5);
+    a.prop_logq_const = h * lg;
+  }
+  a.n_chains = L.n_chains;
+  a.chain_offset = L.chain_offset;
+  a.key = PhiloxKey{(uint32_t)L.seed, (uint32_t)(L.seed >> 32)};
+  a.step_base = L.step_base; a.n_steps = L.n_steps; a.n_skip = L.n_skip;
+  a.state = (T*)L.state;
+  a.out = L.out; a.out_n = L.out_n; a.out_t0 = L.out_t0;
+  a.accept_total = L.accept_total;
+  a.inj_normals = (const T*)L.inj_normals; a.inj_lnu = (const T*)L.inj_lnu;
+  a.diag_logratio = (T*)L.diag_logratio; a.diag_acc = L.diag_acc;
+  return a;
+}
+
+template <class T, int MAXD>
+inline cudaError_t mh_launch_one(const MhLaunch& L, cudaStream_t st) {
+  MhArgs<T> a = make_mh_args<T>(L);
+  const unsigned blocks = (unsigned)((L.n_chains + kMhBlock - 1) / kMhBlock);
+  mh_run_kernel<T, MAXD><<<blocks, kMhBlock, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <class T>
+inline cudaError_t mh_dispatch(const MhLaunch& L, cudaStream_t st) {
+  const int d = L.tgt.dim;
+  if (d < 1 || d > kStageDoubles) return cudaErrorInvalidValue;
+  if (d <= 2) return mh_launch_one<T, 2>(L, st);
+  if (d <= 4) return mh_launch_one<T, 4>(L, st);
+  if (d <= 8) return mh_launch_one<T, 8>(L, st);
+  if (d <= 16) return mh_launch_one<T, 16>(L, st);
+  return mh_launch_one<T, 32>(L, st);
+}
+
+}  // namespace GM_NS
+
+#if GM_EXACT
+cudaError_t launch_mh_exact(const MhLaunch& L, cudaStream_t st) {
+  return L.tgt.dtype == 0 ? exact::mh_dispatch<float>(L, st) : exact::mh_dispatch<double>(L, st);
+}
+#else
+cudaError_t launch_mh_fast(const MhLaunch& L, cudaStream_t st) {
+  return L.tgt.dtype == 0 ? fast::mh_dispatch<float>(L, st) : fast::mh_dispatch<double>(L, st);
+}
+#endif
+
+}  // namespace gm

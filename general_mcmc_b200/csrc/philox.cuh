@@ -1,0 +1,65 @@
+// philox.cuh — counter-based per-chain random streams (RNG contract: include/gmcmc.h).
+// Philox4x32-10 (Salmon et al., SC'11).  Replaces rand::SmallRng / rand_distr ziggurat of the
+// reference (generic_hmc.rs:75,92,197; metropolis_hastings.rs:192,313; euclidean.rs:107-113),
+// whose bit streams are third-party and unpinned by any reference test.
+#pragma once
+#include <cstdint>
+
+namespace gm {
+
+struct PhiloxKey { uint32_t k0, k1; };
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, PhiloxKey k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+    uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+#else
+    uint64_t p0 = (uint64_t)0xD2511F53u * c.x, p1 = (uint64_t)0xCD9E8D57u * c.z;
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+    c = make_uint4(hi1 ^ c.y ^ k.k0, lo1, hi0 ^ c.w ^ k.k1, lo0);
+    k.k0 += 0x9E3779B9u;
+    k.k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+__host__ __device__ __forceinline__ uint4 philox_ctr(uint64_t gchain, uint32_t step, uint32_t stream, uint32_t block) {
+  return make_uint4((uint32_t)gchain, (uint32_t)(gchain >> 32), step, (stream << 24) | block);
+}
+
+// uniforms in (0,1]
+__device__ __forceinline__ float u01(uint32_t r) { return ((float)(r >> 8) + 1.0f) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ double u01d(uint32_t hi, uint32_t lo) {
+  unsigned long long v = (((unsigned long long)hi << 32) | lo) >> 11;
+  return ((double)v + 1.0) * (1.0 / 9007199254740992.0);
+}
+
+// Box–Muller.  f32: 4 normals per block; f64: 2 normals per block.
+__device__ __forceinline__ void normals_from_block(uint4 r, float (&z)[4]) {
+  float u0 = u01(r.x), u1 = u01(r.y), u2 = u01(r.z), u3 = u01(r.w);
+  float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+  float s0, c0, s1, c1;
+  sincospif(2.0f * u1, &s0, &c0);
+  sincospif(2.0f * u3, &s1, &c1);
+  z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+}
+__device__ __forceinline__ void normals_from_block(uint4 r, double (&z)[2]) {
+  double u0 = u01d(r.x, r.y), u1 = u01d(r.z, r.w);
+  double rr = sqrt(-2.0 * log(u0));
+  double s, c;
+  sincospi(2.0 * u1, &s, &c);
+  z[0] = rr * c; z[1] = rr * s;
+}
+
+template <class T> struct NormalsPerBlock;
+template <> struct NormalsPerBlock<float> { static constexpr int value = 4; };
+template <> struct NormalsPerBlock<double> { static constexpr int value = 2; };
+
+template <class T> __device__ __forceinline__ T accept_uniform(uint4 r);
+template <> __device__ __forceinline__ float accept_uniform<float>(uint4 r) { return u01(r.x); }
+template <> __device__ __forceinline__ double accept_uniform<double>(uint4 r) { return u01d(r.x, r.y); }
+
+}  // namespace gm

@@ -1,0 +1,1109 @@
+// runtime.cu — host runtime behind the C ABI of include/gmcmc.h: contexts, targets, samplers, run
+// orchestration, dual averaging, device statistics, NCCL plumbing.  No torch types, no CPU compute
+// fallback: every compute entry point needs a CUDA device.
+//
+// Reference surfaces mirrored here (file:line into /root/reference/src):
+//   HMC::new / set_seed / run / run_progress / step / positions      hmc.rs:113-338
+//   BatchedGenericHMC::{new, set_seed, run, run_positions, step}     batched_hmc.rs:62-215
+//   MetropolisHastings::{new, seed} + ChainRunner::{run, run_progress}   metropolis_hastings.rs:151-218, core.rs:204-406
+//   NUTS::{new, set_seed, run, run_progress}                         nuts.rs:156-304
+//   RunStats::from / split_rhat_mean_ess / basic_stats               stats.rs:342-450
+#include "../../include/gmcmc.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "philox.cuh"
+
+using namespace gm;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_last_error;
+
+gmcmc_status fail(gmcmc_status code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define GM_CU(call)                                                                            \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) return fail(GMCMC_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+#define GM_TRY(call)                        \
+  do {                                      \
+    gmcmc_status s__ = (call);              \
+    if (s__ != GMCMC_OK) return s__;        \
+  } while (0)
+#define GM_REQUIRE(cond, ...)                               \
+  do {                                                      \
+    if (!(cond)) return fail(GMCMC_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen: the library carries no link-time dependency on libnccl, and inside a process
+// that already loaded torch's bundled libnccl.so.2 the same copy is reused.
+// ------------------------------------------------------------------------------------------------
+struct NcclUniqueId { char internal[128]; };
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+constexpr int kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclUint64 = 5, kNcclSum = 0;
+
+NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) return api;
+  api.GetUniqueId = (int (*)(NcclUniqueId*))dlsym(api.handle, "ncclGetUniqueId");
+  api.CommInitRank = (int (*)(void**, int, NcclUniqueId, int))dlsym(api.handle, "ncclCommInitRank");
+  api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
+  api.CommDestroy = (int (*)(void*))dlsym(api.handle, "ncclCommDestroy");
+  api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+  return api;
+}
+
+#define GM_NCCL(call)                                                                              \
+  do {                                                                                             \
+    int r__ = (call);                                                                              \
+    if (r__ != 0) return fail(GMCMC_ERR_NCCL, "%s failed: %s", #call, nccl_api().GetErrorString(r__)); \
+  } while (0)
+
+inline size_t esize(int dtype) { return dtype == GMCMC_F32 ? 4 : 8; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------------
+struct gmcmc_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  int rank = 0, world = 1;
+  void* comm = nullptr;
+  int sm_count = 148;
+};
+
+struct gmcmc_target {
+  gmcmc_ctx* ctx = nullptr;
+  TargetDesc desc{};
+  void* dparams = nullptr;
+  std::vector<double> params;
+  int refs = 1;
+};
+
+enum SamplerType { S_HMC = 0, S_MH = 1, S_NUTS = 2 };
+
+struct PooledDa {   // device-resident dual-averaging state of GMCMC_ADAPT_POOLED (all f64)
+  double h_bar, log_eps_bar, mu, eps, m;
+};
+
+struct gmcmc_sampler {
+  SamplerType type = S_HMC;
+  gmcmc_ctx* ctx = nullptr;
+  gmcmc_target* tgt = nullptr;
+  size_t n_chains = 0;
+  uint64_t chain_offset = 0;
+  int dim = 0, dtype = 0;
+  int epl = 0, lpc = 1;
+  uint64_t seed = 0;
+  uint32_t step_index = 0;     // transitions since creation / re-seed (Philox counter word 2)
+  gmcmc_math_mode math = GMCMC_MATH_FAST;
+  void* d_pos = nullptr;       // [C, d] T
+  // HMC
+  double step_size = 0.0;
+  uint32_t n_leapfrog = 0;
+  void* d_eps = nullptr;       // [1] T (shared step size)
+  gmcmc_adapt_mode adapt = GMCMC_ADAPT_NONE;
+  double target_accept = 0.8;
+  void* d_da[4] = {nullptr, nullptr, nullptr, nullptr};   // per-chain: eps, eps_bar, h_bar, mu  (T [C])
+  uint32_t da_m = 0;           // adaptation iterations consumed so far
+  PooledDa* d_pooled = nullptr;
+  double* d_alpha_part = nullptr;
+  size_t n_alpha_part = 0;
+  double* d_alpha_sum = nullptr;   // [2]: sum alpha, chain count (all-reduced together)
+  // MH
+  double prop_std = 1.0;
+  // NUTS
+  uint32_t max_depth = 0;
+  void* d_nuts = nullptr;      // NutsState (nuts.cu)
+  // counters
+  unsigned long long* d_counts = nullptr;  // [4]: accepts, divergences, grad_evals(NUTS), spare
+  uint64_t transitions = 0;
+  uint64_t hmc_grad_evals = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  uint64_t launches = 0;
+  // library-owned sample buffer
+  void* d_samples = nullptr;
+  size_t samples_cap = 0;
+  // injection + diagnostics
+  void* d_inj_normals = nullptr;
+  void* d_inj_lnu = nullptr;
+  size_t inj_steps = 0;       // pending injected transitions
+  size_t diag_steps = 0;
+  void* d_diag_logacc = nullptr;
+  uint8_t* d_diag_acc = nullptr;
+  void* d_diag_pq = nullptr;
+  void* d_diag_pp = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small kernels owned by the runtime
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void philox_blocks_kernel(const uint4* ctr, size_t n, PhiloxKey key, uint4* out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = philox4x32_10(ctr[i], key);
+}
+
+template <class TI, class TO>
+__global__ void convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = (TO)in[i];
+}
+
+template <class T>
+__global__ void fill_kernel(T* p, size_t n, T v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// fixed-order sum of the per-warp acceptance partials of one adaptation transition -> out[0]; out[1] = chains
+__global__ void __launch_bounds__(256) alpha_reduce_kernel(const double* __restrict__ part, size_t n, double chains,
+                                                           double* __restrict__ out) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (size_t i = threadIdx.x; i < n; i += 256) s += part[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = sh[0]; out[1] = chains; }
+}
+
+// Pooled dual averaging (Hoffman & Gelman Alg. 5 with the constants of generic_nuts.rs:638-641, 882-924),
+// driven by the mean acceptance statistic over ALL chains of all ranks.  One thread; f64.
+template <class T>
+__global__ void pooled_da_update_kernel(PooledDa* st, const double* __restrict__ alpha_sum /*[2]*/, double delta,
+                                        int last, T* __restrict__ eps_out) {
+  const double gamma = 0.05, t0 = 10.0, kappa = 0.75;
+  const double alpha = alpha_sum[0] / alpha_sum[1];
+  const double m = st->m + 1.0;
+  double eta = 1.0 / (m + t0);
+  const double h_bar = (1.0 - eta) * st->h_bar + eta * (delta - alpha);
+  double eps = exp(st->mu - sqrt(m) / gamma * h_bar);
+  eta = pow(m, -kappa);
+  const double log_eps_bar = (1.0 - eta) * st->log_eps_bar + eta * log(eps);
+  if (last) eps = exp(log_eps_bar);
+  st->m = m; st->h_bar = h_bar; st->log_eps_bar = log_eps_bar; st->eps = eps;
+  *eps_out = (T)eps;
+}
+
+// FP32 FMA-pipe peak: 16 independent accumulator chains per thread (roofline denominator for the
+// register-resident HMC kernels; measured, like the driver's HBM/bf16 peaks)
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float a, float b) {
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = (float)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  if (s == 123.456f) out[0] = s;   // never true in practice; keeps the loop alive
+}
+
+gmcmc_status make_target_desc(const gmcmc_target* t, TargetDesc* out) {
+  *out = t->desc;
+  return GMCMC_OK;
+}
+
+gmcmc_status ensure_samples(gmcmc_sampler* s, size_t bytes) {
+  if (bytes <= s->samples_cap && s->d_samples) return GMCMC_OK;
+  if (s->d_samples) { cudaFree(s->d_samples); s->d_samples = nullptr; s->samples_cap = 0; }
+  if (bytes == 0) return GMCMC_OK;
+  GM_CU(cudaMalloc(&s->d_samples, bytes));
+  s->samples_cap = bytes;
+  return GMCMC_OK;
+}
+
+inline int out_dtype_of(const gmcmc_sampler* s) { return s->type == S_MH ? (int)GMCMC_F64 : s->dtype; }
+
+gmcmc_status set_eps_device(gmcmc_sampler* s, double eps) {
+  if (s->dtype == GMCMC_F32) {
+    float v = (float)eps;
+    GM_CU(cudaMemcpyAsync(s->d_eps, &v, 4, cudaMemcpyHostToDevice, s->ctx->stream));
+  } else {
+    GM_CU(cudaMemcpyAsync(s->d_eps, &eps, 8, cudaMemcpyHostToDevice, s->ctx->stream));
+  }
+  GM_CU(cudaStreamSynchronize(s->ctx->stream));  // the source is a stack variable
+  return GMCMC_OK;
+}
+
+gmcmc_status all_reduce(gmcmc_ctx* ctx, void* buf, size_t count, int nccl_dtype) {
+  if (ctx->world <= 1) return GMCMC_OK;
+  GM_NCCL(nccl_api().AllReduce(buf, buf, count, nccl_dtype, kNcclSum, ctx->comm, ctx->stream));
+  return GMCMC_OK;
+}
+
+// One launch of the HMC trajectory kernel covering run-local transitions [first, first + count).
+gmcmc_status hmc_segment(gmcmc_sampler* s, size_t first, size_t count, size_t n_discard, size_t n_collect,
+                         void* out, bool use_injection, size_t inj_first, bool want_alpha, bool per_chain_da,
+                         uint32_t da_n_adapt) {
+  if (count == 0) return GMCMC_OK;
+  HmcLaunch L{};
+  GM_TRY(make_target_desc(s->tgt, &L.tgt));
+  L.n_chains = s->n_chains;
+  L.chain_offset = s->chain_offset;
+  L.seed = s->seed;
+  L.step_base = s->step_index + (uint32_t)first;
+  L.positions = s->d_pos;
+  L.eps = s->d_eps;
+  L.eps_stride = 0;
+  L.n_leapfrog = s->n_leapfrog;
+  L.n_steps = (uint32_t)count;
+  const size_t skip = first >= n_discard ? 0 : std::min(count, n_discard - first);
+  L.n_skip = (uint32_t)skip;
+  L.out = (out && skip < count) ? out : nullptr;
+  L.out_n = n_collect;
+  L.out_t0 = (uint32_t)(first >= n_discard ? first - n_discard : 0);
+  L.accept_total = s->d_counts + 0;
+  L.diverge_total = s->d_counts + 1;
+  L.alpha_part = want_alpha ? s->d_alpha_part : nullptr;
+  if (per_chain_da) {
+    L.da_eps = s->d_da[0]; L.da_eps_bar = s->d_da[1]; L.da_h_bar = s->d_da[2]; L.da_mu = s->d_da[3];
+    L.da_m_base = s->da_m + (uint32_t)first;
+    L.da_n_adapt = da_n_adapt;
+    L.da_delta = s->target_accept;
+  }
+  const size_t es = esize(s->dtype);
+  if (use_injection) {
+    L.inj_normals = (const char*)s->d_inj_normals + inj_first * s->n_chains * s->dim * es;
+    L.inj_lnu = (const char*)s->d_inj_lnu + inj_first * s->n_chains * es;
+    L.diag_logacc = (char*)s->d_diag_logacc + inj_first * s->n_chains * es;
+    L.diag_acc = s->d_diag_acc + inj_first * s->n_chains;
+    L.diag_pq = (char*)s->d_diag_pq + inj_first * s->n_chains * s->dim * es;
+    L.diag_pp = (char*)s->d_diag_pp + inj_first * s->n_chains * s->dim * es;
+  }
+  L.epl = s->epl; L.lpc = s->lpc;
+  cudaError_t e = (s->math == GMCMC_MATH_EXACT) ? launch_hmc_exact(L, s->ctx->stream) : launch_hmc_fast(L, s->ctx->stream);
+  if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "HMC kernel launch failed: %s", cudaGetErrorString(e));
+  s->launches += 1;
+  return GMCMC_OK;
+}
+
+gmcmc_status mh_segment(gmcmc_sampler* s, size_t first, size_t count, size_t n_discard, size_t n_collect, void* out,
+                        bool use_injection, size_t inj_first) {
+  if (count == 0) return GMCMC_OK;
+  MhLaunch L{};
+  GM_TRY(make_target_desc(s->tgt, &L.tgt));
+  L.prop_std = s->prop_std;
+  L.n_chains = s->n_chains;
+  L.chain_offset = s->chain_offset;
+  L.seed = s->seed;
+  L.step_base = s->step_index + (uint32_t)first;
+  L.state = s->d_pos;
+  L.n_steps = (uint32_t)count;
+  const size_t skip = first >= n_discard ? 0 : std::min(count, n_discard - first);
+  L.n_skip = (uint32_t)skip;
+  L.out = (out && skip < count) ? (double*)out : nullptr;
+  L.out_n = n_collect;
+  L.out_t0 = (uint32_t)(first >= n_discard ? first - n_discard : 0);
+  L.accept_total = s->d_counts + 0;
+  const size_t es = esize(s->dtype);
+  if (use_injection) {
+    L.inj_normals = (const char*)s->d_inj_normals + inj_first * s->n_chains * s->dim * es;
+    L.inj_lnu = (const char*)s->d_inj_lnu + inj_first * s->n_chains * es;
+    L.diag_logratio = (char*)s->d_diag_logacc + inj_first * s->n_chains * es;
+    L.diag_acc = s->d_diag_acc + inj_first * s->n_chains;
+  }
+  cudaError_t e = (s->math == GMCMC_MATH_EXACT) ? launch_mh_exact(L, s->ctx->stream) : launch_mh_fast(L, s->ctx->stream);
+  if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "MH kernel launch failed: %s", cudaGetErrorString(e));
+  s->launches += 1;
+  return GMCMC_OK;
+}
+
+}  // namespace
+
+// NUTS lives in nuts.cu
+namespace gm {
+gmcmc_status nuts_create_state(gmcmc_sampler* s, double init_step_size);
+void nuts_destroy_state(gmcmc_sampler* s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// run orchestration (device output)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+gmcmc_status run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void* d_out) {
+  gmcmc_ctx* ctx = s->ctx;
+  GM_CU(cudaSetDevice(ctx->device));
+  const size_t total = n_collect + n_discard;
+  GM_REQUIRE(total < 0xffffffffull - s->step_index, "transition counter would overflow 32 bits");
+  s->launches = 0;
+  GM_CU(cudaEventRecord(s->ev0, ctx->stream));
+  const size_t inj = std::min(s->inj_steps, total);
+  const size_t inj_first = s->diag_steps - s->inj_steps;  // offset of the first unconsumed injected transition
+
+  if (s->type == S_MH) {
+    GM_TRY(mh_segment(s, 0, inj, n_discard, n_collect, d_out, true, inj_first));
+    GM_TRY(mh_segment(s, inj, total - inj, n_discard, n_collect, d_out, false, 0));
+  } else if (s->type == S_HMC) {
+    if (s->adapt == GMCMC_ADAPT_POOLED && n_discard > 0) {
+      GM_REQUIRE(inj == 0, "injection cannot be combined with pooled adaptation");
+      // one transition per launch during warm-up: kernel -> fixed-order reduce -> (NCCL all-reduce) -> update
+      for (size_t t = 0; t < n_discard; ++t) {
+        GM_TRY(hmc_segment(s, t, 1, n_discard, n_collect, nullptr, false, 0, true, false, 0));
+        alpha_reduce_kernel<<<1, 256, 0, ctx->stream>>>(s->d_alpha_part, s->n_alpha_part, (double)s->n_chains, s->d_alpha_sum);
+        GM_TRY(all_reduce(ctx, s->d_alpha_sum, 2, kNcclFloat64));
+        const int last = (t + 1 == n_discard) ? 1 : 0;
+        if (s->dtype == GMCMC_F32)
+          pooled_da_update_kernel<float><<<1, 1, 0, ctx->stream>>>(s->d_pooled, s->d_alpha_sum, s->target_accept, last, (float*)s->d_eps);
+        else
+          pooled_da_update_kernel<double><<<1, 1, 0, ctx->stream>>>(s->d_pooled, s->d_alpha_sum, s->target_accept, last, (double*)s->d_eps);
+        s->launches += 2;
+      }
+      GM_CU(cudaGetLastError());
+      s->da_m += (uint32_t)n_discard;
+      GM_TRY(hmc_segment(s, n_discard, n_collect, n_discard, n_collect, d_out, false, 0, false, false, 0));
+    } else {
+      const bool pc = (s->adapt == GMCMC_ADAPT_PER_CHAIN);
+      const uint32_t n_adapt = pc ? s->da_m + (uint32_t)n_discard : 0;
+      GM_TRY(hmc_segment(s, 0, inj, n_discard, n_collect, d_out, true, inj_first, false, pc, n_adapt));
+      GM_TRY(hmc_segment(s, inj, total - inj, n_discard, n_collect, d_out, false, 0, false, pc, n_adapt));
+      if (pc) s->da_m += (uint32_t)n_discard;
+    }
+    s->hmc_grad_evals += (uint64_t)total * s->n_chains * s->n_leapfrog;
+  } else {
+    return fail(GMCMC_ERR_UNSUPPORTED, "NUTS sampling is not available in this build");
+  }
+  GM_CU(cudaEventRecord(s->ev1, ctx->stream));
+  s->timed = true;
+  s->inj_steps -= inj;
+  s->step_index += (uint32_t)total;
+  s->transitions += (uint64_t)total * s->n_chains;
+  return GMCMC_OK;
+}
+
+gmcmc_status convert_on_device(gmcmc_ctx* ctx, const void* in, int in_dtype, void* out, int out_dtype, size_t n) {
+  const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16);
+  if (in_dtype == GMCMC_F32 && out_dtype == GMCMC_F64)
+    convert_kernel<float, double><<<blocks, 256, 0, ctx->stream>>>((const float*)in, (double*)out, n);
+  else if (in_dtype == GMCMC_F64 && out_dtype == GMCMC_F32)
+    convert_kernel<double, float><<<blocks, 256, 0, ctx->stream>>>((const double*)in, (float*)out, n);
+  else
+    return fail(GMCMC_ERR_INVALID, "bad dtype conversion");
+  GM_CU(cudaGetLastError());
+  return GMCMC_OK;
+}
+
+// ---- statistics ---------------------------------------------------------------------------------
+struct StatsBuffers {
+  void* tw = nullptr; float* part_spec = nullptr; double* part_mom = nullptr; float* spec = nullptr;
+  double* mom = nullptr; float* out = nullptr;
+  ~StatsBuffers() {
+    cudaFree(tw); cudaFree(part_spec); cudaFree(part_mom); cudaFree(spec); cudaFree(mom); cudaFree(out);
+  }
+};
+
+gmcmc_status device_split_rhat_ess(gmcmc_ctx* ctx, const void* d_samples, size_t C, size_t n, size_t p, int dtype,
+                                   float* rhat, float* rhat_std, float* ess) {
+  GM_REQUIRE(C >= 1 && n >= 4 && p >= 1, "split_rhat_ess needs C >= 1, n >= 4, p >= 1 (got %zu, %zu, %zu)", C, n, p);
+  GM_CU(cudaSetDevice(ctx->device));
+  StatsLaunch S{};
+  S.samples = d_samples; S.dtype = dtype; S.C = C; S.n = n; S.p = (int)p;
+  S.N = stats_npad(n);
+  if (S.N > 16384) return fail(GMCMC_ERR_UNSUPPORTED, "series of %zu draws exceed the in-kernel FFT (max 16384 padded)", n);
+  S.log2n = 0;
+  while (((size_t)1 << S.log2n) < S.N) ++S.log2n;
+  S.ppb = stats_ppb(S.N);
+  const int pblocks = (int)((p + S.ppb - 1) / S.ppb);
+  int groups = (ctx->sm_count * 4 + pblocks - 1) / pblocks;
+  groups = (int)std::max<size_t>(1, std::min<size_t>((size_t)groups, C));
+  S.n_groups = groups;
+  const size_t nk = S.N / 2 + 1;
+  StatsBuffers B;
+  std::vector<float> tw(S.N);   // N/2 (cos, sin) pairs
+  stats_fill_twiddles(S.N, tw.data());
+  GM_CU(cudaMalloc(&B.tw, std::max<size_t>(S.N, 2) * sizeof(float)));
+  GM_CU(cudaMemcpyAsync(B.tw, tw.data(), S.N * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  GM_CU(cudaMalloc(&B.part_spec, (size_t)groups * p * nk * sizeof(float)));
+  GM_CU(cudaMalloc(&B.part_mom, (size_t)groups * p * 3 * sizeof(double)));
+  GM_CU(cudaMalloc(&B.spec, p * nk * sizeof(float)));
+  GM_CU(cudaMalloc(&B.mom, (p * 3 + 1) * sizeof(double)));
+  GM_CU(cudaMalloc(&B.out, 3 * p * sizeof(float)));
+  S.tw = B.tw; S.part_spec = B.part_spec; S.part_mom = B.part_mom; S.spec = B.spec; S.mom = B.mom;
+  S.rhat = B.out; S.rhat_std = B.out + p; S.ess = B.out + 2 * p; S.acov = nullptr;
+  cudaError_t e = launch_stats_accumulate(S, ctx->stream);
+  if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "stats_accumulate launch failed: %s", cudaGetErrorString(e));
+  e = launch_stats_reduce(S, ctx->stream);
+  if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "stats_reduce launch failed: %s", cudaGetErrorString(e));
+  double total_chains = (double)C;
+  if (ctx->world > 1) {
+    // A2 + A3: moments (+ chain count) in f64, chain-summed power spectrum in f32
+    const double cc = (double)C;
+    GM_CU(cudaMemcpyAsync(B.mom + p * 3, &cc, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    GM_TRY(all_reduce(ctx, B.mom, p * 3 + 1, kNcclFloat64));
+    GM_TRY(all_reduce(ctx, B.spec, p * nk, kNcclFloat32));
+    GM_CU(cudaMemcpyAsync(&total_chains, B.mom + p * 3, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GM_CU(cudaStreamSynchronize(ctx->stream));
+  }
+  e = launch_stats_finalize(S, total_chains, ctx->stream);
+  if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "stats_finalize launch failed: %s", cudaGetErrorString(e));
+  std::vector<float> host(3 * p);
+  GM_CU(cudaMemcpyAsync(host.data(), B.out, 3 * p * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CU(cudaStreamSynchronize(ctx->stream));
+  if (rhat) std::memcpy(rhat, host.data(), p * sizeof(float));
+  if (rhat_std) std::memcpy(rhat_std, host.data() + p, p * sizeof(float));
+  if (ess) std::memcpy(ess, host.data() + 2 * p, p * sizeof(float));
+  return GMCMC_OK;
+}
+
+// basic_stats, stats.rs:342-368: sort descending, median = data[len/2], std with ddof = 1; f32 throughout
+gmcmc_basic_stats basic_stats(std::vector<float> v) {
+  std::sort(v.begin(), v.end(), [](float a, float b) { return a > b; });
+  gmcmc_basic_stats r;
+  r.min = v.back(); r.median = v[v.size() / 2]; r.max = v.front();
+  float sum = 0.f;
+  for (float x : v) sum += x;
+  r.mean = sum / (float)v.size();
+  float ss = 0.f;
+  for (float x : v) ss += (x - r.mean) * (x - r.mean);
+  r.std = std::sqrt(ss / ((float)v.size() - 1.0f));
+  return r;
+}
+
+gmcmc_status stats_on_device(gmcmc_ctx* ctx, const void* d_samples, size_t C, size_t n, size_t p, int dtype,
+                             gmcmc_run_stats_t* out) {
+  std::vector<float> rhat(p), rstd(p), ess(p);
+  GM_TRY(device_split_rhat_ess(ctx, d_samples, C, n, p, dtype, rhat.data(), rstd.data(), ess.data()));
+  out->ess = basic_stats(ess);
+  out->rhat = basic_stats(rhat);
+  out->rhat_std = basic_stats(rstd);
+  return GMCMC_OK;
+}
+
+struct TempDevice {
+  void* p = nullptr;
+  ~TempDevice() { cudaFree(p); }
+};
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* gmcmc_last_error(void) { return g_last_error.c_str(); }
+const char* gmcmc_version(void) { return "gmcmc-b200 0.1.0 (sm_100a)"; }
+
+gmcmc_status gmcmc_ctx_create(int device, gmcmc_ctx** out) { return gmcmc_ctx_create_dist(device, 0, 1, nullptr, out); }
+
+gmcmc_status gmcmc_nccl_unique_id(void* out128) {
+  GM_REQUIRE(out128, "null output");
+  NcclApi& api = nccl_api();
+  if (!api.ok) return fail(GMCMC_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  NcclUniqueId id;
+  GM_NCCL(api.GetUniqueId(&id));
+  std::memcpy(out128, &id, 128);
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_ctx_create_dist(int device, int rank, int world, const void* nccl_id, gmcmc_ctx** out) {
+  GM_REQUIRE(out, "null output");
+  GM_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank/world %d/%d", rank, world);
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(GMCMC_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  GM_REQUIRE(device >= 0 && device < n_dev, "device %d out of range (%d devices)", device, n_dev);
+  cudaDeviceProp prop;
+  GM_CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(GMCMC_ERR_CUDA, "device %d is sm_%d%d; the kernels are built for sm_100a only", device, prop.major, prop.minor);
+  GM_CU(cudaSetDevice(device));
+  gmcmc_ctx* c = new gmcmc_ctx();
+  c->device = device; c->rank = rank; c->world = world; c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return fail(GMCMC_ERR_CUDA, "stream creation failed");
+  }
+  if (world > 1) {
+    NcclApi& api = nccl_api();
+    if (!api.ok) { delete c; return fail(GMCMC_ERR_NCCL, "libnccl.so.2 could not be loaded"); }
+    if (!nccl_id) { delete c; return fail(GMCMC_ERR_INVALID, "nccl_id required when world > 1"); }
+    NcclUniqueId id;
+    std::memcpy(&id, nccl_id, 128);
+    int r = api.CommInitRank(&c->comm, world, id, rank);
+    if (r != 0) { delete c; return fail(GMCMC_ERR_NCCL, "ncclCommInitRank failed: %s", api.GetErrorString(r)); }
+  }
+  *out = c;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_ctx_destroy(gmcmc_ctx* c) {
+  if (!c) return GMCMC_OK;
+  cudaSetDevice(c->device);
+  if (c->comm) nccl_api().CommDestroy(c->comm);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_ctx_synchronize(gmcmc_ctx* c) {
+  GM_REQUIRE(c, "null context");
+  GM_CU(cudaSetDevice(c->device));
+  GM_CU(cudaStreamSynchronize(c->stream));
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_ctx_stream(gmcmc_ctx* c, void** out_stream) {
+  GM_REQUIRE(c && out_stream, "null argument");
+  *out_stream = (void*)c->stream;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_ctx_all_reduce_f64(gmcmc_ctx* c, double* host_inout, size_t n) {
+  GM_REQUIRE(c && host_inout, "null argument");
+  if (c->world <= 1) return GMCMC_OK;
+  GM_CU(cudaSetDevice(c->device));
+  TempDevice t;
+  GM_CU(cudaMalloc(&t.p, n * sizeof(double)));
+  GM_CU(cudaMemcpyAsync(t.p, host_inout, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  GM_TRY(all_reduce(c, t.p, n, kNcclFloat64));
+  GM_CU(cudaMemcpyAsync(host_inout, t.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  GM_CU(cudaStreamSynchronize(c->stream));
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_host_alloc(size_t bytes, void** out) {
+  GM_REQUIRE(out, "null output");
+  GM_CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return GMCMC_OK;
+}
+gmcmc_status gmcmc_host_free(void* p) {
+  if (p) GM_CU(cudaFreeHost(p));
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_measure_fp32_peak(gmcmc_ctx* c, double* tflops) {
+  GM_REQUIRE(c && tflops, "null argument");
+  GM_CU(cudaSetDevice(c->device));
+  TempDevice t;
+  GM_CU(cudaMalloc(&t.p, 16));
+  cudaEvent_t e0, e1;
+  GM_CU(cudaEventCreate(&e0));
+  GM_CU(cudaEventCreate(&e1));
+  const int iters = 8192, blocks = c->sm_count * 8;
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    GM_CU(cudaEventRecord(e0, c->stream));
+    ffma_peak_kernel<<<blocks, 256, 0, c->stream>>>((float*)t.p, iters, 0.999f, 0.001f);
+    GM_CU(cudaEventRecord(e1, c->stream));
+    GM_CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    GM_CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 16.0 * iters * 256.0 * blocks;
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops = best;
+  return GMCMC_OK;
+}
+
+// ---- targets ------------------------------------------------------------------------------------
+gmcmc_status gmcmc_target_create(gmcmc_ctx* ctx, gmcmc_target_kind kind, gmcmc_dtype dtype, int dim,
+                                 const double* params, size_t n_params, gmcmc_target** out) {
+  GM_REQUIRE(ctx && out, "null argument");
+  GM_REQUIRE(dim >= 1, "dim must be >= 1");
+  GM_REQUIRE(dtype == GMCMC_F32 || dtype == GMCMC_F64, "bad dtype");
+  GM_REQUIRE(params || n_params == 0, "null params");
+  GM_CU(cudaSetDevice(ctx->device));
+  gmcmc_target* t = new gmcmc_target();
+  t->ctx = ctx;
+  t->params.assign(params, params + n_params);
+  TargetDesc& d = t->desc;
+  d.kind = (int)kind; d.dtype = (int)dtype; d.dim = dim; d.dparams = nullptr; d.n_comp = 0;
+  for (int i = 0; i < kMaxScalarParams; ++i) d.sp[i] = 0.0;
+  size_t need = 0;
+  size_t dev_off = 0, dev_len = 0;   // slice of params that goes to the device block
+  switch (kind) {
+    case GMCMC_TARGET_ISO_GAUSS: need = 1; break;
+    case GMCMC_TARGET_GAUSS2D: case GMCMC_TARGET_DIFF_GAUSS2D: need = 6; break;
+    case GMCMC_TARGET_ROSENBROCK2D: need = 2; break;
+    case GMCMC_TARGET_ROSENBROCK_ND: need = 0; break;
+    case GMCMC_TARGET_DENSE_GAUSS: need = (size_t)dim + (size_t)dim * dim + 1; dev_off = 0; dev_len = need; break;
+    case GMCMC_TARGET_GAUSS_MIXTURE: {
+      if (n_params < 2) { delete t; return fail(GMCMC_ERR_INVALID, "mixture params: [K, sigma, w[K], mu[K*d]]"); }
+      const int K = (int)params[0];
+      if (K < 1 || K > 8) { delete t; return fail(GMCMC_ERR_INVALID, "mixture components must be 1..8"); }
+      need = 2 + (size_t)K + (size_t)K * dim; dev_off = 2; dev_len = need - 2; d.n_comp = K;
+      break;
+    }
+    default: delete t; return fail(GMCMC_ERR_INVALID, "unknown target kind %d", (int)kind);
+  }
+  if (n_params != need) { delete t; return fail(GMCMC_ERR_INVALID, "target kind %d with dim %d needs %zu params, got %zu", (int)kind, dim, need, n_params); }
+  if ((kind == GMCMC_TARGET_GAUSS2D || kind == GMCMC_TARGET_DIFF_GAUSS2D || kind == GMCMC_TARGET_ROSENBROCK2D) && dim != 2) {
+    delete t;
+    return fail(GMCMC_ERR_INVALID, "target kind %d is 2-dimensional", (int)kind);
+  }
+  for (size_t i = 0; i < std::min<size_t>(n_params, kMaxScalarParams); ++i) d.sp[i] = params[i];
+  if (dev_len) {
+    const size_t es = esize(dtype);
+    std::vector<char> host(dev_len * es);
+    for (size_t i = 0; i < dev_len; ++i) {
+      if (dtype == GMCMC_F32) ((float*)host.data())[i] = (float)params[dev_off + i];
+      else ((double*)host.data())[i] = params[dev_off + i];
+    }
+    if (cudaMalloc(&t->dparams, dev_len * es) != cudaSuccess ||
+        cudaMemcpy(t->dparams, host.data(), dev_len * es, cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaFree(t->dparams);
+      delete t;
+      return fail(GMCMC_ERR_CUDA, "target parameter upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    d.dparams = t->dparams;
+  }
+  *out = t;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_target_destroy(gmcmc_target* t) {
+  if (!t) return GMCMC_OK;
+  if (--t->refs > 0) return GMCMC_OK;
+  cudaSetDevice(t->ctx->device);
+  cudaFree(t->dparams);
+  delete t;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_target_logp_grad(gmcmc_target* t, const void* x_host, size_t n, void* logp_out, void* grad_out,
+                                    gmcmc_math_mode mode) {
+  GM_REQUIRE(t && x_host && logp_out, "null argument");
+  if (n == 0) return GMCMC_OK;
+  gmcmc_ctx* ctx = t->ctx;
+  GM_CU(cudaSetDevice(ctx->device));
+  EvalLaunch E{};
+  E.tgt = t->desc;
+  if (!choose_decomposition(t->desc.dim, t->desc.dtype, t->desc.kind, &E.epl, &E.lpc))
+    return fail(GMCMC_ERR_UNSUPPORTED, "dim %d is not supported by the register-resident kernels", t->desc.dim);
+  const size_t es = esize(t->desc.dtype), d = (size_t)t->desc.dim;
+  TempDevice dx, dl, dg;
+  GM_CU(cudaMalloc(&dx.p, n * d * es));
+  GM_CU(cudaMalloc(&dl.p, n * es));
+  if (grad_out) GM_CU(cudaMalloc(&dg.p, n * d * es));
+  GM_CU(cudaMemcpyAsync(dx.p, x_host, n * d * es, cudaMemcpyHostToDevice, ctx->stream));
+  E.n = n; E.x = dx.p; E.logp = dl.p; E.grad = dg.p;
+  cudaError_t e = (mode == GMCMC_MATH_EXACT) ? launch_eval_exact(E, ctx->stream) : launch_eval_fast(E, ctx->stream);
+  if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "eval kernel launch failed: %s", cudaGetErrorString(e));
+  GM_CU(cudaMemcpyAsync(logp_out, dl.p, n * es, cudaMemcpyDeviceToHost, ctx->stream));
+  if (grad_out) GM_CU(cudaMemcpyAsync(grad_out, dg.p, n * d * es, cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CU(cudaStreamSynchronize(ctx->stream));
+  return GMCMC_OK;
+}
+
+// ---- samplers -----------------------------------------------------------------------------------
+static gmcmc_status sampler_common(gmcmc_ctx* ctx, gmcmc_target* tgt, size_t n_chains, uint64_t chain_offset,
+                                   const void* init_host, uint64_t seed, SamplerType type, gmcmc_sampler** out) {
+  GM_REQUIRE(ctx && tgt && out && init_host, "null argument");
+  GM_REQUIRE(tgt->ctx == ctx, "target belongs to another context");
+  GM_REQUIRE(n_chains >= 1, "n_chains must be >= 1");
+  GM_CU(cudaSetDevice(ctx->device));
+  gmcmc_sampler* s = new gmcmc_sampler();
+  s->type = type; s->ctx = ctx; s->tgt = tgt; tgt->refs += 1;
+  s->n_chains = n_chains; s->chain_offset = chain_offset;
+  s->dim = tgt->desc.dim; s->dtype = tgt->desc.dtype; s->seed = seed;
+  const size_t bytes = n_chains * (size_t)s->dim * esize(s->dtype);
+  bool ok = cudaMalloc(&s->d_pos, bytes) == cudaSuccess &&
+            cudaMemcpy(s->d_pos, init_host, bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMalloc(&s->d_counts, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMemset(s->d_counts, 0, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaEventCreate(&s->ev0) == cudaSuccess && cudaEventCreate(&s->ev1) == cudaSuccess;
+  if (!ok) {
+    gmcmc_status st = fail(GMCMC_ERR_CUDA, "sampler allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    gmcmc_sampler_destroy(s);
+    return st;
+  }
+  *out = s;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_hmc_create(gmcmc_ctx* ctx, gmcmc_target* tgt, size_t n_chains, uint64_t chain_offset,
+                              const void* init_host, double step_size, uint32_t n_leapfrog, uint64_t seed,
+                              gmcmc_sampler** out) {
+  GM_REQUIRE(tgt, "null target");
+  GM_REQUIRE(step_size > 0.0, "step_size must be positive");
+  int epl = 0, lpc = 0;
+  if (!choose_decomposition(tgt->desc.dim, tgt->desc.dtype, tgt->desc.kind, &epl, &lpc))
+    return fail(GMCMC_ERR_UNSUPPORTED, "dim %d (dtype %d) is not supported by the HMC kernels", tgt->desc.dim, tgt->desc.dtype);
+  gmcmc_sampler* s = nullptr;
+  GM_TRY(sampler_common(ctx, tgt, n_chains, chain_offset, init_host, seed, S_HMC, &s));
+  s->epl = epl; s->lpc = lpc; s->step_size = step_size; s->n_leapfrog = n_leapfrog;
+  s->n_alpha_part = (n_chains * (size_t)lpc + 31) / 32;
+  bool ok = cudaMalloc(&s->d_eps, 8) == cudaSuccess &&
+            cudaMalloc((void**)&s->d_alpha_part, s->n_alpha_part * sizeof(double)) == cudaSuccess &&
+            cudaMalloc((void**)&s->d_alpha_sum, 2 * sizeof(double)) == cudaSuccess &&
+            cudaMalloc((void**)&s->d_pooled, sizeof(PooledDa)) == cudaSuccess;
+  if (!ok) {
+    gmcmc_status st = fail(GMCMC_ERR_CUDA, "sampler allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    gmcmc_sampler_destroy(s);
+    return st;
+  }
+  gmcmc_status st = set_eps_device(s, step_size);
+  if (st != GMCMC_OK) { gmcmc_sampler_destroy(s); return st; }
+  *out = s;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_mh_create(gmcmc_ctx* ctx, gmcmc_target* tgt, double proposal_std, size_t n_chains,
+                             uint64_t chain_offset, const void* init_host, uint64_t seed, gmcmc_sampler** out) {
+  GM_REQUIRE(tgt, "null target");
+  GM_REQUIRE(proposal_std > 0.0, "proposal_std must be positive");
+  const int k = tgt->desc.kind;
+  if (!(k == 0 || k == 1 || k == 2 || k == 4 || k == 5) || tgt->desc.dim > 32)
+    return fail(GMCMC_ERR_UNSUPPORTED, "MH kernel supports targets ISO_GAUSS, GAUSS2D, DIFF_GAUSS2D, ROSENBROCK2D, ROSENBROCK_ND with dim <= 32");
+  gmcmc_sampler* s = nullptr;
+  GM_TRY(sampler_common(ctx, tgt, n_chains, chain_offset, init_host, seed, S_MH, &s));
+  s->prop_std = proposal_std;
+  *out = s;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_nuts_create(gmcmc_ctx* ctx, gmcmc_target* tgt, size_t n_chains, uint64_t chain_offset,
+                               const void* init_host, double target_accept, uint32_t max_depth,
+                               double init_step_size, uint64_t seed, gmcmc_sampler** out) {
+  (void)ctx; (void)tgt; (void)n_chains; (void)chain_offset; (void)init_host; (void)target_accept; (void)max_depth;
+  (void)init_step_size; (void)seed; (void)out;
+  return fail(GMCMC_ERR_UNSUPPORTED, "NUTS is not available in this build");
+}
+
+gmcmc_status gmcmc_sampler_destroy(gmcmc_sampler* s) {
+  if (!s) return GMCMC_OK;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  cudaFree(s->d_pos); cudaFree(s->d_eps); cudaFree(s->d_counts); cudaFree(s->d_samples);
+  for (void* p : s->d_da) cudaFree(p);
+  cudaFree(s->d_pooled); cudaFree(s->d_alpha_part); cudaFree(s->d_alpha_sum);
+  cudaFree(s->d_inj_normals); cudaFree(s->d_inj_lnu);
+  cudaFree(s->d_diag_logacc); cudaFree(s->d_diag_acc); cudaFree(s->d_diag_pq); cudaFree(s->d_diag_pp);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  gmcmc_target_destroy(s->tgt);
+  delete s;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_set_seed(gmcmc_sampler* s, uint64_t seed) {
+  GM_REQUIRE(s, "null sampler");
+  s->seed = seed;
+  s->step_index = 0;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_set_math_mode(gmcmc_sampler* s, gmcmc_math_mode m) {
+  GM_REQUIRE(s, "null sampler");
+  GM_REQUIRE(m == GMCMC_MATH_FAST || m == GMCMC_MATH_EXACT, "bad math mode");
+  s->math = m;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_set_step_size(gmcmc_sampler* s, double step_size) {
+  GM_REQUIRE(s && s->type == S_HMC, "set_step_size applies to HMC samplers");
+  GM_REQUIRE(step_size > 0.0, "step_size must be positive");
+  GM_CU(cudaSetDevice(s->ctx->device));
+  s->step_size = step_size;
+  return set_eps_device(s, step_size);
+}
+
+gmcmc_status gmcmc_set_adaptation(gmcmc_sampler* s, gmcmc_adapt_mode mode, double target_accept) {
+  GM_REQUIRE(s && s->type == S_HMC, "set_adaptation applies to HMC samplers (NUTS always adapts per chain)");
+  GM_REQUIRE(target_accept > 0.0 && target_accept < 1.0, "target_accept must be in (0, 1)");
+  gmcmc_ctx* ctx = s->ctx;
+  GM_CU(cudaSetDevice(ctx->device));
+  s->adapt = mode;
+  s->target_accept = target_accept;
+  s->da_m = 0;
+  const double eps0 = s->step_size;
+  if (mode == GMCMC_ADAPT_POOLED) {
+    PooledDa h{0.0, 0.0, std::log(10.0 * eps0), eps0, 0.0};
+    GM_CU(cudaMemcpy(s->d_pooled, &h, sizeof h, cudaMemcpyHostToDevice));
+  } else if (mode == GMCMC_ADAPT_PER_CHAIN) {
+    const size_t es = esize(s->dtype), C = s->n_chains;
+    for (int i = 0; i < 4; ++i)
+      if (!s->d_da[i]) GM_CU(cudaMalloc(&s->d_da[i], C * es));
+    const unsigned blocks = (unsigned)std::min<size_t>((C + 255) / 256, 4096);
+    if (s->dtype == GMCMC_F32) {
+      fill_kernel<float><<<blocks, 256, 0, ctx->stream>>>((float*)s->d_da[0], C, (float)eps0);
+      fill_kernel<float><<<blocks, 256, 0, ctx->stream>>>((float*)s->d_da[1], C, 1.0f);
+      fill_kernel<float><<<blocks, 256, 0, ctx->stream>>>((float*)s->d_da[2], C, 0.0f);
+      fill_kernel<float><<<blocks, 256, 0, ctx->stream>>>((float*)s->d_da[3], C, std::log(10.0f * (float)eps0));
+    } else {
+      fill_kernel<double><<<blocks, 256, 0, ctx->stream>>>((double*)s->d_da[0], C, eps0);
+      fill_kernel<double><<<blocks, 256, 0, ctx->stream>>>((double*)s->d_da[1], C, 1.0);
+      fill_kernel<double><<<blocks, 256, 0, ctx->stream>>>((double*)s->d_da[2], C, 0.0);
+      fill_kernel<double><<<blocks, 256, 0, ctx->stream>>>((double*)s->d_da[3], C, std::log(10.0 * eps0));
+    }
+    GM_CU(cudaGetLastError());
+  }
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_inject(gmcmc_sampler* s, const void* normals, const void* ln_u, size_t n_steps) {
+  GM_REQUIRE(s && normals && ln_u, "null argument");
+  GM_REQUIRE(s->type == S_HMC || s->type == S_MH, "use gmcmc_nuts_inject for NUTS");
+  GM_REQUIRE(n_steps >= 1, "n_steps must be >= 1");
+  GM_CU(cudaSetDevice(s->ctx->device));
+  GM_CU(cudaStreamSynchronize(s->ctx->stream));
+  cudaFree(s->d_inj_normals); cudaFree(s->d_inj_lnu);
+  cudaFree(s->d_diag_logacc); cudaFree(s->d_diag_acc); cudaFree(s->d_diag_pq); cudaFree(s->d_diag_pp);
+  s->d_inj_normals = s->d_inj_lnu = s->d_diag_logacc = s->d_diag_pq = s->d_diag_pp = nullptr;
+  s->d_diag_acc = nullptr;
+  s->inj_steps = s->diag_steps = 0;
+  const size_t es = esize(s->dtype), C = s->n_chains, d = (size_t)s->dim;
+  GM_CU(cudaMalloc(&s->d_inj_normals, n_steps * C * d * es));
+  GM_CU(cudaMalloc(&s->d_inj_lnu, n_steps * C * es));
+  GM_CU(cudaMalloc(&s->d_diag_logacc, n_steps * C * es));
+  GM_CU(cudaMalloc((void**)&s->d_diag_acc, n_steps * C));
+  GM_CU(cudaMemset(s->d_diag_acc, 0, n_steps * C));
+  if (s->type == S_HMC) {
+    GM_CU(cudaMalloc(&s->d_diag_pq, n_steps * C * d * es));
+    GM_CU(cudaMalloc(&s->d_diag_pp, n_steps * C * d * es));
+  }
+  GM_CU(cudaMemcpy(s->d_inj_normals, normals, n_steps * C * d * es, cudaMemcpyHostToDevice));
+  GM_CU(cudaMemcpy(s->d_inj_lnu, ln_u, n_steps * C * es, cudaMemcpyHostToDevice));
+  s->inj_steps = s->diag_steps = n_steps;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_nuts_inject(gmcmc_sampler* s, const double* normals, size_t n_norm, const double* exp1,
+                               size_t n_exp, const double* unif, size_t n_unif) {
+  (void)s; (void)normals; (void)n_norm; (void)exp1; (void)n_exp; (void)unif; (void)n_unif;
+  return fail(GMCMC_ERR_UNSUPPORTED, "NUTS is not available in this build");
+}
+
+gmcmc_status gmcmc_read_diagnostics(gmcmc_sampler* s, void* log_accept, uint8_t* accepted, void* prop_q, void* prop_p) {
+  GM_REQUIRE(s, "null sampler");
+  if (s->diag_steps == 0) return fail(GMCMC_ERR_STATE, "no injected transitions recorded");
+  GM_CU(cudaSetDevice(s->ctx->device));
+  GM_CU(cudaStreamSynchronize(s->ctx->stream));
+  const size_t es = esize(s->dtype), C = s->n_chains, d = (size_t)s->dim, n = s->diag_steps;
+  if (log_accept) GM_CU(cudaMemcpy(log_accept, s->d_diag_logacc, n * C * es, cudaMemcpyDeviceToHost));
+  if (accepted) GM_CU(cudaMemcpy(accepted, s->d_diag_acc, n * C, cudaMemcpyDeviceToHost));
+  if (prop_q) {
+    GM_REQUIRE(s->d_diag_pq, "proposal diagnostics are recorded for HMC only");
+    GM_CU(cudaMemcpy(prop_q, s->d_diag_pq, n * C * d * es, cudaMemcpyDeviceToHost));
+  }
+  if (prop_p) {
+    GM_REQUIRE(s->d_diag_pp, "proposal diagnostics are recorded for HMC only");
+    GM_CU(cudaMemcpy(prop_p, s->d_diag_pp, n * C * d * es, cudaMemcpyDeviceToHost));
+  }
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_step(gmcmc_sampler* s) {
+  GM_REQUIRE(s, "null sampler");
+  return run_into(s, 0, 1, nullptr);
+}
+
+gmcmc_status gmcmc_run_device(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void** out_dev) {
+  GM_REQUIRE(s, "null sampler");
+  GM_CU(cudaSetDevice(s->ctx->device));
+  const size_t bytes = s->n_chains * n_collect * (size_t)s->dim * esize(out_dtype_of(s));
+  GM_TRY(ensure_samples(s, bytes));
+  GM_TRY(run_into(s, n_collect, n_discard, s->d_samples));
+  if (out_dev) *out_dev = s->d_samples;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_run(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void* out_host, gmcmc_dtype out_dtype) {
+  GM_REQUIRE(s && (out_host || n_collect == 0), "null argument");
+  void* d = nullptr;
+  GM_TRY(gmcmc_run_device(s, n_collect, n_discard, &d));
+  const size_t n = s->n_chains * n_collect * (size_t)s->dim;
+  gmcmc_ctx* ctx = s->ctx;
+  if (n == 0) { GM_CU(cudaStreamSynchronize(ctx->stream)); return GMCMC_OK; }
+  const int src = out_dtype_of(s);
+  if ((int)out_dtype == src) {
+    GM_CU(cudaMemcpyAsync(out_host, d, n * esize(src), cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    TempDevice t;
+    GM_CU(cudaMalloc(&t.p, n * esize(out_dtype)));
+    GM_TRY(convert_on_device(ctx, d, src, t.p, out_dtype, n));
+    GM_CU(cudaMemcpyAsync(out_host, t.p, n * esize(out_dtype), cudaMemcpyDeviceToHost, ctx->stream));
+    GM_CU(cudaStreamSynchronize(ctx->stream));
+  }
+  GM_CU(cudaStreamSynchronize(ctx->stream));
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_run_stats(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void* out_host_or_null,
+                             gmcmc_dtype out_dtype, gmcmc_run_stats_t* stats) {
+  GM_REQUIRE(s && stats, "null argument");
+  void* d = nullptr;
+  GM_TRY(gmcmc_run_device(s, n_collect, n_discard, &d));
+  const int src = out_dtype_of(s);
+  GM_TRY(stats_on_device(s->ctx, d, s->n_chains, n_collect, (size_t)s->dim, src, stats));
+  if (out_host_or_null) {
+    const size_t n = s->n_chains * n_collect * (size_t)s->dim;
+    if ((int)out_dtype == src) {
+      GM_CU(cudaMemcpy(out_host_or_null, d, n * esize(src), cudaMemcpyDeviceToHost));
+    } else {
+      TempDevice t;
+      GM_CU(cudaMalloc(&t.p, n * esize(out_dtype)));
+      GM_TRY(convert_on_device(s->ctx, d, src, t.p, out_dtype, n));
+      GM_CU(cudaStreamSynchronize(s->ctx->stream));
+      GM_CU(cudaMemcpy(out_host_or_null, t.p, n * esize(out_dtype), cudaMemcpyDeviceToHost));
+    }
+  }
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_positions(gmcmc_sampler* s, void* out_host) {
+  GM_REQUIRE(s && out_host, "null argument");
+  GM_CU(cudaSetDevice(s->ctx->device));
+  GM_CU(cudaStreamSynchronize(s->ctx->stream));
+  GM_CU(cudaMemcpy(out_host, s->d_pos, s->n_chains * (size_t)s->dim * esize(s->dtype), cudaMemcpyDeviceToHost));
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_set_positions(gmcmc_sampler* s, const void* init_host) {
+  GM_REQUIRE(s && init_host, "null argument");
+  GM_CU(cudaSetDevice(s->ctx->device));
+  GM_CU(cudaMemcpyAsync(s->d_pos, init_host, s->n_chains * (size_t)s->dim * esize(s->dtype), cudaMemcpyHostToDevice,
+                        s->ctx->stream));
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_counters_get(gmcmc_sampler* s, gmcmc_counters* out) {
+  GM_REQUIRE(s && out, "null argument");
+  GM_CU(cudaSetDevice(s->ctx->device));
+  GM_CU(cudaStreamSynchronize(s->ctx->stream));
+  unsigned long long h[4];
+  GM_CU(cudaMemcpy(h, s->d_counts, sizeof h, cudaMemcpyDeviceToHost));
+  out->transitions = s->transitions;
+  out->accepts = h[0];
+  out->divergences = h[1];
+  out->grad_evals = s->type == S_HMC ? s->hmc_grad_evals : h[2];
+  out->step_size = s->step_size;
+  if (s->type == S_HMC) {
+    if (s->adapt == GMCMC_ADAPT_POOLED && s->da_m > 0) {
+      PooledDa p;
+      GM_CU(cudaMemcpy(&p, s->d_pooled, sizeof p, cudaMemcpyDeviceToHost));
+      out->step_size = p.eps;
+    } else if (s->adapt == GMCMC_ADAPT_PER_CHAIN && s->da_m > 0) {
+      const size_t C = s->n_chains;
+      double sum = 0.0;
+      if (s->dtype == GMCMC_F32) {
+        std::vector<float> v(C);
+        GM_CU(cudaMemcpy(v.data(), s->d_da[0], C * 4, cudaMemcpyDeviceToHost));
+        for (float x : v) sum += x;
+      } else {
+        std::vector<double> v(C);
+        GM_CU(cudaMemcpy(v.data(), s->d_da[0], C * 8, cudaMemcpyDeviceToHost));
+        for (double x : v) sum += x;
+      }
+      out->step_size = sum / (double)C;
+    }
+  }
+  float ms = 0.f;
+  if (s->timed) GM_CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+  out->kernel_ms = ms;
+  out->launches = s->launches;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_sampler_info(gmcmc_sampler* s, size_t* n_chains, int* dim, gmcmc_dtype* dtype) {
+  GM_REQUIRE(s, "null sampler");
+  if (n_chains) *n_chains = s->n_chains;
+  if (dim) *dim = s->dim;
+  if (dtype) *dtype = (gmcmc_dtype)s->dtype;
+  return GMCMC_OK;
+}
+
+// ---- diagnostics --------------------------------------------------------------------------------
+static gmcmc_status stage_samples(gmcmc_ctx* ctx, const void* samples, size_t bytes, int on_device, TempDevice* tmp,
+                                  const void** d_ptr) {
+  if (on_device) { *d_ptr = samples; return GMCMC_OK; }
+  GM_CU(cudaSetDevice(ctx->device));
+  GM_CU(cudaMalloc(&tmp->p, bytes));
+  GM_CU(cudaMemcpyAsync(tmp->p, samples, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  *d_ptr = tmp->p;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_split_rhat_ess(gmcmc_ctx* ctx, const void* samples, size_t C, size_t n, size_t p, gmcmc_dtype dtype,
+                                  int on_device, float* rhat, float* ess) {
+  GM_REQUIRE(ctx && samples, "null argument");
+  TempDevice tmp;
+  const void* d = nullptr;
+  GM_TRY(stage_samples(ctx, samples, C * n * p * esize(dtype), on_device, &tmp, &d));
+  return device_split_rhat_ess(ctx, d, C, n, p, dtype, rhat, nullptr, ess);
+}
+
+gmcmc_status gmcmc_run_stats_from(gmcmc_ctx* ctx, const void* samples, size_t C, size_t n, size_t p, gmcmc_dtype dtype,
+                                  int on_device, gmcmc_run_stats_t* out) {
+  GM_REQUIRE(ctx && samples && out, "null argument");
+  TempDevice tmp;
+  const void* d = nullptr;
+  GM_TRY(stage_samples(ctx, samples, C * n * p * esize(dtype), on_device, &tmp, &d));
+  return stats_on_device(ctx, d, C, n, p, dtype, out);
+}
+
+gmcmc_status gmcmc_philox_blocks(gmcmc_ctx* ctx, const uint32_t* ctr_host, size_t n, const uint32_t* key, uint32_t* out_host) {
+  GM_REQUIRE(ctx && ctr_host && key && out_host, "null argument");
+  if (n == 0) return GMCMC_OK;
+  GM_CU(cudaSetDevice(ctx->device));
+  TempDevice a, b;
+  GM_CU(cudaMalloc(&a.p, n * 16));
+  GM_CU(cudaMalloc(&b.p, n * 16));
+  GM_CU(cudaMemcpyAsync(a.p, ctr_host, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  philox_blocks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint4*)a.p, n, PhiloxKey{key[0], key[1]}, (uint4*)b.p);
+  GM_CU(cudaGetLastError());
+  GM_CU(cudaMemcpyAsync(out_host, b.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CU(cudaStreamSynchronize(ctx->stream));
+  return GMCMC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,215 @@
+/* gmcmc.h — C ABI of the B200-native many-chain sampling hot path of general-mcmc.
+ *
+ * The reference crate (SauersML/general-mcmc 0.8.0) has no FFI: its boundary is the Rust trait /
+ * constructor surface.  A thin Rust shim keeps those signatures and binds the entry
+ * points below; each entry point cites the reference interface it replaces (file:line into
+ * /root/reference/src).  Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns gmcmc_status; nothing throws or aborts across the boundary (the crate's
+ *     release profile is panic = "abort", Cargo.toml:54); detail via gmcmc_last_error() (thread-local).
+ *   - inputs are borrowed for the call and copied; outputs go to caller-owned host buffers, or to
+ *     library-owned device buffers for the *_device calls (valid until the next run or the destroy).
+ *   - a sampler handle is NOT thread-safe (mirrors `&mut self`); distinct handles may be used from
+ *     distinct threads.  One context = one GPU = one process rank.
+ *   - there is NO CPU fallback: every compute entry point fails with GMCMC_ERR_CUDA when no sm_100
+ *     device is usable.
+ *
+ * Sample layout: [chains, samples, dim], C-contiguous (core.rs:219-229, batched_hmc.rs:98-110,
+ * hmc.rs:179-180).  MH output is always f64 (Trace -> f64, core.rs:34-51); HMC/NUTS output is the
+ * sampler's scalar type.
+ *
+ * RNG contract (replaces rand::SmallRng / rand_distr ziggurat, whose streams are third-party and
+ * unpinned by any reference test — SURVEY §8c): Philox4x32-10, key = (seed_lo, seed_hi),
+ *   counter = (gchain_lo, gchain_hi, transition_index, (stream << 24) | block)
+ * where gchain = chain_offset + local chain index (so results do not depend on how chains are sharded
+ * over GPUs) and transition_index counts transitions since the sampler was created / re-seeded.
+ *   stream 0: N(0,1) draws for the momentum (HMC/NUTS) or the proposal noise (MH);
+ *             f32: block b -> elements 4b..4b+3 (Box–Muller on (r0,r1) and (r2,r3));
+ *             f64: block b -> elements 2b, 2b+1 (53-bit uniforms from (r0,r1) and (r2,r3));
+ *   stream 1: block 0 -> accept uniform (r0 [f32] or (r0,r1) [f64]); NUTS: r2/r3 -> Exp(1) draw;
+ *   stream 2: NUTS tree uniforms, block = draw index / 4 (see gmcmc_nuts_create).
+ * Uniforms are in (0,1]:  f32 ((r>>8)+1)*2^-24,  f64 ((r64>>11)+1)*2^-53.
+ */
+#ifndef GMCMC_H
+#define GMCMC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gmcmc_ctx gmcmc_ctx;
+typedef struct gmcmc_target gmcmc_target;
+typedef struct gmcmc_sampler gmcmc_sampler;
+
+typedef enum {
+  GMCMC_OK = 0,
+  GMCMC_ERR_INVALID = 1,     /* bad argument / shape */
+  GMCMC_ERR_CUDA = 2,        /* CUDA runtime error or no usable device */
+  GMCMC_ERR_UNSUPPORTED = 3, /* combination not implemented (e.g. dim too large for a kernel) */
+  GMCMC_ERR_NCCL = 4,
+  GMCMC_ERR_STATE = 5        /* call not valid in the sampler's current state */
+} gmcmc_status;
+
+typedef enum { GMCMC_F32 = 0, GMCMC_F64 = 1 } gmcmc_dtype;
+
+/* Built-in targets.  `params` of gmcmc_target_create are doubles, cast once to the sampler dtype
+ * (as the reference constructors do). */
+typedef enum {
+  GMCMC_TARGET_ISO_GAUSS = 0,     /* distributions.rs:398-406  params: [std]                         any dim */
+  GMCMC_TARGET_GAUSS2D = 1,       /* distributions.rs:191-208  params: [m0,m1, a,b,c,d] (cov rows)   dim 2   */
+  GMCMC_TARGET_DIFF_GAUSS2D = 2,  /* distributions.rs:215-291  params: [m0,m1, c00,c01,c10,c11]      dim 2   */
+  GMCMC_TARGET_DENSE_GAUSS = 3,   /* N-D form of :265-291      params: [mu[d], P[d*d] row-major, norm_const]  */
+  GMCMC_TARGET_ROSENBROCK2D = 4,  /* distributions.rs:495-515  params: [a,b]                         dim 2   */
+  GMCMC_TARGET_ROSENBROCK_ND = 5, /* distributions.rs:535-555  params: none                          any dim */
+  GMCMC_TARGET_GAUSS_MIXTURE = 6  /* isotropic mixture         params: [K, sigma, w[K], mu[K*d]]     any dim */
+} gmcmc_target_kind;
+
+typedef enum {
+  GMCMC_MATH_FAST = 0,  /* FMA contraction, merged half-kicks, shuffle-tree reductions */
+  GMCMC_MATH_EXACT = 1  /* reference operation order, no contraction, sequential sums: bit-for-bit the
+                           CPU oracle for transcendental-free targets (parity mode) */
+} gmcmc_math_mode;
+
+typedef enum {
+  GMCMC_ADAPT_NONE = 0,      /* fixed step size: the reference's HMC (batched_hmc.rs:35) */
+  GMCMC_ADAPT_PER_CHAIN = 1, /* per-chain dual averaging: the reference's NUTS (generic_nuts.rs:882-924) */
+  GMCMC_ADAPT_POOLED = 2     /* one step size from the mean acceptance statistic over ALL chains of all
+                                ranks (NCCL all-reduce); new mode named by BASELINE.json north_star */
+} gmcmc_adapt_mode;
+
+/* RunStats / BasicStats, stats.rs:370-415 (name field dropped: "ESS" / "Split R-hat"). */
+typedef struct { float min, median, max, mean, std; } gmcmc_basic_stats;
+typedef struct {
+  gmcmc_basic_stats ess;
+  gmcmc_basic_stats rhat;     /* reference orientation sqrt(W / var_hat), stats.rs:452-454 */
+  gmcmc_basic_stats rhat_std; /* standard orientation sqrt(var_hat / W), reported alongside */
+} gmcmc_run_stats_t;
+
+typedef struct {
+  uint64_t transitions;  /* chain-transitions taken by this rank since creation */
+  uint64_t accepts;      /* accepted proposals (this rank) */
+  uint64_t grad_evals;   /* algorithmic gradient evaluations: HMC L per transition; NUTS leapfrogs taken */
+  uint64_t divergences;  /* non-finite log-accept (HMC) / s' = false by energy (NUTS) */
+  double step_size;      /* current (pooled or mean per-chain) step size */
+  double kernel_ms;      /* device time of the sampling kernels of the last run (CUDA events) */
+  uint64_t launches;     /* kernel launches issued by the last run */
+} gmcmc_counters;
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* One context per process/GPU.  rank/world describe the chain sharding: rank r of
+ * `world` owns a contiguous global chain range given per sampler by chain_offset. */
+gmcmc_status gmcmc_ctx_create(int device, gmcmc_ctx** out);
+/* Multi-GPU: `nccl_id` is the 128-byte ncclUniqueId produced by gmcmc_nccl_unique_id on rank 0 and
+ * distributed by the host (torch.distributed / MPI / the Rust shim). */
+gmcmc_status gmcmc_nccl_unique_id(void* out128);
+gmcmc_status gmcmc_ctx_create_dist(int device, int rank, int world, const void* nccl_id, gmcmc_ctx** out);
+gmcmc_status gmcmc_ctx_destroy(gmcmc_ctx*);
+gmcmc_status gmcmc_ctx_synchronize(gmcmc_ctx*);
+/* the CUDA stream all work of this context is issued on (cudaStream_t as void*) */
+gmcmc_status gmcmc_ctx_stream(gmcmc_ctx*, void** out_stream);
+
+/* sum-all-reduce of a small host f64 vector over the ranks of a distributed context (no-op when
+ * world == 1); used by the host shim to combine per-rank counters. */
+gmcmc_status gmcmc_ctx_all_reduce_f64(gmcmc_ctx*, double* host_inout, size_t n);
+/* page-locked host memory for sample tensors (so gmcmc_run copies at full PCIe rate) */
+gmcmc_status gmcmc_host_alloc(size_t bytes, void** out);
+gmcmc_status gmcmc_host_free(void* p);
+
+/* measured FP32 FMA-pipe peak of this GPU in TFLOP/s (roofline denominator of the register-resident
+ * trajectory kernels; the driver's MEASURED_PEAKS.json only holds HBM and bf16 tensor peaks) */
+gmcmc_status gmcmc_measure_fp32_peak(gmcmc_ctx*, double* tflops);
+
+/* ---- targets (distributions.rs traits Target / BatchedGradientTarget / GradientTarget :67-110) */
+gmcmc_status gmcmc_target_create(gmcmc_ctx*, gmcmc_target_kind kind, gmcmc_dtype dtype, int dim,
+                                 const double* params, size_t n_params, gmcmc_target** out);
+gmcmc_status gmcmc_target_destroy(gmcmc_target*);
+/* logp and gradient for a batch of host positions [n, dim] (≙ BatchedHamiltonianTarget::logp_and_grad,
+ * batched_hmc.rs:18-22).  grad_out may be NULL. */
+gmcmc_status gmcmc_target_logp_grad(gmcmc_target*, const void* x_host, size_t n, void* logp_out,
+                                    void* grad_out, gmcmc_math_mode mode);
+
+/* ---- samplers ------------------------------------------------------------------------------ */
+/* ≙ HMC::new (hmc.rs:113-134) / BatchedGenericHMC::new (batched_hmc.rs:62-84).
+ * init_host: [n_chains, dim] row-major in the target's dtype.  chain_offset: global index of local
+ * chain 0 (0 on a single GPU). */
+gmcmc_status gmcmc_hmc_create(gmcmc_ctx*, gmcmc_target*, size_t n_chains, uint64_t chain_offset,
+                              const void* init_host, double step_size, uint32_t n_leapfrog,
+                              uint64_t seed, gmcmc_sampler** out);
+/* ≙ MetropolisHastings::new + seed (metropolis_hastings.rs:151-197) with an IsotropicGaussian
+ * proposal (distributions.rs:349-390). */
+gmcmc_status gmcmc_mh_create(gmcmc_ctx*, gmcmc_target*, double proposal_std, size_t n_chains,
+                             uint64_t chain_offset, const void* init_host, uint64_t seed,
+                             gmcmc_sampler** out);
+/* ≙ NUTS::new (nuts.rs:156-190) / GenericNUTS::new (generic_nuts.rs:370-398), identity mass.
+ * max_depth 0 = uncapped like the reference up to an internal safety cap of 20.
+ * init_step_size <= 0: find_reasonable_epsilon (generic_nuts.rs:1025-1102) per chain. */
+gmcmc_status gmcmc_nuts_create(gmcmc_ctx*, gmcmc_target*, size_t n_chains, uint64_t chain_offset,
+                               const void* init_host, double target_accept, uint32_t max_depth,
+                               double init_step_size, uint64_t seed, gmcmc_sampler** out);
+gmcmc_status gmcmc_sampler_destroy(gmcmc_sampler*);
+
+gmcmc_status gmcmc_set_seed(gmcmc_sampler*, uint64_t seed);  /* ≙ set_seed / seed */
+gmcmc_status gmcmc_set_math_mode(gmcmc_sampler*, gmcmc_math_mode);
+/* HMC step-size adaptation during the discard phase of the next run (dual averaging, constants of
+ * generic_nuts.rs:638-641: gamma 0.05, t0 10, kappa 0.75, mu = ln(10 eps0)). */
+gmcmc_status gmcmc_set_adaptation(gmcmc_sampler*, gmcmc_adapt_mode, double target_accept);
+gmcmc_status gmcmc_set_step_size(gmcmc_sampler*, double step_size);
+
+/* Test hook for per-step equivalence: the next `n_steps` transitions consume these host arrays
+ * instead of Philox.  HMC: normals [n_steps, n_chains, dim], ln_u [n_steps, n_chains].
+ * MH: same shapes (normals = proposal noise).  NUTS: see gmcmc_nuts_inject. */
+gmcmc_status gmcmc_inject(gmcmc_sampler*, const void* normals, const void* ln_u, size_t n_steps);
+/* NUTS: per-chain streams in the reference's draw order: normals [C, n_norm],
+ * exp1 [C, n_exp], unif [C, n_unif], all f64. */
+gmcmc_status gmcmc_nuts_inject(gmcmc_sampler*, const double* normals, size_t n_norm, const double* exp1,
+                               size_t n_exp, const double* unif, size_t n_unif);
+/* Per-step diagnostics of the injected transitions (HMC/MH): log_accept [n_steps, C] (sampler dtype),
+ * accepted [n_steps, C] (u8), prop_q / prop_p [n_steps, C, dim] (HMC only; end of trajectory).
+ * Any pointer may be NULL.  Valid after the run that consumed the injection. */
+gmcmc_status gmcmc_read_diagnostics(gmcmc_sampler*, void* log_accept, uint8_t* accepted, void* prop_q,
+                                    void* prop_p);
+
+gmcmc_status gmcmc_step(gmcmc_sampler*); /* ≙ HMC::step (hmc.rs:308), MarkovChain::step (core.rs:79-85) */
+/* ≙ HMC::run (hmc.rs:164-181), BatchedGenericHMC::run (batched_hmc.rs:93-112), ChainRunner::run
+ * (core.rs:219-229), NUTS::run (nuts.rs:214-257).  out_host: [C, n_collect, dim] of out_dtype. */
+gmcmc_status gmcmc_run(gmcmc_sampler*, size_t n_collect, size_t n_discard, void* out_host,
+                       gmcmc_dtype out_dtype);
+/* ≙ BatchedGenericHMC::run_positions (batched_hmc.rs:115-123): samples stay on the device.
+ * *out_dev: library-owned [C, n_collect, dim] (sampler dtype; f64 for MH). */
+gmcmc_status gmcmc_run_device(gmcmc_sampler*, size_t n_collect, size_t n_discard, void** out_dev);
+/* ≙ run_progress (hmc.rs:245-306, core.rs:251-403, generic_nuts.rs:414-548) without the terminal UI:
+ * samples (optional, may be NULL) + RunStats computed on the device over ALL ranks' chains. */
+gmcmc_status gmcmc_run_stats(gmcmc_sampler*, size_t n_collect, size_t n_discard, void* out_host_or_null,
+                             gmcmc_dtype out_dtype, gmcmc_run_stats_t* stats);
+gmcmc_status gmcmc_positions(gmcmc_sampler*, void* out_host); /* ≙ positions() hmc.rs:318 */
+/* overwrite the chains' current positions from a host [C, dim] array (restart from new initial
+ * positions without rebuilding the sampler; ≙ constructing HMC::new with other initial_positions) */
+gmcmc_status gmcmc_set_positions(gmcmc_sampler*, const void* init_host);
+gmcmc_status gmcmc_counters_get(gmcmc_sampler*, gmcmc_counters* out);
+gmcmc_status gmcmc_sampler_info(gmcmc_sampler*, size_t* n_chains, int* dim, gmcmc_dtype* dtype);
+
+/* ---- diagnostics (stats.rs:439-450 split_rhat_mean_ess) -------------------------------------- */
+/* samples: [C, n, p] of `dtype`, host (on_device = 0) or device pointer.  rhat/ess: host float[p].
+ * rhat is the reference orientation sqrt(W/var_hat).  With a distributed context, C is this rank's
+ * shard and the result covers all ranks' chains. */
+gmcmc_status gmcmc_split_rhat_ess(gmcmc_ctx*, const void* samples, size_t C, size_t n, size_t p,
+                                  gmcmc_dtype dtype, int on_device, float* rhat, float* ess);
+/* ≙ RunStats::from (stats.rs:383-394) */
+gmcmc_status gmcmc_run_stats_from(gmcmc_ctx*, const void* samples, size_t C, size_t n, size_t p,
+                                  gmcmc_dtype dtype, int on_device, gmcmc_run_stats_t* out);
+
+/* raw Philox4x32-10 blocks computed on the device (contract check): ctr [n,4], key [2] -> out [n,4] */
+gmcmc_status gmcmc_philox_blocks(gmcmc_ctx*, const uint32_t* ctr_host, size_t n, const uint32_t* key,
+                                 uint32_t* out_host);
+
+const char* gmcmc_last_error(void);
+const char* gmcmc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMCMC_H */
