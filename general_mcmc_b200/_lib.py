@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgmcmc.so")
+LIB_PATH = os.environ.get("GMCMC_LIB") or os.path.join(_HERE, "libgmcmc.so")
 
 F32, F64 = 0, 1
 MATH_FAST, MATH_EXACT = 0, 1

@@ -11,12 +11,15 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-BUILD = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libgmcmc.so")
+# tuning builds: GMCMC_VARIANT=name GMCMC_DEFINES="-DGM_MINB=5" python build.py -> libgmcmc_name.so
+_VARIANT = os.environ.get("GMCMC_VARIANT", "")
+BUILD = os.path.join(HERE, "build" + ("_" + _VARIANT if _VARIANT else ""))
+LIB = os.path.join(HERE, "libgmcmc%s.so" % ("_" + _VARIANT if _VARIANT else ""))
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC]
+COMMON = (["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC]
+          + os.environ.get("GMCMC_DEFINES", "").split())
 
 # per-target K1 translation units, each compiled in both math modes
 K1_TARGETS = ["k_rosen", "k_iso", "k_dense", "k_mix", "k_rosen2d", "k_dgauss2d", "k_gauss2d"]

@@ -31,8 +31,9 @@ cudaError_t launch_hmc_exact(const HmcLaunch& L, cudaStream_t st) { GM_ROUTE(lau
 cudaError_t launch_eval_fast(const EvalLaunch& E, cudaStream_t st) { GM_ROUTE(launch_eval_, fast, E, st) }
 cudaError_t launch_eval_exact(const EvalLaunch& E, cudaStream_t st) { GM_ROUTE(launch_eval_, exact, E, st) }
 
-// Decomposition: minimise padded slots (compute), penalising non exact fits (masking costs ~30 %);
-// ties go to more elements per lane (more ILP, fewer shuffles).  f64 is capped at 16 elements per lane
+// Decomposition: minimise padded slots (compute), penalising non exact fits (masking costs ~30 %) and
+// lanes per chain; ties go to more elements per lane (more ILP, fewer shuffles).  Lanes past the end of
+// the chain own no coordinate and only take part in the shuffles.  f64 is capped at 16 elements per lane
 // (4 live arrays x 16 x 2 registers).  GMCMC_EPL / GMCMC_LPC override for tuning.
 bool choose_decomposition(int dim, int dtype, int kind, int* epl, int* lpc) {
   if (dim <= 0) return false;
@@ -59,8 +60,9 @@ bool choose_decomposition(int dim, int dtype, int kind, int* epl, int* lpc) {
     for (int e : menu) {
       if (dtype == 1 && e > 16) continue;
       if (e * l < dim) continue;
-      if ((l - 1) * e >= dim) continue;  // last lane would own nothing
-      double cost = (double)e * l * ((e * l == dim) ? 1.0 : 1.3);
+      // padded slots cost compute (masking ~30 %); every extra lane costs shuffles in the stencil halo
+      // and the reduction trees
+      double cost = (double)e * l * ((e * l == dim) ? 1.0 : 1.3) + 4.0 * l;
       if (cost < best - 1e-9 || (cost < best + 1e-9 && e > be)) { best = cost; be = e; bl = l; }
     }
   if (!be) return false;

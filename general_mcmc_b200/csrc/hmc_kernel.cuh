@@ -26,6 +26,9 @@
 #ifndef GM_EXACT
 #define GM_EXACT 0
 #endif
+#ifndef GM_MINB
+#define GM_MINB 4   // resident CTAs per SM the trajectory kernel is register-budgeted for (tuned on B200)
+#endif
 #if GM_EXACT
 #define GM_NS exact
 #else
@@ -335,6 +338,89 @@ __device__ __forceinline__ T eval_target(TagGauss2D, const T (&x)[EPL], T (&g)[E
   return -T(0.5) * (v0 * d0 + v1 * d1);
 }
 
+// ----------------------------------------------------------------------------------------------
+// eval_kick: gradient at x, then the momentum kick p += coef * g applied `NK` times (NK = 2 is the
+// reference's two consecutive half-kicks with the same gradient, batched_hmc.rs:187 + :175).  Returns
+// the log density when WANT_LOGP.  Generic version: gradient slice in registers, then the kick.
+// ----------------------------------------------------------------------------------------------
+template <class T, int EPL, bool PADDED, bool WANT_LOGP, int NK, class TAG>
+__device__ __forceinline__ T eval_kick(TAG, const T (&x)[EPL], T (&p)[EPL], const T coef, const Lane& ln,
+                                       const TParams<T>& tp, T* row) {
+  T g[EPL];
+  const T lp = eval_target<T, EPL, PADDED, WANT_LOGP>(TAG{}, x, g, ln, tp, row);
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) {
+    p[j] = p[j] + g[j] * coef;
+    if constexpr (NK == 2) p[j] = p[j] + g[j] * coef;
+  }
+  return lp;
+}
+
+// RosenbrockND: the gradient never materialises — each coordinate's stencil value goes straight into
+// its momentum (6 FMAs per coordinate per leapfrog in fast mode: drift 1, t 1, gradient 3, kick 1).
+template <class T, int EPL, bool PADDED, bool WANT_LOGP, int NK>
+__device__ __forceinline__ T eval_kick(TagRosenbrockND, const T (&x)[EPL], T (&p)[EPL], const T coef, const Lane& ln,
+                                       const TParams<T>&, T*) {
+  const T x_next_lane = __shfl_down_sync(kFull, x[0], 1);
+  T gt[EPL];     // fast: t_j ; exact: gt_j = -200 t_j
+  T terms[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) {
+    const T xn = (j + 1 < EPL) ? x[j + 1] : x_next_lane;
+    bool has_low;
+    if constexpr (PADDED) has_low = (ln.lo + j) < (ln.d - 1);
+    else has_low = (j + 1 < EPL) ? true : !ln.last;
+    T t = xn - x[j] * x[j];
+    if (!has_low) t = T(0);
+    if constexpr (kExact) {
+      if constexpr (WANT_LOGP) {
+        T u = (-x[j]) + T(1);
+        terms[j] = has_low ? ((t * t) * T(100) + u * u) : T(0);
+      }
+      gt[j] = T(-200) * t;
+    } else {
+      if constexpr (WANT_LOGP) {
+        T u = T(1) - x[j];
+        terms[j] = has_low ? (T(100) * t * t + u * u) : T(0);
+      }
+      gt[j] = t;
+    }
+  }
+  T prev = __shfl_up_sync(kFull, gt[EPL - 1], 1);
+  if (ln.first) prev = T(0);
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) {
+    const T gp = (j == 0) ? prev : gt[j - 1];
+    bool has_low;
+    if constexpr (PADDED) has_low = (ln.lo + j) < (ln.d - 1);
+    else has_low = (j + 1 < EPL) ? true : !ln.last;
+    T gi;
+    if constexpr (kExact) {
+      T u = (-x[j]) + T(1);
+      if (has_low) {
+        gi = (T(-2) * (gt[j] * x[j])) + T(2) * u;
+        if (ln.lo + j > 0) gi = gi + gp;
+      } else {
+        gi = (ln.lo + j > 0 && ln.lo + j < ln.d) ? gp : T(0);
+      }
+    } else {
+      T a = T(400) * gt[j] - T(2);
+      T lowterm = x[j] * a + T(2);
+      if (!has_low) lowterm = T(0);
+      gi = T(-200) * gp + lowterm;
+      if constexpr (PADDED) { if (ln.lo + j >= ln.d) gi = T(0); }
+    }
+    p[j] = p[j] + gi * coef;
+    if constexpr (NK == 2) p[j] = p[j] + gi * coef;
+  }
+  if constexpr (WANT_LOGP) {
+    int nl = ln.d - 1 - ln.lo;
+    nl = nl < 0 ? 0 : (nl > EPL ? EPL : nl);
+    return -chain_sum<T, EPL>(terms, nl, ln);
+  }
+  return T(0);
+}
+
 template <class T>
 __host__ inline TParams<T> make_tparams(const TargetDesc& td) {
   TParams<T> tp;
@@ -401,9 +487,9 @@ template <class T> struct VecOf;
 template <> struct VecOf<float> { using type = float4; static constexpr int n = 4; };
 template <> struct VecOf<double> { using type = double2; static constexpr int n = 2; };
 
-// Cooperative, coalesced copy of the warp's staged rows to [chain, slot, :] of the sample tensor.
+// Cooperative, coalesced copy of the warp's position rows to [chain, slot, :] of the sample tensor.
 template <class T>
-__device__ __forceinline__ void store_rows(const T* warp_stage, int d, int d_pad, int chains_in_warp,
+__device__ __forceinline__ void store_rows(const T* warp_rows, int d, int d_pad, int chains_in_warp,
                                            size_t first_chain, size_t n_chains, T* out, size_t out_n,
                                            size_t slot) {
   const int lane = threadIdx.x & 31;
@@ -414,7 +500,7 @@ __device__ __forceinline__ void store_rows(const T* warp_stage, int d, int d_pad
     for (int c = 0; c < chains_in_warp; ++c) {
       size_t chain = first_chain + c;
       if (chain >= n_chains) break;
-      const V* src = reinterpret_cast<const V*>(warp_stage + (size_t)c * d_pad);
+      const V* src = reinterpret_cast<const V*>(warp_rows + (size_t)c * d_pad);
       V* dst = reinterpret_cast<V*>(out + (chain * out_n + slot) * (size_t)d);
       for (int i = lane; i < nv; i += 32) __stcs(dst + i, src[i]);
     }
@@ -422,35 +508,44 @@ __device__ __forceinline__ void store_rows(const T* warp_stage, int d, int d_pad
     for (int c = 0; c < chains_in_warp; ++c) {
       size_t chain = first_chain + c;
       if (chain >= n_chains) break;
-      const T* src = warp_stage + (size_t)c * d_pad;
+      const T* src = warp_rows + (size_t)c * d_pad;
       T* dst = out + (chain * out_n + slot) * (size_t)d;
       for (int i = lane; i < d; i += 32) __stcs(dst + i, src[i]);
     }
   }
 }
 
+// Shared memory per warp: [chains_in_warp][d_pad] current (accepted) positions — the row that is
+// streamed to the sample tensor — followed by the same shape of scratch (Philox normals / dense
+// target staging).  Registers hold only the moving point q and the momentum p.
 template <class T, int EPL, class TAG, bool PADDED>
-__global__ void __launch_bounds__(kHmcBlock) hmc_run_kernel(const HmcArgs<T> a) {
+__global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* stage = reinterpret_cast<T*>(smem_raw);
+  T* smem = reinterpret_cast<T*>(smem_raw);
 
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const Lane ln = make_lane<EPL>(tid, a.lpc, a.d);
   const size_t chain = (size_t)(tid / a.lpc);
   const bool active = chain < a.n_chains;
+  const int lane = threadIdx.x & 31;
   const int chains_in_warp = 32 / a.lpc;
   const int warp_in_block = threadIdx.x >> 5;
-  const int chain_in_warp = (threadIdx.x & 31) / a.lpc;
-  T* warp_stage = stage + (size_t)warp_in_block * chains_in_warp * a.d_pad;
-  T* row = warp_stage + (size_t)chain_in_warp * a.d_pad;
+  const int chain_in_warp = lane / a.lpc;
+  const size_t warp_elems = (size_t)chains_in_warp * a.d_pad;
+  T* warp_pos = smem + (size_t)warp_in_block * 2 * warp_elems;
+  T* warp_scr = warp_pos + warp_elems;
+  T* pos_row = warp_pos + (size_t)chain_in_warp * a.d_pad;
+  T* row = warp_scr + (size_t)chain_in_warp * a.d_pad;
   const size_t warp_first_chain = (size_t)((tid & ~31) / a.lpc);
   const unsigned long long gchain = a.chain_offset + chain;
 
-  // current position -> registers
-  T qc[EPL];
-#pragma unroll
-  for (int j = 0; j < EPL; ++j)
-    qc[j] = (active && j < ln.nvalid) ? a.positions[chain * a.d + ln.lo + j] : T(1);
+  // current positions -> shared rows (coalesced); chains past the end get a harmless point
+  for (int c = 0; c < chains_in_warp; ++c) {
+    const size_t ch = warp_first_chain + c;
+    for (int i = lane; i < a.d_pad; i += 32)
+      warp_pos[(size_t)c * a.d_pad + i] = (ch < a.n_chains && i < a.d) ? a.positions[ch * a.d + i] : T(1);
+  }
+  __syncwarp();
 
   T eps = active ? a.eps[a.eps_stride ? chain : 0] : T(0.01);
   // per-chain dual averaging state (GMCMC_ADAPT_PER_CHAIN; generic_nuts.rs:882-924)
@@ -465,7 +560,7 @@ __global__ void __launch_bounds__(kHmcBlock) hmc_run_kernel(const HmcArgs<T> a) 
 
   for (uint32_t s = 0; s < a.n_steps; ++s) {
     const uint32_t step = a.step_base + s;
-    T q[EPL], p[EPL], g[EPL];
+    T q[EPL], p[EPL];
 
     // ---- 1. momentum ~ N(0, I)   (batched_hmc.rs:131 / generic_hmc.rs:177)
     if (a.inj_normals) {
@@ -475,10 +570,9 @@ __global__ void __launch_bounds__(kHmcBlock) hmc_run_kernel(const HmcArgs<T> a) 
     } else {
       constexpr int NPB = NormalsPerBlock<T>::value;
       const int nblocks = (a.d + NPB - 1) / NPB;
-      __syncwarp();
       for (int b = ln.part; b < nblocks; b += a.lpc) {
         T z[NPB];
-        normals_from_block(philox4x32_10(philox_ctr(gchain, step, 0u, (uint32_t)b), a.key), z);
+        normals_from_block<kExact>(philox4x32_10(philox_ctr(gchain, step, 0u, (uint32_t)b), a.key), z);
 #pragma unroll
         for (int k = 0; k < NPB; ++k)
           if (b * NPB + k < a.d_pad) row[b * NPB + k] = z[k];
@@ -489,45 +583,43 @@ __global__ void __launch_bounds__(kHmcBlock) hmc_run_kernel(const HmcArgs<T> a) 
       __syncwarp();
     }
 
-    // ---- 2. kinetic energy, log density and gradient at the current point (batched_hmc.rs:134-138)
+    // ---- 2. kinetic energy, then log density + first kick at the current point (batched_hmc.rs:134-138)
     T terms[EPL];
 #pragma unroll
-    for (int j = 0; j < EPL; ++j) { q[j] = qc[j]; terms[j] = p[j] * p[j]; }
+    for (int j = 0; j < EPL; ++j) {
+      q[j] = (j < ln.nvalid) ? pos_row[ln.lo + j] : T(1);
+      terms[j] = p[j] * p[j];
+    }
     const T ke0 = chain_sum<T, EPL>(terms, ln.nvalid, ln) * T(0.5);
-    const T logp0 = eval_target<T, EPL, PADDED, true>(TAG{}, q, g, ln, a.tp, row);
 
     // ---- 3. L leapfrog steps (batched_hmc.rs:166-190 / generic_hmc.rs:204-221)
-    T logp1 = logp0;
-    if constexpr (kExact) {
-      const T half = T(0.5) * eps;
-      for (uint32_t l = 0; l < a.L; ++l) {
-#pragma unroll
-        for (int j = 0; j < EPL; ++j) p[j] = p[j] + g[j] * half;
+    const T half = T(0.5) * eps;
+    T logp0, logp1;
+    if (a.L == 0) {
+      T g[EPL];
+      logp0 = logp1 = eval_target<T, EPL, PADDED, true>(TAG{}, q, g, ln, a.tp, row);
+    } else if constexpr (kExact) {
+      // reference order: (p += g half ; q += p eps ; g = grad(q) ; p += g half) x L, kicks never merged
+      logp0 = eval_kick<T, EPL, PADDED, true, 1>(TAG{}, q, p, half, ln, a.tp, row);
+      for (uint32_t l = 0; l + 1 < a.L; ++l) {
 #pragma unroll
         for (int j = 0; j < EPL; ++j) q[j] = q[j] + p[j] * eps;
-        logp1 = eval_target<T, EPL, PADDED, true>(TAG{}, q, g, ln, a.tp, row);
-#pragma unroll
-        for (int j = 0; j < EPL; ++j) p[j] = p[j] + g[j] * half;
+        eval_kick<T, EPL, PADDED, false, 2>(TAG{}, q, p, half, ln, a.tp, row);
       }
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) q[j] = q[j] + p[j] * eps;
+      logp1 = eval_kick<T, EPL, PADDED, true, 1>(TAG{}, q, p, half, ln, a.tp, row);
     } else {
-      // merged kicks: p += eps/2 g ; (q += eps p ; g = grad(q) ; p += eps g) x (L-1) ; last kick eps/2
-      const T half = T(0.5) * eps;
-      if (a.L > 0) {
-#pragma unroll
-        for (int j = 0; j < EPL; ++j) p[j] += half * g[j];
-        for (uint32_t l = 0; l + 1 < a.L; ++l) {
-#pragma unroll
-          for (int j = 0; j < EPL; ++j) q[j] += eps * p[j];
-          eval_target<T, EPL, PADDED, false>(TAG{}, q, g, ln, a.tp, row);
-#pragma unroll
-          for (int j = 0; j < EPL; ++j) p[j] += eps * g[j];
-        }
+      // merged kicks: p += eps/2 g ; (q += eps p ; p += eps grad(q)) x (L-1) ; q += eps p ; p += eps/2 grad(q)
+      logp0 = eval_kick<T, EPL, PADDED, true, 1>(TAG{}, q, p, half, ln, a.tp, row);
+      for (uint32_t l = 0; l + 1 < a.L; ++l) {
 #pragma unroll
         for (int j = 0; j < EPL; ++j) q[j] += eps * p[j];
-        logp1 = eval_target<T, EPL, PADDED, true>(TAG{}, q, g, ln, a.tp, row);
-#pragma unroll
-        for (int j = 0; j < EPL; ++j) p[j] += half * g[j];
+        eval_kick<T, EPL, PADDED, false, 1>(TAG{}, q, p, eps, ln, a.tp, row);
       }
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) q[j] += eps * p[j];
+      logp1 = eval_kick<T, EPL, PADDED, true, 1>(TAG{}, q, p, half, ln, a.tp, row);
     }
 
     // ---- 4. Hamiltonian + Metropolis accept (batched_hmc.rs:148-162 / generic_hmc.rs:195-200)
@@ -544,7 +636,8 @@ __global__ void __launch_bounds__(kHmcBlock) hmc_run_kernel(const HmcArgs<T> a) 
     const bool accept = (ln_u <= log_accept);
     if (accept) {
 #pragma unroll
-      for (int j = 0; j < EPL; ++j) qc[j] = q[j];
+      for (int j = 0; j < EPL; ++j)
+        if (j < ln.nvalid) pos_row[ln.lo + j] = q[j];
     }
     const bool finite = (log_accept == log_accept) && (fabs(log_accept) < T(INFINITY));
     const T alpha = finite ? min(T(1), exp(log_accept)) : (log_accept > T(0) ? T(1) : T(0));
@@ -578,27 +671,23 @@ __global__ void __launch_bounds__(kHmcBlock) hmc_run_kernel(const HmcArgs<T> a) 
       }
     }
 
-    // ---- 6. write-out [chain, slot, :]   (hmc.rs:173-180 stack+permute, fused)
+    // ---- 6. write-out [chain, slot, :] straight from the position rows (hmc.rs:173-180 stack+permute, fused)
+    __syncwarp();
     if (s >= a.n_skip && a.out) {
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < EPL; ++j)
-        if (j < ln.nvalid) row[ln.lo + j] = qc[j];
-      __syncwarp();
-      store_rows<T>(warp_stage, a.d, a.d_pad, chains_in_warp, warp_first_chain, a.n_chains, a.out, a.out_n,
+      store_rows<T>(warp_pos, a.d, a.d_pad, chains_in_warp, warp_first_chain, a.n_chains, a.out, a.out_n,
                     (size_t)a.out_t0 + (s - a.n_skip));
       __syncwarp();
     }
   }
 
   // ---- state back to HBM
-  if (active) {
-#pragma unroll
-    for (int j = 0; j < EPL; ++j)
-      if (j < ln.nvalid) a.positions[chain * a.d + ln.lo + j] = qc[j];
-    if (per_chain_da && ln.part == 0) {
-      a.da_eps[chain] = eps; a.da_eps_bar[chain] = da_eps_bar; a.da_h_bar[chain] = da_h_bar;
-    }
+  for (int c = 0; c < chains_in_warp; ++c) {
+    const size_t ch = warp_first_chain + c;
+    if (ch >= a.n_chains) break;
+    for (int i = lane; i < a.d; i += 32) a.positions[ch * a.d + i] = warp_pos[(size_t)c * a.d_pad + i];
+  }
+  if (active && per_chain_da && ln.part == 0) {
+    a.da_eps[chain] = eps; a.da_eps_bar[chain] = da_eps_bar; a.da_h_bar[chain] = da_h_bar;
   }
   // counters: warp reduce, one atomic per warp
   for (int o = 16; o > 0; o >>= 1) {
@@ -606,7 +695,7 @@ __global__ void __launch_bounds__(kHmcBlock) hmc_run_kernel(const HmcArgs<T> a) 
     n_diverge += __shfl_xor_sync(kFull, n_diverge, o);
     alpha_acc += __shfl_xor_sync(kFull, alpha_acc, o);   // xor tree: same value on every lane, fixed order
   }
-  if ((threadIdx.x & 31) == 0) {
+  if (lane == 0) {
     if (n_accept) atomicAdd(a.accept_total, (unsigned long long)n_accept);
     if (n_diverge) atomicAdd(a.diverge_total, (unsigned long long)n_diverge);
     if (a.alpha_part) a.alpha_part[(size_t)(blockIdx.x * blockDim.x + threadIdx.x) >> 5] = alpha_acc;
@@ -672,7 +761,7 @@ inline cudaError_t launch_one(const HmcLaunch& L, cudaStream_t st) {
   HmcArgs<T> a = make_args<T>(L);
   const size_t threads = L.n_chains * (size_t)L.lpc;
   const unsigned blocks = (unsigned)((threads + kHmcBlock - 1) / kHmcBlock);
-  const size_t smem = (size_t)(kHmcBlock / L.lpc) * a.d_pad * sizeof(T);
+  const size_t smem = 2 * (size_t)(kHmcBlock / L.lpc) * a.d_pad * sizeof(T);
   auto kern = hmc_run_kernel<T, EPL, TAG, PADDED>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kMhBlock) mh_run_kernel(const MhArgs<T> a) {
       for (int b = 0; b < (MAXD + NPB - 1) / NPB; ++b) {
         if (b * NPB < d) {
           T zb[NPB];
-          normals_from_block(philox4x32_10(philox_ctr(gchain, step, 0u, (uint32_t)b), a.key), zb);
+          normals_from_block<true>(philox4x32_10(philox_ctr(gchain, step, 0u, (uint32_t)b), a.key), zb);
 #pragma unroll
           for (int k = 0; k < NPB; ++k)
             if (b * NPB + k < MAXD) z[b * NPB + k] = zb[k];

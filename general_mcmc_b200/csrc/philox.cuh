@@ -38,14 +38,35 @@ __device__ __forceinline__ double u01d(uint32_t hi, uint32_t lo) {
 }
 
 // Box–Muller.  f32: 4 normals per block; f64: 2 normals per block.
+// ACCURATE = false (fast math mode, f32): MUFU approximations (lg2/sqrt/sin/cos.approx, abs. error of the
+// normals ~1e-6, far below Monte-Carlo resolution); ACCURATE = true: libdevice logf / sqrtf / sincospif.
+template <bool ACCURATE>
 __device__ __forceinline__ void normals_from_block(uint4 r, float (&z)[4]) {
   float u0 = u01(r.x), u1 = u01(r.y), u2 = u01(r.z), u3 = u01(r.w);
-  float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
-  float s0, c0, s1, c1;
-  sincospif(2.0f * u1, &s0, &c0);
-  sincospif(2.0f * u3, &s1, &c1);
-  z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+  if constexpr (ACCURATE) {
+    float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+    float s0, c0, s1, c1;
+    sincospif(2.0f * u1, &s0, &c0);
+    sincospif(2.0f * u3, &s1, &c1);
+    z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+  } else {
+    // -2 ln u = (-2 ln 2) lg2 u ; angle 2 pi (u - 1/2) in [-pi, pi] where sin/cos.approx are most accurate
+    float r0, r1, s0, c0, s1, c1;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(u0));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(u2));
+    r0 *= -1.3862943611198906f; r1 *= -1.3862943611198906f;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(r0));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(r1));
+    const float a0 = fmaf(u1, 6.283185307179586f, -3.141592653589793f);
+    const float a1 = fmaf(u3, 6.283185307179586f, -3.141592653589793f);
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(a0));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c0) : "f"(a0));
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(a1));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c1) : "f"(a1));
+    z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+  }
 }
+template <bool ACCURATE>
 __device__ __forceinline__ void normals_from_block(uint4 r, double (&z)[2]) {
   double u0 = u01d(r.x, r.y), u1 = u01d(r.z, r.w);
   double rr = sqrt(-2.0 * log(u0));

@@ -139,9 +139,11 @@ def test_hmc_per_step_equivalence_fast_mode(ctx, oracle, dtype, tol, d, L, eps):
     diag = s.diagnostics()
     assert _rel(diag["prop_q"], ref["prop_q"]) <= tol
     assert _rel(diag["prop_p"], ref["prop_p"]) <= tol * 50      # momenta scale with |grad| ~ 1e2..1e3
-    # log accept is a difference of O(d*100) energies: tolerance relative to the energy scale
-    escale = np.abs(ref["logp_cur"]).max() + 1.0
-    assert np.max(np.abs(diag["log_accept"].astype(np.float64) - ref["log_accept"])) <= tol * escale * 8
+    # log accept is a difference of large energies: tolerance relative to each chain's own energy scale
+    ke = 0.5 * (mom[0].astype(np.float64) ** 2).sum(-1) + 0.5 * (ref["prop_p"][0].astype(np.float64) ** 2).sum(-1)
+    escale = (np.abs(ref["logp_cur"][0]) + np.abs(ref["logp_prop"][0]) + ke + 1.0)[None, :]
+    err = np.abs(diag["log_accept"].astype(np.float64) - ref["log_accept"])
+    assert np.all(err <= tol * escale * 8)
     margin = np.abs(ref["log_accept"].astype(np.float64) - ln_u)
     safe = margin > tol * escale * 8
     assert np.array_equal(diag["accepted"][safe], ref["accepted"][safe])
@@ -220,7 +222,7 @@ def test_mh_fast_mode_matches_oracle(ctx, oracle, dtype, tol):
     diag = s.diagnostics()
     # decisions can only differ at razor-thin margins; the chains that never hit one must match fully
     margin = np.abs(ref["log_ratio"].astype(np.float64) - ln_u)
-    thin = (margin < tol * 100).any(axis=0)
+    thin = (margin < tol * 8 * (1.0 + np.abs(ref["log_ratio"]))).any(axis=0)
     assert thin.sum() <= Cn // 200
     ok = ~thin
     assert np.array_equal(diag["accepted"][:, ok], ref["accepted"][:, ok])
@@ -307,28 +309,30 @@ def test_ess_iid_uniform_reference_bands(ctx):
 def test_hmc_gaussian2d_distribution_and_reference_ess_band(ctx):
     """hmc.rs:513-669: DiffableGaussian2D mu=[0,1], cov=[[4,2],[2,3]], eps 0.1, L 10: mean/cov within
     Monte-Carlo error, R-hat < 1.01 at many chains."""
-    Cn = 4096
+    Cn = 1024
     tgt = gm.DiffableGaussian2D([0.0, 1.0], [[4.0, 2.0], [2.0, 3.0]])
     s = gm.HMC(tgt, np.zeros((Cn, 2), np.float32), 0.1, 10, seed=42, ctx=ctx)
     out, st = s.run_progress(1000, 500)
+    per_chain_ess = st.ess.min / Cn
+    assert 35 < per_chain_ess < 100          # reference band (3 chains x 1000 draws): ESS in [135, 230] => 45..77 per chain
+    # split R-hat is ~ sqrt(1 + 1/ESS_per_split_chain): < 1.01 needs ~4000 draws per chain at this autocorrelation
+    out, st = s.run_progress(6000, 0)
     flat = out.reshape(-1, 2).astype(np.float64)
     assert np.allclose(flat.mean(0), [0.0, 1.0], atol=0.02)
     assert np.allclose(np.cov(flat.T), [[4.0, 2.0], [2.0, 3.0]], atol=0.06)
     assert st.rhat_std.max < 1.01 and st.rhat.min > 0.99
-    per_chain_ess = st.ess.min / Cn
-    assert 35 < per_chain_ess < 100          # reference band (3 chains x 1000 draws): ESS in [135, 230] => 45..77 per chain
     c = s.counters()
     assert 0.85 < c.accept_rate <= 1.0
-    assert c.grad_evals == Cn * 1500 * 10
+    assert c.grad_evals == Cn * 7500 * 10
 
 
 def test_mh_gaussian2d_distribution(ctx):
     """metropolis_hastings.rs:342-406 / tests/metrohast_2d_gaussian_test.rs: mean within 0.3, cov within 0.5
     (far tighter here with many chains)."""
-    Cn = 8192
+    Cn = 1024
     tgt = gm.Gaussian2D([0.0, 1.0], [[4.0, 2.0], [2.0, 3.0]])
     s = gm.MetropolisHastings(tgt, gm.IsotropicGaussian(1.0), np.zeros((Cn, 2)), ctx=ctx).seed(42)
-    out, st = s.run_progress(1000, 500)
+    out, st = s.run_progress(12000, 500)
     flat = out.reshape(-1, 2)
     assert np.allclose(flat.mean(0), [0.0, 1.0], atol=0.03)
     assert np.allclose(np.cov(flat.T), [[4.0, 2.0], [2.0, 3.0]], atol=0.08)
