@@ -36,7 +36,10 @@ N_LEAPFROG = 32
 STEP_SIZE = 0.01
 TRANSITIONS_PER_LAUNCH = 100
 E2E_TRANSITIONS = 16
-FLOP_PER_GRAD_EVAL = 21 * DIM        # 15(d-1) target + 6d integrator, FMA = 2
+# Algorithmic FP32 work per gradient evaluation per chain: 6 FMAs per coordinate (t_i, 400 t_i - 2, x_i(.) + 2,
+# - 200 t_{i-1} + (.), p += eps g, q += eps p) = 12 flop x d.  SURVEY 8(d)'s 21 d counted mul and add separately and a
+# log-density per leapfrog; the log density is only needed at the two trajectory ends (kernel K1).
+FLOP_PER_GRAD_EVAL = 12 * DIM
 BYTES_PER_STEP_PER_CHAIN = DIM * 4   # sample write-out, f32
 
 

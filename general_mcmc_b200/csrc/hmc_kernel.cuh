@@ -27,7 +27,7 @@
 #define GM_EXACT 0
 #endif
 #ifndef GM_MINB
-#define GM_MINB 4   // resident CTAs per SM the trajectory kernel is register-budgeted for (tuned on B200)
+#define GM_MINB 3   // resident CTAs per SM the trajectory kernel is register-budgeted for (tuned on B200)
 #endif
 #if GM_EXACT
 #define GM_NS exact
@@ -67,29 +67,31 @@ __device__ __forceinline__ Lane make_lane(int tid_in_grid, int lpc, int d) {
   return ln;
 }
 
-// Sum of per-lane term arrays over the whole chain; every lane of the chain gets the result.
+// Sum of per-lane term arrays over the whole chain; every lane of the chain gets the result.  Slots
+// past the end of the chain must hold exact zeros (adding +0 never changes a sum), so there is no mask.
 // EXACT: strict left-to-right order over coordinates (lane k continues lane k-1's running sum).
 template <class T, int EPL>
-__device__ __forceinline__ T chain_sum(const T (&terms)[EPL], int n, const Lane& ln) {
+__device__ __forceinline__ T chain_sum(const T (&terms)[EPL], const Lane& ln) {
   if constexpr (kExact) {
     T s = T(0);
     for (int k = 0; k < ln.lpc; ++k) {
       if (ln.part == k) {
 #pragma unroll
-        for (int j = 0; j < EPL; ++j)
-          if (j < n) s = s + terms[j];
+        for (int j = 0; j < EPL; ++j) s = s + terms[j];
       }
       s = __shfl_sync(kFull, s, ln.gbase + k);
     }
     return s;
   } else {
-    T s0 = T(0), s1 = T(0);
+    T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
 #pragma unroll
     for (int j = 0; j < EPL; ++j) {
-      T v = (j < n) ? terms[j] : T(0);
-      if (j & 1) s1 += v; else s0 += v;
+      if ((j & 3) == 0) s0 += terms[j];
+      else if ((j & 3) == 1) s1 += terms[j];
+      else if ((j & 3) == 2) s2 += terms[j];
+      else s3 += terms[j];
     }
-    T s = s0 + s1;
+    T s = (s0 + s1) + (s2 + s3);
     for (int o = ln.lpc >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
     return s;
   }
@@ -183,7 +185,7 @@ __device__ __forceinline__ T eval_target(TagRosenbrockND, const T (&x)[EPL], T (
     // number of coordinates with a "low" term in this lane: i < d-1
     int nl = ln.d - 1 - ln.lo;
     nl = nl < 0 ? 0 : (nl > EPL ? EPL : nl);
-    return -chain_sum<T, EPL>(terms, nl, ln);
+    return -chain_sum<T, EPL>(terms, ln);
   }
   return T(0);
 }
@@ -196,11 +198,11 @@ __device__ __forceinline__ T eval_target(TagIsoGauss, const T (&x)[EPL], T (&g)[
   T terms[EPL];
 #pragma unroll
   for (int j = 0; j < EPL; ++j) {
-    terms[j] = x[j] * x[j];
+    terms[j] = (j < ln.nvalid) ? (x[j] * x[j]) : T(0);
     g[j] = (j < ln.nvalid) ? (-x[j] / var) : T(0);
   }
   if constexpr (!WANT_LOGP) return T(0);
-  T sum = chain_sum<T, EPL>(terms, ln.nvalid, ln);
+  T sum = chain_sum<T, EPL>(terms, ln);
   return -T(0.5) * sum / var;
 }
 
@@ -239,7 +241,7 @@ __device__ __forceinline__ T eval_target(TagDenseGauss, const T (&x)[EPL], T (&g
     terms[j] = z[j] * delta[j];
   }
   if constexpr (!WANT_LOGP) return T(0);
-  T quad = chain_sum<T, EPL>(terms, ln.nvalid, ln);
+  T quad = chain_sum<T, EPL>(terms, ln);
   const T nc = tp.dp[(size_t)d + (size_t)d * d];
   return nc - quad * T(0.5);
 }
@@ -268,7 +270,7 @@ __device__ __forceinline__ T eval_target(TagMixture, const T (&x)[EPL], T (&g)[E
         T df = (j < ln.nvalid) ? (x[j] - mu[(size_t)k * d + ln.lo + j]) : T(0);
         terms[j] = df * df;
       }
-      T sq = chain_sum<T, EPL>(terms, ln.nvalid, ln);
+      T sq = chain_sum<T, EPL>(terms, ln);
       a[k] = log(w[k]) - T(0.5) * sq * inv_var;
       amax = max(amax, a[k]);
     }
@@ -416,7 +418,7 @@ __device__ __forceinline__ T eval_kick(TagRosenbrockND, const T (&x)[EPL], T (&p
   if constexpr (WANT_LOGP) {
     int nl = ln.d - 1 - ln.lo;
     nl = nl < 0 ? 0 : (nl > EPL ? EPL : nl);
-    return -chain_sum<T, EPL>(terms, nl, ln);
+    return -chain_sum<T, EPL>(terms, ln);
   }
   return T(0);
 }
@@ -462,7 +464,8 @@ struct HmcArgs {
   PhiloxKey key;
   uint32_t step_base;
   T* positions;
-  const T* eps;
+  const T* eps;         // device step size (null: use eps_val)
+  T eps_val;            // step size known on the host at launch time (constant-bank operand)
   int eps_stride;
   int d, d_pad, lpc;
   uint32_t L, n_steps, n_skip;
@@ -487,30 +490,62 @@ template <class T> struct VecOf;
 template <> struct VecOf<float> { using type = float4; static constexpr int n = 4; };
 template <> struct VecOf<double> { using type = double2; static constexpr int n = 2; };
 
-// Cooperative, coalesced copy of the warp's position rows to [chain, slot, :] of the sample tensor.
-template <class T>
-__device__ __forceinline__ void store_rows(const T* warp_rows, int d, int d_pad, int chains_in_warp,
-                                           size_t first_chain, size_t n_chains, T* out, size_t out_n,
-                                           size_t slot) {
+// Write-out plan of one lane: the warp's position rows ([chains_in_warp][d_pad] in shared memory) are
+// copied to [chain, slot, :] of the sample tensor as a flat list of vectors (float4 / double2, or
+// scalars when d is not a multiple of the vector width); lane l owns list items l, l+32, ...  The
+// shared-memory index and the global offset (relative to the warp's first chain, slot 0) of each item
+// do not depend on the transition, so they are computed once per launch.
+template <class T, int EPL>
+struct StorePlan {
+  static constexpr int VN = VecOf<T>::n;
+  static constexpr int KMAX = (EPL + VN - 1) / VN + 1;   // vector items per lane (upper bound)
+  static constexpr int KMAX_S = EPL + 1;                  // scalar items per lane (upper bound)
+  bool vec;
+  int n_items;            // total items of the warp
+  unsigned soff[KMAX];    // shared-memory element index
+  unsigned goff[KMAX];    // global element offset
+};
+
+template <class T, int EPL>
+__device__ __forceinline__ void make_store_plan(StorePlan<T, EPL>& pl, int d, int d_pad, int chains_in_warp,
+                                                size_t first_chain, size_t n_chains, size_t out_n) {
+  constexpr int VN = StorePlan<T, EPL>::VN;
   const int lane = threadIdx.x & 31;
-  using V = typename VecOf<T>::type;
-  constexpr int VN = VecOf<T>::n;
-  if ((d % VN) == 0) {
-    const int nv = d / VN;
-    for (int c = 0; c < chains_in_warp; ++c) {
-      size_t chain = first_chain + c;
-      if (chain >= n_chains) break;
-      const V* src = reinterpret_cast<const V*>(warp_rows + (size_t)c * d_pad);
-      V* dst = reinterpret_cast<V*>(out + (chain * out_n + slot) * (size_t)d);
-      for (int i = lane; i < nv; i += 32) __stcs(dst + i, src[i]);
+  size_t live = n_chains > first_chain ? n_chains - first_chain : 0;
+  const int nch = live < (size_t)chains_in_warp ? (int)live : chains_in_warp;
+  pl.vec = (d % VN) == 0 && (out_n * (size_t)d * chains_in_warp) < 0xffffffffull;
+  if (pl.vec) {
+    const int per = d / VN;
+    pl.n_items = nch * per;
+#pragma unroll
+    for (int k = 0; k < StorePlan<T, EPL>::KMAX; ++k) {
+      const int f = lane + 32 * k;
+      const int c = f / per, i = f - c * per;
+      pl.soff[k] = (unsigned)(c * d_pad + i * VN);
+      pl.goff[k] = (unsigned)((size_t)c * out_n * d + (size_t)i * VN);
     }
   } else {
-    for (int c = 0; c < chains_in_warp; ++c) {
-      size_t chain = first_chain + c;
-      if (chain >= n_chains) break;
-      const T* src = warp_rows + (size_t)c * d_pad;
-      T* dst = out + (chain * out_n + slot) * (size_t)d;
-      for (int i = lane; i < d; i += 32) __stcs(dst + i, src[i]);
+    pl.n_items = nch * d;
+  }
+}
+
+template <class T, int EPL>
+__device__ __forceinline__ void store_rows(const StorePlan<T, EPL>& pl, const T* warp_rows, int d, int d_pad,
+                                           T* out_warp /* &out[first_chain, slot, 0] */, size_t out_n) {
+  const int lane = threadIdx.x & 31;
+  using V = typename VecOf<T>::type;
+  if (pl.vec) {
+    V v[StorePlan<T, EPL>::KMAX];
+#pragma unroll
+    for (int k = 0; k < StorePlan<T, EPL>::KMAX; ++k)
+      if (lane + 32 * k < pl.n_items) v[k] = *reinterpret_cast<const V*>(warp_rows + pl.soff[k]);
+#pragma unroll
+    for (int k = 0; k < StorePlan<T, EPL>::KMAX; ++k)
+      if (lane + 32 * k < pl.n_items) __stcs(reinterpret_cast<V*>(out_warp + pl.goff[k]), v[k]);
+  } else {
+    for (int f = lane; f < pl.n_items; f += 32) {
+      const int c = f / d, i = f - c * d;
+      __stcs(out_warp + (size_t)c * out_n * d + i, warp_rows[c * d_pad + i]);
     }
   }
 }
@@ -547,7 +582,10 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
   }
   __syncwarp();
 
-  T eps = active ? a.eps[a.eps_stride ? chain : 0] : T(0.01);
+  StorePlan<T, EPL> plan;
+  make_store_plan<T, EPL>(plan, a.d, a.d_pad, chains_in_warp, warp_first_chain, a.n_chains, a.out_n);
+
+  T eps = a.eps ? (active ? a.eps[a.eps_stride ? chain : 0] : T(0.01)) : a.eps_val;
   // per-chain dual averaging state (GMCMC_ADAPT_PER_CHAIN; generic_nuts.rs:882-924)
   T da_eps_bar = T(1), da_h_bar = T(0), da_mu = T(0);
   const bool per_chain_da = a.da_eps != nullptr;
@@ -557,6 +595,10 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
 
   unsigned int n_accept = 0, n_diverge = 0;
   double alpha_acc = 0.0;
+  // log density of the current point, carried from transition to transition: it is the same function
+  // of the same position the reference re-evaluates (batched_hmc.rs:138), hence bit-identical
+  T logp_cur = T(0);
+  bool have_logp_cur = false;
 
   for (uint32_t s = 0; s < a.n_steps; ++s) {
     const uint32_t step = a.step_base + s;
@@ -573,13 +615,18 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
       for (int b = ln.part; b < nblocks; b += a.lpc) {
         T z[NPB];
         normals_from_block<kExact>(philox4x32_10(philox_ctr(gchain, step, 0u, (uint32_t)b), a.key), z);
-#pragma unroll
-        for (int k = 0; k < NPB; ++k)
-          if (b * NPB + k < a.d_pad) row[b * NPB + k] = z[k];
+        // d_pad is a multiple of 4, so a block is either entirely inside the row or entirely outside
+        if (b * NPB < a.d_pad) {
+          using V = typename VecOf<T>::type;
+          V v;
+          if constexpr (NPB == 4) v = V{z[0], z[1], z[2], z[3]};
+          else v = V{z[0], z[1]};
+          *reinterpret_cast<V*>(row + b * NPB) = v;
+        }
       }
       __syncwarp();
 #pragma unroll
-      for (int j = 0; j < EPL; ++j) p[j] = (j < ln.nvalid) ? row[ln.lo + j] : T(0);
+      for (int j = 0; j < EPL; ++j) p[j] = (!PADDED || j < ln.nvalid) ? row[ln.lo + j] : T(0);
       __syncwarp();
     }
 
@@ -587,10 +634,10 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
     T terms[EPL];
 #pragma unroll
     for (int j = 0; j < EPL; ++j) {
-      q[j] = (j < ln.nvalid) ? pos_row[ln.lo + j] : T(1);
+      q[j] = (!PADDED || j < ln.nvalid) ? pos_row[ln.lo + j] : T(1);
       terms[j] = p[j] * p[j];
     }
-    const T ke0 = chain_sum<T, EPL>(terms, ln.nvalid, ln) * T(0.5);
+    const T ke0 = chain_sum<T, EPL>(terms, ln) * T(0.5);
 
     // ---- 3. L leapfrog steps (batched_hmc.rs:166-190 / generic_hmc.rs:204-221)
     const T half = T(0.5) * eps;
@@ -600,7 +647,8 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
       logp0 = logp1 = eval_target<T, EPL, PADDED, true>(TAG{}, q, g, ln, a.tp, row);
     } else if constexpr (kExact) {
       // reference order: (p += g half ; q += p eps ; g = grad(q) ; p += g half) x L, kicks never merged
-      logp0 = eval_kick<T, EPL, PADDED, true, 1>(TAG{}, q, p, half, ln, a.tp, row);
+      if (have_logp_cur) { eval_kick<T, EPL, PADDED, false, 1>(TAG{}, q, p, half, ln, a.tp, row); logp0 = logp_cur; }
+      else logp0 = eval_kick<T, EPL, PADDED, true, 1>(TAG{}, q, p, half, ln, a.tp, row);
       for (uint32_t l = 0; l + 1 < a.L; ++l) {
 #pragma unroll
         for (int j = 0; j < EPL; ++j) q[j] = q[j] + p[j] * eps;
@@ -611,7 +659,8 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
       logp1 = eval_kick<T, EPL, PADDED, true, 1>(TAG{}, q, p, half, ln, a.tp, row);
     } else {
       // merged kicks: p += eps/2 g ; (q += eps p ; p += eps grad(q)) x (L-1) ; q += eps p ; p += eps/2 grad(q)
-      logp0 = eval_kick<T, EPL, PADDED, true, 1>(TAG{}, q, p, half, ln, a.tp, row);
+      if (have_logp_cur) { eval_kick<T, EPL, PADDED, false, 1>(TAG{}, q, p, half, ln, a.tp, row); logp0 = logp_cur; }
+      else logp0 = eval_kick<T, EPL, PADDED, true, 1>(TAG{}, q, p, half, ln, a.tp, row);
       for (uint32_t l = 0; l + 1 < a.L; ++l) {
 #pragma unroll
         for (int j = 0; j < EPL; ++j) q[j] += eps * p[j];
@@ -625,7 +674,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
     // ---- 4. Hamiltonian + Metropolis accept (batched_hmc.rs:148-162 / generic_hmc.rs:195-200)
 #pragma unroll
     for (int j = 0; j < EPL; ++j) terms[j] = p[j] * p[j];
-    const T ke1 = chain_sum<T, EPL>(terms, ln.nvalid, ln) * T(0.5);
+    const T ke1 = chain_sum<T, EPL>(terms, ln) * T(0.5);
     const T log_accept = (logp1 - logp0) + (ke0 - ke1);
     T ln_u;
     if (a.inj_lnu) {
@@ -637,8 +686,10 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
     if (accept) {
 #pragma unroll
       for (int j = 0; j < EPL; ++j)
-        if (j < ln.nvalid) pos_row[ln.lo + j] = q[j];
+        if (!PADDED || j < ln.nvalid) pos_row[ln.lo + j] = q[j];
     }
+    logp_cur = accept ? logp1 : logp0;
+    have_logp_cur = true;
     const bool finite = (log_accept == log_accept) && (fabs(log_accept) < T(INFINITY));
     const T alpha = finite ? min(T(1), exp(log_accept)) : (log_accept > T(0) ? T(1) : T(0));
     if (active && ln.part == 0) {
@@ -674,8 +725,8 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
     // ---- 6. write-out [chain, slot, :] straight from the position rows (hmc.rs:173-180 stack+permute, fused)
     __syncwarp();
     if (s >= a.n_skip && a.out) {
-      store_rows<T>(warp_pos, a.d, a.d_pad, chains_in_warp, warp_first_chain, a.n_chains, a.out, a.out_n,
-                    (size_t)a.out_t0 + (s - a.n_skip));
+      store_rows<T, EPL>(plan, warp_pos, a.d, a.d_pad,
+                         a.out + (warp_first_chain * a.out_n + (size_t)a.out_t0 + (s - a.n_skip)) * (size_t)a.d, a.out_n);
       __syncwarp();
     }
   }
@@ -740,6 +791,7 @@ inline HmcArgs<T> make_args(const HmcLaunch& L) {
   a.step_base = L.step_base;
   a.positions = (T*)L.positions;
   a.eps = (const T*)L.eps;
+  a.eps_val = (T)L.eps_val;
   a.eps_stride = L.eps_stride;
   a.d = L.tgt.dim;
   constexpr int VN = VecOf<T>::n;

@@ -28,7 +28,8 @@ struct HmcLaunch {
   uint64_t seed;
   uint32_t step_base;    // transition index of the first transition of this launch
   void* positions;       // [C, d] T, in/out
-  const void* eps;       // device step size(s), T
+  const void* eps;       // device step size(s), T; null: eps_val is used
+  double eps_val;        // step size passed by value (fixed step size known on the host)
   int eps_stride;        // 0: one shared scalar, 1: per chain
   uint32_t n_leapfrog;
   uint32_t n_steps;      // transitions in this launch

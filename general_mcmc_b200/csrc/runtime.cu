@@ -146,6 +146,7 @@ struct gmcmc_sampler {
   double step_size = 0.0;
   uint32_t n_leapfrog = 0;
   void* d_eps = nullptr;       // [1] T (shared step size)
+  bool eps_device_only = false; // the current step size was produced on the device and not yet read back
   gmcmc_adapt_mode adapt = GMCMC_ADAPT_NONE;
   double target_accept = 0.8;
   void* d_da[4] = {nullptr, nullptr, nullptr, nullptr};   // per-chain: eps, eps_bar, h_bar, mu  (T [C])
@@ -295,7 +296,10 @@ gmcmc_status hmc_segment(gmcmc_sampler* s, size_t first, size_t count, size_t n_
   L.seed = s->seed;
   L.step_base = s->step_index + (uint32_t)first;
   L.positions = s->d_pos;
-  L.eps = s->d_eps;
+  // fixed step size known on the host: pass it by value (constant-bank operand of the drift/kick FMAs)
+  const bool eps_on_host = !want_alpha && !per_chain_da && !s->eps_device_only;
+  L.eps = eps_on_host ? nullptr : s->d_eps;
+  L.eps_val = s->step_size;
   L.eps_stride = 0;
   L.n_leapfrog = s->n_leapfrog;
   L.n_steps = (uint32_t)count;
@@ -403,6 +407,13 @@ gmcmc_status run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void
       }
       GM_CU(cudaGetLastError());
       s->da_m += (uint32_t)n_discard;
+      {
+        // adapted step size back to the host once (8 bytes): the collection launch takes it by value
+        PooledDa h;
+        GM_CU(cudaMemcpyAsync(&h, s->d_pooled, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        GM_CU(cudaStreamSynchronize(ctx->stream));
+        s->step_size = (s->dtype == GMCMC_F32) ? (double)(float)h.eps : h.eps;
+      }
       GM_TRY(hmc_segment(s, n_discard, n_collect, n_discard, n_collect, d_out, false, 0, false, false, 0));
     } else {
       const bool pc = (s->adapt == GMCMC_ADAPT_PER_CHAIN);
