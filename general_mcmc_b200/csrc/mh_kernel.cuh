@@ -36,7 +36,10 @@ namespace GM_NS {
 
 constexpr bool kMhExact = (GM_EXACT != 0);
 constexpr int kMhBlock = 128;
-constexpr int kStageDoubles = 32;            // doubles staged per chain between flushes (256 B)
+#ifndef GM_MH_STAGE
+#define GM_MH_STAGE 32
+#endif
+constexpr int kStageDoubles = GM_MH_STAGE;   // doubles staged per chain between flushes (256 B)
 constexpr int kStageStride = kStageDoubles + 1;  // +1: conflict-free column writes
 
 template <class T>
@@ -64,22 +67,38 @@ struct MhArgs {
 };
 
 // Target::unnorm_logp for the MH path (distributions.rs:107-110): log density only.
-template <class T, int MAXD>
-__device__ __forceinline__ T mh_logp(const MhArgs<T>& a, const T (&x)[MAXD]) {
-  const int d = a.d;
-  switch (a.kind) {
+// Loop invariants of a target, evaluated once per thread with the reference's own expressions (so the
+// values are the ones distributions.rs:195-207 recomputes on every call).
+template <class T>
+struct MhInv { T c0, c1, c2, c3; };
+
+template <class T, int KIND>
+__device__ __forceinline__ MhInv<T> mh_prepare(const MhArgs<T>& a) {
+  MhInv<T> v{T(0), T(0), T(0), T(0)};
+  if constexpr (KIND == 0) {
+    v.c0 = a.sp[0] * a.sp[0];
+  } else if constexpr (KIND == 1) {
+    const T ca = a.sp[2], cb = a.sp[3], cc = a.sp[4], cd = a.sp[5];
+    const T det = ca * cd - cb * cc;
+    v.c0 = cd / det; v.c1 = (-cb) / det; v.c2 = (-cc) / det; v.c3 = ca / det;
+  }
+  return v;
+}
+
+template <class T, int MAXD, int KIND, bool FULL>
+__device__ __forceinline__ T mh_logp(const MhArgs<T>& a, const MhInv<T>& inv, const T (&x)[MAXD]) {
+  const int d = FULL ? MAXD : a.d;
+  switch (KIND) {
     case 0: {  // IsotropicGaussian, distributions.rs:398-406
       T sum = T(0);
 #pragma unroll
       for (int i = 0; i < MAXD; ++i)
         if (i < d) sum = sum + x[i] * x[i];
-      return -T(0.5) * sum / (a.sp[0] * a.sp[0]);
+      return -T(0.5) * sum / inv.c0;
     }
     case 1: {  // Gaussian2D, distributions.rs:195-207
-      const T ca = a.sp[2], cb = a.sp[3], cc = a.sp[4], cd = a.sp[5];
-      const T det = ca * cd - cb * cc;
       const T d0 = x[0] - a.sp[0], d1 = x[MAXD > 1 ? 1 : 0] - a.sp[1];
-      const T i00 = cd / det, i01 = (-cb) / det, i10 = (-cc) / det, i11 = ca / det;
+      const T i00 = inv.c0, i01 = inv.c1, i10 = inv.c2, i11 = inv.c3;
       const T v0 = d0 * i00 + d1 * i10;
       const T v1 = d0 * i01 + d1 * i11;
       return -T(0.5) * (v0 * d0 + v1 * d1);
@@ -113,13 +132,13 @@ __device__ __forceinline__ T mh_logp(const MhArgs<T>& a, const T (&x)[MAXD]) {
 }
 
 // IsotropicGaussian::logp(from, to), distributions.rs:378-390
-template <class T, int MAXD>
+template <class T, int MAXD, bool FULL>
 __device__ __forceinline__ T mh_logq(const MhArgs<T>& a, const T (&from)[MAXD], const T (&to)[MAXD]) {
   T lp = T(0);
   const T var = a.prop_std * a.prop_std;
 #pragma unroll
   for (int i = 0; i < MAXD; ++i) {
-    if (i < a.d) {
+    if (FULL || i < a.d) {
       const T diff = to[i] - from[i];
       const T exponent = -(diff * diff) / (T(2) * var);
       lp = lp + exponent;
@@ -128,43 +147,75 @@ __device__ __forceinline__ T mh_logq(const MhArgs<T>& a, const T (&from)[MAXD], 
   return lp + a.prop_logq_const;
 }
 
-template <class T, int MAXD>
-__global__ void __launch_bounds__(kMhBlock) mh_run_kernel(const MhArgs<T> a) {
+#ifndef GM_MH_MINB
+#define GM_MH_MINB 6
+#endif
+
+// One launch = n_skip discarded transitions, then (n_steps - n_skip) recorded ones.  INSTR = the
+// instrumented variant used by the parity tests (injected normals / ln u, per-step diagnostics).
+template <class T, int MAXD, int KIND, bool FULL, bool INSTR>
+__global__ void __launch_bounds__(kMhBlock, GM_MH_MINB) mh_run_kernel(const MhArgs<T> a) {
   __shared__ double stage[kMhBlock * kStageStride];
 
   const size_t chain = (size_t)blockIdx.x * kMhBlock + threadIdx.x;
   const bool active = chain < a.n_chains;
   const unsigned long long gchain = a.chain_offset + chain;
-  const int d = a.d;
+  const int d = FULL ? MAXD : a.d;
   const int lane = threadIdx.x & 31;
   const int warp_row0 = threadIdx.x & ~31;
   const size_t warp_first_chain = (size_t)blockIdx.x * kMhBlock + warp_row0;
   const int steps_per_flush = kStageDoubles / d;  // >= 1 (d <= kStageDoubles)
+  // rows of this warp that exist (the last warp of the grid may be ragged)
+  const int warp_rows = a.n_chains > warp_first_chain
+                            ? (int)(a.n_chains - warp_first_chain < 32 ? a.n_chains - warp_first_chain : 32) : 0;
+  const size_t row_pitch = a.out_n * (size_t)d;                       // doubles between consecutive chains
+  double* out_lane = a.out ? a.out + (warp_first_chain * a.out_n + a.out_t0) * (size_t)d + lane : nullptr;
+  const double* stage_lane = stage + warp_row0 * kStageStride + lane;
+  double* const stage_row = stage + threadIdx.x * kStageStride;
+  const PhiloxRoundKeys rk = philox_round_keys(a.key);
 
   T x[MAXD];
 #pragma unroll
-  for (int i = 0; i < MAXD; ++i) x[i] = (active && i < d) ? a.state[chain * d + i] : T(0);
-  T lp_cur = mh_logp<T, MAXD>(a, x);
+  for (int i = 0; i < MAXD; ++i) x[i] = (active && (FULL || i < d)) ? a.state[chain * d + i] : T(0);
+  const MhInv<T> inv = mh_prepare<T, KIND>(a);
+  T lp_cur = mh_logp<T, MAXD, KIND, FULL>(a, inv, x);
 
   unsigned int n_accept = 0;
-  int staged = 0;                 // steps currently in the stage
-  size_t flush_slot = a.out_t0;   // sample slot of stage column 0
+  int staged = 0;                 // doubles currently in this chain's stage row
 
-  for (uint32_t s = 0; s < a.n_steps; ++s) {
+  // one transition; returns nothing, updates x / lp_cur / n_accept
+  auto transition = [&](const uint32_t s) {
     const uint32_t step = a.step_base + s;
     // ---- proposal noise (distributions.rs:368-376): stream 0 of the RNG contract
     T z[MAXD];
-    if (a.inj_normals) {
+    uint4 blk0 = make_uint4(0u, 0u, 0u, 0u);
+    if (INSTR && a.inj_normals) {
 #pragma unroll
       for (int i = 0; i < MAXD; ++i)
-        z[i] = (active && i < d) ? a.inj_normals[((size_t)s * a.n_chains + chain) * d + i] : T(0);
+        z[i] = (active && (FULL || i < d)) ? a.inj_normals[((size_t)s * a.n_chains + chain) * d + i] : T(0);
+    } else if constexpr (!kMhExact) {
+      // fast mode (both dtypes): 24-bit uniforms + MUFU Box-Muller, 4 normals per block.  For d <= 2 the
+      // second half of block 0 is left for the accept uniform (one Philox block per transition).
+#pragma unroll
+      for (int b = 0; b < (MAXD + 3) / 4; ++b) {
+        if (FULL || b * 4 < d) {
+          const uint4 r = philox4x32_10(philox_ctr(gchain, step, 0u, (uint32_t)b), rk);
+          if (b == 0) blk0 = r;
+          float zb[4];
+          if constexpr (MAXD <= 2) normals_pair_fast(r.x, r.y, zb[0], zb[1]);
+          else normals_from_block<false>(r, zb);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (b * 4 + k < MAXD) z[b * 4 + k] = (T)zb[k];
+        }
+      }
     } else {
       constexpr int NPB = NormalsPerBlock<T>::value;
 #pragma unroll
       for (int b = 0; b < (MAXD + NPB - 1) / NPB; ++b) {
-        if (b * NPB < d) {
+        if (FULL || b * NPB < d) {
           T zb[NPB];
-          normals_from_block<true>(philox4x32_10(philox_ctr(gchain, step, 0u, (uint32_t)b), a.key), zb);
+          normals_from_block<true>(philox4x32_10(philox_ctr(gchain, step, 0u, (uint32_t)b), rk), zb);
 #pragma unroll
           for (int k = 0; k < NPB; ++k)
             if (b * NPB + k < MAXD) z[b * NPB + k] = zb[k];
@@ -173,61 +224,97 @@ __global__ void __launch_bounds__(kMhBlock) mh_run_kernel(const MhArgs<T> a) {
     }
     T xp[MAXD];
 #pragma unroll
-    for (int i = 0; i < MAXD; ++i) xp[i] = (i < d) ? (x[i] + z[i] * a.prop_std) : T(0);
+    for (int i = 0; i < MAXD; ++i) xp[i] = (FULL || i < d) ? (x[i] + z[i] * a.prop_std) : T(0);
 
     // ---- log acceptance ratio (metropolis_hastings.rs:308-312)
-    const T lp_prop = mh_logp<T, MAXD>(a, xp);
+    const T lp_prop = mh_logp<T, MAXD, KIND, FULL>(a, inv, xp);
     T log_ratio;
     if constexpr (kMhExact) {
-      const T q_fwd = mh_logq<T, MAXD>(a, x, xp);
-      const T q_bwd = mh_logq<T, MAXD>(a, xp, x);
+      const T q_fwd = mh_logq<T, MAXD, FULL>(a, x, xp);
+      const T q_bwd = mh_logq<T, MAXD, FULL>(a, xp, x);
       log_ratio = (lp_prop + q_bwd) - (lp_cur + q_fwd);
     } else {
       log_ratio = lp_prop - lp_cur;  // symmetric proposal: q_fwd == q_bwd bit-for-bit
     }
-    // ---- accept iff log_ratio > ln u (strict; metropolis_hastings.rs:313-316): stream 1
-    T ln_u;
-    if (a.inj_lnu) ln_u = active ? a.inj_lnu[(size_t)s * a.n_chains + chain] : T(0);
-    else ln_u = log(accept_uniform<T>(philox4x32_10(philox_ctr(gchain, step, 1u, 0u), a.key)));
-    const bool accept = log_ratio > ln_u;
-    if (accept) {
-#pragma unroll
-      for (int i = 0; i < MAXD; ++i) x[i] = xp[i];
-      lp_cur = lp_prop;
+    // ---- accept iff log_ratio > ln u (strict; metropolis_hastings.rs:313-316)
+    bool accept;
+    if (INSTR && a.inj_lnu) {
+      const T ln_u = active ? a.inj_lnu[(size_t)s * a.n_chains + chain] : T(0);
+      accept = log_ratio > ln_u;
+    } else if constexpr (kMhExact) {
+      const T ln_u = log(accept_uniform<T>(philox4x32_10(philox_ctr(gchain, step, 1u, 0u), rk)));
+      accept = log_ratio > ln_u;
+    } else {
+      // fast mode: the uniform comes from words 2-3 of block 0 when d <= 2, else from stream 1.  The f32
+      // MUFU logarithm of its leading 24 bits decides unless the margin is inside the error bound; only
+      // then is the full-width uniform built and its logarithm evaluated in T, so the decision is always
+      // the one the full-precision comparison gives.
+      uint4 r = blk0;
+      if (MAXD > 2) { r = philox4x32_10(philox_ctr(gchain, step, 1u, 0u), rk); r.z = r.x; r.w = r.y; }
+      float l2;
+      asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u01(r.z)));
+      const float ln_u32 = l2 * 0.6931471805599453f;
+      const float lr32 = (float)log_ratio;
+      const float diff = lr32 - ln_u32;
+      // error bound of diff: 2^-24 truncation of u + ~1e-6 (1 + |ln u|) MUFU + 1e-7 |log_ratio|
+      if (fabsf(diff) > 2e-5f * (1.0f + fabsf(ln_u32) + fabsf(lr32))) {
+        accept = diff > 0.0f;
+      } else {
+        T u;
+        if constexpr (sizeof(T) == 8) u = u01d(r.z, r.w); else u = u01(r.z);
+        accept = log_ratio > log(u);
+      }
     }
-    if (active) n_accept += accept ? 1u : 0u;
-    if (a.diag_logratio && active) {
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i) x[i] = accept ? xp[i] : x[i];
+    lp_cur = accept ? lp_prop : lp_cur;
+    n_accept += (accept && active) ? 1u : 0u;
+    if (INSTR && a.diag_logratio && active) {
       a.diag_logratio[(size_t)s * a.n_chains + chain] = log_ratio;
       a.diag_acc[(size_t)s * a.n_chains + chain] = accept ? 1 : 0;
     }
+  };
 
-    // ---- write-out: stage -> [chain, slot, :] in f64
-    if (s >= a.n_skip && a.out) {
-#pragma unroll
-      for (int i = 0; i < MAXD; ++i)
-        if (i < d) stage[threadIdx.x * kStageStride + staged * d + i] = (double)x[i];
-      ++staged;
-      const bool last = (s + 1 == a.n_steps);
-      if (staged == steps_per_flush || last) {
-        __syncwarp();
-        const int ncols = staged * d;
-        for (int r = 0; r < 32; ++r) {
-          const size_t c = warp_first_chain + r;
-          if (c >= a.n_chains) break;
-          if (lane < ncols)
-            __stcs(a.out + (c * a.out_n + flush_slot) * (size_t)d + lane, stage[(warp_row0 + r) * kStageStride + lane]);
-        }
-        __syncwarp();
-        flush_slot += staged;
-        staged = 0;
+  // stage -> [chain, slot .. slot + staged/d, :] for the warp's rows (256 contiguous bytes per chain)
+  auto flush = [&]() {
+    __syncwarp();
+    if (lane < staged) {
+      double* dst = out_lane;
+      const double* src = stage_lane;
+      if (warp_rows == 32) {
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) { __stcs(dst, *src); dst += row_pitch; src += kStageStride; }
+      } else {
+        for (int r = 0; r < warp_rows; ++r) { __stcs(dst, *src); dst += row_pitch; src += kStageStride; }
       }
     }
+    __syncwarp();
+    out_lane += staged;
+    staged = 0;
+  };
+
+  uint32_t s = 0;
+  const uint32_t n_skip = a.n_skip < a.n_steps ? a.n_skip : a.n_steps;
+  for (; s < n_skip; ++s) transition(s);                 // burn-in: nothing recorded
+  if (out_lane) {
+    const int flush_at = steps_per_flush * d;
+    for (; s < a.n_steps; ++s) {
+      transition(s);
+#pragma unroll
+      for (int i = 0; i < MAXD; ++i)
+        if (FULL || i < d) stage_row[staged + i] = (double)x[i];
+      staged += d;
+      if (staged == flush_at) flush();
+    }
+    if (staged) flush();
+  } else {
+    for (; s < a.n_steps; ++s) transition(s);
   }
 
   if (active) {
 #pragma unroll
     for (int i = 0; i < MAXD; ++i)
-      if (i < d) a.state[chain * d + i] = x[i];
+      if (FULL || i < d) a.state[chain * d + i] = x[i];
   }
   for (int o = 16; o > 0; o >>= 1) n_accept += __shfl_xor_sync(0xffffffffu, n_accept, o);
   if (lane == 0 && n_accept) atomicAdd(a.accept_total, (unsigned long long)n_accept);
@@ -285,23 +372,44 @@ inline MhArgs<T> make_mh_args(const MhLaunch& L) {
   return a;
 }
 
-template <class T, int MAXD>
+template <class T, int MAXD, int KIND, bool FULL>
 inline cudaError_t mh_launch_one(const MhLaunch& L, cudaStream_t st) {
   MhArgs<T> a = make_mh_args<T>(L);
   const unsigned blocks = (unsigned)((L.n_chains + kMhBlock - 1) / kMhBlock);
-  mh_run_kernel<T, MAXD><<<blocks, kMhBlock, 0, st>>>(a);
+  if (a.inj_normals || a.inj_lnu || a.diag_logratio)
+    mh_run_kernel<T, MAXD, KIND, FULL, true><<<blocks, kMhBlock, 0, st>>>(a);
+  else
+    mh_run_kernel<T, MAXD, KIND, FULL, false><<<blocks, kMhBlock, 0, st>>>(a);
   return cudaGetLastError();
+}
+
+template <class T, int MAXD, int KIND>
+inline cudaError_t mh_launch_full(const MhLaunch& L, cudaStream_t st) {
+  if (L.tgt.dim == MAXD) return mh_launch_one<T, MAXD, KIND, true>(L, st);
+  return mh_launch_one<T, MAXD, KIND, false>(L, st);
+}
+
+template <class T, int KIND>
+inline cudaError_t mh_dispatch_dim(const MhLaunch& L, cudaStream_t st) {
+  const int d = L.tgt.dim;
+  if (d < 1 || d > kStageDoubles) return cudaErrorInvalidValue;
+  if (d <= 2) return mh_launch_full<T, 2, KIND>(L, st);
+  if (d <= 4) return mh_launch_full<T, 4, KIND>(L, st);
+  if (d <= 8) return mh_launch_full<T, 8, KIND>(L, st);
+  if (d <= 16) return mh_launch_full<T, 16, KIND>(L, st);
+  return mh_launch_full<T, 32, KIND>(L, st);
 }
 
 template <class T>
 inline cudaError_t mh_dispatch(const MhLaunch& L, cudaStream_t st) {
-  const int d = L.tgt.dim;
-  if (d < 1 || d > kStageDoubles) return cudaErrorInvalidValue;
-  if (d <= 2) return mh_launch_one<T, 2>(L, st);
-  if (d <= 4) return mh_launch_one<T, 4>(L, st);
-  if (d <= 8) return mh_launch_one<T, 8>(L, st);
-  if (d <= 16) return mh_launch_one<T, 16>(L, st);
-  return mh_launch_one<T, 32>(L, st);
+  switch (L.tgt.kind) {
+    case 0: return mh_dispatch_dim<T, 0>(L, st);
+    case 5: return mh_dispatch_dim<T, 5>(L, st);
+    case 1: return L.tgt.dim == 2 ? mh_launch_one<T, 2, 1, true>(L, st) : cudaErrorInvalidValue;
+    case 2: return L.tgt.dim == 2 ? mh_launch_one<T, 2, 2, true>(L, st) : cudaErrorInvalidValue;
+    case 4: return L.tgt.dim == 2 ? mh_launch_one<T, 2, 4, true>(L, st) : cudaErrorInvalidValue;
+  }
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace GM_NS

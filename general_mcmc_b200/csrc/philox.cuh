@@ -26,6 +26,24 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, PhiloxKey k) {
   return c;
 }
 
+// Round keys of a launch-constant key, computed once (the key schedule is 20 additions per block otherwise).
+struct PhiloxRoundKeys { uint32_t k0[10], k1[10]; };
+__host__ __device__ __forceinline__ PhiloxRoundKeys philox_round_keys(PhiloxKey k) {
+  PhiloxRoundKeys rk;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) { rk.k0[r] = k.k0 + (uint32_t)r * 0x9E3779B9u; rk.k1[r] = k.k1 + (uint32_t)r * 0xBB67AE85u; }
+  return rk;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxRoundKeys& rk) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ rk.k0[r], lo1, hi0 ^ c.w ^ rk.k1[r], lo0);
+  }
+  return c;
+}
+
 __host__ __device__ __forceinline__ uint4 philox_ctr(uint64_t gchain, uint32_t step, uint32_t stream, uint32_t block) {
   return make_uint4((uint32_t)gchain, (uint32_t)(gchain >> 32), step, (stream << 24) | block);
 }
@@ -73,6 +91,20 @@ __device__ __forceinline__ void normals_from_block(uint4 r, double (&z)[2]) {
   double s, c;
   sincospi(2.0 * u1, &s, &c);
   z[0] = rr * c; z[1] = rr * s;
+}
+
+// two normals from two 32-bit words (fast path of the 2-D MH kernel; same arithmetic as the first half
+// of normals_from_block<false>)
+__device__ __forceinline__ void normals_pair_fast(uint32_t w0, uint32_t w1, float& z0, float& z1) {
+  float r0, s0, c0;
+  const float u0 = u01(w0), u1 = u01(w1);
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(u0));
+  r0 *= -1.3862943611198906f;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(r0));
+  const float a0 = fmaf(u1, 6.283185307179586f, -3.141592653589793f);
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s0) : "f"(a0));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c0) : "f"(a0));
+  z0 = r0 * c0; z1 = r0 * s0;
 }
 
 template <class T> struct NormalsPerBlock;
