@@ -483,7 +483,16 @@ class NUTS(_Sampler):
                                           C.c_double(init_step_size), C.c_uint64(seed), C.byref(h)))
         self._h = h
 
+    def state(self):
+        """Per-chain step sizes, accumulated leapfrogs and (when streams were injected) consumed draws."""
+        eps = np.empty(self.n_chains, self.dtype)
+        leap = np.empty(self.n_chains, np.int64)
+        used = np.zeros((self.n_chains, 3), np.uint64) if getattr(self, "_injected", False) else None
+        L.check(L.lib().gmcmc_nuts_state(self._h, L.ptr(eps), L.ptr(leap), L.ptr(used)))
+        return {"eps": eps, "leapfrogs": leap, "used": used}
+
     def inject_streams(self, normals, exp1, unif):
+        self._injected = True
         normals = np.ascontiguousarray(normals, np.float64)
         exp1 = np.ascontiguousarray(exp1, np.float64)
         unif = np.ascontiguousarray(unif, np.float64)

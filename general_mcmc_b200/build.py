@@ -23,6 +23,7 @@ COMMON = (["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUD
 
 # per-target K1 translation units, each compiled in both math modes
 K1_TARGETS = ["k_rosen", "k_iso", "k_dense", "k_mix", "k_rosen2d", "k_dgauss2d", "k_gauss2d"]
+NUTS_TARGETS = ["n_rosen", "n_iso", "n_dense", "n_mix", "n_rosen2d", "n_dgauss2d"]
 EXACT_FLAGS = ["-DGM_EXACT=1", "--fmad=false"]
 
 
@@ -39,9 +40,12 @@ def _units():
     for t in K1_TARGETS:
         units.append((t + ".cu", t + "_fast.o", []))
         units.append((t + ".cu", t + "_exact.o", EXACT_FLAGS))
+    for t in NUTS_TARGETS:
+        units.append((t + ".cu", t + "_fast.o", []))
+        units.append((t + ".cu", t + "_exact.o", EXACT_FLAGS))
     units.append(("mh_fast.cu", "mh_fast.o", []))
     units.append(("mh_exact.cu", "mh_exact.o", ["--fmad=false"]))
-    for extra in ("nuts_fast.cu", "nuts_exact.cu", "dense_tc.cu"):
+    for extra in ("dense_tc.cu",):
         if os.path.exists(os.path.join(CSRC, extra)):
             flags = ["--fmad=false"] if extra.endswith("_exact.cu") else []
             units.append((extra, extra[:-3] + ".o", flags))

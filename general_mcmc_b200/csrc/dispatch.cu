@@ -14,6 +14,23 @@ namespace gm {
 GM_DECL(rosen) GM_DECL(iso) GM_DECL(dense) GM_DECL(mix) GM_DECL(rosen2d) GM_DECL(dgauss2d) GM_DECL(gauss2d)
 #undef GM_DECL
 
+#define GM_DECL_N(fn)                                                      \
+  cudaError_t launch_nuts_##fn##_fast(const NutsLaunch&, cudaStream_t);    \
+  cudaError_t launch_nuts_##fn##_exact(const NutsLaunch&, cudaStream_t);
+GM_DECL_N(rosen) GM_DECL_N(iso) GM_DECL_N(dense) GM_DECL_N(mix) GM_DECL_N(rosen2d) GM_DECL_N(dgauss2d)
+#undef GM_DECL_N
+
+#define GM_ROUTE_N(mode, L, st)                           \
+  switch ((L).tgt.kind) {                                 \
+    case 0: return launch_nuts_iso_##mode(L, st);         \
+    case 2: return launch_nuts_dgauss2d_##mode(L, st);    \
+    case 3: return launch_nuts_dense_##mode(L, st);       \
+    case 4: return launch_nuts_rosen2d_##mode(L, st);     \
+    case 5: return launch_nuts_rosen_##mode(L, st);       \
+    case 6: return launch_nuts_mix_##mode(L, st);         \
+  }                                                       \
+  return cudaErrorInvalidValue;
+
 #define GM_ROUTE(prefix, mode, L, st)                     \
   switch ((L).tgt.kind) {                                 \
     case 0: return prefix##iso_##mode(L, st);             \
@@ -30,6 +47,32 @@ cudaError_t launch_hmc_fast(const HmcLaunch& L, cudaStream_t st) { GM_ROUTE(laun
 cudaError_t launch_hmc_exact(const HmcLaunch& L, cudaStream_t st) { GM_ROUTE(launch_hmc_, exact, L, st) }
 cudaError_t launch_eval_fast(const EvalLaunch& E, cudaStream_t st) { GM_ROUTE(launch_eval_, fast, E, st) }
 cudaError_t launch_eval_exact(const EvalLaunch& E, cudaStream_t st) { GM_ROUTE(launch_eval_, exact, E, st) }
+
+cudaError_t launch_nuts_fast(const NutsLaunch& L, cudaStream_t st) { GM_ROUTE_N(fast, L, st) }
+cudaError_t launch_nuts_exact(const NutsLaunch& L, cudaStream_t st) { GM_ROUTE_N(exact, L, st) }
+
+// NUTS kernels are instantiated for EPL 4, 8, 25 (f32) / 13 (f64) with runtime masking; 2-D targets use EPL 2.
+bool choose_nuts_decomposition(int dim, int dtype, int kind, int* epl, int* lpc) {
+  if (dim <= 0 || kind == 1) return false;
+  if (kind == 2 || kind == 4) {
+    if (dim != 2) return false;
+    *epl = 2; *lpc = 1;
+    return true;
+  }
+  const int big = dtype == 0 ? 25 : 13;
+  const int menu[3] = {4, 8, big};
+  double best = 1e30;
+  int be = 0, bl = 0;
+  for (int l = 1; l <= 32; l <<= 1)
+    for (int e : menu) {
+      if (e * l < dim) continue;
+      const double cost = (double)e * l * ((e * l == dim) ? 1.0 : 1.15) + 6.0 * l;
+      if (cost < best - 1e-9 || (cost < best + 1e-9 && e > be)) { best = cost; be = e; bl = l; }
+    }
+  if (!be) return false;
+  *epl = be; *lpc = bl;
+  return true;
+}
 
 // Decomposition: minimise padded slots (compute), penalising non exact fits (masking costs ~30 %) and
 // lanes per chain; ties go to more elements per lane (more ILP, fewer shuffles).  Lanes past the end of

@@ -85,6 +85,33 @@ struct MhLaunch {
   uint8_t* diag_acc;        // [n, C]
 };
 
+struct NutsLaunch {
+  TargetDesc tgt;
+  int init_only;          // 1: run init_chain_state (momentum draw + find_reasonable_epsilon + mu) instead of transitions
+  size_t n_chains;
+  uint64_t chain_offset;
+  uint64_t seed;
+  uint32_t step_base;
+  void* positions;
+  uint32_t n_steps, m_base, n_discard;
+  long long rec_off;
+  int write_init;
+  void* out;
+  size_t out_n;
+  void* eps; void* eps_bar; void* h_bar; void* mu;   // [C] T
+  double target_accept;
+  int max_depth;          // effective cap
+  void* ws_edges; void* ws_first; void* ws_prime;
+  int cap;
+  unsigned long long* leapfrog_total; unsigned long long* diverge_total; unsigned long long* depth_total;
+  long long* chain_leapfrogs;
+  const double* inj_normals; size_t n_norm;
+  const double* inj_exp1; size_t n_exp;
+  const double* inj_unif; size_t n_unif;
+  unsigned long long* inj_used;
+  int epl, lpc;
+};
+
 struct StatsLaunch {
   const void* samples;   // [C, n, p] device, f32 (dtype 0) or f64 (dtype 1)
   int dtype;
@@ -119,6 +146,11 @@ cudaError_t launch_eval_fast(const EvalLaunch&, cudaStream_t);
 cudaError_t launch_eval_exact(const EvalLaunch&, cudaStream_t);
 cudaError_t launch_mh_fast(const MhLaunch&, cudaStream_t);
 cudaError_t launch_mh_exact(const MhLaunch&, cudaStream_t);
+
+cudaError_t launch_nuts_fast(const NutsLaunch&, cudaStream_t);
+cudaError_t launch_nuts_exact(const NutsLaunch&, cudaStream_t);
+bool choose_nuts_decomposition(int dim, int dtype, int kind, int* epl, int* lpc);
+constexpr int kNutsDepthCapHost = 20;
 
 // picks (epl, lpc) for a dimension; returns false if unsupported by the register-resident kernels
 bool choose_decomposition(int dim, int dtype, int kind, int* epl, int* lpc);

@@ -1,0 +1,591 @@
+// nuts_kernel.cuh — K5: No-U-Turn sampler, one launch per run segment (sm_100a).
+//
+// Replaces the host-driven recursion of
+//   GenericNUTSChain::step                      /root/reference/src/generic_nuts.rs:755-925
+//   build_tree_with_mass (13-tuple recursion)   /root/reference/src/generic_nuts.rs:1153-1341
+//   leapfrog_with_mass / stop_criterion         /root/reference/src/generic_nuts.rs:1396-1418, 1357-1378
+//   find_reasonable_epsilon_with_mass           /root/reference/src/generic_nuts.rs:1025-1102
+//   init_chain_state / run                      /root/reference/src/generic_nuts.rs:667-753
+//
+// The recursion becomes an iterative binary-counter tree.  Leaf c of a depth-j subtree build merges
+// with the pending left subtree of every level k whose bit is set in c, in increasing k — exactly the
+// order in which the reference's recursion returns, so the per-node uniforms are consumed in the same
+// (post-order) sequence.  A failed leaf / merge (s' = false) keeps merging through ALL set bits (the
+// reference's ancestors whose left child was valid still merge; ancestors reached through a left child
+// pass the result up untouched).  Only two kinds of vectors are checkpointed:
+//   first[slot]  (q, p) of every even leaf, slot = popcount(c >> 1): the first leaf of every pending
+//                subtree (U-turn test of a merge = first leaf of the left subtree vs. the current leaf)
+//   prime[k]     proposal of the pending subtree at level k >= 1 (level 0: its proposal is its own leaf)
+// alpha' and n_alpha' are plain sums over the leaves of a build, n' is carried per level.
+//
+// Mapping: as K1, a chain is `lpc` adjacent lanes with EPL coordinates each; q, p, grad and the
+// current proposal live in registers.  Chains of one warp progress independently (different tree
+// depths, different transition counts); every loop iteration evaluates ONE gradient per chain and all
+// shuffles are executed by the full warp with per-chain commit masks (warp-level masking of finished
+// or differently-phased chains).
+#pragma once
+#include "hmc_kernel.cuh"
+
+namespace gm {
+namespace GM_NS {
+
+constexpr int kNutsDepthCap = 20;  // safety cap when max_depth == 0 (the reference is uncapped)
+
+template <class T>
+struct NutsArgs {
+  TParams<T> tp;
+  size_t n_chains;
+  unsigned long long chain_offset;
+  PhiloxKey key;
+  uint32_t step_base;     // Philox transition index of the first transition of this launch
+  T* positions;           // [C, d]
+  int d, d_pad, lpc;
+  uint32_t n_steps;       // transitions in this launch
+  uint32_t m_base;        // transitions of this run before the launch: m = m_base + s + 1 (generic_nuts.rs:756)
+  uint32_t n_discard;     // dual averaging adapts while m <= n_discard (generic_nuts.rs:897)
+  long long rec_off;      // transition m is recorded at slot m - rec_off when 0 <= slot < out_n
+  int write_init;         // run(): sample 0 = the initial position when n_discard == 0 (nuts.rs:588-601)
+  T* out;                 // [C, out_n, d] or null
+  size_t out_n;
+  T* eps; T* eps_bar; T* h_bar; T* mu;   // per-chain adaptation state [C]
+  T target_accept;
+  int max_depth;          // effective cap (1..kNutsDepthCap)
+  T* ws_edges;            // [C][6][d]  q-, p-, g-, q+, p+, g+
+  T* ws_first;            // [C][cap][2][d]
+  T* ws_prime;            // [C][cap][d]
+  int cap;
+  unsigned long long* leapfrog_total;
+  unsigned long long* diverge_total;
+  unsigned long long* depth_total;
+  long long* chain_leapfrogs;   // [C] accumulated (may be null)
+  // injected per-chain streams (parity tests); null -> Philox
+  const double* inj_normals; size_t n_norm;
+  const double* inj_exp1; size_t n_exp;
+  const double* inj_unif; size_t n_unif;
+  unsigned long long* inj_used;   // [C][3] consumption counters, in/out
+};
+
+enum NutsPhase : int { NP_START = 0, NP_LEAF = 1, NP_END = 2, NP_DONE = 3 };
+
+template <class T, int EPL>
+__device__ __forceinline__ void load_slice(T (&dst)[EPL], const T* src, const Lane& ln, bool on, T fill) {
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) dst[j] = (on && j < ln.nvalid) ? src[ln.lo + j] : fill;
+}
+template <class T, int EPL>
+__device__ __forceinline__ void store_slice(T* dst, const T (&src)[EPL], const Lane& ln, bool on) {
+#pragma unroll
+  for (int j = 0; j < EPL; ++j)
+    if (on && j < ln.nvalid) dst[ln.lo + j] = src[j];
+}
+
+template <class T, int EPL, class TAG>
+__global__ void __launch_bounds__(kHmcBlock, 2) nuts_run_kernel(const NutsArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* smem = reinterpret_cast<T*>(smem_raw);
+
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const Lane ln = make_lane<EPL>(tid, a.lpc, a.d);
+  const size_t chain = (size_t)(tid / a.lpc);
+  const bool active = chain < a.n_chains;
+  const int lane = threadIdx.x & 31;
+  const int chains_in_warp = 32 / a.lpc;
+  const int chain_in_warp = lane / a.lpc;
+  const size_t warp_elems = (size_t)chains_in_warp * a.d_pad;
+  T* warp_pos = smem + (size_t)(threadIdx.x >> 5) * 2 * warp_elems;
+  T* pos_row = warp_pos + (size_t)chain_in_warp * a.d_pad;
+  T* row = warp_pos + warp_elems + (size_t)chain_in_warp * a.d_pad;
+  const size_t warp_first_chain = (size_t)((tid & ~31) / a.lpc);
+  const unsigned long long gchain = a.chain_offset + chain;
+  const size_t d = (size_t)a.d;
+  const size_t cw = active ? chain : 0;   // workspace row (inactive lanes alias chain 0, never commit)
+
+  T* e_qm = a.ws_edges + (cw * 6 + 0) * d;
+  T* e_pm = a.ws_edges + (cw * 6 + 1) * d;
+  T* e_gm = a.ws_edges + (cw * 6 + 2) * d;
+  T* e_qp = a.ws_edges + (cw * 6 + 3) * d;
+  T* e_pp = a.ws_edges + (cw * 6 + 4) * d;
+  T* e_gp = a.ws_edges + (cw * 6 + 5) * d;
+  T* w_first = a.ws_first + cw * (size_t)a.cap * 2 * d;
+  T* w_prime = a.ws_prime + cw * (size_t)a.cap * d;
+
+  for (int c = 0; c < chains_in_warp; ++c) {
+    const size_t ch = warp_first_chain + c;
+    for (int i = lane; i < a.d_pad; i += 32)
+      warp_pos[(size_t)c * a.d_pad + i] = (ch < a.n_chains && i < a.d) ? a.positions[ch * d + i] : T(1);
+  }
+  __syncwarp();
+  if (a.write_init && a.out && active) {
+#pragma unroll
+    for (int j = 0; j < EPL; ++j)
+      if (j < ln.nvalid) a.out[(chain * a.out_n) * d + ln.lo + j] = pos_row[ln.lo + j];
+  }
+
+  T eps = T(1), eps_bar = T(1), h_bar = T(0), mu = T(0);
+  if (active) { eps = a.eps[chain]; eps_bar = a.eps_bar[chain]; h_bar = a.h_bar[chain]; mu = a.mu[chain]; }
+  unsigned long long i_norm = 0, i_exp = 0, i_unif = 0;
+  const bool inject = a.inj_normals != nullptr;
+  if (inject && active) { i_norm = a.inj_used[chain * 3]; i_exp = a.inj_used[chain * 3 + 1]; i_unif = a.inj_used[chain * 3 + 2]; }
+
+  T q[EPL], p[EPL], g[EPL], prime[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) { q[j] = T(1); p[j] = T(0); g[j] = T(0); prime[j] = T(1); }
+  int n_stack[kNutsDepthCap];
+#pragma unroll
+  for (int k = 0; k < kNutsDepthCap; ++k) n_stack[k] = 0;
+
+  int phase = (active && a.n_steps > 0) ? NP_START : NP_DONE;
+  uint32_t s = 0;          // transition of this launch
+  uint32_t draw = 0;       // uniform draws of the current transition (Philox stream 2)
+  int j_depth = 0, v = 1;
+  unsigned int leaf_i = 0; // leaf index within the current subtree build
+  long long n_tot = 1;
+  int nR = 0, n_alpha = 0;
+  bool sR = true;
+  T alpha_sum = T(0), logu = T(0), joint0 = T(0);
+  unsigned long long my_leapfrogs = 0, my_diverge = 0, my_depth = 0;
+
+  auto next_unif = [&]() -> double {
+    if (inject) {
+      const double u = (i_unif < a.n_unif) ? a.inj_unif[chain * a.n_unif + i_unif] : 0.75;
+      ++i_unif;
+      return u;
+    }
+    const uint4 r = philox4x32_10(philox_ctr(gchain, a.step_base + s, 2u, draw >> 1), a.key);
+    const double u = (draw & 1u) ? u01d(r.z, r.w) : u01d(r.x, r.y);
+    ++draw;
+    return u;
+  };
+
+  for (;;) {
+    // ---- A. momentum for the chains that start a transition (generic_nuts.rs:759-762)
+    const bool is_start = (phase == NP_START);
+    const bool is_leaf = (phase == NP_LEAF);
+    if (__any_sync(kFull, is_start)) {
+      T pn[EPL];
+      if (inject) {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+          const unsigned long long idx = i_norm + (unsigned long long)(ln.lo + j);
+          pn[j] = (is_start && j < ln.nvalid) ? (T)((idx < a.n_norm) ? a.inj_normals[chain * a.n_norm + idx] : 0.0) : T(0);
+        }
+        if (is_start) i_norm += d;
+      } else {
+        constexpr int NPB = NormalsPerBlock<T>::value;
+        const int nblocks = (a.d + NPB - 1) / NPB;
+        for (int b = ln.part; b < nblocks; b += a.lpc) {
+          T z[NPB];
+          normals_from_block<kExact>(philox4x32_10(philox_ctr(gchain, a.step_base + s, 0u, (uint32_t)b), a.key), z);
+#pragma unroll
+          for (int k = 0; k < NPB; ++k)
+            if (b * NPB + k < a.d_pad) row[b * NPB + k] = z[k];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) pn[j] = (j < ln.nvalid) ? row[ln.lo + j] : T(0);
+        __syncwarp();
+      }
+      if (is_start) {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) { p[j] = pn[j]; q[j] = (j < ln.nvalid) ? pos_row[ln.lo + j] : T(1); }
+      }
+    }
+
+    // ---- B. one gradient evaluation per chain: at the position (start) or after a leapfrog drift (leaf)
+    const T veps = (T)v * eps;                 // generic_nuts.rs:1187
+    const T he = veps * T(0.5);                // leapfrog_with_mass :1396-1418
+    if (is_leaf) {
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) p[j] = p[j] + g[j] * he;
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) q[j] = q[j] + p[j] * veps;
+    }
+    T gn[EPL];
+    const T logp = eval_target<T, EPL, true, true>(TAG{}, q, gn, ln, a.tp, row);
+    if (is_start || is_leaf) {
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) g[j] = gn[j];
+    }
+    if (is_leaf) {
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) p[j] = p[j] + g[j] * he;
+    }
+    T terms[EPL];
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) terms[j] = p[j] * p[j];
+    const T ke = T(0.5) * chain_sum<T, EPL>(terms, ln);
+    const T joint = logp - ke;
+
+    bool in_merge = false;
+    if (is_start) {
+      // generic_nuts.rs:765-781
+      joint0 = joint;
+      T e1;
+      if (inject) { e1 = (T)((i_exp < a.n_exp) ? a.inj_exp1[chain * a.n_exp + i_exp] : 1.0); ++i_exp; }
+      else {
+        const uint4 r = philox4x32_10(philox_ctr(gchain, a.step_base + s, 1u, 0u), a.key);
+        e1 = (T)(-log(u01d(r.z, r.w)));
+      }
+      logu = joint0 - e1;
+      store_slice<T, EPL>(e_qm, q, ln, true); store_slice<T, EPL>(e_pm, p, ln, true); store_slice<T, EPL>(e_gm, g, ln, true);
+      store_slice<T, EPL>(e_qp, q, ln, true); store_slice<T, EPL>(e_pp, p, ln, true); store_slice<T, EPL>(e_gp, g, ln, true);
+      j_depth = 0; n_tot = 1; draw = 0;
+      const T u1 = (T)next_unif();             // :783-784
+      v = (u1 < T(0.5)) ? 1 : -1;
+      leaf_i = 0; alpha_sum = T(0); n_alpha = 0;
+      phase = NP_LEAF;
+    } else if (is_leaf) {
+      // leaf of build_tree (j == 0 branch, generic_nuts.rs:1185-1222)
+      ++my_leapfrogs;
+      nR = (logu < joint) ? 1 : 0;
+      sR = (logu - T(1000)) < joint;
+      if (!sR) ++my_diverge;
+      alpha_sum = alpha_sum + min(T(1), (T)exp(joint - joint0));
+      ++n_alpha;
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) prime[j] = q[j];
+      if ((leaf_i & 1u) == 0u) {
+        const int slot = __popc(leaf_i >> 1);
+        store_slice<T, EPL>(w_first + ((size_t)slot * 2 + 0) * d, q, ln, true);
+        store_slice<T, EPL>(w_first + ((size_t)slot * 2 + 1) * d, p, ln, true);
+      }
+      in_merge = true;
+    }
+
+    // ---- C. merges with the pending left subtrees, then the top-level step of the doubling
+    int k = 0;
+    while (__any_sync(kFull, in_merge)) {
+      bool do_merge = false, do_top = false;
+      if (in_merge) {
+        if (k == j_depth) do_top = true;                       // the depth-j subtree is complete (or failed)
+        else if ((leaf_i >> k) & 1u) do_merge = true;          // pending left sibling at level k
+        else if (sR) {                                         // becomes the pending left subtree of level k
+          n_stack[k] = nR;
+          if (k >= 1) store_slice<T, EPL>(w_prime + (size_t)k * d, prime, ln, true);
+          in_merge = false;
+          ++leaf_i;
+        }                                                      // else: failed subtree passed up through a left child
+      }
+      // the other end of the U-turn test: first leaf of the left subtree (merge) / the other trajectory edge (top)
+      T fq[EPL], fp[EPL];
+      const T* src_q = e_qm;
+      const T* src_p = e_pm;
+      if (do_merge) {
+        const unsigned int start = (leaf_i >> (k + 1)) << (k + 1);
+        const int slot = __popc(start >> 1);
+        src_q = w_first + ((size_t)slot * 2 + 0) * d;
+        src_p = w_first + ((size_t)slot * 2 + 1) * d;
+      } else if (do_top) {
+        src_q = (v == 1) ? e_qm : e_qp;
+        src_p = (v == 1) ? e_pm : e_pp;
+      }
+      load_slice<T, EPL>(fq, src_q, ln, do_merge || do_top, T(0));
+      load_slice<T, EPL>(fp, src_p, ln, do_merge || do_top, T(0));
+      // stop_criterion (generic_nuts.rs:1357-1378, identity mass): diff = q+ - q- ; diff.p- >= 0 && diff.p+ >= 0
+      T tm[EPL], tpv[EPL];
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) {
+        const T qplus = (v == 1) ? q[j] : fq[j], qminus = (v == 1) ? fq[j] : q[j];
+        const T pplus = (v == 1) ? p[j] : fp[j], pminus = (v == 1) ? fp[j] : p[j];
+        const T df = qplus - qminus;
+        tm[j] = (j < ln.nvalid) ? df * pminus : T(0);
+        tpv[j] = (j < ln.nvalid) ? df * pplus : T(0);
+      }
+      const T dm = chain_sum<T, EPL>(tm, ln);
+      const T dp = chain_sum<T, EPL>(tpv, ln);
+      const bool crit = (dm >= T(0)) && (dp >= T(0));
+      if (do_merge) {
+        // generic_nuts.rs:1305-1323
+        const double u = next_unif();
+        const int nL = n_stack[k];
+        const int den = (nL + nR) > 1 ? (nL + nR) : 1;
+        if (!(u < ((double)nR / (double)den))) {
+          if (k == 0) {
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) prime[j] = fq[j];
+          } else {
+            load_slice<T, EPL>(prime, w_prime + (size_t)k * d, ln, true, T(1));
+          }
+        }
+        nR += nL;
+        sR = sR && crit;
+      } else if (do_top) {
+        // generic_nuts.rs:803-880: new edge, accept the subtree's proposal, trajectory-level U-turn test
+        if (v == 1) { store_slice<T, EPL>(e_qp, q, ln, true); store_slice<T, EPL>(e_pp, p, ln, true); store_slice<T, EPL>(e_gp, g, ln, true); }
+        else { store_slice<T, EPL>(e_qm, q, ln, true); store_slice<T, EPL>(e_pm, p, ln, true); store_slice<T, EPL>(e_gm, g, ln, true); }
+        const T ratio = (T)nR / (T)n_tot;
+        const T tmp = ratio < T(1) ? ratio : T(1);
+        const T u2 = (T)next_unif();
+        if (sR && (u2 < tmp)) {
+#pragma unroll
+          for (int j = 0; j < EPL; ++j)
+            if (j < ln.nvalid) pos_row[ln.lo + j] = prime[j];
+        }
+        n_tot += nR;
+        bool cont = sR && crit;
+        ++j_depth;
+        if (j_depth >= a.max_depth) cont = false;
+        in_merge = false;
+        if (cont) {
+          const T u1 = (T)next_unif();
+          const int vn = (u1 < T(0.5)) ? 1 : -1;
+          if (vn != v) {
+            load_slice<T, EPL>(q, vn == 1 ? e_qp : e_qm, ln, true, T(1));
+            load_slice<T, EPL>(p, vn == 1 ? e_pp : e_pm, ln, true, T(0));
+            load_slice<T, EPL>(g, vn == 1 ? e_gp : e_gm, ln, true, T(0));
+          }
+          v = vn;
+          leaf_i = 0; alpha_sum = T(0); n_alpha = 0;
+        } else {
+          phase = NP_END;
+        }
+      }
+      ++k;
+    }
+
+    // ---- D. end of the transition: dual averaging (generic_nuts.rs:882-924), write-out
+    if (phase == NP_END) {
+      const uint32_t m = a.m_base + s + 1;
+      my_depth += (unsigned long long)j_depth;
+      T eta = T(1) / (T)(m + 10u);
+      h_bar = (T(1) - eta) * h_bar + eta * (a.target_accept - alpha_sum / (T)n_alpha);
+      if (m <= a.n_discard) {
+        const T mm = (T)m;
+        eps = exp(mu - sqrt(mm) / T(0.05) * h_bar);
+        eta = pow(mm, -T(0.75));
+        eps_bar = exp((T(1) - eta) * log(eps_bar) + eta * log(eps));
+      } else {
+        eps = eps_bar;
+      }
+      const long long slot = (long long)m - a.rec_off;
+      if (a.out && slot >= 0 && slot < (long long)a.out_n) {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j)
+          if (j < ln.nvalid) __stcs(a.out + (chain * a.out_n + (size_t)slot) * d + ln.lo + j, pos_row[ln.lo + j]);
+      }
+      ++s;
+      phase = (s < a.n_steps) ? NP_START : NP_DONE;
+    }
+    if (__all_sync(kFull, phase == NP_DONE)) break;
+  }
+
+  // ---- state back to HBM
+  __syncwarp();
+  for (int c = 0; c < chains_in_warp; ++c) {
+    const size_t ch = warp_first_chain + c;
+    if (ch >= a.n_chains) break;
+    for (int i = lane; i < a.d; i += 32) a.positions[ch * d + i] = warp_pos[(size_t)c * a.d_pad + i];
+  }
+  if (active && ln.part == 0) {
+    a.eps[chain] = eps; a.eps_bar[chain] = eps_bar; a.h_bar[chain] = h_bar;
+    if (inject) { a.inj_used[chain * 3] = i_norm; a.inj_used[chain * 3 + 1] = i_exp; a.inj_used[chain * 3 + 2] = i_unif; }
+    if (a.chain_leapfrogs) a.chain_leapfrogs[chain] += (long long)my_leapfrogs;
+  }
+  if (!(active && ln.part == 0)) { my_leapfrogs = 0; my_diverge = 0; my_depth = 0; }
+  for (int o = 16; o > 0; o >>= 1) {
+    my_leapfrogs += __shfl_xor_sync(kFull, my_leapfrogs, o);
+    my_diverge += __shfl_xor_sync(kFull, my_diverge, o);
+    my_depth += __shfl_xor_sync(kFull, my_depth, o);
+  }
+  if (lane == 0) {
+    if (my_leapfrogs) atomicAdd(a.leapfrog_total, my_leapfrogs);
+    if (my_diverge) atomicAdd(a.diverge_total, my_diverge);
+    if (my_depth) atomicAdd(a.depth_total, my_depth);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// init_chain_state (generic_nuts.rs:731-753): consume d normals; find_reasonable_epsilon when the step
+// size is still the -1 sentinel; mu = ln(10 eps).
+// ----------------------------------------------------------------------------------------------
+template <class T>
+struct NutsInitArgs {
+  TParams<T> tp;
+  size_t n_chains;
+  unsigned long long chain_offset;
+  PhiloxKey key;
+  uint32_t step;          // Philox transition index reserved for this init
+  const T* positions;
+  int d, d_pad, lpc;
+  T* eps; T* mu;
+  const double* inj_normals; size_t n_norm;
+  unsigned long long* inj_used;
+};
+
+template <class T, int EPL, class TAG>
+__global__ void __launch_bounds__(kHmcBlock, 2) nuts_init_kernel(const NutsInitArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* smem = reinterpret_cast<T*>(smem_raw);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const Lane ln = make_lane<EPL>(tid, a.lpc, a.d);
+  const size_t chain = (size_t)(tid / a.lpc);
+  const bool active = chain < a.n_chains;
+  const int lane = threadIdx.x & 31;
+  const int chain_in_warp = lane / a.lpc;
+  T* row = smem + ((size_t)(threadIdx.x >> 5) * (32 / a.lpc) + chain_in_warp) * a.d_pad;
+  const unsigned long long gchain = a.chain_offset + chain;
+  const size_t d = (size_t)a.d;
+
+  T pos[EPL], mom[EPL], g0[EPL], q1[EPL], p1[EPL], g1[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) pos[j] = (active && j < ln.nvalid) ? a.positions[chain * d + ln.lo + j] : T(1);
+  if (a.inj_normals) {
+    unsigned long long i_norm = active ? a.inj_used[chain * 3] : 0;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      const unsigned long long idx = i_norm + (unsigned long long)(ln.lo + j);
+      mom[j] = (active && j < ln.nvalid) ? (T)((idx < a.n_norm) ? a.inj_normals[chain * a.n_norm + idx] : 0.0) : T(0);
+    }
+    if (active && ln.part == 0) a.inj_used[chain * 3] = i_norm + d;
+  } else {
+    constexpr int NPB = NormalsPerBlock<T>::value;
+    const int nblocks = (a.d + NPB - 1) / NPB;
+    for (int b = ln.part; b < nblocks; b += a.lpc) {
+      T z[NPB];
+      normals_from_block<kExact>(philox4x32_10(philox_ctr(gchain, a.step, 0u, (uint32_t)b), a.key), z);
+#pragma unroll
+      for (int k = 0; k < NPB; ++k)
+        if (b * NPB + k < a.d_pad) row[b * NPB + k] = z[k];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) mom[j] = (j < ln.nvalid) ? row[ln.lo + j] : T(0);
+    __syncwarp();
+  }
+  T eps = active ? a.eps[chain] : T(1);
+  const bool need = active && (fabs(eps + T(1)) <= (sizeof(T) == 4 ? T(1.1920929e-07) : T(2.220446049250313e-16)));
+
+  // find_reasonable_epsilon_with_mass, generic_nuts.rs:1025-1102 (identity mass).  stage 0: gradient at
+  // the position; stage 1: halve until finite; stage 2: double / halve until the acceptance crosses 1/2.
+  int stage = need ? 0 : 3;
+  T epsilon = T(1), kfac = T(1), ulogp = T(0), ke_mom = T(0), afac = T(1), e_try = T(1);
+  const T half = T(0.5);
+  const T ln_half = (sizeof(T) == 4) ? (T)-0.6931472f : (T)-0.6931471805599453;
+  const T ln_two = (sizeof(T) == 4) ? (T)0.6931472f : (T)0.6931471805599453;
+  int guard = 0;
+  while (__any_sync(kFull, stage < 3)) {
+    if (stage == 0) {
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) { q1[j] = pos[j]; p1[j] = mom[j]; }
+    } else {
+      const T he = e_try * half;
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) { p1[j] = mom[j] + g0[j] * he; q1[j] = pos[j] + p1[j] * e_try; }
+    }
+    const T lp = eval_target<T, EPL, true, true>(TAG{}, q1, g1, ln, a.tp, row);
+    T terms[EPL], fin[EPL];
+    if (stage != 0) {
+      const T he = e_try * half;
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) p1[j] = p1[j] + g1[j] * he;
+    }
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      terms[j] = p1[j] * p1[j];
+      fin[j] = (j < ln.nvalid && !(fabs(g1[j]) < T(INFINITY))) ? T(1) : T(0);   // counts NaN and +-inf
+    }
+    const T ke = half * chain_sum<T, EPL>(terms, ln);
+    const T bad = chain_sum<T, EPL>(fin, ln);
+    const bool finite = (fabs(lp) < T(INFINITY)) && (bad == T(0));
+    if (stage == 0) {
+      ulogp = lp; ke_mom = ke;
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) g0[j] = g1[j];
+      e_try = epsilon;            // first trial: leapfrog with epsilon = 1
+      stage = 1;
+    } else if (stage == 1) {
+      if (!finite && guard < 200) { kfac = kfac * half; e_try = epsilon * kfac; ++guard; }
+      else {
+        epsilon = half * kfac * epsilon;
+        const T lap = lp - ulogp - (ke - ke_mom);
+        afac = (lap > ln_half) ? T(1) : T(-1);
+        if (afac * lap > -afac * ln_two) { epsilon = epsilon * (afac > T(0) ? T(2) : half); e_try = epsilon; stage = 2; guard = 0; }
+        else stage = 3;
+      }
+    } else if (stage == 2) {
+      const T lap = lp - ulogp - (ke - ke_mom);
+      if (afac * lap > -afac * ln_two && guard < 200) { epsilon = epsilon * (afac > T(0) ? T(2) : half); e_try = epsilon; ++guard; }
+      else stage = 3;
+    }
+  }
+  if (active && ln.part == 0) {
+    if (need) { eps = epsilon; a.eps[chain] = eps; }
+    a.mu[chain] = log(T(10) * eps);
+  }
+}
+
+template <class T>
+inline NutsArgs<T> make_nuts_args(const NutsLaunch& L) {
+  NutsArgs<T> a;
+  a.tp = make_tparams<T>(L.tgt);
+  a.n_chains = L.n_chains; a.chain_offset = L.chain_offset;
+  a.key = PhiloxKey{(uint32_t)L.seed, (uint32_t)(L.seed >> 32)};
+  a.step_base = L.step_base;
+  a.positions = (T*)L.positions;
+  a.d = L.tgt.dim; a.d_pad = ((L.tgt.dim + 3) / 4) * 4; a.lpc = L.lpc;
+  a.n_steps = L.n_steps; a.m_base = L.m_base; a.n_discard = L.n_discard;
+  a.rec_off = L.rec_off; a.write_init = L.write_init;
+  a.out = (T*)L.out; a.out_n = L.out_n;
+  a.eps = (T*)L.eps; a.eps_bar = (T*)L.eps_bar; a.h_bar = (T*)L.h_bar; a.mu = (T*)L.mu;
+  a.target_accept = (T)L.target_accept;
+  a.max_depth = L.max_depth;
+  a.ws_edges = (T*)L.ws_edges; a.ws_first = (T*)L.ws_first; a.ws_prime = (T*)L.ws_prime; a.cap = L.cap;
+  a.leapfrog_total = L.leapfrog_total; a.diverge_total = L.diverge_total; a.depth_total = L.depth_total;
+  a.chain_leapfrogs = L.chain_leapfrogs;
+  a.inj_normals = L.inj_normals; a.n_norm = L.n_norm; a.inj_exp1 = L.inj_exp1; a.n_exp = L.n_exp;
+  a.inj_unif = L.inj_unif; a.n_unif = L.n_unif; a.inj_used = L.inj_used;
+  return a;
+}
+
+template <class T, int EPL, class TAG>
+inline cudaError_t nuts_launch_one(const NutsLaunch& L, cudaStream_t st) {
+  const int d_pad = ((L.tgt.dim + 3) / 4) * 4;
+  const size_t threads = L.n_chains * (size_t)L.lpc;
+  const unsigned blocks = (unsigned)((threads + kHmcBlock - 1) / kHmcBlock);
+  if (L.init_only) {
+    NutsInitArgs<T> a;
+    a.tp = make_tparams<T>(L.tgt);
+    a.n_chains = L.n_chains; a.chain_offset = L.chain_offset;
+    a.key = PhiloxKey{(uint32_t)L.seed, (uint32_t)(L.seed >> 32)};
+    a.step = L.step_base; a.positions = (const T*)L.positions;
+    a.d = L.tgt.dim; a.d_pad = d_pad; a.lpc = L.lpc;
+    a.eps = (T*)L.eps; a.mu = (T*)L.mu;
+    a.inj_normals = L.inj_normals; a.n_norm = L.n_norm; a.inj_used = L.inj_used;
+    const size_t smem = (size_t)(kHmcBlock / L.lpc) * d_pad * sizeof(T);
+    auto kern = nuts_init_kernel<T, EPL, TAG>;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    kern<<<blocks, kHmcBlock, smem, st>>>(a);
+    return cudaGetLastError();
+  }
+  NutsArgs<T> a = make_nuts_args<T>(L);
+  const size_t smem = 2 * (size_t)(kHmcBlock / L.lpc) * d_pad * sizeof(T);
+  auto kern = nuts_run_kernel<T, EPL, TAG>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<blocks, kHmcBlock, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+// EPL menu of the NUTS kernels: {2 (2-D targets), 4, 8, 25 (f32 only), 13 (f64 only)}
+template <class T, class TAG>
+inline cudaError_t nuts_dispatch(const NutsLaunch& L, cudaStream_t st) {
+  switch (L.epl) {
+    case 4: return nuts_launch_one<T, 4, TAG>(L, st);
+    case 8: return nuts_launch_one<T, 8, TAG>(L, st);
+    case 13:
+      if constexpr (sizeof(T) == 8) return nuts_launch_one<T, 13, TAG>(L, st);
+      else return cudaErrorInvalidValue;
+    case 25:
+      if constexpr (sizeof(T) == 4) return nuts_launch_one<T, 25, TAG>(L, st);
+      else return cudaErrorInvalidValue;
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace GM_NS
+}  // namespace gm

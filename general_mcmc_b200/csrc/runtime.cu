@@ -158,8 +158,14 @@ struct gmcmc_sampler {
   // MH
   double prop_std = 1.0;
   // NUTS
-  uint32_t max_depth = 0;
-  void* d_nuts = nullptr;      // NutsState (nuts.cu)
+  uint32_t max_depth = 0;      // effective tree-depth cap
+  void* d_nuts_da[4] = {nullptr, nullptr, nullptr, nullptr};   // eps, eps_bar, h_bar, mu  (T [C])
+  void* d_ws_edges = nullptr; void* d_ws_first = nullptr; void* d_ws_prime = nullptr;
+  long long* d_chain_leapfrogs = nullptr;
+  double* d_nuts_inj[3] = {nullptr, nullptr, nullptr};           // normals, exp1, unif
+  size_t nuts_inj_n[3] = {0, 0, 0};
+  unsigned long long* d_nuts_used = nullptr;                     // [C][3]
+  uint32_t nuts_m = 0, nuts_n_discard = 0;
   // counters
   unsigned long long* d_counts = nullptr;  // [4]: accepts, divergences, grad_evals(NUTS), spare
   uint64_t transitions = 0;
@@ -366,18 +372,63 @@ gmcmc_status mh_segment(gmcmc_sampler* s, size_t first, size_t count, size_t n_d
 
 }  // namespace
 
-// NUTS lives in nuts.cu
-namespace gm {
-gmcmc_status nuts_create_state(gmcmc_sampler* s, double init_step_size);
-void nuts_destroy_state(gmcmc_sampler* s);
-}
 
 // ------------------------------------------------------------------------------------------------
 // run orchestration (device output)
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-gmcmc_status run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void* d_out) {
+gmcmc_status nuts_launch(gmcmc_sampler* s, NutsLaunch& L) {
+  L.tgt = s->tgt->desc;
+  L.n_chains = s->n_chains; L.chain_offset = s->chain_offset; L.seed = s->seed;
+  L.positions = s->d_pos;
+  L.eps = s->d_nuts_da[0]; L.eps_bar = s->d_nuts_da[1]; L.h_bar = s->d_nuts_da[2]; L.mu = s->d_nuts_da[3];
+  L.target_accept = s->target_accept;
+  L.max_depth = (int)s->max_depth;
+  L.ws_edges = s->d_ws_edges; L.ws_first = s->d_ws_first; L.ws_prime = s->d_ws_prime; L.cap = kNutsDepthCapHost;
+  L.leapfrog_total = s->d_counts + 2; L.diverge_total = s->d_counts + 1; L.depth_total = s->d_counts + 3;
+  L.chain_leapfrogs = s->d_chain_leapfrogs;
+  L.inj_normals = s->d_nuts_inj[0]; L.n_norm = s->nuts_inj_n[0];
+  L.inj_exp1 = s->d_nuts_inj[1]; L.n_exp = s->nuts_inj_n[1];
+  L.inj_unif = s->d_nuts_inj[2]; L.n_unif = s->nuts_inj_n[2];
+  L.inj_used = s->d_nuts_used;
+  L.epl = s->epl; L.lpc = s->lpc;
+  cudaError_t e = (s->math == GMCMC_MATH_EXACT) ? launch_nuts_exact(L, s->ctx->stream) : launch_nuts_fast(L, s->ctx->stream);
+  if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "NUTS kernel launch failed: %s", cudaGetErrorString(e));
+  s->launches += 1;
+  return GMCMC_OK;
+}
+
+// NUTS run: init_chain_state, then the transitions.  progress = false mirrors run() (generic_nuts.rs:667-682:
+// total - 1 transitions, sample 0 = the initial position when n_discard == 0); progress = true mirrors
+// run_progress() (:684-727: `total` transitions, every transition after the burn-in is recorded).
+gmcmc_status nuts_run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void* d_out, bool progress) {
+  const size_t total = n_collect + n_discard;
+  NutsLaunch I{};
+  I.init_only = 1;
+  I.step_base = s->step_index;
+  GM_TRY(nuts_launch(s, I));
+  s->step_index += 1;
+  s->nuts_m = 0;
+  s->nuts_n_discard = (uint32_t)n_discard;
+  const size_t n_steps = progress ? total : (total > 0 ? total - 1 : 0);
+  NutsLaunch L{};
+  L.init_only = 0;
+  L.step_base = s->step_index;
+  L.n_steps = (uint32_t)n_steps;
+  L.m_base = 0;
+  L.n_discard = (uint32_t)n_discard;
+  L.rec_off = (long long)n_discard + (progress ? 1 : 0);
+  L.write_init = (!progress && n_discard == 0 && n_collect > 0 && d_out) ? 1 : 0;
+  L.out = d_out; L.out_n = n_collect;
+  if (n_steps > 0 || L.write_init) GM_TRY(nuts_launch(s, L));
+  s->step_index += (uint32_t)n_steps;
+  s->nuts_m = (uint32_t)n_steps;
+  s->transitions += (uint64_t)n_steps * s->n_chains;
+  return GMCMC_OK;
+}
+
+gmcmc_status run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void* d_out, bool progress = false) {
   gmcmc_ctx* ctx = s->ctx;
   GM_CU(cudaSetDevice(ctx->device));
   const size_t total = n_collect + n_discard;
@@ -424,7 +475,10 @@ gmcmc_status run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void
     }
     s->hmc_grad_evals += (uint64_t)total * s->n_chains * s->n_leapfrog;
   } else {
-    return fail(GMCMC_ERR_UNSUPPORTED, "NUTS sampling is not available in this build");
+    GM_TRY(nuts_run_into(s, n_collect, n_discard, d_out, progress));
+    GM_CU(cudaEventRecord(s->ev1, ctx->stream));
+    s->timed = true;
+    return GMCMC_OK;
   }
   GM_CU(cudaEventRecord(s->ev1, ctx->stream));
   s->timed = true;
@@ -825,9 +879,50 @@ gmcmc_status gmcmc_mh_create(gmcmc_ctx* ctx, gmcmc_target* tgt, double proposal_
 gmcmc_status gmcmc_nuts_create(gmcmc_ctx* ctx, gmcmc_target* tgt, size_t n_chains, uint64_t chain_offset,
                                const void* init_host, double target_accept, uint32_t max_depth,
                                double init_step_size, uint64_t seed, gmcmc_sampler** out) {
-  (void)ctx; (void)tgt; (void)n_chains; (void)chain_offset; (void)init_host; (void)target_accept; (void)max_depth;
-  (void)init_step_size; (void)seed; (void)out;
-  return fail(GMCMC_ERR_UNSUPPORTED, "NUTS is not available in this build");
+  GM_REQUIRE(tgt, "null target");
+  GM_REQUIRE(target_accept > 0.0 && target_accept < 1.0, "target_accept must be in (0, 1)");
+  int epl = 0, lpc = 0;
+  if (!choose_nuts_decomposition(tgt->desc.dim, tgt->desc.dtype, tgt->desc.kind, &epl, &lpc))
+    return fail(GMCMC_ERR_UNSUPPORTED, "target kind %d with dim %d is not supported by the NUTS kernels", tgt->desc.kind, tgt->desc.dim);
+  gmcmc_sampler* s = nullptr;
+  GM_TRY(sampler_common(ctx, tgt, n_chains, chain_offset, init_host, seed, S_NUTS, &s));
+  s->epl = epl; s->lpc = lpc;
+  s->target_accept = target_accept;
+  s->max_depth = (max_depth == 0 || max_depth > (uint32_t)kNutsDepthCapHost) ? (uint32_t)kNutsDepthCapHost : max_depth;
+  const size_t es = esize(s->dtype), C = n_chains, d = (size_t)s->dim, cap = (size_t)kNutsDepthCapHost;
+  bool ok = true;
+  for (int i = 0; i < 4; ++i) ok = ok && cudaMalloc(&s->d_nuts_da[i], C * es) == cudaSuccess;
+  ok = ok && cudaMalloc(&s->d_ws_edges, C * 6 * d * es) == cudaSuccess &&
+       cudaMalloc(&s->d_ws_first, C * cap * 2 * d * es) == cudaSuccess &&
+       cudaMalloc(&s->d_ws_prime, C * cap * d * es) == cudaSuccess &&
+       cudaMalloc((void**)&s->d_chain_leapfrogs, C * sizeof(long long)) == cudaSuccess &&
+       cudaMemset(s->d_chain_leapfrogs, 0, C * sizeof(long long)) == cudaSuccess;
+  if (!ok) {
+    gmcmc_status st = fail(GMCMC_ERR_CUDA, "NUTS workspace allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    gmcmc_sampler_destroy(s);
+    return st;
+  }
+  // GenericNUTSChain::new_shared (generic_nuts.rs:630-647): epsilon = -1 (find it), eps_bar = 1, h_bar = 0, mu = ln 10
+  const double eps0 = init_step_size > 0.0 ? init_step_size : -1.0;
+  const unsigned blocks = (unsigned)std::min<size_t>((C + 255) / 256, 4096);
+  if (s->dtype == GMCMC_F32) {
+    fill_kernel<float><<<blocks, 256, 0, ctx->stream>>>((float*)s->d_nuts_da[0], C, (float)eps0);
+    fill_kernel<float><<<blocks, 256, 0, ctx->stream>>>((float*)s->d_nuts_da[1], C, 1.0f);
+    fill_kernel<float><<<blocks, 256, 0, ctx->stream>>>((float*)s->d_nuts_da[2], C, 0.0f);
+    fill_kernel<float><<<blocks, 256, 0, ctx->stream>>>((float*)s->d_nuts_da[3], C, std::log(10.0f));
+  } else {
+    fill_kernel<double><<<blocks, 256, 0, ctx->stream>>>((double*)s->d_nuts_da[0], C, eps0);
+    fill_kernel<double><<<blocks, 256, 0, ctx->stream>>>((double*)s->d_nuts_da[1], C, 1.0);
+    fill_kernel<double><<<blocks, 256, 0, ctx->stream>>>((double*)s->d_nuts_da[2], C, 0.0);
+    fill_kernel<double><<<blocks, 256, 0, ctx->stream>>>((double*)s->d_nuts_da[3], C, std::log(10.0));
+  }
+  if (cudaGetLastError() != cudaSuccess) {
+    gmcmc_status st = fail(GMCMC_ERR_CUDA, "NUTS state initialisation failed");
+    gmcmc_sampler_destroy(s);
+    return st;
+  }
+  *out = s;
+  return GMCMC_OK;
 }
 
 gmcmc_status gmcmc_sampler_destroy(gmcmc_sampler* s) {
@@ -837,6 +932,10 @@ gmcmc_status gmcmc_sampler_destroy(gmcmc_sampler* s) {
   cudaFree(s->d_pos); cudaFree(s->d_eps); cudaFree(s->d_counts); cudaFree(s->d_samples);
   for (void* p : s->d_da) cudaFree(p);
   cudaFree(s->d_pooled); cudaFree(s->d_alpha_part); cudaFree(s->d_alpha_sum);
+  for (void* p : s->d_nuts_da) cudaFree(p);
+  cudaFree(s->d_ws_edges); cudaFree(s->d_ws_first); cudaFree(s->d_ws_prime); cudaFree(s->d_chain_leapfrogs);
+  for (double* p : s->d_nuts_inj) cudaFree(p);
+  cudaFree(s->d_nuts_used);
   cudaFree(s->d_inj_normals); cudaFree(s->d_inj_lnu);
   cudaFree(s->d_diag_logacc); cudaFree(s->d_diag_acc); cudaFree(s->d_diag_pq); cudaFree(s->d_diag_pp);
   if (s->ev0) cudaEventDestroy(s->ev0);
@@ -930,8 +1029,37 @@ gmcmc_status gmcmc_inject(gmcmc_sampler* s, const void* normals, const void* ln_
 
 gmcmc_status gmcmc_nuts_inject(gmcmc_sampler* s, const double* normals, size_t n_norm, const double* exp1,
                                size_t n_exp, const double* unif, size_t n_unif) {
-  (void)s; (void)normals; (void)n_norm; (void)exp1; (void)n_exp; (void)unif; (void)n_unif;
-  return fail(GMCMC_ERR_UNSUPPORTED, "NUTS is not available in this build");
+  GM_REQUIRE(s && s->type == S_NUTS, "gmcmc_nuts_inject applies to NUTS samplers");
+  GM_REQUIRE(normals && exp1 && unif && n_norm && n_exp && n_unif, "null / empty stream");
+  GM_CU(cudaSetDevice(s->ctx->device));
+  GM_CU(cudaStreamSynchronize(s->ctx->stream));
+  const size_t C = s->n_chains;
+  const double* src[3] = {normals, exp1, unif};
+  const size_t n[3] = {n_norm, n_exp, n_unif};
+  for (int i = 0; i < 3; ++i) {
+    cudaFree(s->d_nuts_inj[i]);
+    s->d_nuts_inj[i] = nullptr;
+    GM_CU(cudaMalloc((void**)&s->d_nuts_inj[i], C * n[i] * sizeof(double)));
+    GM_CU(cudaMemcpy(s->d_nuts_inj[i], src[i], C * n[i] * sizeof(double), cudaMemcpyHostToDevice));
+    s->nuts_inj_n[i] = n[i];
+  }
+  if (!s->d_nuts_used) GM_CU(cudaMalloc((void**)&s->d_nuts_used, C * 3 * sizeof(unsigned long long)));
+  GM_CU(cudaMemset(s->d_nuts_used, 0, C * 3 * sizeof(unsigned long long)));
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_nuts_state(gmcmc_sampler* s, void* eps_out, long long* leapfrogs_out, unsigned long long* used_out) {
+  GM_REQUIRE(s && s->type == S_NUTS, "gmcmc_nuts_state applies to NUTS samplers");
+  GM_CU(cudaSetDevice(s->ctx->device));
+  GM_CU(cudaStreamSynchronize(s->ctx->stream));
+  const size_t C = s->n_chains;
+  if (eps_out) GM_CU(cudaMemcpy(eps_out, s->d_nuts_da[0], C * esize(s->dtype), cudaMemcpyDeviceToHost));
+  if (leapfrogs_out) GM_CU(cudaMemcpy(leapfrogs_out, s->d_chain_leapfrogs, C * sizeof(long long), cudaMemcpyDeviceToHost));
+  if (used_out) {
+    GM_REQUIRE(s->d_nuts_used, "no injected streams");
+    GM_CU(cudaMemcpy(used_out, s->d_nuts_used, C * 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  }
+  return GMCMC_OK;
 }
 
 gmcmc_status gmcmc_read_diagnostics(gmcmc_sampler* s, void* log_accept, uint8_t* accepted, void* prop_q, void* prop_p) {
@@ -955,6 +1083,16 @@ gmcmc_status gmcmc_read_diagnostics(gmcmc_sampler* s, void* log_accept, uint8_t*
 
 gmcmc_status gmcmc_step(gmcmc_sampler* s) {
   GM_REQUIRE(s, "null sampler");
+  if (s->type == S_NUTS) {
+    // ≙ GenericNUTSChain::step (generic_nuts.rs:755): continues the counters of the last run
+    GM_CU(cudaSetDevice(s->ctx->device));
+    NutsLaunch L{};
+    L.step_base = s->step_index; L.n_steps = 1; L.m_base = s->nuts_m; L.n_discard = s->nuts_n_discard;
+    L.rec_off = 0; L.out = nullptr; L.out_n = 0;
+    GM_TRY(nuts_launch(s, L));
+    s->step_index += 1; s->nuts_m += 1; s->transitions += s->n_chains;
+    return GMCMC_OK;
+  }
   return run_into(s, 0, 1, nullptr);
 }
 
@@ -993,7 +1131,10 @@ gmcmc_status gmcmc_run_stats(gmcmc_sampler* s, size_t n_collect, size_t n_discar
                              gmcmc_dtype out_dtype, gmcmc_run_stats_t* stats) {
   GM_REQUIRE(s && stats, "null argument");
   void* d = nullptr;
-  GM_TRY(gmcmc_run_device(s, n_collect, n_discard, &d));
+  GM_CU(cudaSetDevice(s->ctx->device));
+  GM_TRY(ensure_samples(s, s->n_chains * n_collect * (size_t)s->dim * esize(out_dtype_of(s))));
+  GM_TRY(run_into(s, n_collect, n_discard, s->d_samples, true));
+  d = s->d_samples;
   const int src = out_dtype_of(s);
   GM_TRY(stats_on_device(s->ctx, d, s->n_chains, n_collect, (size_t)s->dim, src, stats));
   if (out_host_or_null) {
@@ -1057,6 +1198,20 @@ gmcmc_status gmcmc_counters_get(gmcmc_sampler* s, gmcmc_counters* out) {
       }
       out->step_size = sum / (double)C;
     }
+  }
+  if (s->type == S_NUTS) {
+    const size_t C = s->n_chains;
+    double sum = 0.0;
+    if (s->dtype == GMCMC_F32) {
+      std::vector<float> v(C);
+      GM_CU(cudaMemcpy(v.data(), s->d_nuts_da[0], C * 4, cudaMemcpyDeviceToHost));
+      for (float x : v) sum += x;
+    } else {
+      std::vector<double> v(C);
+      GM_CU(cudaMemcpy(v.data(), s->d_nuts_da[0], C * 8, cudaMemcpyDeviceToHost));
+      for (double x : v) sum += x;
+    }
+    out->step_size = sum / (double)C;
   }
   float ms = 0.f;
   if (s->timed) GM_CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));

@@ -167,6 +167,10 @@ gmcmc_status gmcmc_inject(gmcmc_sampler*, const void* normals, const void* ln_u,
  * exp1 [C, n_exp], unif [C, n_unif], all f64. */
 gmcmc_status gmcmc_nuts_inject(gmcmc_sampler*, const double* normals, size_t n_norm, const double* exp1,
                                size_t n_exp, const double* unif, size_t n_unif);
+/* NUTS per-chain state (tests / diagnostics): current step sizes [C] (sampler dtype), accumulated
+ * leapfrogs [C], consumed injected draws [C][3] (normals, exp1, unif).  Any pointer may be NULL. */
+gmcmc_status gmcmc_nuts_state(gmcmc_sampler*, void* eps_out, long long* leapfrogs_out,
+                              unsigned long long* used_out);
 /* Per-step diagnostics of the injected transitions (HMC/MH): log_accept [n_steps, C] (sampler dtype),
  * accepted [n_steps, C] (u8), prop_q / prop_p [n_steps, C, dim] (HMC only; end of trajectory).
  * Any pointer may be NULL.  Valid after the run that consumed the injection. */

@@ -1,0 +1,142 @@
+"""GPU parity tests of the NUTS kernel (K5) against the CPU oracle's recursive restatement of
+generic_nuts.rs, on identical injected per-chain streams (normals, Exp(1), uniforms)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import general_mcmc_b200 as gm  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return gm.default_context()
+
+
+def _streams(Cn, d, steps, seed, n_unif=4000):
+    rng = np.random.default_rng(seed)
+    normals = rng.standard_normal((Cn, d * (steps + 2)))
+    exp1 = rng.exponential(size=(Cn, steps + 2))
+    unif = rng.random((Cn, n_unif))
+    return normals, exp1, unif
+
+
+def _dense(d, seed=0):
+    rng = np.random.default_rng(seed)
+    q, _ = np.linalg.qr(rng.standard_normal((d, d)))
+    lam = np.logspace(-0.5, 1.5, d)
+    return gm.DenseGaussian(np.zeros(d), cov=(q * lam) @ q.T)
+
+
+CASES = [
+    ("iso5_std10", lambda: gm.IsotropicGaussian(10.0, 5), 5, 0.7, 0),
+    ("iso5_depth3", lambda: gm.IsotropicGaussian(10.0, 5), 5, 0.7, 3),
+    ("iso37", lambda: gm.IsotropicGaussian(6.0, 37), 37, 0.9, 0),
+    ("dgauss2d", lambda: gm.DiffableGaussian2D([0.0, 1.0], [[40.0, 20.0], [20.0, 30.0]]), 2, 0.5, 0),
+    ("dense24", lambda: _dense(24), 24, 0.6, 0),
+    ("iso100", lambda: gm.IsotropicGaussian(8.0, 100), 100, 0.8, 6),
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("name,mk,d,eps0,max_depth", CASES, ids=[c[0] for c in CASES])
+def test_nuts_exact_mode_bit_exact_no_adaptation(ctx, oracle, name, mk, d, eps0, max_depth, dtype):
+    """n_discard = 0: the step size is eps0 for the first transition and eps_bar = 1 afterwards (the
+    reference's behaviour, generic_nuts.rs:921-923), so no transcendental enters the trajectory: samples,
+    leapfrog counts and consumed draws must be bit-identical to the recursive oracle."""
+    Cn, n_collect = 48, 7
+    tgt = mk()
+    rng = np.random.default_rng(3)
+    q0 = (rng.standard_normal((Cn, d)) * 3.0).astype(dtype)
+    normals, exp1, unif = _streams(Cn, d, n_collect, seed=5)
+    ref = oracle.nuts_run(tgt.kind, tgt.params(), q0, 0.8, max_depth, eps0, n_collect, 0, normals, exp1, unif)
+    assert not ref["exhausted"].any()
+    s = gm.NUTS(tgt, q0, 0.8, seed=1, ctx=ctx, max_depth=max_depth, init_step_size=eps0).set_math_mode(True)
+    s.inject_streams(normals, exp1, unif)
+    out = s.run(n_collect, 0)
+    st = s.state()
+    assert np.array_equal(st["leapfrogs"], ref["leapfrogs"]), name
+    assert np.array_equal(st["used"].astype(np.int64), ref["used"]), name
+    assert np.array_equal(out, ref["samples"]), name
+    assert np.array_equal(out[:, 0, :], q0)            # run(): sample 0 is the initial position (nuts.rs:588-601)
+    assert ref["leapfrogs"].mean() > 10                # the trees are non-trivial
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_nuts_find_reasonable_epsilon_bit_exact(ctx, oracle, dtype):
+    """run(1, 0) takes no transition: the returned sample is the initial point (nuts.rs:588-601) and the
+    per-chain step size is find_reasonable_epsilon's (generic_nuts.rs:1025-1102; reference KAT: exactly 2.0
+    for N(0, I) at q = [0, 1], p = [1, 0], nuts.rs:508-519)."""
+    tgt = gm.IsotropicGaussian(1.0, 2)
+    q0 = np.array([[0.0, 1.0]], dtype)
+    normals = np.array([[1.0, 0.0, 0.0, 0.0]])
+    s = gm.NUTS(tgt, q0, 0.8, seed=1, ctx=ctx).set_math_mode(True)
+    s.inject_streams(normals, np.ones((1, 2)), np.full((1, 8), 0.3))
+    out = s.run(1, 0)
+    assert np.array_equal(out[:, 0, :], q0)
+    assert s.state()["eps"][0] == dtype(2.0)
+    # many chains, several targets
+    for tgt, d in [(gm.IsotropicGaussian(3.0, 17), 17), (gm.RosenbrockND(10), 10), (_dense(24), 24)]:
+        Cn = 96
+        rng = np.random.default_rng(9)
+        q0 = (1.0 + 0.5 * rng.standard_normal((Cn, d))).astype(dtype)
+        normals, exp1, unif = _streams(Cn, d, 1, seed=11, n_unif=8)
+        ref = oracle.nuts_run(tgt.kind, tgt.params(), q0, 0.8, 0, -1.0, 1, 0, normals, exp1, unif)
+        s = gm.NUTS(tgt, q0, 0.8, seed=1, ctx=ctx).set_math_mode(True)
+        s.inject_streams(normals, exp1, unif)
+        s.run(1, 0)
+        assert np.array_equal(s.state()["eps"], ref["eps"])
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_nuts_with_adaptation_matches_oracle(ctx, oracle, exact):
+    """With warm-up the step size goes through exp / log / pow / sqrt (device libm vs glibc): the first
+    transition is still bit-comparable, later ones agree for the chains whose tree decisions do not sit on a
+    rounding boundary."""
+    Cn, d, n_collect, n_discard = 64, 6, 4, 6
+    tgt = gm.IsotropicGaussian(2.0, d)
+    rng = np.random.default_rng(13)
+    q0 = rng.standard_normal((Cn, d))
+    normals, exp1, unif = _streams(Cn, d, n_collect + n_discard, seed=17)
+    ref = oracle.nuts_run(tgt.kind, tgt.params(), q0, 0.8, 8, -1.0, n_collect, n_discard, normals, exp1, unif)
+    s = gm.NUTS(tgt, q0, 0.8, seed=1, ctx=ctx, max_depth=8).set_math_mode(exact)
+    s.inject_streams(normals, exp1, unif)
+    out = s.run(n_collect, n_discard)
+    st = s.state()
+    same = (st["leapfrogs"] == ref["leapfrogs"])
+    assert same.mean() > 0.9
+    assert np.allclose(out[same], ref["samples"][same], rtol=1e-6, atol=1e-6)
+    assert np.allclose(st["eps"][same], ref["eps"][same], rtol=1e-6)
+
+
+def test_nuts_distribution_gaussian2d_and_rosenbrock_smoke(ctx):
+    """Philox path: NUTS on the 2-D Gaussian of the reference's tests recovers mean / covariance; the
+    Rosenbrock run stays finite and adapts to a sane step size."""
+    Cn = 2048
+    tgt = gm.DiffableGaussian2D([0.0, 1.0], [[4.0, 2.0], [2.0, 3.0]])
+    s = gm.NUTS(tgt, np.zeros((Cn, 2), np.float32), 0.8, seed=42, ctx=ctx, max_depth=10)
+    out, st = s.run_progress(400, 200)
+    flat = out.reshape(-1, 2).astype(np.float64)
+    assert np.isfinite(flat).all()
+    assert np.allclose(flat.mean(0), [0.0, 1.0], atol=0.03)
+    assert np.allclose(np.cov(flat.T), [[4.0, 2.0], [2.0, 3.0]], atol=0.12)
+    assert st.rhat_std.max < 1.02
+    c = s.counters()
+    assert 0.05 < c.step_size < 3.0 and c.grad_evals > Cn * 600
+
+    d = 10
+    q0 = (1.0 + 0.1 * np.random.default_rng(1).standard_normal((512, d))).astype(np.float32)
+    r = gm.NUTS(gm.RosenbrockND(d), q0, 0.8, seed=7, ctx=ctx, max_depth=8)
+    out = r.run(50, 100)
+    assert np.isfinite(out).all()
+    assert 1e-4 < r.counters().step_size < 1.0
+
+
+def test_nuts_sharding_invariance(ctx):
+    Cn, d = 200, 12
+    tgt = gm.IsotropicGaussian(1.5, d)
+    q0 = np.random.default_rng(2).standard_normal((Cn, d)).astype(np.float32)
+    full = gm.NUTS(tgt, q0, 0.8, seed=42, ctx=ctx, max_depth=6).run(6, 4)
+    lo = gm.NUTS(tgt, q0[:72], 0.8, seed=42, ctx=ctx, max_depth=6, chain_offset=0).run(6, 4)
+    hi = gm.NUTS(tgt, q0[72:], 0.8, seed=42, ctx=ctx, max_depth=6, chain_offset=72).run(6, 4)
+    assert np.array_equal(full, np.concatenate([lo, hi]))
