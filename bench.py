@@ -11,7 +11,7 @@ evaluations per chain) including the [chains, samples, dim] sample write-out; `v
 steps x L / device time, inputs resident in HBM.  `e2e` is the same metric through the host-buffer
 C-ABI call gmcmc_run (H2D of the initial positions + D2H of the samples inside the timed region).
 
-Other workloads (extra lines for the record, same JSON shape): mh_gauss2d (config 2).
+Other workloads (extra lines for the record, same JSON shape): mh_gauss2d (config 2), nuts_mixture (config 5).
 
 One process per GPU; under torchrun the ranks shard the chains (weak scaling: fixed chains per GPU),
 no data-path collective; timing = max over ranks of the CUDA-event time between two barriers.
@@ -194,16 +194,9 @@ def run_ours(args, rank, world, local):
     import general_mcmc_b200 as gm
     from general_mcmc_b200 import _lib as L
 
+    from general_mcmc_b200 import dist as gdist
     torch.cuda.set_device(local)
-    nccl_id = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt = torch.tensor(list(gm.Context.nccl_unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(idt, 0)
-        nccl_id = bytes(idt.cpu().tolist())
-    ctx = gm.Context(local, rank, world, nccl_id)
+    ctx = gdist.make_context(local)      # world > 1: torch.distributed (NCCL) rendezvous + libgmcmc's own communicator
     lib = L.lib()
     pk = peaks()
 
@@ -223,7 +216,24 @@ def run_ours(args, rank, world, local):
     stream = torch.cuda.ExternalStream(ctx.stream())
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
-    if args.workload == "mh_gauss2d":
+    counter_units = False
+    if args.workload == "nuts_mixture":
+        chains = args.chains or 65536
+        per_launch = 20
+        K = 4
+        mu = np.stack([(k - 1.5) * (2.0 / np.sqrt(DIM)) * np.ones(DIM) for k in range(K)])
+        tgt = gm.GaussianMixture(np.full(K, 1.0 / K), mu, 1.0)
+        q0 = np.random.default_rng(300 + rank).standard_normal((chains, DIM)).astype(np.float32)
+        s = gm.NUTS(tgt, q0, 0.8, seed=42, ctx=ctx, chain_offset=rank * chains, max_depth=10)
+        s.run_device(1, 100)              # warm-up: per-chain dual averaging (generic_nuts.rs:882-924)
+        unit_per_step = None              # leapfrogs actually taken: read from the device counters
+        counter_units = True
+        metric, unit, dtype = "leapfrog_grad_evals_per_sec", "grad-evals/s", "f32"
+        bytes_per_step = chains * DIM * 4
+        workload = ("cfg5: NUTS, 4-component isotropic Gaussian mixture d=%d, %d chains/GPU, max depth 10, "
+                    "target accept 0.8, f32" % (DIM, chains))
+        e2e_T = 4
+    elif args.workload == "mh_gauss2d":
         chains = args.chains or 1048576
         per_launch = 1000
         x0 = np.random.default_rng(100 + rank).standard_normal((chains, 2))
@@ -253,11 +263,15 @@ def run_ours(args, rank, world, local):
         full, rem = divmod(k, per_launch)
         return [per_launch] * full + ([rem] if rem else [])
 
+    nuts = args.workload == "nuts_mixture"
+    run_dev = (lambda n: s.run_device(n + 1, 0)) if nuts else (lambda n: s.run_device(n, 0))
+
     # ---- warm-up
     for n in launches_for(max(args.warmup, 3)):
-        s.run_device(n, 0)
+        run_dev(n)
     barrier()
-    step_size = s.counters().step_size if args.workload != "mh_gauss2d" else None
+    c_before = s.counters()
+    step_size = c_before.step_size if args.workload != "mh_gauss2d" else None
 
     # ---- timed region: exactly K steps
     flush.fill_(1)
@@ -272,13 +286,19 @@ def run_ours(args, rank, world, local):
     with torch.cuda.stream(stream):
         e0.record(stream)
         for n in plan:
-            s.run_device(n, 0)
+            run_dev(n)
         e1.record(stream)
     barrier()
     t_wall1 = time.time()
     ms = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
-    value = unit_per_step * args.steps * world / (ms * 1e-3)
+    if counter_units:
+        units_local = s.counters().grad_evals - c_before.grad_evals
+        units_total = float(ctx.all_reduce([units_local])[0]) if world > 1 else float(units_local)
+        unit_per_step = units_local / args.steps
+    else:
+        units_total = unit_per_step * args.steps * world
+    value = units_total / (ms * 1e-3)
     kernel_ms_per_launch = ms / len(plan)
 
     # ---- e2e: host buffers through gmcmc_set_positions + gmcmc_run (pinned host memory)
@@ -292,6 +312,7 @@ def run_ours(args, rank, world, local):
         s.set_positions(init_host)
         s.run(e2e_T, 0, out=host_out)
     barrier()
+    c_e2e = s.counters()
     t0 = time.perf_counter()
     for _ in range(e2e_calls):
         L.check(lib.gmcmc_set_positions(s._h, L.ptr(init_host)))
@@ -299,12 +320,26 @@ def run_ours(args, rank, world, local):
     ctx.synchronize()
     t1 = time.perf_counter()
     e2e_s = max_over_ranks(t1 - t0)
-    e2e_value = unit_per_step * e2e_T * e2e_calls * world / e2e_s
+    if counter_units:
+        u_loc = s.counters().grad_evals - c_e2e.grad_evals
+        e2e_value = (float(ctx.all_reduce([u_loc])[0]) if world > 1 else float(u_loc)) / e2e_s
+    else:
+        e2e_value = unit_per_step * e2e_T * e2e_calls * world / e2e_s
     h2d = init_host.nbytes / e2e_T
     d2h = host_out.nbytes / e2e_T
 
     # ---- roofline of the dominant kernel (per launch)
-    if args.workload == "mh_gauss2d":
+    if nuts:
+        fp32_peak = C.c_double(0)
+        L.check(lib.gmcmc_measure_fp32_peak(ctx._h, C.byref(fp32_peak)))
+        flop = (5 * 4 + 6) * DIM      # (5K + 6) d flop per leapfrog
+        tfl = value / world * flop / 1e12
+        roof = {"bound": "fp32", "kernel": "nuts_run_kernel<float,25,Mixture>", "achieved": tfl, "peak": fp32_peak.value,
+                "unit": "TFLOP/s", "frac": tfl / fp32_peak.value if fp32_peak.value else None, "traffic": None,
+                "peak_source": "FFMA micro-benchmark in this run", "algorithmic_flop_per_unit": flop,
+                "mean_leapfrogs_per_transition": unit_per_step / chains,
+                "note": "divergence-limited: chains of a warp build trees of different sizes (warp-level masking)"}
+    elif args.workload == "mh_gauss2d":
         ach = bytes_per_step * per_launch / (kernel_ms_per_launch * 1e-3) / 1e9 if len(plan) and plan[0] == per_launch else \
             bytes_per_step * args.steps / (ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "mh_run_kernel<double,2>", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -359,7 +394,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--warmup", type=int, default=400)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="hmc_rosenbrock", choices=["hmc_rosenbrock", "mh_gauss2d"])
+    ap.add_argument("--workload", default="hmc_rosenbrock", choices=["hmc_rosenbrock", "mh_gauss2d", "nuts_mixture"])
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
