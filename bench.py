@@ -11,7 +11,8 @@ evaluations per chain) including the [chains, samples, dim] sample write-out; `v
 steps x L / device time, inputs resident in HBM.  `e2e` is the same metric through the host-buffer
 C-ABI call gmcmc_run (H2D of the initial positions + D2H of the samples inside the timed region).
 
-Other workloads (extra lines for the record, same JSON shape): mh_gauss2d (config 2), nuts_mixture (config 5).
+Other workloads (extra lines for the record, same JSON shape): mh_gauss2d (config 2), hmc_dense (config 3),
+nuts_mixture (config 5).
 
 One process per GPU; under torchrun the ranks shard the chains (weak scaling: fixed chains per GPU),
 no data-path collective; timing = max over ranks of the CUDA-event time between two barriers.
@@ -217,7 +218,25 @@ def run_ours(args, rank, world, local):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
     counter_units = False
-    if args.workload == "nuts_mixture":
+    dense = args.workload == "hmc_dense"
+    if dense:
+        chains = args.chains or 65536
+        dd = args.dim or 1000
+        per_launch = 2
+        rng = np.random.default_rng(0)
+        qmat, _ = np.linalg.qr(rng.standard_normal((dd, dd)))
+        lam = np.logspace(-1, 1, dd)
+        prec = (qmat / lam) @ qmat.T          # P = Q diag(1/lambda) Q^T  
+        tgt = gm.DenseGaussian(np.zeros(dd), precision=prec)
+        q0 = np.random.default_rng(200 + rank).standard_normal((chains, dd)).astype(np.float32)
+        s = gm.HMC(tgt, q0, 0.05, N_LEAPFROG, seed=42, ctx=ctx, chain_offset=rank * chains)
+        unit_per_step = chains * N_LEAPFROG
+        metric, unit, dtype = "leapfrog_grad_evals_per_sec", "grad-evals/s", "f32 (3xTF32 tensor-core gradient)"
+        bytes_per_step = chains * dd * 4
+        workload = ("cfg3: batched HMC, dense-covariance Gaussian d=%d, %d chains/GPU, L=%d, eps=0.05, f32, "
+                    "tcgen05 gradient GEMM" % (dd, chains, N_LEAPFROG))
+        e2e_T = 2
+    elif args.workload == "nuts_mixture":
         chains = args.chains or 65536
         per_launch = 20
         K = 4
@@ -303,7 +322,7 @@ def run_ours(args, rank, world, local):
 
     # ---- e2e: host buffers through gmcmc_set_positions + gmcmc_run (pinned host memory)
     out_dtype = np.float64 if args.workload == "mh_gauss2d" else np.float32
-    dim = 2 if args.workload == "mh_gauss2d" else DIM
+    dim = 2 if args.workload == "mh_gauss2d" else (dd if dense else DIM)
     host_out, host_ptr = pinned_array(lib, (chains, e2e_T, dim), out_dtype)
     init_host, init_ptr = pinned_array(lib, (chains, dim), s.dtype)
     init_host[...] = s.positions()
@@ -329,7 +348,17 @@ def run_ours(args, rank, world, local):
     d2h = host_out.nbytes / e2e_T
 
     # ---- roofline of the dominant kernel (per launch)
-    if nuts:
+    if dense:
+        flop = 2.0 * dd * dd
+        tfl = value / world * flop / 1e12
+        peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"]) / 2.0
+        roof = {"bound": "tensor", "kernel": "dense_gemm_kick_kernel (tcgen05.mma kind::tf32, 128x256x8)", "achieved": tfl,
+                "peak": peak, "unit": "TFLOP/s", "frac": tfl / peak, "traffic": None,
+                "peak_source": "TF32 dense = half of the measured sustained bf16 peak (%s)" % pk["source"],
+                "algorithmic_flop_per_unit": flop, "executed_tensor_tflops": 3.0 * tfl * (1.0 + 1.0 / N_LEAPFROG),
+                "note": "3xTF32 error-compensated split (hi.hi + lo.hi + hi.lo): the tensor pipe executes 3x the "
+                        "algorithmic flops, and L+1 GEMMs per transition are credited as L"}
+    elif nuts:
         fp32_peak = C.c_double(0)
         L.check(lib.gmcmc_measure_fp32_peak(ctx._h, C.byref(fp32_peak)))
         flop = (5 * 4 + 6) * DIM      # (5K + 6) d flop per leapfrog
@@ -361,7 +390,7 @@ def run_ours(args, rank, world, local):
                                 "this kernel is FP32-pipe bound, not HBM bound (north_star: FP32-pipe utilisation)"}}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and not nuts and not dense:
         if args.workload == "mh_gauss2d":
             r, th, sample = cpu_mh_rate(10.0)
         else:
@@ -394,7 +423,8 @@ def main():
     ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--warmup", type=int, default=400)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="hmc_rosenbrock", choices=["hmc_rosenbrock", "mh_gauss2d", "nuts_mixture"])
+    ap.add_argument("--workload", default="hmc_rosenbrock", choices=["hmc_rosenbrock", "mh_gauss2d", "nuts_mixture", "hmc_dense"])
+    ap.add_argument("--dim", type=int, default=0, help="dimension (hmc_dense only; default 1000)")
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

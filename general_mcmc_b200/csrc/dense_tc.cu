@@ -1,0 +1,547 @@
+// dense_tc.cu — K3: HMC on an N-D dense-covariance Gaussian with the gradient GEMM on the 5th-generation
+// tensor cores (tcgen05 + TMEM + TMA, sm_100a).
+//
+// Reference path replaced: BatchedGenericHMC::step / leapfrog (/root/reference/src/batched_hmc.rs:129-190)
+// with the target of DiffableGaussian2D::unnorm_logp_batch generalised to d dimensions
+// (/root/reference/src/distributions.rs:265-291):  delta = x - mu ; z = delta . P ; logp = c - 1/2 sum(z * delta) ;
+// grad = -z.  z for all chains is a real [chains x d] . [d x d] GEMM per gradient evaluation.
+//
+// Precision: plain TF32 (10-bit mantissa) cannot meet the 1e-5 per-step bar, so both operands are split
+// x = hi + lo with hi = rna_tf32(x), and the accumulator receives  hi.hi + lo.hi + hi.lo  in FP32 (TMEM):
+// three tcgen05.mma.kind::tf32 per K-step, relative error ~2^-21 per product.
+//
+// Structure of one transition (fast math mode, merged half kicks; L + 1 GEMMs):
+//   dense_begin_kernel     p ~ N(0, I) (Philox or injected), ke0, q_prop = q, delta split -> A_hi / A_lo
+//   dense_gemm_kick_kernel z = delta . P ; p -= (eps/2) (-z)...  (epilogue: kick, and at the two trajectory
+//                          ends logp = c - 1/2 z.delta and ke = 1/2 |p|^2, one thread per chain row)
+//   L x { dense_drift_kernel (q_prop += eps p ; delta split) ; dense_gemm_kick_kernel }
+//   dense_accept_kernel    Hamiltonian, Metropolis accept, q <- q_prop, sample row -> [chain, slot, :]
+//
+// dense_gemm_kick_kernel: one CTA per 128 chains, warp-specialised — warp 0 lane 0 issues TMA loads
+// (A_hi, A_lo [128 x 32], P_hi, P_lo [256 x 32], SWIZZLE_128B, 2 stages of 96 KB), warp 1 lane 0 issues the
+// tcgen05.mma (128 x 256 x 8, accumulators double-buffered over the 512 TMEM columns), warps 2-5 drain the
+// accumulator with tcgen05.ld (thread == chain row) and apply the kick.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "kernels.h"
+#include "philox.cuh"
+
+namespace gm {
+
+namespace {
+
+constexpr int kTileM = 128;      // chains per CTA
+constexpr int kTileN = 256;      // accumulator columns per MMA
+constexpr int kTileK = 32;       // floats per K stage (128 bytes = one swizzle row)
+constexpr int kUmmaK = 8;        // tf32 elements per tcgen05.mma
+constexpr int kStages = 2;
+constexpr int kGemmThreads = 192;  // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue
+constexpr uint32_t kABytes = kTileM * kTileK * 4;   // 16 KB
+constexpr uint32_t kBBytes = kTileN * kTileK * 4;   // 32 KB
+constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // 96 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (++spins > (1u << 27)) __trap();   // a lost arrival must fault, never hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor: K-major operand tile, rows of 128 bytes, SWIZZLE_128B (8-row / 1024-byte atoms)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);        // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                            // leading byte offset (unused: K extent = one swizzle row)
+  d |= (uint64_t)((1024 >> 4) & 0x3fff) << 32;       // stride byte offset between 8-row groups, bits [32,46)
+  d |= (uint64_t)1 << 46;                            // descriptor version (sm_100), bits [46,48)
+  d |= (uint64_t)2 << 61;                            // layout type SWIZZLE_128B, bits [61,64)
+  return d;
+}
+
+// instruction descriptor: D f32, A/B tf32, both K-major, M = 128, N = 256
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+struct GemmArgs {
+  int d, kpad, npad;
+  size_t n_chains;
+  float* p;               // [C, d]
+  const float* a_hi;      // [C, kpad]  (delta split, also read by the epilogue for z . delta)
+  const float* a_lo;
+  float coef;             // kick: p -= coef * z   (grad = -z)
+  float norm_const;
+  float* logp_out;        // [C] or null: logp = c - 1/2 sum z * delta
+  float* ke_out;          // [C] or null: 1/2 |p_new|^2
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
+                       const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+                       const GemmArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // carve: stages (1024-byte aligned), then barriers
+  unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(base + (size_t)kStages * kStageBytes);
+  uint64_t* full = bars;                 // [kStages]
+  uint64_t* empty = bars + kStages;      // [kStages]
+  uint64_t* tfull = bars + 2 * kStages;  // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kTileM;
+  const int n_chunks = a.npad / kTileN;
+  const int k_chunks = a.kpad / kTileK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer
+      int it = 0;
+      for (int n = 0; n < n_chunks; ++n) {
+        for (int k = 0; k < k_chunks; ++k, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          unsigned char* st = base + (size_t)s * kStageBytes;
+          mbar_expect_tx(&full[s], kStageBytes);
+          tma_load_2d(st, &map_ahi, &full[s], k * kTileK, m0);
+          tma_load_2d(st + kABytes, &map_alo, &full[s], k * kTileK, m0);
+          tma_load_2d(st + 2 * kABytes, &map_bhi, &full[s], k * kTileK, n * kTileN);
+          tma_load_2d(st + 2 * kABytes + kBBytes, &map_blo, &full[s], k * kTileK, n * kTileN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer
+      int it = 0;
+      for (int n = 0; n < n_chunks; ++n) {
+        const int acc = n & 1;
+        mbar_wait(&tempty[acc], (uint32_t)((n >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kTileN);
+        for (int k = 0; k < k_chunks; ++k, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(base + (size_t)s * kStageBytes);
+          const uint64_t d_ahi = umma_desc(st), d_alo = umma_desc(st + kABytes);
+          const uint64_t d_bhi = umma_desc(st + 2 * kABytes), d_blo = umma_desc(st + 2 * kABytes + kBBytes);
+#pragma unroll
+          for (int kk = 0; kk < kTileK / kUmmaK; ++kk) {
+            const uint64_t adv = (uint64_t)((kk * kUmmaK * 4) >> 4);   // 32 bytes per K step inside the swizzle row
+            tc_mma_tf32(tmem_d, d_alo + adv, d_bhi + adv, kIdesc, (k | kk) ? 1u : 0u);   // small terms first
+            tc_mma_tf32(tmem_d, d_ahi + adv, d_blo + adv, kIdesc, 1u);
+            tc_mma_tf32(tmem_d, d_ahi + adv, d_bhi + adv, kIdesc, 1u);
+          }
+          tc_commit(&empty[s]);           // frees the stage when these MMAs have read it
+        }
+        tc_commit(&tfull[acc]);           // accumulator complete
+      }
+    }
+  } else {
+    // ===== epilogue: thread <-> chain row
+    const int q4 = warp & 3;                     // TMEM lane quarter this warp may access
+    const int r = q4 * 32 + lane;
+    const size_t row = (size_t)m0 + r;
+    const bool live = row < a.n_chains;
+    float quad = 0.f, ke = 0.f;
+    for (int n = 0; n < n_chunks; ++n) {
+      const int acc = n & 1;
+      mbar_wait(&tfull[acc], (uint32_t)((n >> 1) & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int cb = 0; cb < kTileN / 32; ++cb) {
+        float z[32];
+        tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * kTileN + cb * 32), z);
+        const int c0 = n * kTileN + cb * 32;
+        if (live && c0 < a.d) {
+          float* prow = a.p + row * (size_t)a.d + c0;
+          const float* hrow = a.a_hi + row * (size_t)a.kpad + c0;
+          const float* lrow = a.a_lo + row * (size_t)a.kpad + c0;
+          if (c0 + 32 <= a.d && (a.d & 3) == 0) {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              float4 pv = *reinterpret_cast<const float4*>(prow + 4 * v);
+              pv.x = fmaf(-a.coef, z[4 * v + 0], pv.x); pv.y = fmaf(-a.coef, z[4 * v + 1], pv.y);
+              pv.z = fmaf(-a.coef, z[4 * v + 2], pv.z); pv.w = fmaf(-a.coef, z[4 * v + 3], pv.w);
+              *reinterpret_cast<float4*>(prow + 4 * v) = pv;
+              if (a.ke_out) ke += pv.x * pv.x + pv.y * pv.y + pv.z * pv.z + pv.w * pv.w;
+              if (a.logp_out) {
+                const float4 h = *reinterpret_cast<const float4*>(hrow + 4 * v);
+                const float4 l = *reinterpret_cast<const float4*>(lrow + 4 * v);
+                quad += z[4 * v + 0] * (h.x + l.x) + z[4 * v + 1] * (h.y + l.y) + z[4 * v + 2] * (h.z + l.z) + z[4 * v + 3] * (h.w + l.w);
+              }
+            }
+          } else {
+            for (int c = 0; c < 32 && c0 + c < a.d; ++c) {
+              const float pn = fmaf(-a.coef, z[c], prow[c]);
+              prow[c] = pn;
+              if (a.ke_out) ke += pn * pn;
+              if (a.logp_out) quad += z[c] * (hrow[c] + lrow[c]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+    if (live) {
+      if (a.logp_out) a.logp_out[row] = a.norm_const - 0.5f * quad;
+      if (a.ke_out) a.ke_out[row] = 0.5f * ke;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- elementwise kernels -----------------------------------------------------------------------------
+struct BeginArgs {
+  size_t n_chains; int d, kpad;
+  unsigned long long chain_offset; PhiloxKey key; uint32_t step;
+  const float* q; float* q_prop; float* p; const float* mu;
+  float* a_hi; float* a_lo; float* ke0;
+  const float* inj_normals;   // [C, d] for this transition or null
+};
+
+// one warp per chain: momentum, ke0, q_prop = q, delta split
+__global__ void __launch_bounds__(256) dense_begin_kernel(const BeginArgs a) {
+  const size_t chain = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (chain >= a.n_chains) return;
+  const unsigned long long gchain = a.chain_offset + chain;
+  float ke = 0.f;
+  for (int b = lane; b * 4 < a.kpad; b += 32) {
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (b * 4 < a.d) {
+      if (a.inj_normals) {
+        for (int k = 0; k < 4; ++k)
+          if (b * 4 + k < a.d) z[k] = a.inj_normals[chain * a.d + b * 4 + k];
+      } else {
+        normals_from_block<false>(philox4x32_10(philox_ctr(gchain, a.step, 0u, (uint32_t)b), a.key), z);
+      }
+    }
+    float hi[4], lo[4];
+    for (int k = 0; k < 4; ++k) {
+      const int c = b * 4 + k;
+      float dl = 0.f;
+      if (c < a.d) {
+        const float qv = a.q[chain * a.d + c];
+        a.q_prop[chain * a.d + c] = qv;
+        a.p[chain * a.d + c] = z[k];
+        ke += z[k] * z[k];
+        dl = qv - a.mu[c];
+      }
+      hi[k] = tf32_rna(dl);
+      lo[k] = tf32_rna(dl - hi[k]);   // rounded (not hardware-truncated) low part: unbiased
+    }
+    *reinterpret_cast<float4*>(a.a_hi + chain * a.kpad + b * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<float4*>(a.a_lo + chain * a.kpad + b * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  for (int o = 16; o > 0; o >>= 1) ke += __shfl_xor_sync(0xffffffffu, ke, o);
+  if (lane == 0) a.ke0[chain] = 0.5f * ke;
+}
+
+// q_prop += eps * p ; delta split   (grid-stride over [C, kpad / 4] float4 items)
+__global__ void __launch_bounds__(256) dense_drift_kernel(size_t n_chains, int d, int kpad, float eps, float* __restrict__ q_prop,
+                                                          const float* __restrict__ p, const float* __restrict__ mu,
+                                                          float* __restrict__ a_hi, float* __restrict__ a_lo) {
+  const int per = kpad / 4;
+  const size_t total = n_chains * (size_t)per;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t chain = i / per;
+    const int c0 = (int)(i - chain * per) * 4;
+    float hi[4], lo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + k;
+      float dl = 0.f;
+      if (c < d) {
+        const float qn = fmaf(eps, p[chain * d + c], q_prop[chain * d + c]);
+        q_prop[chain * d + c] = qn;
+        dl = qn - mu[c];
+      }
+      hi[k] = tf32_rna(dl);
+      lo[k] = tf32_rna(dl - hi[k]);   // rounded (not hardware-truncated) low part: unbiased
+    }
+    *reinterpret_cast<float4*>(a_hi + chain * kpad + c0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<float4*>(a_lo + chain * kpad + c0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+struct AcceptArgs {
+  size_t n_chains; int d;
+  unsigned long long chain_offset; PhiloxKey key; uint32_t step;
+  float* q; const float* q_prop; const float* p;
+  const float* logp0; const float* logp1; const float* ke0; const float* ke1;
+  float* out; size_t out_n; long long slot;        // slot < 0: not recorded
+  unsigned long long* accept_total; unsigned long long* diverge_total;
+  const float* inj_lnu;      // [C] for this transition or null
+  float* diag_logacc; uint8_t* diag_acc; float* diag_pq; float* diag_pp;   // per-transition slices or null
+};
+
+// one warp per chain: Metropolis accept (batched_hmc.rs:148-162), state update, sample write-out
+__global__ void __launch_bounds__(256) dense_accept_kernel(const AcceptArgs a) {
+  const size_t chain = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (chain >= a.n_chains) return;
+  const float log_accept = (a.logp1[chain] - a.logp0[chain]) + (a.ke0[chain] - a.ke1[chain]);
+  float ln_u;
+  if (a.inj_lnu) ln_u = a.inj_lnu[chain];
+  else ln_u = logf(u01(philox4x32_10(philox_ctr(a.chain_offset + chain, a.step, 1u, 0u), a.key).x));
+  const bool accept = ln_u <= log_accept;
+  const bool finite = (log_accept == log_accept) && (fabsf(log_accept) < INFINITY);
+  float* qrow = a.q + chain * a.d;
+  const float* prow = a.q_prop + chain * a.d;
+  for (int c = lane; c < a.d; c += 32) {
+    const float v = accept ? prow[c] : qrow[c];
+    if (accept) qrow[c] = v;
+    if (a.slot >= 0) __stcs(a.out + (chain * a.out_n + (size_t)a.slot) * a.d + c, v);
+    if (a.diag_pq) { a.diag_pq[chain * a.d + c] = prow[c]; a.diag_pp[chain * a.d + c] = a.p[chain * a.d + c]; }
+  }
+  if (lane == 0) {
+    if (accept) atomicAdd(a.accept_total, 1ull);
+    if (!finite) atomicAdd(a.diverge_total, 1ull);
+    if (a.diag_logacc) { a.diag_logacc[chain] = log_accept; a.diag_acc[chain] = accept ? 1 : 0; }
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D f32 tensor [rows, cols] (cols contiguous), box [box_rows, 32 floats], SWIZZLE_128B
+bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kTileK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline float host_tf32_rna(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;
+  u += 0x1000u;            // round to nearest, ties away from zero (cvt.rna)
+  u &= 0xffffe000u;
+  float r;
+  std::memcpy(&r, &u, 4);
+  return r;
+}
+
+}  // namespace
+
+struct DenseTc {
+  int d = 0, kpad = 0, npad = 0;
+  size_t n_chains = 0;
+  float *p = nullptr, *q_prop = nullptr, *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr, *mu = nullptr;
+  float *logp0 = nullptr, *logp1 = nullptr, *ke0 = nullptr, *ke1 = nullptr;
+  float norm_const = 0.f;
+  CUtensorMap map_ahi, map_alo, map_bhi, map_blo;
+  size_t smem = 0;
+};
+
+void dense_tc_destroy(DenseTc* t) {
+  if (!t) return;
+  cudaFree(t->p); cudaFree(t->q_prop); cudaFree(t->a_hi); cudaFree(t->a_lo); cudaFree(t->b_hi); cudaFree(t->b_lo); cudaFree(t->mu);
+  cudaFree(t->logp0); cudaFree(t->logp1); cudaFree(t->ke0); cudaFree(t->ke1);
+  delete t;
+}
+
+// params: [mu[d], P[d*d] row-major (symmetric), norm_const] in double
+DenseTc* dense_tc_create(size_t n_chains, int d, const double* params, const char** err) {
+  static const char* e_alloc = "dense tensor-core path: device allocation failed";
+  static const char* e_map = "dense tensor-core path: cuTensorMapEncodeTiled unavailable or failed";
+  DenseTc* t = new DenseTc();
+  t->d = d; t->n_chains = n_chains;
+  t->kpad = ((d + kTileK - 1) / kTileK) * kTileK;
+  t->npad = ((d + kTileN - 1) / kTileN) * kTileN;
+  t->norm_const = (float)params[(size_t)d + (size_t)d * d];
+  const size_t C = n_chains;
+  bool ok = cudaMalloc(&t->p, C * d * 4) == cudaSuccess && cudaMalloc(&t->q_prop, C * d * 4) == cudaSuccess &&
+            cudaMalloc(&t->a_hi, C * (size_t)t->kpad * 4) == cudaSuccess && cudaMalloc(&t->a_lo, C * (size_t)t->kpad * 4) == cudaSuccess &&
+            cudaMalloc(&t->b_hi, (size_t)t->npad * t->kpad * 4) == cudaSuccess && cudaMalloc(&t->b_lo, (size_t)t->npad * t->kpad * 4) == cudaSuccess &&
+            cudaMalloc(&t->mu, (size_t)d * 4) == cudaSuccess && cudaMalloc(&t->logp0, C * 4) == cudaSuccess &&
+            cudaMalloc(&t->logp1, C * 4) == cudaSuccess && cudaMalloc(&t->ke0, C * 4) == cudaSuccess && cudaMalloc(&t->ke1, C * 4) == cudaSuccess;
+  if (!ok) { *err = e_alloc; dense_tc_destroy(t); return nullptr; }
+  // B operand: rows = output column n, cols = k (K-major); P symmetric so B[n][k] = P[k][n] = P[n][k]
+  std::vector<float> bh((size_t)t->npad * t->kpad, 0.f), bl((size_t)t->npad * t->kpad, 0.f), mu(d);
+  for (int i = 0; i < d; ++i) mu[i] = (float)params[i];
+  for (int n = 0; n < d; ++n)
+    for (int k = 0; k < d; ++k) {
+      const float v = (float)params[(size_t)d + (size_t)k * d + n];
+      const float hi = host_tf32_rna(v);
+      bh[(size_t)n * t->kpad + k] = hi;
+      bl[(size_t)n * t->kpad + k] = host_tf32_rna(v - hi);
+    }
+  ok = cudaMemcpy(t->b_hi, bh.data(), bh.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+       cudaMemcpy(t->b_lo, bl.data(), bl.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+       cudaMemcpy(t->mu, mu.data(), (size_t)d * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+  if (!ok) { *err = e_alloc; dense_tc_destroy(t); return nullptr; }
+  ok = make_map(&t->map_ahi, t->a_hi, C, (uint64_t)t->kpad, kTileM) && make_map(&t->map_alo, t->a_lo, C, (uint64_t)t->kpad, kTileM) &&
+       make_map(&t->map_bhi, t->b_hi, (uint64_t)t->npad, (uint64_t)t->kpad, kTileN) &&
+       make_map(&t->map_blo, t->b_lo, (uint64_t)t->npad, (uint64_t)t->kpad, kTileN);
+  if (!ok) { *err = e_map; dense_tc_destroy(t); return nullptr; }
+  t->smem = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  if (cudaFuncSetAttribute(dense_gemm_kick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem) != cudaSuccess) {
+    *err = "dense tensor-core path: shared-memory opt-in failed";
+    dense_tc_destroy(t);
+    return nullptr;
+  }
+  return t;
+}
+
+static cudaError_t gemm_kick(DenseTc* t, float coef, float* logp_out, float* ke_out, cudaStream_t st) {
+  GemmArgs g;
+  g.d = t->d; g.kpad = t->kpad; g.npad = t->npad; g.n_chains = t->n_chains;
+  g.p = t->p; g.a_hi = t->a_hi; g.a_lo = t->a_lo; g.coef = coef; g.norm_const = t->norm_const;
+  g.logp_out = logp_out; g.ke_out = ke_out;
+  const unsigned blocks = (unsigned)((t->n_chains + kTileM - 1) / kTileM);
+  dense_gemm_kick_kernel<<<blocks, kGemmThreads, t->smem, st>>>(t->map_ahi, t->map_alo, t->map_bhi, t->map_blo, g);
+  return cudaGetLastError();
+}
+
+// One HMC transition.  q: [C, d] current positions (in/out).  Returns the number of kernel launches (or -1).
+int dense_tc_transition(DenseTc* t, const DenseTcStep& S, cudaStream_t st) {
+  const size_t C = t->n_chains;
+  const unsigned wblocks = (unsigned)((C * 32 + 255) / 256);
+  int launches = 0;
+  BeginArgs b;
+  b.n_chains = C; b.d = t->d; b.kpad = t->kpad; b.chain_offset = S.chain_offset;
+  b.key = PhiloxKey{(uint32_t)S.seed, (uint32_t)(S.seed >> 32)}; b.step = S.step;
+  b.q = (const float*)S.q; b.q_prop = t->q_prop; b.p = t->p; b.mu = t->mu; b.a_hi = t->a_hi; b.a_lo = t->a_lo; b.ke0 = t->ke0;
+  b.inj_normals = (const float*)S.inj_normals;
+  dense_begin_kernel<<<wblocks, 256, 0, st>>>(b);
+  ++launches;
+  const float eps = (float)S.eps, half = 0.5f * eps;
+  // gradient at the current point: log density + first half kick
+  if (gemm_kick(t, S.n_leapfrog > 0 ? half : 0.f, t->logp0, S.n_leapfrog > 0 ? nullptr : t->ke1, st) != cudaSuccess) return -1;
+  ++launches;
+  const unsigned dblocks = (unsigned)std::min<size_t>((C * (size_t)(t->kpad / 4) + 255) / 256, (size_t)148 * 32);
+  for (uint32_t l = 0; l < S.n_leapfrog; ++l) {
+    dense_drift_kernel<<<dblocks, 256, 0, st>>>(C, t->d, t->kpad, eps, t->q_prop, t->p, t->mu, t->a_hi, t->a_lo);
+    const bool last = (l + 1 == S.n_leapfrog);
+    if (gemm_kick(t, last ? half : eps, last ? t->logp1 : nullptr, last ? t->ke1 : nullptr, st) != cudaSuccess) return -1;
+    launches += 2;
+  }
+  AcceptArgs a;
+  a.n_chains = C; a.d = t->d; a.chain_offset = S.chain_offset; a.key = b.key; a.step = S.step;
+  a.q = (float*)S.q; a.q_prop = t->q_prop; a.p = t->p;
+  a.logp0 = t->logp0; a.logp1 = S.n_leapfrog > 0 ? t->logp1 : t->logp0; a.ke0 = t->ke0; a.ke1 = t->ke1;
+  a.out = (float*)S.out; a.out_n = S.out_n; a.slot = S.slot;
+  a.accept_total = S.accept_total; a.diverge_total = S.diverge_total;
+  a.inj_lnu = (const float*)S.inj_lnu;
+  a.diag_logacc = (float*)S.diag_logacc; a.diag_acc = S.diag_acc; a.diag_pq = (float*)S.diag_pq; a.diag_pp = (float*)S.diag_pp;
+  dense_accept_kernel<<<wblocks, 256, 0, st>>>(a);
+  ++launches;
+  if (cudaGetLastError() != cudaSuccess) return -1;
+  return launches;
+}
+
+}  // namespace gm

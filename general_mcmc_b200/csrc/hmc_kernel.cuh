@@ -249,6 +249,8 @@ __device__ __forceinline__ T eval_target(TagDenseGauss, const T (&x)[EPL], T (&g
 // Isotropic Gaussian mixture (synthetic target of BASELINE cfg5):
 //   logp = logsumexp_k( ln w_k - |x - mu_k|^2 / (2 sigma^2) ),  grad = sum_k r_k (mu_k - x) / sigma^2
 constexpr int kMaxComp = 8;
+// The component loops are deliberately NOT unrolled (K is a runtime value): unrolling 8 components x EPL
+// coordinates made the NUTS kernel ~200 KB of code and instruction-fetch bound.
 template <class T, int EPL, bool PADDED, bool WANT_LOGP>
 __device__ __forceinline__ T eval_target(TagMixture, const T (&x)[EPL], T (&g)[EPL], const Lane& ln,
                                          const TParams<T>& tp, T*) {
@@ -258,35 +260,40 @@ __device__ __forceinline__ T eval_target(TagMixture, const T (&x)[EPL], T (&g)[E
   const T inv_var = T(1) / (sigma * sigma);
   const T* w = tp.dp;
   const T* mu = tp.dp + K;
-  T a[kMaxComp];
+  T a[kMaxComp];          // dynamically indexed: lives in (L1-resident) local memory
   T amax = -INFINITY;
+#pragma unroll 1
+  for (int k = 0; k < K; ++k) {
+    const T* muk = mu + (size_t)k * d + ln.lo;
+    T terms[EPL];
 #pragma unroll
-  for (int k = 0; k < kMaxComp; ++k) {
-    a[k] = -INFINITY;
-    if (k < K) {
-      T terms[EPL];
-#pragma unroll
-      for (int j = 0; j < EPL; ++j) {
-        T df = (j < ln.nvalid) ? (x[j] - mu[(size_t)k * d + ln.lo + j]) : T(0);
-        terms[j] = df * df;
-      }
-      T sq = chain_sum<T, EPL>(terms, ln);
-      a[k] = log(w[k]) - T(0.5) * sq * inv_var;
-      amax = max(amax, a[k]);
+    for (int j = 0; j < EPL; ++j) {
+      const T df = (j < ln.nvalid) ? (x[j] - muk[j]) : T(0);
+      terms[j] = df * df;
     }
+    const T sq = chain_sum<T, EPL>(terms, ln);
+    const T ak = log(w[k]) - T(0.5) * sq * inv_var;
+    a[k] = ak;
+    amax = max(amax, ak);
   }
   T se = T(0);
+#pragma unroll 1
+  for (int k = 0; k < K; ++k) { const T e = exp(a[k] - amax); a[k] = e; se = se + e; }
+  T acc[EPL];
 #pragma unroll
-  for (int k = 0; k < kMaxComp; ++k)
-    if (k < K) { a[k] = exp(a[k] - amax); se = se + a[k]; }
+  for (int j = 0; j < EPL; ++j) acc[j] = T(0);
+#pragma unroll 1
+  for (int k = 0; k < K; ++k) {
+    const T* muk = mu + (size_t)k * d + ln.lo;
+    const T rk = a[k] / se;
 #pragma unroll
-  for (int j = 0; j < EPL; ++j) {
-    T acc = T(0);
-#pragma unroll
-    for (int k = 0; k < kMaxComp; ++k)
-      if (k < K && j < ln.nvalid) acc = acc + (a[k] / se) * (mu[(size_t)k * d + ln.lo + j] - x[j]);
-    g[j] = acc * inv_var;
+    for (int j = 0; j < EPL; ++j) {
+      const T dm = (j < ln.nvalid) ? (muk[j] - x[j]) : T(0);
+      acc[j] = acc[j] + rk * dm;
+    }
   }
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) g[j] = acc[j] * inv_var;
   return amax + log(se);
 }
 

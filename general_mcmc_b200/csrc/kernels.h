@@ -85,6 +85,23 @@ struct MhLaunch {
   uint8_t* diag_acc;        // [n, C]
 };
 
+// K3: dense-Gaussian HMC with the gradient GEMM on tcgen05 (dense_tc.cu)
+struct DenseTc;
+struct DenseTcStep {
+  void* q;                 // [C, d] f32 current positions, in/out
+  uint64_t chain_offset, seed;
+  uint32_t step;           // Philox transition index
+  double eps;
+  uint32_t n_leapfrog;
+  void* out; size_t out_n; long long slot;     // slot < 0: transition not recorded
+  unsigned long long* accept_total; unsigned long long* diverge_total;
+  const void* inj_normals; const void* inj_lnu;          // this transition's slices, or null
+  void* diag_logacc; uint8_t* diag_acc; void* diag_pq; void* diag_pp;
+};
+DenseTc* dense_tc_create(size_t n_chains, int d, const double* params, const char** err);
+void dense_tc_destroy(DenseTc*);
+int dense_tc_transition(DenseTc*, const DenseTcStep&, cudaStream_t);
+
 struct NutsLaunch {
   TargetDesc tgt;
   int init_only;          // 1: run init_chain_state (momentum draw + find_reasonable_epsilon + mu) instead of transitions

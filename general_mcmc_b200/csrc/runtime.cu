@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -147,6 +148,7 @@ struct gmcmc_sampler {
   uint32_t n_leapfrog = 0;
   void* d_eps = nullptr;       // [1] T (shared step size)
   bool eps_device_only = false; // the current step size was produced on the device and not yet read back
+  DenseTc* dense_tc = nullptr;  // tensor-core path of the dense Gaussian (f32, fast mode, fixed step size)
   gmcmc_adapt_mode adapt = GMCMC_ADAPT_NONE;
   double target_accept = 0.8;
   void* d_da[4] = {nullptr, nullptr, nullptr, nullptr};   // per-chain: eps, eps_bar, h_bar, mu  (T [C])
@@ -441,6 +443,29 @@ gmcmc_status run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void
   if (s->type == S_MH) {
     GM_TRY(mh_segment(s, 0, inj, n_discard, n_collect, d_out, true, inj_first));
     GM_TRY(mh_segment(s, inj, total - inj, n_discard, n_collect, d_out, false, 0));
+  } else if (s->type == S_HMC && s->dense_tc && s->math == GMCMC_MATH_FAST && s->adapt == GMCMC_ADAPT_NONE) {
+    // K3: host loop over transitions, L + 1 tensor-core GEMMs each
+    const size_t es = 4, C = s->n_chains, d = (size_t)s->dim;
+    for (size_t t = 0; t < total; ++t) {
+      DenseTcStep S{};
+      S.q = s->d_pos; S.chain_offset = s->chain_offset; S.seed = s->seed;
+      S.step = s->step_index + (uint32_t)t; S.eps = s->step_size; S.n_leapfrog = s->n_leapfrog;
+      S.out = d_out; S.out_n = n_collect; S.slot = (t >= n_discard && d_out) ? (long long)(t - n_discard) : -1;
+      S.accept_total = s->d_counts + 0; S.diverge_total = s->d_counts + 1;
+      if (t < inj) {
+        const size_t i = inj_first + t;
+        S.inj_normals = (const char*)s->d_inj_normals + i * C * d * es;
+        S.inj_lnu = (const char*)s->d_inj_lnu + i * C * es;
+        S.diag_logacc = (char*)s->d_diag_logacc + i * C * es;
+        S.diag_acc = s->d_diag_acc + i * C;
+        S.diag_pq = (char*)s->d_diag_pq + i * C * d * es;
+        S.diag_pp = (char*)s->d_diag_pp + i * C * d * es;
+      }
+      const int n = dense_tc_transition(s->dense_tc, S, ctx->stream);
+      if (n < 0) return fail(GMCMC_ERR_CUDA, "dense tensor-core transition failed: %s", cudaGetErrorString(cudaGetLastError()));
+      s->launches += (uint64_t)n;
+    }
+    s->hmc_grad_evals += (uint64_t)total * s->n_chains * s->n_leapfrog;
   } else if (s->type == S_HMC) {
     if (s->adapt == GMCMC_ADAPT_POOLED && n_discard > 0) {
       GM_REQUIRE(inj == 0, "injection cannot be combined with pooled adaptation");
@@ -858,6 +883,18 @@ gmcmc_status gmcmc_hmc_create(gmcmc_ctx* ctx, gmcmc_target* tgt, size_t n_chains
   }
   gmcmc_status st = set_eps_device(s, step_size);
   if (st != GMCMC_OK) { gmcmc_sampler_destroy(s); return st; }
+  // dense Gaussian, f32, d >= 64: the gradient GEMM runs on the tensor cores (K3) in fast math mode
+  const char* no_tc = std::getenv("GMCMC_DENSE_TC");
+  if (tgt->desc.kind == GMCMC_TARGET_DENSE_GAUSS && tgt->desc.dtype == GMCMC_F32 && tgt->desc.dim >= 64 &&
+      !(no_tc && no_tc[0] == '0')) {
+    const char* err = nullptr;
+    s->dense_tc = dense_tc_create(n_chains, tgt->desc.dim, tgt->params.data(), &err);
+    if (!s->dense_tc) {
+      gmcmc_status st2 = fail(GMCMC_ERR_CUDA, "%s", err ? err : "dense tensor-core path setup failed");
+      gmcmc_sampler_destroy(s);
+      return st2;
+    }
+  }
   *out = s;
   return GMCMC_OK;
 }
@@ -932,6 +969,7 @@ gmcmc_status gmcmc_sampler_destroy(gmcmc_sampler* s) {
   cudaFree(s->d_pos); cudaFree(s->d_eps); cudaFree(s->d_counts); cudaFree(s->d_samples);
   for (void* p : s->d_da) cudaFree(p);
   cudaFree(s->d_pooled); cudaFree(s->d_alpha_part); cudaFree(s->d_alpha_sum);
+  dense_tc_destroy(s->dense_tc);
   for (void* p : s->d_nuts_da) cudaFree(p);
   cudaFree(s->d_ws_edges); cudaFree(s->d_ws_first); cudaFree(s->d_ws_prime); cudaFree(s->d_chain_leapfrogs);
   for (double* p : s->d_nuts_inj) cudaFree(p);
