@@ -389,6 +389,31 @@ def run_ours(args, rank, world, local):
                         "note": "state is register-resident for all L steps; HBM carries only the sample write-out, so "
                                 "this kernel is FP32-pipe bound, not HBM bound (north_star: FP32-pipe utilisation)"}}
 
+    # ---- min-ESS/sec (BASELINE metric, second half): collect n_ess draws per chain, reduce ESS / R-hat on the device
+    ess = None
+    if args.workload == "hmc_rosenbrock" and not args.no_ess:
+        n_ess = 500
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        with torch.cuda.stream(stream):
+            ev[0].record(stream)
+            dptr = s.run_device(n_ess, 0)
+            ev[1].record(stream)
+        st = L.RunStatsC()
+        t_s0 = time.perf_counter()
+        L.check(lib.gmcmc_run_stats_from(ctx._h, C.c_void_p(dptr), C.c_size_t(chains), C.c_size_t(n_ess), C.c_size_t(DIM),
+                                         L.F32, 1, C.byref(st)))
+        ctx.synchronize()
+        t_s1 = time.perf_counter()
+        sample_ms = max_over_ranks(ev[0].elapsed_time(ev[1]))
+        stats_ms = max_over_ranks((t_s1 - t_s0) * 1e3)
+        ess = {"min_ess": st.ess.min, "median_ess": st.ess.median, "min_ess_per_sec": st.ess.min / (sample_ms * 1e-3),
+               "draws_per_chain": n_ess, "chains_total": chains * world, "sampling_ms": sample_ms,
+               "split_rhat_max": st.rhat_std.max,
+               "device_stats_ms": stats_ms, "stats_read_gbs": chains * n_ess * DIM * 4 / (stats_ms * 1e-3) / 1e9,
+               "note": "ESS per stats.rs:523-573 over ALL ranks' chains, reduced on the device (K4 + NCCL A2/A3); "
+                       "seconds = sampling time of these draws (stats excluded), SURVEY 8(d)"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and not nuts and not dense:
         if args.workload == "mh_gauss2d":
@@ -408,8 +433,11 @@ def run_ours(args, rank, world, local):
                                  "launch and each launch streams %.0f MB of samples (> 126 MB L2), so nothing is "
                                  "reused from L2 between launches" % (bytes_per_step * per_launch / 1e6)},
                 "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "calls": e2e_calls, "transitions_per_call": e2e_T, "host_memory": "pinned"},
-                "gpu_launches": len(plan), "roofline": roof, "cpu_baseline": cpu, "clocks": clk}
+                        "calls": e2e_calls, "transitions_per_call": e2e_T, "host_memory": "pinned",
+                        "pcie_gbs": (h2d + d2h) * e2e_T * e2e_calls / e2e_s / 1e9,
+                        "note": "gmcmc_set_positions + gmcmc_run into host memory: the [chains, samples, dim] tensor "
+                                "crosses PCIe every call, which bounds this figure"},
+                "gpu_launches": len(plan), "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "ess": ess}
         print(json.dumps(line), flush=True)
     lib.gmcmc_host_free(host_ptr)
     lib.gmcmc_host_free(init_ptr)
@@ -427,6 +455,7 @@ def main():
     ap.add_argument("--dim", type=int, default=0, help="dimension (hmc_dense only; default 1000)")
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ess", action="store_true", help="skip the min-ESS/sec leg")
     args = ap.parse_args()
     rank, world, local = dist_env()
     if args.impl == "reference":

@@ -14,7 +14,8 @@
 //   dense_begin_kernel     p ~ N(0, I) (Philox or injected), ke0, q_prop = q, delta split -> A_hi / A_lo
 //   dense_gemm_kick_kernel z = delta . P ; p -= (eps/2) (-z)...  (epilogue: kick, and at the two trajectory
 //                          ends logp = c - 1/2 z.delta and ke = 1/2 |p|^2, one thread per chain row)
-//   L x { dense_drift_kernel (q_prop += eps p ; delta split) ; dense_gemm_kick_kernel }
+//   L x dense_gemm_kick_kernel — each epilogue also applies the NEXT leapfrog's drift (q_prop += eps p) and writes the
+//                          split delta of the next GEMM into the other A buffer (ping-pong), so there is no separate drift pass
 //   dense_accept_kernel    Hamiltonian, Metropolis accept, q <- q_prop, sample row -> [chain, slot, :]
 //
 // dense_gemm_kick_kernel: one CTA per 128 chains, warp-specialised — warp 0 lane 0 issues TMA loads
@@ -39,9 +40,13 @@ namespace {
 
 constexpr int kTileM = 128;      // chains per CTA
 constexpr int kTileN = 256;      // accumulator columns per MMA
-constexpr int kTileK = 32;       // floats per K stage (128 bytes = one swizzle row)
+#ifndef GM_TC_TILEK
+#define GM_TC_TILEK 16
+#endif
+constexpr int kTileK = GM_TC_TILEK;   // floats per K stage: 16 (64-byte rows, SWIZZLE_64B, 4 stages) or 32 (128-byte rows, 2 stages)
 constexpr int kUmmaK = 8;        // tf32 elements per tcgen05.mma
-constexpr int kStages = 2;
+constexpr int kStages = kTileK == 16 ? 4 : 2;
+constexpr int kKPadUnit = 32;    // K is padded to a multiple of 32 floats in both layouts
 constexpr int kGemmThreads = 192;  // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue
 constexpr uint32_t kABytes = kTileM * kTileK * 4;   // 16 KB
 constexpr uint32_t kBBytes = kTileN * kTileK * 4;   // 32 KB
@@ -112,14 +117,15 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// shared-memory matrix descriptor: K-major operand tile, rows of 128 bytes, SWIZZLE_128B (8-row / 1024-byte atoms)
+// shared-memory matrix descriptor: K-major operand tile, rows of kTileK floats, swizzle width = row width (8-row atoms)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3fff);        // start address, bits [0,14)
   d |= (uint64_t)0 << 16;                            // leading byte offset (unused: K extent = one swizzle row)
-  d |= (uint64_t)((1024 >> 4) & 0x3fff) << 32;       // stride byte offset between 8-row groups, bits [32,46)
+  constexpr uint32_t kRowBytes = kTileK * 4;         // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+  d |= (uint64_t)(((8 * kRowBytes) >> 4) & 0x3fff) << 32;   // stride byte offset between 8-row groups, bits [32,46)
   d |= (uint64_t)1 << 46;                            // descriptor version (sm_100), bits [46,48)
-  d |= (uint64_t)2 << 61;                            // layout type SWIZZLE_128B, bits [61,64)
+  d |= (uint64_t)(kRowBytes == 128 ? 2 : 4) << 61;   // layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, bits [61,64)
   return d;
 }
 
@@ -142,6 +148,12 @@ struct GemmArgs {
   float norm_const;
   float* logp_out;        // [C] or null: logp = c - 1/2 sum z * delta
   float* ke_out;          // [C] or null: 1/2 |p_new|^2
+  // fused drift of the NEXT leapfrog (null q_prop: none): q_prop += drift_eps * p_new ; delta split -> next A buffers
+  float* q_prop;          // [C, d]
+  const float* mu;        // [d]
+  float* a_hi_next;       // [C, kpad]
+  float* a_lo_next;
+  float drift_eps;
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -225,12 +237,14 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
       }
     }
   } else {
-    // ===== epilogue: thread <-> chain row
+    // ===== epilogue.  tcgen05.ld hands every thread one accumulator ROW (32 columns at a time); the tile is
+    // transposed through shared memory so that global accesses run along rows: lane <-> column, one 128-byte
+    // line per warp instruction for p, q_prop and the next A operand.
     const int q4 = warp & 3;                     // TMEM lane quarter this warp may access
-    const int r = q4 * 32 + lane;
-    const size_t row = (size_t)m0 + r;
-    const bool live = row < a.n_chains;
-    float quad = 0.f, ke = 0.f;
+    float* tr = reinterpret_cast<float*>(base + (size_t)kStages * kStageBytes + 256) + (size_t)(warp - 2) * 32 * 33;
+    const size_t row0 = (size_t)m0 + (size_t)q4 * 32;
+    const int nrows = row0 < a.n_chains ? (int)((a.n_chains - row0) < 32 ? (a.n_chains - row0) : 32) : 0;
+    float quad = 0.f, ke = 0.f;                  // lane r holds the sums of row r
     for (int n = 0; n < n_chunks; ++n) {
       const int acc = n & 1;
       mbar_wait(&tfull[acc], (uint32_t)((n >> 1) & 1));
@@ -240,30 +254,48 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
         float z[32];
         tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * kTileN + cb * 32), z);
         const int c0 = n * kTileN + cb * 32;
-        if (live && c0 < a.d) {
-          float* prow = a.p + row * (size_t)a.d + c0;
-          const float* hrow = a.a_hi + row * (size_t)a.kpad + c0;
-          const float* lrow = a.a_lo + row * (size_t)a.kpad + c0;
-          if (c0 + 32 <= a.d && (a.d & 3) == 0) {
+        if (c0 >= a.d) continue;                 // padded columns (warp-uniform)
+        __syncwarp();
 #pragma unroll
-            for (int v = 0; v < 8; ++v) {
-              float4 pv = *reinterpret_cast<const float4*>(prow + 4 * v);
-              pv.x = fmaf(-a.coef, z[4 * v + 0], pv.x); pv.y = fmaf(-a.coef, z[4 * v + 1], pv.y);
-              pv.z = fmaf(-a.coef, z[4 * v + 2], pv.z); pv.w = fmaf(-a.coef, z[4 * v + 3], pv.w);
-              *reinterpret_cast<float4*>(prow + 4 * v) = pv;
-              if (a.ke_out) ke += pv.x * pv.x + pv.y * pv.y + pv.z * pv.z + pv.w * pv.w;
-              if (a.logp_out) {
-                const float4 h = *reinterpret_cast<const float4*>(hrow + 4 * v);
-                const float4 l = *reinterpret_cast<const float4*>(lrow + 4 * v);
-                quad += z[4 * v + 0] * (h.x + l.x) + z[4 * v + 1] * (h.y + l.y) + z[4 * v + 2] * (h.z + l.z) + z[4 * v + 3] * (h.w + l.w);
+        for (int c = 0; c < 32; ++c) tr[lane * 33 + c] = z[c];
+        __syncwarp();
+        const int col = c0 + lane;
+        const bool col_ok = col < a.d;
+        const float muv = (a.q_prop && col_ok) ? a.mu[col] : 0.f;
+        // all 32 rows' loads are issued before the first use (memory-level parallelism: 64 lines in flight per warp)
+        float pv[32], qv[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          pv[r] = 0.f; qv[r] = 0.f;
+          if (r < nrows && col_ok) {
+            pv[r] = a.p[(row0 + r) * (size_t)a.d + col];
+            if (a.q_prop) qv[r] = a.q_prop[(row0 + r) * (size_t)a.d + col];
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          if (r < nrows) {
+            const size_t row = row0 + r;
+            const float zv = tr[r * 33 + lane];
+            float pn = 0.f, dl = 0.f;
+            if (col_ok) {
+              pn = fmaf(-a.coef, zv, pv[r]);
+              a.p[row * (size_t)a.d + col] = pn;
+              if (a.logp_out) dl = a.a_hi[row * (size_t)a.kpad + col] + a.a_lo[row * (size_t)a.kpad + col];
+              if (a.q_prop) {
+                const float qn = fmaf(a.drift_eps, pn, qv[r]);
+                a.q_prop[row * (size_t)a.d + col] = qn;
+                const float dn = qn - muv;
+                const float hi = tf32_rna(dn);
+                a.a_hi_next[row * (size_t)a.kpad + col] = hi;
+                a.a_lo_next[row * (size_t)a.kpad + col] = tf32_rna(dn - hi);
               }
             }
-          } else {
-            for (int c = 0; c < 32 && c0 + c < a.d; ++c) {
-              const float pn = fmaf(-a.coef, z[c], prow[c]);
-              prow[c] = pn;
-              if (a.ke_out) ke += pn * pn;
-              if (a.logp_out) quad += z[c] * (hrow[c] + lrow[c]);
+            if (a.logp_out || a.ke_out) {          // trajectory ends only: row sums over the 32 columns
+              float s1 = zv * dl, s2 = pn * pn;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+              if (lane == r) { quad += s1; ke += s2; }
             }
           }
         }
@@ -272,9 +304,9 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
-    if (live) {
-      if (a.logp_out) a.logp_out[row] = a.norm_const - 0.5f * quad;
-      if (a.ke_out) a.ke_out[row] = 0.5f * ke;
+    if (lane < nrows) {
+      if (a.logp_out) a.logp_out[row0 + lane] = a.norm_const - 0.5f * quad;
+      if (a.ke_out) a.ke_out[row0 + lane] = 0.5f * ke;
     }
   }
   tc_fence_before();
@@ -330,33 +362,6 @@ __global__ void __launch_bounds__(256) dense_begin_kernel(const BeginArgs a) {
   }
   for (int o = 16; o > 0; o >>= 1) ke += __shfl_xor_sync(0xffffffffu, ke, o);
   if (lane == 0) a.ke0[chain] = 0.5f * ke;
-}
-
-// q_prop += eps * p ; delta split   (grid-stride over [C, kpad / 4] float4 items)
-__global__ void __launch_bounds__(256) dense_drift_kernel(size_t n_chains, int d, int kpad, float eps, float* __restrict__ q_prop,
-                                                          const float* __restrict__ p, const float* __restrict__ mu,
-                                                          float* __restrict__ a_hi, float* __restrict__ a_lo) {
-  const int per = kpad / 4;
-  const size_t total = n_chains * (size_t)per;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t chain = i / per;
-    const int c0 = (int)(i - chain * per) * 4;
-    float hi[4], lo[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = c0 + k;
-      float dl = 0.f;
-      if (c < d) {
-        const float qn = fmaf(eps, p[chain * d + c], q_prop[chain * d + c]);
-        q_prop[chain * d + c] = qn;
-        dl = qn - mu[c];
-      }
-      hi[k] = tf32_rna(dl);
-      lo[k] = tf32_rna(dl - hi[k]);   // rounded (not hardware-truncated) low part: unbiased
-    }
-    *reinterpret_cast<float4*>(a_hi + chain * kpad + c0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<float4*>(a_lo + chain * kpad + c0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-  }
 }
 
 struct AcceptArgs {
@@ -421,7 +426,7 @@ bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uin
   cuuint32_t box[2] = {(cuuint32_t)kTileK, box_rows};
   cuuint32_t estr[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+             kTileK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 inline float host_tf32_rna(float x) {
@@ -440,16 +445,17 @@ inline float host_tf32_rna(float x) {
 struct DenseTc {
   int d = 0, kpad = 0, npad = 0;
   size_t n_chains = 0;
-  float *p = nullptr, *q_prop = nullptr, *a_hi = nullptr, *a_lo = nullptr, *b_hi = nullptr, *b_lo = nullptr, *mu = nullptr;
+  float *p = nullptr, *q_prop = nullptr, *a_hi = nullptr, *a_lo = nullptr, *a_hi2 = nullptr, *a_lo2 = nullptr;
+  float *b_hi = nullptr, *b_lo = nullptr, *mu = nullptr;
   float *logp0 = nullptr, *logp1 = nullptr, *ke0 = nullptr, *ke1 = nullptr;
   float norm_const = 0.f;
-  CUtensorMap map_ahi, map_alo, map_bhi, map_blo;
+  CUtensorMap map_ahi, map_alo, map_ahi2, map_alo2, map_bhi, map_blo;
   size_t smem = 0;
 };
 
 void dense_tc_destroy(DenseTc* t) {
   if (!t) return;
-  cudaFree(t->p); cudaFree(t->q_prop); cudaFree(t->a_hi); cudaFree(t->a_lo); cudaFree(t->b_hi); cudaFree(t->b_lo); cudaFree(t->mu);
+  cudaFree(t->p); cudaFree(t->q_prop); cudaFree(t->a_hi); cudaFree(t->a_lo); cudaFree(t->a_hi2); cudaFree(t->a_lo2); cudaFree(t->b_hi); cudaFree(t->b_lo); cudaFree(t->mu);
   cudaFree(t->logp0); cudaFree(t->logp1); cudaFree(t->ke0); cudaFree(t->ke1);
   delete t;
 }
@@ -460,12 +466,14 @@ DenseTc* dense_tc_create(size_t n_chains, int d, const double* params, const cha
   static const char* e_map = "dense tensor-core path: cuTensorMapEncodeTiled unavailable or failed";
   DenseTc* t = new DenseTc();
   t->d = d; t->n_chains = n_chains;
-  t->kpad = ((d + kTileK - 1) / kTileK) * kTileK;
+  t->kpad = ((d + kKPadUnit - 1) / kKPadUnit) * kKPadUnit;
   t->npad = ((d + kTileN - 1) / kTileN) * kTileN;
   t->norm_const = (float)params[(size_t)d + (size_t)d * d];
   const size_t C = n_chains;
   bool ok = cudaMalloc(&t->p, C * d * 4) == cudaSuccess && cudaMalloc(&t->q_prop, C * d * 4) == cudaSuccess &&
             cudaMalloc(&t->a_hi, C * (size_t)t->kpad * 4) == cudaSuccess && cudaMalloc(&t->a_lo, C * (size_t)t->kpad * 4) == cudaSuccess &&
+            cudaMalloc(&t->a_hi2, C * (size_t)t->kpad * 4) == cudaSuccess && cudaMalloc(&t->a_lo2, C * (size_t)t->kpad * 4) == cudaSuccess &&
+            cudaMemset(t->a_hi2, 0, C * (size_t)t->kpad * 4) == cudaSuccess && cudaMemset(t->a_lo2, 0, C * (size_t)t->kpad * 4) == cudaSuccess &&
             cudaMalloc(&t->b_hi, (size_t)t->npad * t->kpad * 4) == cudaSuccess && cudaMalloc(&t->b_lo, (size_t)t->npad * t->kpad * 4) == cudaSuccess &&
             cudaMalloc(&t->mu, (size_t)d * 4) == cudaSuccess && cudaMalloc(&t->logp0, C * 4) == cudaSuccess &&
             cudaMalloc(&t->logp1, C * 4) == cudaSuccess && cudaMalloc(&t->ke0, C * 4) == cudaSuccess && cudaMalloc(&t->ke1, C * 4) == cudaSuccess;
@@ -485,10 +493,11 @@ DenseTc* dense_tc_create(size_t n_chains, int d, const double* params, const cha
        cudaMemcpy(t->mu, mu.data(), (size_t)d * 4, cudaMemcpyHostToDevice) == cudaSuccess;
   if (!ok) { *err = e_alloc; dense_tc_destroy(t); return nullptr; }
   ok = make_map(&t->map_ahi, t->a_hi, C, (uint64_t)t->kpad, kTileM) && make_map(&t->map_alo, t->a_lo, C, (uint64_t)t->kpad, kTileM) &&
+       make_map(&t->map_ahi2, t->a_hi2, C, (uint64_t)t->kpad, kTileM) && make_map(&t->map_alo2, t->a_lo2, C, (uint64_t)t->kpad, kTileM) &&
        make_map(&t->map_bhi, t->b_hi, (uint64_t)t->npad, (uint64_t)t->kpad, kTileN) &&
        make_map(&t->map_blo, t->b_lo, (uint64_t)t->npad, (uint64_t)t->kpad, kTileN);
   if (!ok) { *err = e_map; dense_tc_destroy(t); return nullptr; }
-  t->smem = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  t->smem = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + 4 * 32 * 33 * 4 /*epilogue transpose*/;
   if (cudaFuncSetAttribute(dense_gemm_kick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem) != cudaSuccess) {
     *err = "dense tensor-core path: shared-memory opt-in failed";
     dense_tc_destroy(t);
@@ -497,13 +506,17 @@ DenseTc* dense_tc_create(size_t n_chains, int d, const double* params, const cha
   return t;
 }
 
-static cudaError_t gemm_kick(DenseTc* t, float coef, float* logp_out, float* ke_out, cudaStream_t st) {
+// GEMM on A buffer `buf` (0 / 1); drift_eps != 0 fuses the next leapfrog's drift and writes the other A buffer
+static cudaError_t gemm_kick(DenseTc* t, int buf, float coef, float drift_eps, float* logp_out, float* ke_out, cudaStream_t st) {
   GemmArgs g;
   g.d = t->d; g.kpad = t->kpad; g.npad = t->npad; g.n_chains = t->n_chains;
-  g.p = t->p; g.a_hi = t->a_hi; g.a_lo = t->a_lo; g.coef = coef; g.norm_const = t->norm_const;
+  g.p = t->p; g.a_hi = buf ? t->a_hi2 : t->a_hi; g.a_lo = buf ? t->a_lo2 : t->a_lo; g.coef = coef; g.norm_const = t->norm_const;
   g.logp_out = logp_out; g.ke_out = ke_out;
+  g.q_prop = drift_eps != 0.f ? t->q_prop : nullptr; g.mu = t->mu;
+  g.a_hi_next = buf ? t->a_hi : t->a_hi2; g.a_lo_next = buf ? t->a_lo : t->a_lo2; g.drift_eps = drift_eps;
   const unsigned blocks = (unsigned)((t->n_chains + kTileM - 1) / kTileM);
-  dense_gemm_kick_kernel<<<blocks, kGemmThreads, t->smem, st>>>(t->map_ahi, t->map_alo, t->map_bhi, t->map_blo, g);
+  if (buf) dense_gemm_kick_kernel<<<blocks, kGemmThreads, t->smem, st>>>(t->map_ahi2, t->map_alo2, t->map_bhi, t->map_blo, g);
+  else dense_gemm_kick_kernel<<<blocks, kGemmThreads, t->smem, st>>>(t->map_ahi, t->map_alo, t->map_bhi, t->map_blo, g);
   return cudaGetLastError();
 }
 
@@ -520,15 +533,20 @@ int dense_tc_transition(DenseTc* t, const DenseTcStep& S, cudaStream_t st) {
   dense_begin_kernel<<<wblocks, 256, 0, st>>>(b);
   ++launches;
   const float eps = (float)S.eps, half = 0.5f * eps;
-  // gradient at the current point: log density + first half kick
-  if (gemm_kick(t, S.n_leapfrog > 0 ? half : 0.f, t->logp0, S.n_leapfrog > 0 ? nullptr : t->ke1, st) != cudaSuccess) return -1;
-  ++launches;
-  const unsigned dblocks = (unsigned)std::min<size_t>((C * (size_t)(t->kpad / 4) + 255) / 256, (size_t)148 * 32);
-  for (uint32_t l = 0; l < S.n_leapfrog; ++l) {
-    dense_drift_kernel<<<dblocks, 256, 0, st>>>(C, t->d, t->kpad, eps, t->q_prop, t->p, t->mu, t->a_hi, t->a_lo);
-    const bool last = (l + 1 == S.n_leapfrog);
-    if (gemm_kick(t, last ? half : eps, last ? t->logp1 : nullptr, last ? t->ke1 : nullptr, st) != cudaSuccess) return -1;
-    launches += 2;
+  // GEMM 0: gradient at the current point (log density, first half kick, drift of leapfrog 1);
+  // GEMM l (1 <= l < L): kick eps + drift of leapfrog l + 1;  GEMM L: last half kick, log density, kinetic energy
+  if (S.n_leapfrog == 0) {
+    if (gemm_kick(t, 0, 0.f, 0.f, t->logp0, t->ke1, st) != cudaSuccess) return -1;
+    ++launches;
+  } else {
+    if (gemm_kick(t, 0, half, eps, t->logp0, nullptr, st) != cudaSuccess) return -1;
+    ++launches;
+    for (uint32_t l = 1; l <= S.n_leapfrog; ++l) {
+      const bool last = (l == S.n_leapfrog);
+      if (gemm_kick(t, (int)(l & 1u), last ? half : eps, last ? 0.f : eps, last ? t->logp1 : nullptr, last ? t->ke1 : nullptr, st) != cudaSuccess)
+        return -1;
+      ++launches;
+    }
   }
   AcceptArgs a;
   a.n_chains = C; a.d = t->d; a.chain_offset = S.chain_offset; a.key = b.key; a.step = S.step;
