@@ -400,11 +400,13 @@ def run_ours(args, rank, world, local):
             dptr = s.run_device(n_ess, 0)
             ev[1].record(stream)
         st = L.RunStatsC()
-        t_s0 = time.perf_counter()
-        L.check(lib.gmcmc_run_stats_from(ctx._h, C.c_void_p(dptr), C.c_size_t(chains), C.c_size_t(n_ess), C.c_size_t(DIM),
-                                         L.F32, 1, C.byref(st)))
-        ctx.synchronize()
-        t_s1 = time.perf_counter()
+        for _ in range(2):       # the first call pays one-time kernel loading; the second is timed
+            ctx.synchronize()
+            t_s0 = time.perf_counter()
+            L.check(lib.gmcmc_run_stats_from(ctx._h, C.c_void_p(dptr), C.c_size_t(chains), C.c_size_t(n_ess), C.c_size_t(DIM),
+                                             L.F32, 1, C.byref(st)))
+            ctx.synchronize()
+            t_s1 = time.perf_counter()
         sample_ms = max_over_ranks(ev[0].elapsed_time(ev[1]))
         stats_ms = max_over_ranks((t_s1 - t_s0) * 1e3)
         ess = {"min_ess": st.ess.min, "median_ess": st.ess.median, "min_ess_per_sec": st.ess.min / (sample_ms * 1e-3),

@@ -21,7 +21,8 @@
 // dense_gemm_kick_kernel: one CTA per 128 chains, warp-specialised — warp 0 lane 0 issues TMA loads
 // (A_hi, A_lo [128 x 32], P_hi, P_lo [256 x 32], SWIZZLE_128B, 2 stages of 96 KB), warp 1 lane 0 issues the
 // tcgen05.mma (128 x 256 x 8, accumulators double-buffered over the 512 TMEM columns), warps 2-5 drain the
-// accumulator with tcgen05.ld (thread == chain row) and apply the kick.
+// accumulator with tcgen05.ld, transpose it through shared memory and apply the kick (+ next drift) with
+// row-contiguous global accesses (8 epilogue warps: two per TMEM lane quarter).
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -47,7 +48,8 @@ constexpr int kTileK = GM_TC_TILEK;   // floats per K stage: 16 (64-byte rows, S
 constexpr int kUmmaK = 8;        // tf32 elements per tcgen05.mma
 constexpr int kStages = kTileK == 16 ? 4 : 2;
 constexpr int kKPadUnit = 32;    // K is padded to a multiple of 32 floats in both layouts
-constexpr int kGemmThreads = 192;  // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue
+constexpr int kEpiWarps = 8;        // two warps per TMEM lane quarter, interleaved over the 32-column blocks
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
 constexpr uint32_t kABytes = kTileM * kTileK * 4;   // 16 KB
 constexpr uint32_t kBBytes = kTileN * kTileK * 4;   // 32 KB
 constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // 96 KB
@@ -177,7 +179,7 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -242,6 +244,7 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
     // line per warp instruction for p, q_prop and the next A operand.
     const int q4 = warp & 3;                     // TMEM lane quarter this warp may access
     float* tr = reinterpret_cast<float*>(base + (size_t)kStages * kStageBytes + 256) + (size_t)(warp - 2) * 32 * 33;
+    const int cb_first = (warp - 2) >> 2;         // warps 2-5 take the even 32-column blocks, warps 6-9 the odd ones
     const size_t row0 = (size_t)m0 + (size_t)q4 * 32;
     const int nrows = row0 < a.n_chains ? (int)((a.n_chains - row0) < 32 ? (a.n_chains - row0) : 32) : 0;
     float quad = 0.f, ke = 0.f;                  // lane r holds the sums of row r
@@ -250,7 +253,7 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
       mbar_wait(&tfull[acc], (uint32_t)((n >> 1) & 1));
       tc_fence_after();
 #pragma unroll 1
-      for (int cb = 0; cb < kTileN / 32; ++cb) {
+      for (int cb = cb_first; cb < kTileN / 32; cb += kEpiWarps / 4) {
         float z[32];
         tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * kTileN + cb * 32), z);
         const int c0 = n * kTileN + cb * 32;
@@ -262,40 +265,45 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
         const int col = c0 + lane;
         const bool col_ok = col < a.d;
         const float muv = (a.q_prop && col_ok) ? a.mu[col] : 0.f;
-        // all 32 rows' loads are issued before the first use (memory-level parallelism: 64 lines in flight per warp)
-        float pv[32], qv[32];
+        // 16 rows at a time; all their loads are issued before the first use (32 lines in flight per warp)
+#pragma unroll 1
+        for (int rb = 0; rb < 32; rb += 16) {
+          float pv[16], qv[16];
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          pv[r] = 0.f; qv[r] = 0.f;
-          if (r < nrows && col_ok) {
-            pv[r] = a.p[(row0 + r) * (size_t)a.d + col];
-            if (a.q_prop) qv[r] = a.q_prop[(row0 + r) * (size_t)a.d + col];
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          if (r < nrows) {
-            const size_t row = row0 + r;
-            const float zv = tr[r * 33 + lane];
-            float pn = 0.f, dl = 0.f;
-            if (col_ok) {
-              pn = fmaf(-a.coef, zv, pv[r]);
-              a.p[row * (size_t)a.d + col] = pn;
-              if (a.logp_out) dl = a.a_hi[row * (size_t)a.kpad + col] + a.a_lo[row * (size_t)a.kpad + col];
-              if (a.q_prop) {
-                const float qn = fmaf(a.drift_eps, pn, qv[r]);
-                a.q_prop[row * (size_t)a.d + col] = qn;
-                const float dn = qn - muv;
-                const float hi = tf32_rna(dn);
-                a.a_hi_next[row * (size_t)a.kpad + col] = hi;
-                a.a_lo_next[row * (size_t)a.kpad + col] = tf32_rna(dn - hi);
-              }
+          for (int rr = 0; rr < 16; ++rr) {
+            const int r = rb + rr;
+            pv[rr] = 0.f; qv[rr] = 0.f;
+            if (r < nrows && col_ok) {
+              pv[rr] = a.p[(row0 + r) * (size_t)a.d + col];
+              if (a.q_prop) qv[rr] = a.q_prop[(row0 + r) * (size_t)a.d + col];
             }
-            if (a.logp_out || a.ke_out) {          // trajectory ends only: row sums over the 32 columns
-              float s1 = zv * dl, s2 = pn * pn;
+          }
 #pragma unroll
-              for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-              if (lane == r) { quad += s1; ke += s2; }
+          for (int rr = 0; rr < 16; ++rr) {
+            const int r = rb + rr;
+            if (r < nrows) {
+              const size_t row = row0 + r;
+              const float zv = tr[r * 33 + lane];
+              float pn = 0.f, dl = 0.f;
+              if (col_ok) {
+                pn = fmaf(-a.coef, zv, pv[rr]);
+                a.p[row * (size_t)a.d + col] = pn;
+                if (a.logp_out) dl = a.a_hi[row * (size_t)a.kpad + col] + a.a_lo[row * (size_t)a.kpad + col];
+                if (a.q_prop) {
+                  const float qn = fmaf(a.drift_eps, pn, qv[rr]);
+                  a.q_prop[row * (size_t)a.d + col] = qn;
+                  const float dn = qn - muv;
+                  const float hi = tf32_rna(dn);
+                  a.a_hi_next[row * (size_t)a.kpad + col] = hi;
+                  a.a_lo_next[row * (size_t)a.kpad + col] = tf32_rna(dn - hi);
+                }
+              }
+              if (a.logp_out || a.ke_out) {          // trajectory ends only: row sums over the 32 columns
+                float s1 = zv * dl, s2 = pn * pn;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+                if (lane == r) { quad += s1; ke += s2; }
+              }
             }
           }
         }
@@ -304,9 +312,17 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
-    if (lane < nrows) {
-      if (a.logp_out) a.logp_out[row0 + lane] = a.norm_const - 0.5f * quad;
-      if (a.ke_out) a.ke_out[row0 + lane] = 0.5f * ke;
+    // the two warps of a quarter hold partial row sums (even / odd column blocks): combine through shared memory
+    if (a.logp_out || a.ke_out) {
+      float* red = tr;                       // this warp's transpose tile is free now
+      __syncwarp();
+      red[lane] = quad; red[32 + lane] = ke;
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory");   // epilogue warps only
+      if (cb_first == 0 && lane < nrows) {
+        const float* other = tr + (size_t)4 * 32 * 33;   // partner warp (same quarter, odd blocks)
+        if (a.logp_out) a.logp_out[row0 + lane] = a.norm_const - 0.5f * (quad + other[lane]);
+        if (a.ke_out) a.ke_out[row0 + lane] = 0.5f * (ke + other[32 + lane]);
+      }
     }
   }
   tc_fence_before();
@@ -497,7 +513,7 @@ DenseTc* dense_tc_create(size_t n_chains, int d, const double* params, const cha
        make_map(&t->map_bhi, t->b_hi, (uint64_t)t->npad, (uint64_t)t->kpad, kTileN) &&
        make_map(&t->map_blo, t->b_lo, (uint64_t)t->npad, (uint64_t)t->kpad, kTileN);
   if (!ok) { *err = e_map; dense_tc_destroy(t); return nullptr; }
-  t->smem = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + 4 * 32 * 33 * 4 /*epilogue transpose*/;
+  t->smem = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + (size_t)kEpiWarps * 32 * 33 * 4 /*epilogue transpose*/;
   if (cudaFuncSetAttribute(dense_gemm_kick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem) != cudaSuccess) {
     *err = "dense tensor-core path: shared-memory opt-in failed";
     dense_tc_destroy(t);

@@ -30,8 +30,8 @@ namespace gm {
 
 namespace {
 
-constexpr int kStatsBlock = 256;
-constexpr int kMaxPpb = 8;  // parameters per CTA (8 f32 = one 32-byte sector)
+constexpr int kStatsBlock = 512;
+constexpr int kMaxPpb = 32;  // parameters per CTA (32 f32 = one 128-byte line per draw; fewer when the FFT is long)
 
 __device__ __forceinline__ unsigned bitrev(unsigned v, int log2n) { return __brev(v) >> (32 - log2n); }
 
@@ -45,8 +45,8 @@ __device__ __forceinline__ void smem_fft(float* re, float* im, int nser, int N, 
     const int hl = 1 << (s - 1);        // half length of this stage's butterflies
     const int tw_stride = N >> s;       // twiddle index stride
     for (int b = threadIdx.x; b < total; b += blockDim.x) {
-      const int ser = b / half_n;
-      const int bb = b - ser * half_n;
+      const int ser = b >> (log2n - 1);          // half_n = 2^(log2n - 1)
+      const int bb = b & (half_n - 1);
       const int grp = bb >> (s - 1);
       const int k = bb & (hl - 1);
       const int i = ser * N + (grp << s) + k;
@@ -83,7 +83,7 @@ stats_accumulate(const TIN* __restrict__ samples, size_t C, size_t n, int p, int
   const int nwarps = kStatsBlock / 32;
 
   for (int i = threadIdx.x; i < ppb * N; i += kStatsBlock) acc[i] = 0.f;
-  if (threadIdx.x < kMaxPpb * 3) mom[threadIdx.x / 3][threadIdx.x % 3] = 0.0;
+  if (threadIdx.x < kMaxPpb * 3) mom[threadIdx.x / 3][threadIdx.x % 3] = 0.0;   // kMaxPpb * 3 = 96 <= blockDim
   __syncthreads();
 
   // contiguous chain range of this group
@@ -240,7 +240,7 @@ size_t stats_npad(size_t n) {
 int stats_ppb(size_t N) {
   // re + im + acc = 12 bytes per (parameter, bin); keep the CTA under ~192 KB of shared memory
   int ppb = kMaxPpb;
-  while (ppb > 1 && (size_t)ppb * N * 12 > 192 * 1024) ppb >>= 1;
+  while (ppb > 1 && (size_t)ppb * N * 12 > 200 * 1024) ppb >>= 1;
   return ppb;
 }
 
