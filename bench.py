@@ -157,14 +157,16 @@ def run_reference(args, rank, world):
     if args.workload == "mh_gauss2d":
         rate, threads, sample = cpu_mh_rate(30.0)
         metric, unit = "mh_chain_steps_per_sec", "chain-steps/s"
-        cfg = {"workload": "cfg2: batched MH Gaussian2D, IsotropicGaussian proposal, f64 (CPU sample)"}
+        cfg = {"workload": "cfg2: batched MH, Gaussian2D target, IsotropicGaussian proposal, %d chains/GPU, f64 state and output"
+                           % (args.chains or 1048576)}
         dtype = "f64"
     else:
         t0 = time.time()
         # bounded: a sample of chains, K transitions capped by a time budget
         rate, threads, sample = cpu_hmc_rate(min(60.0, max(5.0, 0.02 * args.steps)))
         metric, unit = "leapfrog_grad_evals_per_sec", "grad-evals/s"
-        cfg = {"workload": "cfg4 shard: batched HMC RosenbrockND d=100 L=32 f32 (CPU sample)"}
+        cfg = {"workload": ("cfg4 shard: batched HMC, RosenbrockND d=%d, %d chains/GPU, L=%d, f32, pooled dual-averaging "
+                            "warm-up then fixed step" % (DIM, args.chains or CHAINS_PER_GPU, N_LEAPFROG))}
         dtype = "f32"
         del t0
     line = {"impl": "reference", "metric": metric, "value": rate, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
