@@ -15,6 +15,7 @@ Samples come back as numpy arrays [chains, samples, dim] (core.rs:219-229, hmc.r
 float64, HMC/NUTS in the sampler's dtype.  All arithmetic happens in libgmcmc.so on the GPU.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -212,6 +213,41 @@ class GaussianMixture(_Target):
 
     def params(self):
         return np.concatenate([[self.weights.size, self.sigma], self.weights, self.means.ravel()])
+
+
+class CustomTarget(_Target):
+    """A user-written device target compiled ahead of time into a plugin (csrc/gmcmc_custom_target.cuh);
+    ≙ implementing GradientTarget / BatchedGradientTarget (distributions.rs:67-90) in the reference."""
+    kind = 7
+
+    def __init__(self, plugin_path, dim, params=()):
+        self.plugin_path = os.path.abspath(plugin_path)
+        self.dim = int(dim)
+        self._params = np.asarray(params, np.float64).ravel()
+
+    def params(self):
+        return self._params
+
+    def _create(self, ctx, dtype):
+        p = np.ascontiguousarray(self._params, dtype=np.float64)
+        h = C.c_void_p()
+        L.check(L.lib().gmcmc_target_create_custom(ctx._h, self.plugin_path.encode(), L.dtype_code(dtype), L.ptr(p),
+                                                   C.c_size_t(p.size), C.byref(h)))
+        return h
+
+
+def build_custom_target(source, out=None, extra_flags=()):
+    """nvcc-compiles a custom-target source (see csrc/gmcmc_custom_target.cuh) into a plugin .so for sm_100a."""
+    import shutil
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = out or os.path.splitext(source)[0] + ".so"
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc, "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
+           "-shared", "-I", os.path.join(here, "csrc"), "-I", os.path.join(os.path.dirname(here), "include"),
+           *extra_flags, source, "-o", out]
+    subprocess.check_call(cmd)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -149,6 +149,17 @@ struct StatsLaunch {
   float* acov;           // [p, n/2] mean autocovariance (optional, may be null)
 };
 
+// custom-target plugins (gmcmc_custom_target.cuh): the launchers a plugin instantiates for its target
+constexpr int kCustomAbiVersion = 1;
+constexpr int kTargetCustom = 7;      // TargetDesc.kind of a plugin target
+struct CustomTargetVTable {
+  int abi_version;
+  int dim;
+  cudaError_t (*launch_hmc)(const HmcLaunch&, cudaStream_t);
+  cudaError_t (*launch_eval)(const EvalLaunch&, cudaStream_t);
+  cudaError_t (*launch_nuts)(const NutsLaunch&, cudaStream_t);
+};
+
 size_t stats_npad(size_t n);
 int stats_ppb(size_t N);
 void stats_fill_twiddles(size_t N, float* host_tw);

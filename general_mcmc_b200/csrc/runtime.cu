@@ -123,6 +123,8 @@ struct gmcmc_target {
   void* dparams = nullptr;
   std::vector<double> params;
   int refs = 1;
+  const CustomTargetVTable* custom = nullptr;   // plugin target (gmcmc_target_create_custom)
+  void* plugin = nullptr;                       // dlopen handle
 };
 
 enum SamplerType { S_HMC = 0, S_MH = 1, S_NUTS = 2 };
@@ -335,7 +337,8 @@ gmcmc_status hmc_segment(gmcmc_sampler* s, size_t first, size_t count, size_t n_
     L.diag_pp = (char*)s->d_diag_pp + inj_first * s->n_chains * s->dim * es;
   }
   L.epl = s->epl; L.lpc = s->lpc;
-  cudaError_t e = (s->math == GMCMC_MATH_EXACT) ? launch_hmc_exact(L, s->ctx->stream) : launch_hmc_fast(L, s->ctx->stream);
+  cudaError_t e = s->tgt->custom ? s->tgt->custom->launch_hmc(L, s->ctx->stream)
+                  : (s->math == GMCMC_MATH_EXACT) ? launch_hmc_exact(L, s->ctx->stream) : launch_hmc_fast(L, s->ctx->stream);
   if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "HMC kernel launch failed: %s", cudaGetErrorString(e));
   s->launches += 1;
   return GMCMC_OK;
@@ -395,7 +398,8 @@ gmcmc_status nuts_launch(gmcmc_sampler* s, NutsLaunch& L) {
   L.inj_unif = s->d_nuts_inj[2]; L.n_unif = s->nuts_inj_n[2];
   L.inj_used = s->d_nuts_used;
   L.epl = s->epl; L.lpc = s->lpc;
-  cudaError_t e = (s->math == GMCMC_MATH_EXACT) ? launch_nuts_exact(L, s->ctx->stream) : launch_nuts_fast(L, s->ctx->stream);
+  cudaError_t e = s->tgt->custom ? s->tgt->custom->launch_nuts(L, s->ctx->stream)
+                  : (s->math == GMCMC_MATH_EXACT) ? launch_nuts_exact(L, s->ctx->stream) : launch_nuts_fast(L, s->ctx->stream);
   if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "NUTS kernel launch failed: %s", cudaGetErrorString(e));
   s->launches += 1;
   return GMCMC_OK;
@@ -805,7 +809,49 @@ gmcmc_status gmcmc_target_destroy(gmcmc_target* t) {
   if (--t->refs > 0) return GMCMC_OK;
   cudaSetDevice(t->ctx->device);
   cudaFree(t->dparams);
+  if (t->plugin) dlclose(t->plugin);
   delete t;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_target_create_custom(gmcmc_ctx* ctx, const char* plugin_path, gmcmc_dtype dtype, const double* params,
+                                        size_t n_params, gmcmc_target** out) {
+  GM_REQUIRE(ctx && plugin_path && out, "null argument");
+  GM_REQUIRE(dtype == GMCMC_F32 || dtype == GMCMC_F64, "bad dtype");
+  GM_REQUIRE(params || n_params == 0, "null params");
+  GM_CU(cudaSetDevice(ctx->device));
+  void* h = dlopen(plugin_path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) return fail(GMCMC_ERR_INVALID, "cannot load custom-target plugin %s: %s", plugin_path, dlerror());
+  typedef const CustomTargetVTable* (*EntryFn)(void);
+  EntryFn entry = (EntryFn)dlsym(h, "gmcmc_custom_entry");
+  if (!entry) { dlclose(h); return fail(GMCMC_ERR_INVALID, "%s does not export gmcmc_custom_entry (GMCMC_REGISTER_CUSTOM_TARGET)", plugin_path); }
+  const CustomTargetVTable* vt = entry();
+  if (!vt || vt->abi_version != kCustomAbiVersion || vt->dim < 1 || vt->dim > 32) {
+    dlclose(h);
+    return fail(GMCMC_ERR_INVALID, "custom-target plugin %s has an incompatible ABI version or dimension", plugin_path);
+  }
+  gmcmc_target* t = new gmcmc_target();
+  t->ctx = ctx; t->custom = vt; t->plugin = h;
+  t->params.assign(params, params + n_params);
+  TargetDesc& d = t->desc;
+  d.kind = kTargetCustom; d.dtype = (int)dtype; d.dim = vt->dim; d.dparams = nullptr; d.n_comp = 0;
+  for (int i = 0; i < kMaxScalarParams; ++i) d.sp[i] = i < (int)n_params ? params[i] : 0.0;
+  if (n_params) {
+    const size_t es = esize(dtype);
+    std::vector<char> host(n_params * es);
+    for (size_t i = 0; i < n_params; ++i) {
+      if (dtype == GMCMC_F32) ((float*)host.data())[i] = (float)params[i];
+      else ((double*)host.data())[i] = params[i];
+    }
+    if (cudaMalloc(&t->dparams, n_params * es) != cudaSuccess ||
+        cudaMemcpy(t->dparams, host.data(), n_params * es, cudaMemcpyHostToDevice) != cudaSuccess) {
+      gmcmc_status st = fail(GMCMC_ERR_CUDA, "custom target parameter upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+      gmcmc_target_destroy(t);
+      return st;
+    }
+    d.dparams = t->dparams;
+  }
+  *out = t;
   return GMCMC_OK;
 }
 
@@ -817,7 +863,8 @@ gmcmc_status gmcmc_target_logp_grad(gmcmc_target* t, const void* x_host, size_t 
   GM_CU(cudaSetDevice(ctx->device));
   EvalLaunch E{};
   E.tgt = t->desc;
-  if (!choose_decomposition(t->desc.dim, t->desc.dtype, t->desc.kind, &E.epl, &E.lpc))
+  if (t->custom) { E.epl = t->desc.dim; E.lpc = 1; }
+  else if (!choose_decomposition(t->desc.dim, t->desc.dtype, t->desc.kind, &E.epl, &E.lpc))
     return fail(GMCMC_ERR_UNSUPPORTED, "dim %d is not supported by the register-resident kernels", t->desc.dim);
   const size_t es = esize(t->desc.dtype), d = (size_t)t->desc.dim;
   TempDevice dx, dl, dg;
@@ -826,7 +873,8 @@ gmcmc_status gmcmc_target_logp_grad(gmcmc_target* t, const void* x_host, size_t 
   if (grad_out) GM_CU(cudaMalloc(&dg.p, n * d * es));
   GM_CU(cudaMemcpyAsync(dx.p, x_host, n * d * es, cudaMemcpyHostToDevice, ctx->stream));
   E.n = n; E.x = dx.p; E.logp = dl.p; E.grad = dg.p;
-  cudaError_t e = (mode == GMCMC_MATH_EXACT) ? launch_eval_exact(E, ctx->stream) : launch_eval_fast(E, ctx->stream);
+  cudaError_t e = t->custom ? t->custom->launch_eval(E, ctx->stream)
+                  : (mode == GMCMC_MATH_EXACT) ? launch_eval_exact(E, ctx->stream) : launch_eval_fast(E, ctx->stream);
   if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "eval kernel launch failed: %s", cudaGetErrorString(e));
   GM_CU(cudaMemcpyAsync(logp_out, dl.p, n * es, cudaMemcpyDeviceToHost, ctx->stream));
   if (grad_out) GM_CU(cudaMemcpyAsync(grad_out, dg.p, n * d * es, cudaMemcpyDeviceToHost, ctx->stream));
@@ -866,7 +914,8 @@ gmcmc_status gmcmc_hmc_create(gmcmc_ctx* ctx, gmcmc_target* tgt, size_t n_chains
   GM_REQUIRE(tgt, "null target");
   GM_REQUIRE(step_size > 0.0, "step_size must be positive");
   int epl = 0, lpc = 0;
-  if (!choose_decomposition(tgt->desc.dim, tgt->desc.dtype, tgt->desc.kind, &epl, &lpc))
+  if (tgt->custom) { epl = tgt->desc.dim; lpc = 1; }
+  else if (!choose_decomposition(tgt->desc.dim, tgt->desc.dtype, tgt->desc.kind, &epl, &lpc))
     return fail(GMCMC_ERR_UNSUPPORTED, "dim %d (dtype %d) is not supported by the HMC kernels", tgt->desc.dim, tgt->desc.dtype);
   gmcmc_sampler* s = nullptr;
   GM_TRY(sampler_common(ctx, tgt, n_chains, chain_offset, init_host, seed, S_HMC, &s));
@@ -904,6 +953,7 @@ gmcmc_status gmcmc_mh_create(gmcmc_ctx* ctx, gmcmc_target* tgt, double proposal_
   GM_REQUIRE(tgt, "null target");
   GM_REQUIRE(proposal_std > 0.0, "proposal_std must be positive");
   const int k = tgt->desc.kind;
+  if (tgt->custom) return fail(GMCMC_ERR_UNSUPPORTED, "custom targets are available for HMC and NUTS");
   if (!(k == 0 || k == 1 || k == 2 || k == 4 || k == 5) || tgt->desc.dim > 32)
     return fail(GMCMC_ERR_UNSUPPORTED, "MH kernel supports targets ISO_GAUSS, GAUSS2D, DIFF_GAUSS2D, ROSENBROCK2D, ROSENBROCK_ND with dim <= 32");
   gmcmc_sampler* s = nullptr;
@@ -919,7 +969,8 @@ gmcmc_status gmcmc_nuts_create(gmcmc_ctx* ctx, gmcmc_target* tgt, size_t n_chain
   GM_REQUIRE(tgt, "null target");
   GM_REQUIRE(target_accept > 0.0 && target_accept < 1.0, "target_accept must be in (0, 1)");
   int epl = 0, lpc = 0;
-  if (!choose_nuts_decomposition(tgt->desc.dim, tgt->desc.dtype, tgt->desc.kind, &epl, &lpc))
+  if (tgt->custom) { epl = tgt->desc.dim; lpc = 1; }
+  else if (!choose_nuts_decomposition(tgt->desc.dim, tgt->desc.dtype, tgt->desc.kind, &epl, &lpc))
     return fail(GMCMC_ERR_UNSUPPORTED, "target kind %d with dim %d is not supported by the NUTS kernels", tgt->desc.kind, tgt->desc.dim);
   gmcmc_sampler* s = nullptr;
   GM_TRY(sampler_common(ctx, tgt, n_chains, chain_offset, init_host, seed, S_NUTS, &s));

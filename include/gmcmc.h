@@ -126,6 +126,12 @@ gmcmc_status gmcmc_measure_fp32_peak(gmcmc_ctx*, double* tflops);
 /* ---- targets (distributions.rs traits Target / BatchedGradientTarget / GradientTarget :67-110) */
 gmcmc_status gmcmc_target_create(gmcmc_ctx*, gmcmc_target_kind kind, gmcmc_dtype dtype, int dim,
                                  const double* params, size_t n_params, gmcmc_target** out);
+/* Custom target = a user-written device log-density-and-gradient function compiled AHEAD OF TIME with nvcc
+ * into a plugin shared library (general_mcmc_b200/csrc/gmcmc_custom_target.cuh, GMCMC_REGISTER_CUSTOM_TARGET);
+ * ≙ a user impl of GradientTarget / BatchedGradientTarget (distributions.rs:67-90).  `params` are converted
+ * to `dtype` and handed to the device function.  Usable with gmcmc_hmc_create and gmcmc_nuts_create. */
+gmcmc_status gmcmc_target_create_custom(gmcmc_ctx*, const char* plugin_path, gmcmc_dtype dtype,
+                                        const double* params, size_t n_params, gmcmc_target** out);
 gmcmc_status gmcmc_target_destroy(gmcmc_target*);
 /* logp and gradient for a batch of host positions [n, dim] (≙ BatchedHamiltonianTarget::logp_and_grad,
  * batched_hmc.rs:18-22).  grad_out may be NULL. */

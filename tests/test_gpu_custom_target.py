@@ -1,0 +1,60 @@
+"""Ahead-of-time compiled custom targets (north star: "custom targets plug in as AOT-compiled device logp/grad
+functions registered through the same C ABI"): tests/plugins/banana.cu is compiled with nvcc against
+csrc/gmcmc_custom_target.cuh and driven through gmcmc_target_create_custom."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import general_mcmc_b200 as gm  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "plugins", "banana.cu")
+SO = os.path.join(HERE, "plugins", "banana.so")
+
+
+@pytest.fixture(scope="module")
+def banana():
+    hdr = os.path.join(os.path.dirname(HERE), "general_mcmc_b200", "csrc", "gmcmc_custom_target.cuh")
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
+        gm.build_custom_target(SRC, SO)
+    return gm.CustomTarget(SO, 3, [1.5, 0.3])
+
+
+def _ref(x, s=1.5, b=0.3):
+    r = x[:, 1] - b * x[:, 0] ** 2
+    u = x[:, 2] - 1.0
+    lp = -0.5 * x[:, 0] ** 2 / s**2 - 0.5 * r * r - 2.0 * u * u
+    g = np.stack([-x[:, 0] / s**2 + 2 * b * x[:, 0] * r, -r, -4.0 * u], axis=1)
+    return lp, g
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-5), (np.float64, 1e-13)])
+def test_custom_target_logp_grad(banana, dtype, tol):
+    x = np.random.default_rng(0).standard_normal((513, 3)).astype(dtype)
+    lp, g = banana.logp_and_grad(x)
+    rlp, rg = _ref(x.astype(np.float64))
+    assert np.allclose(lp, rlp, rtol=tol, atol=tol * 10)
+    assert np.allclose(g, rg, rtol=tol, atol=tol * 10)
+
+
+def test_custom_target_hmc_and_nuts_sample_it(banana):
+    Cn = 4096
+    q0 = np.zeros((Cn, 3), np.float32)
+    q0[:, 2] = 1.0
+    s = gm.HMC(banana, q0, 0.15, 10, seed=42)
+    out, st = s.run_progress(600, 300)
+    flat = out[:, ::5].reshape(-1, 3).astype(np.float64)
+    assert abs(flat[:, 0].var() - 2.25) < 0.08          # x0 ~ N(0, 1.5^2)
+    assert abs(flat[:, 1].mean() - 0.3 * 2.25) < 0.04   # E[x1] = b s^2
+    assert abs(flat[:, 2].mean() - 1.0) < 0.01 and abs(flat[:, 2].var() - 0.25) < 0.01
+    assert s.counters().accept_rate > 0.8
+    n = gm.NUTS(banana, q0[:1024], 0.8, seed=7, max_depth=8)
+    o2 = n.run(300, 200)
+    f2 = o2.reshape(-1, 3).astype(np.float64)
+    assert np.isfinite(f2).all()
+    assert abs(f2[:, 0].var() - 2.25) < 0.2 and abs(f2[:, 2].mean() - 1.0) < 0.03
+    with pytest.raises(gm.GmcmcError):
+        gm.MetropolisHastings(banana, gm.IsotropicGaussian(1.0), q0.astype(np.float64))
