@@ -977,7 +977,8 @@ gmcmc_status gmcmc_nuts_create(gmcmc_ctx* ctx, gmcmc_target* tgt, size_t n_chain
   s->epl = epl; s->lpc = lpc;
   s->target_accept = target_accept;
   s->max_depth = (max_depth == 0 || max_depth > (uint32_t)kNutsDepthCapHost) ? (uint32_t)kNutsDepthCapHost : max_depth;
-  const size_t es = esize(s->dtype), C = n_chains, d = (size_t)s->dim, cap = (size_t)kNutsDepthCapHost;
+  const size_t es = esize(s->dtype), C = n_chains, cap = (size_t)kNutsDepthCapHost;
+  const size_t d = (size_t)lpc * (size_t)((epl + 3) / 4 * 4);   // lane-padded workspace vectors (nuts_kernel.cuh)
   bool ok = true;
   for (int i = 0; i < 4; ++i) ok = ok && cudaMalloc(&s->d_nuts_da[i], C * es) == cudaSuccess;
   ok = ok && cudaMalloc(&s->d_ws_edges, C * 6 * d * es) == cudaSuccess &&
