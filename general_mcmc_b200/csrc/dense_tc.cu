@@ -48,7 +48,11 @@ constexpr int kTileK = GM_TC_TILEK;   // floats per K stage: 16 (64-byte rows, S
 constexpr int kUmmaK = 8;        // tf32 elements per tcgen05.mma
 constexpr int kStages = kTileK == 16 ? 4 : 2;
 constexpr int kKPadUnit = 32;    // K is padded to a multiple of 32 floats in both layouts
-constexpr int kEpiWarps = 8;        // two warps per TMEM lane quarter, interleaved over the 32-column blocks
+#ifndef GM_TC_CLUSTER
+#define GM_TC_CLUSTER 2          // CTAs per cluster sharing every P tile through TMA multicast (1 = no cluster)
+#endif
+constexpr int kCluster = GM_TC_CLUSTER;
+constexpr int kEpiWarps = 8;        // two warps per TMEM lane quarter, interleaved over the 32-column blocks (16 measured the same)
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
 constexpr uint32_t kABytes = kTileM * kTileK * 4;   // 16 KB
 constexpr uint32_t kBBytes = kTileN * kTileK * 4;   // 32 KB
@@ -87,6 +91,26 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
           smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -162,6 +186,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                        const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                        const GemmArgs a) {
+  // With kCluster = 2 the two CTAs of a cluster work on different chain tiles but walk the same (n, k) schedule:
+  // each loads HALF of every P tile (map_b* then describe [kTileN / 2 x kTileK] boxes) and multicasts it into both
+  // CTAs' stages, halving the L2 -> SM traffic of the dominant operand.  A stage may be refilled only when the MMAs
+  // of BOTH CTAs have released it, so the `empty` barriers take two (multicast) commits.
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: stages (1024-byte aligned), then barriers
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -178,7 +206,7 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
   const int k_chunks = a.kpad / kTileK;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kCluster); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -188,8 +216,11 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster > 1) cluster_sync_all();     // peer barriers are initialised before any remote arrival
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = kCluster > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << kCluster) - 1u);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -204,8 +235,15 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
           mbar_expect_tx(&full[s], kStageBytes);
           tma_load_2d(st, &map_ahi, &full[s], k * kTileK, m0);
           tma_load_2d(st + kABytes, &map_alo, &full[s], k * kTileK, m0);
-          tma_load_2d(st + 2 * kABytes, &map_bhi, &full[s], k * kTileK, n * kTileN);
-          tma_load_2d(st + 2 * kABytes + kBBytes, &map_blo, &full[s], k * kTileK, n * kTileN);
+          if constexpr (kCluster > 1) {
+            const int half_rows = kTileN / kCluster;
+            const uint32_t off = crank * (uint32_t)(half_rows * kTileK * 4);
+            tma_load_2d_mc(st + 2 * kABytes + off, &map_bhi, &full[s], k * kTileK, n * kTileN + (int)crank * half_rows, kMask);
+            tma_load_2d_mc(st + 2 * kABytes + kBBytes + off, &map_blo, &full[s], k * kTileK, n * kTileN + (int)crank * half_rows, kMask);
+          } else {
+            tma_load_2d(st + 2 * kABytes, &map_bhi, &full[s], k * kTileK, n * kTileN);
+            tma_load_2d(st + 2 * kABytes + kBBytes, &map_blo, &full[s], k * kTileK, n * kTileN);
+          }
         }
       }
     }
@@ -233,7 +271,8 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
             tc_mma_tf32(tmem_d, d_ahi + adv, d_blo + adv, kIdesc, 1u);
             tc_mma_tf32(tmem_d, d_ahi + adv, d_bhi + adv, kIdesc, 1u);
           }
-          tc_commit(&empty[s]);           // frees the stage when these MMAs have read it
+          if constexpr (kCluster > 1) tc_commit_mc(&empty[s], kMask);   // both CTAs' producers wait for both MMAs
+          else tc_commit(&empty[s]);      // frees the stage when these MMAs have read it
         }
         tc_commit(&tfull[acc]);           // accumulator complete
       }
@@ -243,8 +282,8 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
     // transposed through shared memory so that global accesses run along rows: lane <-> column, one 128-byte
     // line per warp instruction for p, q_prop and the next A operand.
     const int q4 = warp & 3;                     // TMEM lane quarter this warp may access
-    float* tr = reinterpret_cast<float*>(base + (size_t)kStages * kStageBytes + 256) + (size_t)(warp - 2) * 32 * 33;
-    const int cb_first = (warp - 2) >> 2;         // warps 2-5 take the even 32-column blocks, warps 6-9 the odd ones
+    float* tr = reinterpret_cast<float*>(base + (size_t)kStages * kStageBytes + 256) + (size_t)(warp - 2) * 16 * 33;
+    const int cb_first = (warp - 2) >> 2;         // the kEpiWarps / 4 warps of a quarter interleave over the 32-column blocks
     const size_t row0 = (size_t)m0 + (size_t)q4 * 32;
     const int nrows = row0 < a.n_chains ? (int)((a.n_chains - row0) < 32 ? (a.n_chains - row0) : 32) : 0;
     float quad = 0.f, ke = 0.f;                  // lane r holds the sums of row r
@@ -258,16 +297,19 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
         tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * kTileN + cb * 32), z);
         const int c0 = n * kTileN + cb * 32;
         if (c0 >= a.d) continue;                 // padded columns (warp-uniform)
-        __syncwarp();
-#pragma unroll
-        for (int c = 0; c < 32; ++c) tr[lane * 33 + c] = z[c];
-        __syncwarp();
         const int col = c0 + lane;
         const bool col_ok = col < a.d;
         const float muv = (a.q_prop && col_ok) ? a.mu[col] : 0.f;
         // 16 rows at a time; all their loads are issued before the first use (32 lines in flight per warp)
 #pragma unroll 1
         for (int rb = 0; rb < 32; rb += 16) {
+          // transpose 16 accumulator rows through shared memory: lanes rb..rb+15 own them
+          __syncwarp();
+          if ((lane & 16) == rb) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) tr[(lane & 15) * 33 + c] = z[c];
+          }
+          __syncwarp();
           float pv[16], qv[16];
 #pragma unroll
           for (int rr = 0; rr < 16; ++rr) {
@@ -283,7 +325,7 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
             const int r = rb + rr;
             if (r < nrows) {
               const size_t row = row0 + r;
-              const float zv = tr[r * 33 + lane];
+              const float zv = tr[rr * 33 + lane];
               float pn = 0.f, dl = 0.f;
               if (col_ok) {
                 pn = fmaf(-a.coef, zv, pv[rr]);
@@ -319,14 +361,20 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
       red[lane] = quad; red[32 + lane] = ke;
       asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory");   // epilogue warps only
       if (cb_first == 0 && lane < nrows) {
-        const float* other = tr + (size_t)4 * 32 * 33;   // partner warp (same quarter, odd blocks)
-        if (a.logp_out) a.logp_out[row0 + lane] = a.norm_const - 0.5f * (quad + other[lane]);
-        if (a.ke_out) a.ke_out[row0 + lane] = 0.5f * (ke + other[32 + lane]);
+        float qsum = quad, ksum = ke;
+#pragma unroll
+        for (int w = 1; w < kEpiWarps / 4; ++w) {          // partner warps of the same quarter
+          const float* other = tr + (size_t)(4 * w) * 16 * 33;
+          qsum += other[lane]; ksum += other[32 + lane];
+        }
+        if (a.logp_out) a.logp_out[row0 + lane] = a.norm_const - 0.5f * qsum;
+        if (a.ke_out) a.ke_out[row0 + lane] = 0.5f * ksum;
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster > 1) cluster_sync_all();     // no CTA exits while its peer can still multicast into it
   if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -510,10 +558,10 @@ DenseTc* dense_tc_create(size_t n_chains, int d, const double* params, const cha
   if (!ok) { *err = e_alloc; dense_tc_destroy(t); return nullptr; }
   ok = make_map(&t->map_ahi, t->a_hi, C, (uint64_t)t->kpad, kTileM) && make_map(&t->map_alo, t->a_lo, C, (uint64_t)t->kpad, kTileM) &&
        make_map(&t->map_ahi2, t->a_hi2, C, (uint64_t)t->kpad, kTileM) && make_map(&t->map_alo2, t->a_lo2, C, (uint64_t)t->kpad, kTileM) &&
-       make_map(&t->map_bhi, t->b_hi, (uint64_t)t->npad, (uint64_t)t->kpad, kTileN) &&
-       make_map(&t->map_blo, t->b_lo, (uint64_t)t->npad, (uint64_t)t->kpad, kTileN);
+       make_map(&t->map_bhi, t->b_hi, (uint64_t)t->npad, (uint64_t)t->kpad, kTileN / kCluster) &&
+       make_map(&t->map_blo, t->b_lo, (uint64_t)t->npad, (uint64_t)t->kpad, kTileN / kCluster);
   if (!ok) { *err = e_map; dense_tc_destroy(t); return nullptr; }
-  t->smem = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + (size_t)kEpiWarps * 32 * 33 * 4 /*epilogue transpose*/;
+  t->smem = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + (size_t)kEpiWarps * 16 * 33 * 4 /*epilogue transpose*/;
   if (cudaFuncSetAttribute(dense_gemm_kick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem) != cudaSuccess) {
     *err = "dense tensor-core path: shared-memory opt-in failed";
     dense_tc_destroy(t);
@@ -530,10 +578,16 @@ static cudaError_t gemm_kick(DenseTc* t, int buf, float coef, float drift_eps, f
   g.logp_out = logp_out; g.ke_out = ke_out;
   g.q_prop = drift_eps != 0.f ? t->q_prop : nullptr; g.mu = t->mu;
   g.a_hi_next = buf ? t->a_hi : t->a_hi2; g.a_lo_next = buf ? t->a_lo : t->a_lo2; g.drift_eps = drift_eps;
-  const unsigned blocks = (unsigned)((t->n_chains + kTileM - 1) / kTileM);
-  if (buf) dense_gemm_kick_kernel<<<blocks, kGemmThreads, t->smem, st>>>(t->map_ahi2, t->map_alo2, t->map_bhi, t->map_blo, g);
-  else dense_gemm_kick_kernel<<<blocks, kGemmThreads, t->smem, st>>>(t->map_ahi, t->map_alo, t->map_bhi, t->map_blo, g);
-  return cudaGetLastError();
+  unsigned blocks = (unsigned)((t->n_chains + kTileM - 1) / kTileM);
+  blocks = (blocks + kCluster - 1) / kCluster * kCluster;   // whole clusters; a surplus CTA only feeds the multicast
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = t->smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (buf) return cudaLaunchKernelEx(&cfg, dense_gemm_kick_kernel, t->map_ahi2, t->map_alo2, t->map_bhi, t->map_blo, g);
+  return cudaLaunchKernelEx(&cfg, dense_gemm_kick_kernel, t->map_ahi, t->map_alo, t->map_bhi, t->map_blo, g);
 }
 
 // One HMC transition.  q: [C, d] current positions (in/out).  Returns the number of kernel launches (or -1).

@@ -1196,8 +1196,66 @@ gmcmc_status gmcmc_run_device(gmcmc_sampler* s, size_t n_collect, size_t n_disca
   return GMCMC_OK;
 }
 
+// gmcmc_run fast path: chains are independent, so the run is cut into chain chunks whose kernels overlap the
+// device->host copy of the previous chunk (copy stream + events).  Plain runs only (no injection, no adaptation
+// in flight, same dtype), HMC (register kernels) and MH.
+static bool can_pipeline(const gmcmc_sampler* s, size_t n_collect, gmcmc_dtype out_dtype) {
+  if (n_collect == 0 || s->inj_steps > 0 || (int)out_dtype != out_dtype_of(s)) return false;
+  if (s->type == S_MH) return s->n_chains >= 65536;
+  if (s->type == S_HMC) return s->adapt == GMCMC_ADAPT_NONE && !(s->dense_tc && s->math == GMCMC_MATH_FAST) && s->n_chains >= 16384;
+  return false;
+}
+
+static gmcmc_status run_pipelined(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void* out_host) {
+  gmcmc_ctx* ctx = s->ctx;
+  const size_t C = s->n_chains, d = (size_t)s->dim, es_out = esize(out_dtype_of(s)), es = esize(s->dtype);
+  const size_t total = n_collect + n_discard;
+  GM_REQUIRE(total < 0xffffffffull - s->step_index, "transition counter would overflow 32 bits");
+  GM_TRY(ensure_samples(s, C * n_collect * d * es_out));
+  const int n_chunks = 4;
+  cudaEvent_t done[n_chunks];
+  for (int i = 0; i < n_chunks; ++i) GM_CU(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+  s->launches = 0;
+  GM_CU(cudaEventRecord(s->ev0, ctx->stream));
+  // the chunk boundaries are multiples of 1024 chains so that every chunk starts on a CTA / warp boundary
+  gmcmc_sampler view = *s;
+  gmcmc_status st = GMCMC_OK;
+  for (int i = 0; i < n_chunks && st == GMCMC_OK; ++i) {
+    const size_t c0 = (C * i / n_chunks) / 1024 * 1024, c1 = (i + 1 == n_chunks) ? C : (C * (i + 1) / n_chunks) / 1024 * 1024;
+    if (c1 <= c0) { cudaEventRecord(done[i], ctx->stream); continue; }
+    view.n_chains = c1 - c0;
+    view.chain_offset = s->chain_offset + c0;
+    view.d_pos = (char*)s->d_pos + c0 * d * es;
+    view.d_alpha_part = s->d_alpha_part;
+    void* d_out = (char*)s->d_samples + c0 * n_collect * d * es_out;
+    if (s->type == S_MH) st = mh_segment(&view, 0, total, n_discard, n_collect, d_out, false, 0);
+    else st = hmc_segment(&view, 0, total, n_discard, n_collect, d_out, false, 0, false, false, 0);
+    if (st != GMCMC_OK) break;
+    s->launches += 1;
+    cudaEventRecord(done[i], ctx->stream);
+    cudaStreamWaitEvent(ctx->copy_stream, done[i], 0);
+    cudaMemcpyAsync((char*)out_host + c0 * n_collect * d * es_out, d_out, (c1 - c0) * n_collect * d * es_out,
+                    cudaMemcpyDeviceToHost, ctx->copy_stream);
+  }
+  GM_CU(cudaEventRecord(s->ev1, ctx->stream));
+  s->timed = true;
+  cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream);
+  cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < n_chunks; ++i) cudaEventDestroy(done[i]);
+  if (st != GMCMC_OK) return st;
+  if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(GMCMC_ERR_CUDA, "pipelined run failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  s->step_index += (uint32_t)total;
+  s->transitions += (uint64_t)total * C;
+  if (s->type == S_HMC) s->hmc_grad_evals += (uint64_t)total * C * s->n_leapfrog;
+  return GMCMC_OK;
+}
+
 gmcmc_status gmcmc_run(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void* out_host, gmcmc_dtype out_dtype) {
   GM_REQUIRE(s && (out_host || n_collect == 0), "null argument");
+  if (can_pipeline(s, n_collect, out_dtype)) {
+    GM_CU(cudaSetDevice(s->ctx->device));
+    return run_pipelined(s, n_collect, n_discard, out_host);
+  }
   void* d = nullptr;
   GM_TRY(gmcmc_run_device(s, n_collect, n_discard, &d));
   const size_t n = s->n_chains * n_collect * (size_t)s->dim;
