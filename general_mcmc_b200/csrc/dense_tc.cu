@@ -7,22 +7,24 @@
 // grad = -z.  z for all chains is a real [chains x d] . [d x d] GEMM per gradient evaluation.
 //
 // Precision: plain TF32 (10-bit mantissa) cannot meet the 1e-5 per-step bar, so both operands are split
-// x = hi + lo with hi = rna_tf32(x), and the accumulator receives  hi.hi + lo.hi + hi.lo  in FP32 (TMEM):
-// three tcgen05.mma.kind::tf32 per K-step, relative error ~2^-21 per product.
+// x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi), and the accumulator receives hi.hi + lo.hi + hi.lo in
+// FP32 (TMEM): three tcgen05.mma.kind::tf32 per K-step.
 //
-// Structure of one transition (fast math mode, merged half kicks; L + 1 GEMMs):
-//   dense_begin_kernel     p ~ N(0, I) (Philox or injected), ke0, q_prop = q, delta split -> A_hi / A_lo
-//   dense_gemm_kick_kernel z = delta . P ; p -= (eps/2) (-z)...  (epilogue: kick, and at the two trajectory
-//                          ends logp = c - 1/2 z.delta and ke = 1/2 |p|^2, one thread per chain row)
-//   L x dense_gemm_kick_kernel — each epilogue also applies the NEXT leapfrog's drift (q_prop += eps p) and writes the
-//                          split delta of the next GEMM into the other A buffer (ping-pong), so there is no separate drift pass
-//   dense_accept_kernel    Hamiltonian, Metropolis accept, q <- q_prop, sample row -> [chain, slot, :]
+// State: the trajectory runs in delta-space.  p [C, d] and delta [C, kpad] (two ping-pong buffers, padded columns
+// zero) are the only per-leapfrog HBM arrays: 16 bytes per coordinate per leapfrog.  One transition (fast math
+// mode, merged half kicks) = L + 1 GEMM launches between a begin and an accept kernel:
+//   dense_begin_kernel     p ~ N(0, I) (Philox or injected), ke0, delta = q - mu
+//   dense_gemm_kick_kernel z = delta . P; epilogue: kick p -= c z, NEXT drift delta' = delta + eps p (other buffer),
+//                          and at the two trajectory ends logp = c - 1/2 z.delta, ke = 1/2 |p|^2
+//   dense_accept_kernel    Hamiltonian, Metropolis accept, q <- delta + mu, sample row -> [chain, slot, :]
 //
-// dense_gemm_kick_kernel: one CTA per 128 chains, warp-specialised — warp 0 lane 0 issues TMA loads
-// (A_hi, A_lo [128 x 32], P_hi, P_lo [256 x 32], SWIZZLE_128B, 2 stages of 96 KB), warp 1 lane 0 issues the
-// tcgen05.mma (128 x 256 x 8, accumulators double-buffered over the 512 TMEM columns), warps 2-5 drain the
-// accumulator with tcgen05.ld, transpose it through shared memory and apply the kick (+ next drift) with
-// row-contiguous global accesses (8 epilogue warps: two per TMEM lane quarter).
+// dense_gemm_kick_kernel — one CTA per 128 chains, clusters of 2 CTAs, 15 warps:
+//   warp 0      TMA loads of the raw f32 delta tile [128 x 16] (ring of 4)
+//   warp 1      TMA loads of P_hi / P_lo [256 x 16]: each CTA of the cluster loads half of every tile and multicasts it
+//   warp 2      tcgen05.mma issue (one elected lane; 128 x 256 x 8, accumulators double-buffered over the 512 TMEM cols)
+//   warps 3-6   split the raw tile into hi / lo operand tiles in shared memory (element-wise, so the TMA swizzle
+//               is preserved) — the split never touches HBM
+//   warps 7-14  epilogue: tcgen05.ld, transpose through shared memory, row-contiguous global updates
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -41,22 +43,23 @@ namespace {
 
 constexpr int kTileM = 128;      // chains per CTA
 constexpr int kTileN = 256;      // accumulator columns per MMA
-#ifndef GM_TC_TILEK
-#define GM_TC_TILEK 16
-#endif
-constexpr int kTileK = GM_TC_TILEK;   // floats per K stage: 16 (64-byte rows, SWIZZLE_64B, 4 stages) or 32 (128-byte rows, 2 stages)
+constexpr int kTileK = 16;       // floats per K stage: 64-byte rows, SWIZZLE_64B
 constexpr int kUmmaK = 8;        // tf32 elements per tcgen05.mma
-constexpr int kStages = kTileK == 16 ? 4 : 2;
+constexpr int kStages = 3;       // operand stages (A_hi, A_lo, P_hi, P_lo)
+constexpr int kRawStages = 4;    // raw delta tiles in flight ahead of the split
 constexpr int kKPadUnit = 32;    // K is padded to a multiple of 32 floats in both layouts
 #ifndef GM_TC_CLUSTER
 #define GM_TC_CLUSTER 2          // CTAs per cluster sharing every P tile through TMA multicast (1 = no cluster)
 #endif
 constexpr int kCluster = GM_TC_CLUSTER;
-constexpr int kEpiWarps = 8;        // two warps per TMEM lane quarter, interleaved over the 32-column blocks (16 measured the same)
-constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
-constexpr uint32_t kABytes = kTileM * kTileK * 4;   // 16 KB
-constexpr uint32_t kBBytes = kTileN * kTileK * 4;   // 32 KB
-constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // 96 KB
+constexpr int kEpiWarps = 8;        // two warps per TMEM lane quarter, interleaved over the 32-column blocks
+constexpr int kCvtWarps = 4;
+constexpr int kFirstCvtWarp = 3, kFirstEpiWarp = kFirstCvtWarp + kCvtWarps;
+constexpr int kGemmThreads = 32 * (kFirstEpiWarp + kEpiWarps);
+constexpr uint32_t kABytes = kTileM * kTileK * 4;   // 8 KB
+constexpr uint32_t kBBytes = kTileN * kTileK * 4;   // 16 KB
+constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // 48 KB
+constexpr uint32_t kRawBytes = kABytes;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -151,7 +154,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   constexpr uint32_t kRowBytes = kTileK * 4;         // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
   d |= (uint64_t)(((8 * kRowBytes) >> 4) & 0x3fff) << 32;   // stride byte offset between 8-row groups, bits [32,46)
   d |= (uint64_t)1 << 46;                            // descriptor version (sm_100), bits [46,48)
-  d |= (uint64_t)(kRowBytes == 128 ? 2 : 4) << 61;   // layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, bits [61,64)
+  d |= (uint64_t)4 << 61;                            // layout type SWIZZLE_64B, bits [61,64)
   return d;
 }
 
@@ -168,45 +171,41 @@ struct GemmArgs {
   int d, kpad, npad;
   size_t n_chains;
   float* p;               // [C, d]
-  const float* a_hi;      // [C, kpad]  (delta split, also read by the epilogue for z . delta)
-  const float* a_lo;
+  const float* dl;        // [C, kpad] delta read by this GEMM (also the A operand, via TMA)
+  float* dl_next;         // [C, kpad] delta after the next drift, or null
   float coef;             // kick: p -= coef * z   (grad = -z)
+  float drift_eps;
   float norm_const;
   float* logp_out;        // [C] or null: logp = c - 1/2 sum z * delta
   float* ke_out;          // [C] or null: 1/2 |p_new|^2
-  // fused drift of the NEXT leapfrog (null q_prop: none): q_prop += drift_eps * p_new ; delta split -> next A buffers
-  float* q_prop;          // [C, d]
-  const float* mu;        // [d]
-  float* a_hi_next;       // [C, kpad]
-  float* a_lo_next;
-  float drift_eps;
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
-dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
-                       const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
-                       const GemmArgs a) {
-  // With kCluster = 2 the two CTAs of a cluster work on different chain tiles but walk the same (n, k) schedule:
-  // each loads HALF of every P tile (map_b* then describe [kTileN / 2 x kTileK] boxes) and multicasts it into both
-  // CTAs' stages, halving the L2 -> SM traffic of the dominant operand.  A stage may be refilled only when the MMAs
-  // of BOTH CTAs have released it, so the `empty` barriers take two (multicast) commits.
+dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_constant__ CUtensorMap map_bhi,
+                       const __grid_constant__ CUtensorMap map_blo, const GemmArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // carve: stages (1024-byte aligned), then barriers
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(base + (size_t)kStages * kStageBytes);
-  uint64_t* full = bars;                 // [kStages]
-  uint64_t* empty = bars + kStages;      // [kStages]
-  uint64_t* tfull = bars + 2 * kStages;  // [2]
-  uint64_t* tempty = tfull + 2;          // [2]
+  unsigned char* raw_base = base + (size_t)kStages * kStageBytes;
+  uint64_t* bars = (uint64_t*)(raw_base + (size_t)kRawStages * kRawBytes);
+  uint64_t* b_full = bars;                         // [kStages]    P tiles landed (TMA tx)
+  uint64_t* a_full = b_full + kStages;             // [kStages]    hi / lo tiles written by the split warps
+  uint64_t* empty = a_full + kStages;              // [kStages]    stage released by the MMAs of BOTH CTAs
+  uint64_t* raw_full = empty + kStages;            // [kRawStages] raw delta tile landed
+  uint64_t* raw_empty = raw_full + kRawStages;     // [kRawStages] raw tile consumed by the split warps
+  uint64_t* tfull = raw_empty + kRawStages;        // [2] accumulator complete
+  uint64_t* tempty = tfull + 2;                    // [2] accumulator drained
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  float* tr_base = reinterpret_cast<float*>(raw_base + (size_t)kRawStages * kRawBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kTileM;
   const int n_chunks = a.npad / kTileN;
   const int k_chunks = a.kpad / kTileK;
+  const int n_iters = n_chunks * k_chunks;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kCluster); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&a_full[i], kCvtWarps); mbar_init(&empty[i], kCluster); }
+    for (int i = 0; i < kRawStages; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], kCvtWarps); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -224,30 +223,35 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer
-      int it = 0;
-      for (int n = 0; n < n_chunks; ++n) {
-        for (int k = 0; k < k_chunks; ++k, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (uint32_t)(it / kStages) & 1u;
-          mbar_wait(&empty[s], ph ^ 1u);
-          unsigned char* st = base + (size_t)s * kStageBytes;
-          mbar_expect_tx(&full[s], kStageBytes);
-          tma_load_2d(st, &map_ahi, &full[s], k * kTileK, m0);
-          tma_load_2d(st + kABytes, &map_alo, &full[s], k * kTileK, m0);
-          if constexpr (kCluster > 1) {
-            const int half_rows = kTileN / kCluster;
-            const uint32_t off = crank * (uint32_t)(half_rows * kTileK * 4);
-            tma_load_2d_mc(st + 2 * kABytes + off, &map_bhi, &full[s], k * kTileK, n * kTileN + (int)crank * half_rows, kMask);
-            tma_load_2d_mc(st + 2 * kABytes + kBBytes + off, &map_blo, &full[s], k * kTileK, n * kTileN + (int)crank * half_rows, kMask);
-          } else {
-            tma_load_2d(st + 2 * kABytes, &map_bhi, &full[s], k * kTileK, n * kTileN);
-            tma_load_2d(st + 2 * kABytes + kBBytes, &map_blo, &full[s], k * kTileK, n * kTileN);
-          }
-        }
+      // ===== raw delta tiles (re-streamed once per column chunk; the 512 KB row block stays L2-resident)
+      for (int it = 0; it < n_iters; ++it) {
+        const int r = it % kRawStages;
+        mbar_wait(&raw_empty[r], ((uint32_t)(it / kRawStages) & 1u) ^ 1u);
+        mbar_expect_tx(&raw_full[r], kRawBytes);
+        tma_load_2d(raw_base + (size_t)r * kRawBytes, &map_dl, &raw_full[r], (it % k_chunks) * kTileK, m0);
       }
     }
   } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== P tiles: my half of every tile, multicast to the cluster
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % kStages;
+        const int n = it / k_chunks, k = it % k_chunks;
+        mbar_wait(&empty[s], ((uint32_t)(it / kStages) & 1u) ^ 1u);
+        unsigned char* st = base + (size_t)s * kStageBytes + 2 * kABytes;
+        mbar_expect_tx(&b_full[s], 2 * kBBytes);
+        if constexpr (kCluster > 1) {
+          const int half_rows = kTileN / kCluster;
+          const uint32_t off = crank * (uint32_t)(half_rows * kTileK * 4);
+          tma_load_2d_mc(st + off, &map_bhi, &b_full[s], k * kTileK, n * kTileN + (int)crank * half_rows, kMask);
+          tma_load_2d_mc(st + kBBytes + off, &map_blo, &b_full[s], k * kTileK, n * kTileN + (int)crank * half_rows, kMask);
+        } else {
+          tma_load_2d(st, &map_bhi, &b_full[s], k * kTileK, n * kTileN);
+          tma_load_2d(st + kBBytes, &map_blo, &b_full[s], k * kTileK, n * kTileN);
+        }
+      }
+    }
+  } else if (warp == 2) {
     if (lane == 0) {
       // ===== MMA issuer
       int it = 0;
@@ -259,7 +263,8 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
         for (int k = 0; k < k_chunks; ++k, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (uint32_t)(it / kStages) & 1u;
-          mbar_wait(&full[s], ph);
+          mbar_wait(&a_full[s], ph);
+          mbar_wait(&b_full[s], ph);
           tc_fence_after();
           const uint32_t st = smem_u32(base + (size_t)s * kStageBytes);
           const uint64_t d_ahi = umma_desc(st), d_alo = umma_desc(st + kABytes);
@@ -272,18 +277,44 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
             tc_mma_tf32(tmem_d, d_ahi + adv, d_bhi + adv, kIdesc, 1u);
           }
           if constexpr (kCluster > 1) tc_commit_mc(&empty[s], kMask);   // both CTAs' producers wait for both MMAs
-          else tc_commit(&empty[s]);      // frees the stage when these MMAs have read it
+          else tc_commit(&empty[s]);
         }
         tc_commit(&tfull[acc]);           // accumulator complete
       }
     }
+  } else if (warp < kFirstEpiWarp) {
+    // ===== operand split: raw f32 tile -> hi = rna_tf32(x), lo = rna_tf32(x - hi), same (swizzled) byte offsets
+    const int t = (warp - kFirstCvtWarp) * 32 + lane;          // 0..127
+    for (int it = 0; it < n_iters; ++it) {
+      const int r = it % kRawStages, s = it % kStages;
+      mbar_wait(&raw_full[r], (uint32_t)(it / kRawStages) & 1u);
+      mbar_wait(&empty[s], ((uint32_t)(it / kStages) & 1u) ^ 1u);
+      const float4* src = reinterpret_cast<const float4*>(raw_base + (size_t)r * kRawBytes);
+      float4* dhi = reinterpret_cast<float4*>(base + (size_t)s * kStageBytes);
+      float4* dlo = reinterpret_cast<float4*>(base + (size_t)s * kStageBytes + kABytes);
+#pragma unroll
+      for (int i = 0; i < (int)(kRawBytes / 16) / (32 * kCvtWarps); ++i) {
+        const float4 x = src[t + i * 32 * kCvtWarps];
+        float4 h, l;
+        h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
+        l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
+        dhi[t + i * 32 * kCvtWarps] = h;
+        dlo[t + i * 32 * kCvtWarps] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&a_full[s]); mbar_arrive(&raw_empty[r]); }
+    }
   } else {
-    // ===== epilogue.  tcgen05.ld hands every thread one accumulator ROW (32 columns at a time); the tile is
-    // transposed through shared memory so that global accesses run along rows: lane <-> column, one 128-byte
-    // line per warp instruction for p, q_prop and the next A operand.
+    // ===== epilogue.  tcgen05.ld hands every thread one accumulator ROW (32 columns at a time); 16 rows at a time
+    // are transposed through shared memory so that global accesses run along rows: lane <-> column, one 128-byte
+    // line per warp instruction for p and delta.
+    const int ew = warp - kFirstEpiWarp;
     const int q4 = warp & 3;                     // TMEM lane quarter this warp may access
-    float* tr = reinterpret_cast<float*>(base + (size_t)kStages * kStageBytes + 256) + (size_t)(warp - 2) * 16 * 33;
-    const int cb_first = (warp - 2) >> 2;         // the kEpiWarps / 4 warps of a quarter interleave over the 32-column blocks
+    float* tr = tr_base + (size_t)ew * 16 * 33;
+    // the kEpiWarps / 4 warps that share a quarter interleave over the 32-column blocks
+    int cb_first = 0;
+    for (int w = kFirstEpiWarp; w < warp; ++w) cb_first += ((w & 3) == q4) ? 1 : 0;
     const size_t row0 = (size_t)m0 + (size_t)q4 * 32;
     const int nrows = row0 < a.n_chains ? (int)((a.n_chains - row0) < 32 ? (a.n_chains - row0) : 32) : 0;
     float quad = 0.f, ke = 0.f;                  // lane r holds the sums of row r
@@ -299,25 +330,22 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
         if (c0 >= a.d) continue;                 // padded columns (warp-uniform)
         const int col = c0 + lane;
         const bool col_ok = col < a.d;
-        const float muv = (a.q_prop && col_ok) ? a.mu[col] : 0.f;
-        // 16 rows at a time; all their loads are issued before the first use (32 lines in flight per warp)
 #pragma unroll 1
         for (int rb = 0; rb < 32; rb += 16) {
-          // transpose 16 accumulator rows through shared memory: lanes rb..rb+15 own them
           __syncwarp();
           if ((lane & 16) == rb) {
 #pragma unroll
             for (int c = 0; c < 32; ++c) tr[(lane & 15) * 33 + c] = z[c];
           }
           __syncwarp();
-          float pv[16], qv[16];
+          float pv[16], dv[16];
 #pragma unroll
           for (int rr = 0; rr < 16; ++rr) {
             const int r = rb + rr;
-            pv[rr] = 0.f; qv[rr] = 0.f;
+            pv[rr] = 0.f; dv[rr] = 0.f;
             if (r < nrows && col_ok) {
-              pv[rr] = a.p[(row0 + r) * (size_t)a.d + col];
-              if (a.q_prop) qv[rr] = a.q_prop[(row0 + r) * (size_t)a.d + col];
+              pv[rr] = __ldcs(a.p + (row0 + r) * (size_t)a.d + col);
+              dv[rr] = a.dl[(row0 + r) * (size_t)a.kpad + col];
             }
           }
 #pragma unroll
@@ -326,22 +354,14 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
             if (r < nrows) {
               const size_t row = row0 + r;
               const float zv = tr[rr * 33 + lane];
-              float pn = 0.f, dl = 0.f;
+              float pn = 0.f;
               if (col_ok) {
                 pn = fmaf(-a.coef, zv, pv[rr]);
-                a.p[row * (size_t)a.d + col] = pn;
-                if (a.logp_out) dl = a.a_hi[row * (size_t)a.kpad + col] + a.a_lo[row * (size_t)a.kpad + col];
-                if (a.q_prop) {
-                  const float qn = fmaf(a.drift_eps, pn, qv[rr]);
-                  a.q_prop[row * (size_t)a.d + col] = qn;
-                  const float dn = qn - muv;
-                  const float hi = tf32_rna(dn);
-                  a.a_hi_next[row * (size_t)a.kpad + col] = hi;
-                  a.a_lo_next[row * (size_t)a.kpad + col] = tf32_rna(dn - hi);
-                }
+                __stcs(a.p + row * (size_t)a.d + col, pn);
+                if (a.dl_next) a.dl_next[row * (size_t)a.kpad + col] = fmaf(a.drift_eps, pn, dv[rr]);
               }
               if (a.logp_out || a.ke_out) {          // trajectory ends only: row sums over the 32 columns
-                float s1 = zv * dl, s2 = pn * pn;
+                float s1 = zv * dv[rr], s2 = pn * pn;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
                 if (lane == r) { quad += s1; ke += s2; }
@@ -354,18 +374,15 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
-    // the two warps of a quarter hold partial row sums (even / odd column blocks): combine through shared memory
+    // the warps of a quarter hold partial row sums (interleaved column blocks): combine through shared memory
     if (a.logp_out || a.ke_out) {
-      float* red = tr;                       // this warp's transpose tile is free now
       __syncwarp();
-      red[lane] = quad; red[32 + lane] = ke;
+      tr[lane] = quad; tr[32 + lane] = ke;
       asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory");   // epilogue warps only
       if (cb_first == 0 && lane < nrows) {
-        float qsum = quad, ksum = ke;
-#pragma unroll
-        for (int w = 1; w < kEpiWarps / 4; ++w) {          // partner warps of the same quarter
-          const float* other = tr + (size_t)(4 * w) * 16 * 33;
-          qsum += other[lane]; ksum += other[32 + lane];
+        float qsum = 0.f, ksum = 0.f;
+        for (int w = 0; w < kEpiWarps; ++w) {
+          if (((w + kFirstEpiWarp) & 3) == q4) { qsum += tr_base[(size_t)w * 16 * 33 + lane]; ksum += tr_base[(size_t)w * 16 * 33 + 32 + lane]; }
         }
         if (a.logp_out) a.logp_out[row0 + lane] = a.norm_const - 0.5f * qsum;
         if (a.ke_out) a.ke_out[row0 + lane] = 0.5f * ksum;
@@ -385,12 +402,11 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid
 struct BeginArgs {
   size_t n_chains; int d, kpad;
   unsigned long long chain_offset; PhiloxKey key; uint32_t step;
-  const float* q; float* q_prop; float* p; const float* mu;
-  float* a_hi; float* a_lo; float* ke0;
+  const float* q; float* p; const float* mu; float* dl; float* ke0;
   const float* inj_normals;   // [C, d] for this transition or null
 };
 
-// one warp per chain: momentum, ke0, q_prop = q, delta split
+// one warp per chain: momentum, ke0, delta = q - mu (padded columns zero)
 __global__ void __launch_bounds__(256) dense_begin_kernel(const BeginArgs a) {
   const size_t chain = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -407,31 +423,26 @@ __global__ void __launch_bounds__(256) dense_begin_kernel(const BeginArgs a) {
         normals_from_block<false>(philox4x32_10(philox_ctr(gchain, a.step, 0u, (uint32_t)b), a.key), z);
       }
     }
-    float hi[4], lo[4];
+    float dl[4];
     for (int k = 0; k < 4; ++k) {
       const int c = b * 4 + k;
-      float dl = 0.f;
+      dl[k] = 0.f;
       if (c < a.d) {
-        const float qv = a.q[chain * a.d + c];
-        a.q_prop[chain * a.d + c] = qv;
         a.p[chain * a.d + c] = z[k];
         ke += z[k] * z[k];
-        dl = qv - a.mu[c];
+        dl[k] = a.q[chain * a.d + c] - a.mu[c];
       }
-      hi[k] = tf32_rna(dl);
-      lo[k] = tf32_rna(dl - hi[k]);   // rounded (not hardware-truncated) low part: unbiased
     }
-    *reinterpret_cast<float4*>(a.a_hi + chain * a.kpad + b * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<float4*>(a.a_lo + chain * a.kpad + b * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<float4*>(a.dl + chain * a.kpad + b * 4) = make_float4(dl[0], dl[1], dl[2], dl[3]);
   }
   for (int o = 16; o > 0; o >>= 1) ke += __shfl_xor_sync(0xffffffffu, ke, o);
   if (lane == 0) a.ke0[chain] = 0.5f * ke;
 }
 
 struct AcceptArgs {
-  size_t n_chains; int d;
+  size_t n_chains; int d, kpad;
   unsigned long long chain_offset; PhiloxKey key; uint32_t step;
-  float* q; const float* q_prop; const float* p;
+  float* q; const float* dl; const float* mu; const float* p;
   const float* logp0; const float* logp1; const float* ke0; const float* ke1;
   float* out; size_t out_n; long long slot;        // slot < 0: not recorded
   unsigned long long* accept_total; unsigned long long* diverge_total;
@@ -439,7 +450,7 @@ struct AcceptArgs {
   float* diag_logacc; uint8_t* diag_acc; float* diag_pq; float* diag_pp;   // per-transition slices or null
 };
 
-// one warp per chain: Metropolis accept (batched_hmc.rs:148-162), state update, sample write-out
+// one warp per chain: Metropolis accept (batched_hmc.rs:148-162), q <- delta + mu, sample write-out
 __global__ void __launch_bounds__(256) dense_accept_kernel(const AcceptArgs a) {
   const size_t chain = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -451,12 +462,13 @@ __global__ void __launch_bounds__(256) dense_accept_kernel(const AcceptArgs a) {
   const bool accept = ln_u <= log_accept;
   const bool finite = (log_accept == log_accept) && (fabsf(log_accept) < INFINITY);
   float* qrow = a.q + chain * a.d;
-  const float* prow = a.q_prop + chain * a.d;
+  const float* drow = a.dl + chain * a.kpad;
   for (int c = lane; c < a.d; c += 32) {
-    const float v = accept ? prow[c] : qrow[c];
+    const float prop = drow[c] + a.mu[c];
+    const float v = accept ? prop : qrow[c];
     if (accept) qrow[c] = v;
     if (a.slot >= 0) __stcs(a.out + (chain * a.out_n + (size_t)a.slot) * a.d + c, v);
-    if (a.diag_pq) { a.diag_pq[chain * a.d + c] = prow[c]; a.diag_pp[chain * a.d + c] = a.p[chain * a.d + c]; }
+    if (a.diag_pq) { a.diag_pq[chain * a.d + c] = prop; a.diag_pp[chain * a.d + c] = a.p[chain * a.d + c]; }
   }
   if (lane == 0) {
     if (accept) atomicAdd(a.accept_total, 1ull);
@@ -481,7 +493,7 @@ EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-// 2-D f32 tensor [rows, cols] (cols contiguous), box [box_rows, 32 floats], SWIZZLE_128B
+// 2-D f32 tensor [rows, cols] (cols contiguous), box [box_rows, kTileK floats], SWIZZLE_64B
 bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return false;
@@ -490,7 +502,7 @@ bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uin
   cuuint32_t box[2] = {(cuuint32_t)kTileK, box_rows};
   cuuint32_t estr[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             kTileK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 inline float host_tf32_rna(float x) {
@@ -509,17 +521,16 @@ inline float host_tf32_rna(float x) {
 struct DenseTc {
   int d = 0, kpad = 0, npad = 0;
   size_t n_chains = 0;
-  float *p = nullptr, *q_prop = nullptr, *a_hi = nullptr, *a_lo = nullptr, *a_hi2 = nullptr, *a_lo2 = nullptr;
-  float *b_hi = nullptr, *b_lo = nullptr, *mu = nullptr;
+  float *p = nullptr, *dl[2] = {nullptr, nullptr}, *b_hi = nullptr, *b_lo = nullptr, *mu = nullptr;
   float *logp0 = nullptr, *logp1 = nullptr, *ke0 = nullptr, *ke1 = nullptr;
   float norm_const = 0.f;
-  CUtensorMap map_ahi, map_alo, map_ahi2, map_alo2, map_bhi, map_blo;
+  CUtensorMap map_dl[2], map_bhi, map_blo;
   size_t smem = 0;
 };
 
 void dense_tc_destroy(DenseTc* t) {
   if (!t) return;
-  cudaFree(t->p); cudaFree(t->q_prop); cudaFree(t->a_hi); cudaFree(t->a_lo); cudaFree(t->a_hi2); cudaFree(t->a_lo2); cudaFree(t->b_hi); cudaFree(t->b_lo); cudaFree(t->mu);
+  cudaFree(t->p); cudaFree(t->dl[0]); cudaFree(t->dl[1]); cudaFree(t->b_hi); cudaFree(t->b_lo); cudaFree(t->mu);
   cudaFree(t->logp0); cudaFree(t->logp1); cudaFree(t->ke0); cudaFree(t->ke1);
   delete t;
 }
@@ -534,10 +545,9 @@ DenseTc* dense_tc_create(size_t n_chains, int d, const double* params, const cha
   t->npad = ((d + kTileN - 1) / kTileN) * kTileN;
   t->norm_const = (float)params[(size_t)d + (size_t)d * d];
   const size_t C = n_chains;
-  bool ok = cudaMalloc(&t->p, C * d * 4) == cudaSuccess && cudaMalloc(&t->q_prop, C * d * 4) == cudaSuccess &&
-            cudaMalloc(&t->a_hi, C * (size_t)t->kpad * 4) == cudaSuccess && cudaMalloc(&t->a_lo, C * (size_t)t->kpad * 4) == cudaSuccess &&
-            cudaMalloc(&t->a_hi2, C * (size_t)t->kpad * 4) == cudaSuccess && cudaMalloc(&t->a_lo2, C * (size_t)t->kpad * 4) == cudaSuccess &&
-            cudaMemset(t->a_hi2, 0, C * (size_t)t->kpad * 4) == cudaSuccess && cudaMemset(t->a_lo2, 0, C * (size_t)t->kpad * 4) == cudaSuccess &&
+  bool ok = cudaMalloc(&t->p, C * d * 4) == cudaSuccess &&
+            cudaMalloc(&t->dl[0], C * (size_t)t->kpad * 4) == cudaSuccess && cudaMalloc(&t->dl[1], C * (size_t)t->kpad * 4) == cudaSuccess &&
+            cudaMemset(t->dl[1], 0, C * (size_t)t->kpad * 4) == cudaSuccess &&
             cudaMalloc(&t->b_hi, (size_t)t->npad * t->kpad * 4) == cudaSuccess && cudaMalloc(&t->b_lo, (size_t)t->npad * t->kpad * 4) == cudaSuccess &&
             cudaMalloc(&t->mu, (size_t)d * 4) == cudaSuccess && cudaMalloc(&t->logp0, C * 4) == cudaSuccess &&
             cudaMalloc(&t->logp1, C * 4) == cudaSuccess && cudaMalloc(&t->ke0, C * 4) == cudaSuccess && cudaMalloc(&t->ke1, C * 4) == cudaSuccess;
@@ -556,12 +566,12 @@ DenseTc* dense_tc_create(size_t n_chains, int d, const double* params, const cha
        cudaMemcpy(t->b_lo, bl.data(), bl.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
        cudaMemcpy(t->mu, mu.data(), (size_t)d * 4, cudaMemcpyHostToDevice) == cudaSuccess;
   if (!ok) { *err = e_alloc; dense_tc_destroy(t); return nullptr; }
-  ok = make_map(&t->map_ahi, t->a_hi, C, (uint64_t)t->kpad, kTileM) && make_map(&t->map_alo, t->a_lo, C, (uint64_t)t->kpad, kTileM) &&
-       make_map(&t->map_ahi2, t->a_hi2, C, (uint64_t)t->kpad, kTileM) && make_map(&t->map_alo2, t->a_lo2, C, (uint64_t)t->kpad, kTileM) &&
+  ok = make_map(&t->map_dl[0], t->dl[0], C, (uint64_t)t->kpad, kTileM) && make_map(&t->map_dl[1], t->dl[1], C, (uint64_t)t->kpad, kTileM) &&
        make_map(&t->map_bhi, t->b_hi, (uint64_t)t->npad, (uint64_t)t->kpad, kTileN / kCluster) &&
        make_map(&t->map_blo, t->b_lo, (uint64_t)t->npad, (uint64_t)t->kpad, kTileN / kCluster);
   if (!ok) { *err = e_map; dense_tc_destroy(t); return nullptr; }
-  t->smem = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + (size_t)kEpiWarps * 16 * 33 * 4 /*epilogue transpose*/;
+  t->smem = (size_t)kStages * kStageBytes + (size_t)kRawStages * kRawBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ +
+            (size_t)kEpiWarps * 16 * 33 * 4 /*epilogue transpose*/;
   if (cudaFuncSetAttribute(dense_gemm_kick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem) != cudaSuccess) {
     *err = "dense tensor-core path: shared-memory opt-in failed";
     dense_tc_destroy(t);
@@ -570,14 +580,13 @@ DenseTc* dense_tc_create(size_t n_chains, int d, const double* params, const cha
   return t;
 }
 
-// GEMM on A buffer `buf` (0 / 1); drift_eps != 0 fuses the next leapfrog's drift and writes the other A buffer
+// GEMM on delta buffer `buf` (0 / 1); drift_eps != 0 fuses the next leapfrog's drift and writes the other buffer
 static cudaError_t gemm_kick(DenseTc* t, int buf, float coef, float drift_eps, float* logp_out, float* ke_out, cudaStream_t st) {
   GemmArgs g;
   g.d = t->d; g.kpad = t->kpad; g.npad = t->npad; g.n_chains = t->n_chains;
-  g.p = t->p; g.a_hi = buf ? t->a_hi2 : t->a_hi; g.a_lo = buf ? t->a_lo2 : t->a_lo; g.coef = coef; g.norm_const = t->norm_const;
+  g.p = t->p; g.dl = t->dl[buf]; g.dl_next = drift_eps != 0.f ? t->dl[buf ^ 1] : nullptr;
+  g.coef = coef; g.drift_eps = drift_eps; g.norm_const = t->norm_const;
   g.logp_out = logp_out; g.ke_out = ke_out;
-  g.q_prop = drift_eps != 0.f ? t->q_prop : nullptr; g.mu = t->mu;
-  g.a_hi_next = buf ? t->a_hi : t->a_hi2; g.a_lo_next = buf ? t->a_lo : t->a_lo2; g.drift_eps = drift_eps;
   unsigned blocks = (unsigned)((t->n_chains + kTileM - 1) / kTileM);
   blocks = (blocks + kCluster - 1) / kCluster * kCluster;   // whole clusters; a surplus CTA only feeds the multicast
   cudaLaunchConfig_t cfg = {};
@@ -586,8 +595,7 @@ static cudaError_t gemm_kick(DenseTc* t, int buf, float coef, float drift_eps, f
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (buf) return cudaLaunchKernelEx(&cfg, dense_gemm_kick_kernel, t->map_ahi2, t->map_alo2, t->map_bhi, t->map_blo, g);
-  return cudaLaunchKernelEx(&cfg, dense_gemm_kick_kernel, t->map_ahi, t->map_alo, t->map_bhi, t->map_blo, g);
+  return cudaLaunchKernelEx(&cfg, dense_gemm_kick_kernel, t->map_dl[buf], t->map_bhi, t->map_blo, g);
 }
 
 // One HMC transition.  q: [C, d] current positions (in/out).  Returns the number of kernel launches (or -1).
@@ -598,13 +606,14 @@ int dense_tc_transition(DenseTc* t, const DenseTcStep& S, cudaStream_t st) {
   BeginArgs b;
   b.n_chains = C; b.d = t->d; b.kpad = t->kpad; b.chain_offset = S.chain_offset;
   b.key = PhiloxKey{(uint32_t)S.seed, (uint32_t)(S.seed >> 32)}; b.step = S.step;
-  b.q = (const float*)S.q; b.q_prop = t->q_prop; b.p = t->p; b.mu = t->mu; b.a_hi = t->a_hi; b.a_lo = t->a_lo; b.ke0 = t->ke0;
+  b.q = (const float*)S.q; b.p = t->p; b.mu = t->mu; b.dl = t->dl[0]; b.ke0 = t->ke0;
   b.inj_normals = (const float*)S.inj_normals;
   dense_begin_kernel<<<wblocks, 256, 0, st>>>(b);
   ++launches;
   const float eps = (float)S.eps, half = 0.5f * eps;
   // GEMM 0: gradient at the current point (log density, first half kick, drift of leapfrog 1);
   // GEMM l (1 <= l < L): kick eps + drift of leapfrog l + 1;  GEMM L: last half kick, log density, kinetic energy
+  int final_buf = 0;
   if (S.n_leapfrog == 0) {
     if (gemm_kick(t, 0, 0.f, 0.f, t->logp0, t->ke1, st) != cudaSuccess) return -1;
     ++launches;
@@ -617,10 +626,11 @@ int dense_tc_transition(DenseTc* t, const DenseTcStep& S, cudaStream_t st) {
         return -1;
       ++launches;
     }
+    final_buf = (int)(S.n_leapfrog & 1u);
   }
   AcceptArgs a;
-  a.n_chains = C; a.d = t->d; a.chain_offset = S.chain_offset; a.key = b.key; a.step = S.step;
-  a.q = (float*)S.q; a.q_prop = t->q_prop; a.p = t->p;
+  a.n_chains = C; a.d = t->d; a.kpad = t->kpad; a.chain_offset = S.chain_offset; a.key = b.key; a.step = S.step;
+  a.q = (float*)S.q; a.dl = t->dl[final_buf]; a.mu = t->mu; a.p = t->p;
   a.logp0 = t->logp0; a.logp1 = S.n_leapfrog > 0 ? t->logp1 : t->logp0; a.ke0 = t->ke0; a.ke1 = t->ke1;
   a.out = (float*)S.out; a.out_n = S.out_n; a.slot = S.slot;
   a.accept_total = S.accept_total; a.diverge_total = S.diverge_total;
