@@ -41,6 +41,11 @@ namespace GM_NS {
 constexpr bool kExact = (GM_EXACT != 0);
 constexpr unsigned kFull = 0xffffffffu;
 
+template <class T> struct VecOf;
+template <> struct VecOf<float> { using type = float4; static constexpr int n = 4; };
+template <> struct VecOf<double> { using type = double2; static constexpr int n = 2; };
+
+
 struct Lane {
   int part;       // which slice of the chain this lane owns
   int lpc;        // lanes per chain
@@ -111,6 +116,7 @@ template <class T>
 struct TParams {          // per-launch target parameters in T
   T sp[kMaxScalarParams];
   const T* dp;            // device block (dense Gaussian: mu[d], P[d*d], nc; mixture: w[K], mu[K*d])
+  const T* smem_mu;       // mixture means staged in shared memory, lane-padded [K][lpc][roundup(EPL, 4)], or null
   int n_comp;
   // derived for DiffableGaussian2D (distributions.rs:229-253)
   T inv_cov[2][2];
@@ -251,6 +257,36 @@ __device__ __forceinline__ T eval_target(TagDenseGauss, const T (&x)[EPL], T (&g
 constexpr int kMaxComp = 8;
 // The component loops are deliberately NOT unrolled (K is a runtime value): unrolling 8 components x EPL
 // coordinates made the NUTS kernel ~200 KB of code and instruction-fetch bound.
+// this lane's slice of component k's mean: from the lane-padded shared-memory copy (vector loads) or from HBM / L1
+template <class T, int EPL>
+__device__ __forceinline__ void mixture_mean_slice(T (&m)[EPL], const TParams<T>& tp, const T* mu, int k, int d, const Lane& ln) {
+  if (tp.smem_mu) {
+    using V = typename VecOf<T>::type;
+    constexpr int VN = VecOf<T>::n;
+    constexpr int EPLP = (EPL + 3) / 4 * 4;
+    const V* s = reinterpret_cast<const V*>(tp.smem_mu + ((size_t)k * ln.lpc + ln.part) * EPLP);
+#pragma unroll
+    for (int i = 0; i < EPLP / VN; ++i) {
+      if (i * VN < EPL) {
+        const V v = s[i];
+        if constexpr (VN == 4) {
+          m[i * 4] = v.x;
+          if (i * 4 + 1 < EPL) m[i * 4 + 1 < EPL ? i * 4 + 1 : 0] = v.y;
+          if (i * 4 + 2 < EPL) m[i * 4 + 2 < EPL ? i * 4 + 2 : 0] = v.z;
+          if (i * 4 + 3 < EPL) m[i * 4 + 3 < EPL ? i * 4 + 3 : 0] = v.w;
+        } else {
+          m[i * 2] = v.x;
+          if (i * 2 + 1 < EPL) m[i * 2 + 1 < EPL ? i * 2 + 1 : 0] = v.y;
+        }
+      }
+    }
+  } else {
+    const T* muk = mu + (size_t)k * d + ln.lo;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) m[j] = (j < ln.nvalid) ? muk[j] : T(0);
+  }
+}
+
 template <class T, int EPL, bool PADDED, bool WANT_LOGP>
 __device__ __forceinline__ T eval_target(TagMixture, const T (&x)[EPL], T (&g)[EPL], const Lane& ln,
                                          const TParams<T>& tp, T*) {
@@ -264,11 +300,11 @@ __device__ __forceinline__ T eval_target(TagMixture, const T (&x)[EPL], T (&g)[E
   T amax = -INFINITY;
 #pragma unroll 1
   for (int k = 0; k < K; ++k) {
-    const T* muk = mu + (size_t)k * d + ln.lo;
-    T terms[EPL];
+    T m[EPL], terms[EPL];
+    mixture_mean_slice<T, EPL>(m, tp, mu, k, d, ln);
 #pragma unroll
     for (int j = 0; j < EPL; ++j) {
-      const T df = (j < ln.nvalid) ? (x[j] - muk[j]) : T(0);
+      const T df = (!PADDED || j < ln.nvalid) ? (x[j] - m[j]) : T(0);
       terms[j] = df * df;
     }
     const T sq = chain_sum<T, EPL>(terms, ln);
@@ -284,11 +320,12 @@ __device__ __forceinline__ T eval_target(TagMixture, const T (&x)[EPL], T (&g)[E
   for (int j = 0; j < EPL; ++j) acc[j] = T(0);
 #pragma unroll 1
   for (int k = 0; k < K; ++k) {
-    const T* muk = mu + (size_t)k * d + ln.lo;
+    T m[EPL];
+    mixture_mean_slice<T, EPL>(m, tp, mu, k, d, ln);
     const T rk = a[k] / se;
 #pragma unroll
     for (int j = 0; j < EPL; ++j) {
-      const T dm = (j < ln.nvalid) ? (muk[j] - x[j]) : T(0);
+      const T dm = (!PADDED || j < ln.nvalid) ? (m[j] - x[j]) : T(0);
       acc[j] = acc[j] + rk * dm;
     }
   }
@@ -435,6 +472,7 @@ __host__ inline TParams<T> make_tparams(const TargetDesc& td) {
   TParams<T> tp;
   for (int i = 0; i < kMaxScalarParams; ++i) tp.sp[i] = (T)td.sp[i];
   tp.dp = (const T*)td.dparams;
+  tp.smem_mu = nullptr;
   tp.n_comp = td.n_comp;
   tp.inv_cov[0][0] = tp.inv_cov[0][1] = tp.inv_cov[1][0] = tp.inv_cov[1][1] = T(0);
   tp.norm_const = T(0);
@@ -493,9 +531,6 @@ struct HmcArgs {
   T* diag_pp;
 };
 
-template <class T> struct VecOf;
-template <> struct VecOf<float> { using type = float4; static constexpr int n = 4; };
-template <> struct VecOf<double> { using type = double2; static constexpr int n = 2; };
 
 // Write-out plan of one lane: the warp's position rows ([chains_in_warp][d_pad] in shared memory) are
 // copied to [chain, slot, :] of the sample tensor as a flat list of vectors (float4 / double2, or

@@ -26,6 +26,8 @@
 #pragma once
 #include "hmc_kernel.cuh"
 
+#include <type_traits>
+
 namespace gm {
 namespace GM_NS {
 
@@ -183,6 +185,22 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
     for (int i = lane; i < a.d_pad; i += 32)
       warp_pos[(size_t)c * a.d_pad + i] = (ch < a.n_chains && i < a.d) ? a.positions[ch * d + i] : T(1);
   }
+  // mixture: component means staged once per CTA in shared memory, lane-padded for vector loads
+  TParams<T> tp = a.tp;
+  if constexpr (std::is_same<TAG, TagMixture>::value) {
+    constexpr int EPLP = Eplp<EPL>::value;
+    T* smu = smem + (size_t)(kHmcBlock >> 5) * 2 * warp_elems;
+    const int K = a.tp.n_comp;
+    const T* gmu = a.tp.dp + K;
+    for (int i = threadIdx.x; i < K * a.lpc * EPLP; i += blockDim.x) {
+      const int k = i / (a.lpc * EPLP), rem = i - k * (a.lpc * EPLP);
+      const int part = rem / EPLP, j = rem - part * EPLP;
+      const int col = part * EPL + j;
+      smu[i] = (j < EPL && col < a.d) ? gmu[(size_t)k * a.d + col] : T(0);
+    }
+    tp.smem_mu = smu;
+    __syncthreads();
+  }
   __syncwarp();
   if (a.write_init && a.out && active) {
 #pragma unroll
@@ -271,7 +289,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
     }
     // every chain is in the START, LEAF or DONE phase here, and a finished chain never reads g again: the
     // gradient is written in place
-    const T logp = eval_target<T, EPL, PADDED, true>(TAG{}, q, g, ln, a.tp, row);
+    const T logp = eval_target<T, EPL, PADDED, true>(TAG{}, q, g, ln, tp, row);
     if (is_leaf) {
 #pragma unroll
       for (int j = 0; j < EPL; ++j) p[j] = p[j] + g[j] * he;
@@ -625,7 +643,8 @@ inline cudaError_t nuts_launch_one(const NutsLaunch& L, cudaStream_t st) {
     return cudaGetLastError();
   }
   NutsArgs<T> a = make_nuts_args<T>(L);
-  const size_t smem = 2 * (size_t)(kHmcBlock / L.lpc) * d_pad * sizeof(T);
+  size_t smem = 2 * (size_t)(kHmcBlock / L.lpc) * d_pad * sizeof(T);
+  if (std::is_same<TAG, TagMixture>::value) smem += (size_t)L.tgt.n_comp * L.lpc * Eplp<EPL>::value * sizeof(T);
   auto kern = (L.epl * L.lpc == L.tgt.dim) ? nuts_run_kernel<T, EPL, TAG, false> : nuts_run_kernel<T, EPL, TAG, true>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
