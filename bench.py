@@ -240,7 +240,7 @@ def run_ours(args, rank, world, local):
         e2e_T = 2
     elif args.workload == "nuts_mixture":
         chains = args.chains or 65536
-        per_launch = 20
+        per_launch = 200          # tree sizes are heavy-tailed: long launches let the chain queue balance them
         K = 4
         mu = np.stack([(k - 1.5) * (2.0 / np.sqrt(DIM)) * np.ones(DIM) for k in range(K)])
         tgt = gm.GaussianMixture(np.full(K, 1.0 / K), mu, 1.0)

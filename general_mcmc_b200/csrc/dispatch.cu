@@ -61,17 +61,27 @@ bool choose_nuts_decomposition(int dim, int dtype, int kind, int* epl, int* lpc)
   }
   const int big = dtype == 0 ? 25 : 13;
   const int menu[3] = {4, 8, big};
-  double best = 1e30;
-  int be = 0, bl = 0;
-  for (int l = 1; l <= 32; l <<= 1)
-    for (int e : menu) {
-      if (e * l < dim) continue;
-      const double cost = (double)e * l * ((e * l == dim) ? 1.0 : 1.15) + 6.0 * l;
-      if (cost < best - 1e-9 || (cost < best + 1e-9 && e > be)) { best = cost; be = e; bl = l; }
+  {
+    const char* e_env = std::getenv("GMCMC_NUTS_EPL");
+    const char* l_env = std::getenv("GMCMC_NUTS_LPC");
+    if (e_env && l_env) {
+      const int e = std::atoi(e_env), l = std::atoi(l_env);
+      if ((e == 4 || e == 8 || e == big) && l >= 1 && l <= 32 && (l & (l - 1)) == 0 && e * l >= dim) {
+        *epl = e; *lpc = l;
+        return true;
+      }
     }
-  if (!be) return false;
-  *epl = be; *lpc = bl;
-  return true;
+  }
+  // NUTS iterations are latency-bound (dependent global / shuffle / transcendental chains), so chains are spread over
+  // MANY lanes with few coordinates each (short instruction streams, low register count, more chains in flight):
+  // 8 coordinates per lane while that fits a warp, the wide slices beyond.  Measured on B200 at d = 100: (8, 16)
+  // 4.6e8 leapfrogs/s, (25, 4) 4.0e8, (4, 32) 2.7e8.
+  if (dim <= 4) { *epl = 4; *lpc = 1; return true; }
+  for (int l = 1; l <= 32; l <<= 1)
+    if (8 * l >= dim) { *epl = 8; *lpc = l; return true; }
+  for (int l = 16; l <= 32; l <<= 1)
+    if (big * l >= dim) { *epl = big; *lpc = l; return true; }
+  return false;
 }
 
 // Decomposition: minimise padded slots (compute), penalising non exact fits (masking costs ~30 %) and

@@ -126,6 +126,7 @@ struct NutsLaunch {
   const double* inj_exp1; size_t n_exp;
   const double* inj_unif; size_t n_unif;
   unsigned long long* inj_used;
+  unsigned long long* queue;    // [1] device counter of the dynamic chain queue
   int epl, lpc;
 };
 

@@ -65,6 +65,7 @@ struct NutsArgs {
   const double* inj_exp1; size_t n_exp;
   const double* inj_unif; size_t n_unif;
   unsigned long long* inj_used;   // [C][3] consumption counters, in/out
+  unsigned long long* queue;      // [1] next chain to hand out (initialised to the number of lane groups of the grid)
 };
 
 enum NutsPhase : int { NP_START = 0, NP_LEAF = 1, NP_END = 2, NP_DONE = 3 };
@@ -154,10 +155,14 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* smem = reinterpret_cast<T*>(smem_raw);
 
+  // Lane groups are persistent workers: group `slot` starts with chain `slot` and, whenever its chain has finished
+  // all its transitions, takes the next chain from a global queue — tree sizes are heavy-tailed (a few chains build
+  // 20x larger trees), so a static chain -> lane-group assignment would leave most of the GPU waiting for them.
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const Lane ln = make_lane<EPL>(tid, a.lpc, a.d);
-  const size_t chain = (size_t)(tid / a.lpc);
-  const bool active = chain < a.n_chains;
+  const size_t slot_id = (size_t)(tid / a.lpc);      // workspace row of this lane group
+  size_t chain = slot_id;
+  bool active = chain < a.n_chains;
   const int lane = threadIdx.x & 31;
   const int chains_in_warp = 32 / a.lpc;
   const int chain_in_warp = lane / a.lpc;
@@ -165,11 +170,10 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
   T* warp_pos = smem + (size_t)(threadIdx.x >> 5) * 2 * warp_elems;
   T* pos_row = warp_pos + (size_t)chain_in_warp * a.d_pad;
   T* row = warp_pos + warp_elems + (size_t)chain_in_warp * a.d_pad;
-  const size_t warp_first_chain = (size_t)((tid & ~31) / a.lpc);
-  const unsigned long long gchain = a.chain_offset + chain;
+  unsigned long long gchain = a.chain_offset + chain;
   const size_t d = (size_t)a.d;
   const size_t wd = (size_t)a.lpc * Eplp<EPL>::value;   // lane-padded workspace vector length
-  const size_t cw = active ? chain : 0;   // workspace row (inactive lanes alias chain 0, never commit)
+  const size_t cw = slot_id;
 
   T* e_qm = a.ws_edges + (cw * 6 + 0) * wd;
   T* e_pm = a.ws_edges + (cw * 6 + 1) * wd;
@@ -180,11 +184,6 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
   T* w_first = a.ws_first + cw * (size_t)a.cap * 2 * wd;
   T* w_prime = a.ws_prime + cw * (size_t)a.cap * wd;
 
-  for (int c = 0; c < chains_in_warp; ++c) {
-    const size_t ch = warp_first_chain + c;
-    for (int i = lane; i < a.d_pad; i += 32)
-      warp_pos[(size_t)c * a.d_pad + i] = (ch < a.n_chains && i < a.d) ? a.positions[ch * d + i] : T(1);
-  }
   // mixture: component means staged once per CTA in shared memory, lane-padded for vector loads
   TParams<T> tp = a.tp;
   if constexpr (std::is_same<TAG, TagMixture>::value) {
@@ -201,18 +200,45 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
     tp.smem_mu = smu;
     __syncthreads();
   }
-  __syncwarp();
-  if (a.write_init && a.out && active) {
-#pragma unroll
-    for (int j = 0; j < EPL; ++j)
-      if (j < ln.nvalid) a.out[(chain * a.out_n) * d + ln.lo + j] = pos_row[ln.lo + j];
-  }
 
   T eps = T(1), eps_bar = T(1), h_bar = T(0), mu = T(0);
-  if (active) { eps = a.eps[chain]; eps_bar = a.eps_bar[chain]; h_bar = a.h_bar[chain]; mu = a.mu[chain]; }
   unsigned long long i_norm = 0, i_exp = 0, i_unif = 0;
   const bool inject = a.inj_normals != nullptr;
-  if (inject && active) { i_norm = a.inj_used[chain * 3]; i_exp = a.inj_used[chain * 3 + 1]; i_unif = a.inj_used[chain * 3 + 2]; }
+  unsigned long long my_leapfrogs = 0, my_diverge = 0, my_depth = 0, chain_leaps = 0;
+
+  // per-chain state in / out (each lane moves its own slice of the position row)
+  auto load_chain = [&]() {
+#pragma unroll
+    for (int j = 0; j < EPL; ++j)
+      if (j < ln.nvalid) pos_row[ln.lo + j] = a.positions[chain * d + ln.lo + j];
+    eps = a.eps[chain]; eps_bar = a.eps_bar[chain]; h_bar = a.h_bar[chain]; mu = a.mu[chain];
+    if (inject) { i_norm = a.inj_used[chain * 3]; i_exp = a.inj_used[chain * 3 + 1]; i_unif = a.inj_used[chain * 3 + 2]; }
+    if (a.write_init && a.out) {
+#pragma unroll
+      for (int j = 0; j < EPL; ++j)
+        if (j < ln.nvalid) a.out[(chain * a.out_n) * d + ln.lo + j] = pos_row[ln.lo + j];
+    }
+    chain_leaps = 0;
+    gchain = a.chain_offset + chain;
+  };
+  auto store_chain = [&]() {
+#pragma unroll
+    for (int j = 0; j < EPL; ++j)
+      if (j < ln.nvalid) a.positions[chain * d + ln.lo + j] = pos_row[ln.lo + j];
+    if (ln.part == 0) {
+      a.eps[chain] = eps; a.eps_bar[chain] = eps_bar; a.h_bar[chain] = h_bar;
+      if (inject) { a.inj_used[chain * 3] = i_norm; a.inj_used[chain * 3 + 1] = i_exp; a.inj_used[chain * 3 + 2] = i_unif; }
+      if (a.chain_leapfrogs) a.chain_leapfrogs[chain] += (long long)chain_leaps;
+    }
+  };
+  if (active) load_chain();
+  else {
+#pragma unroll
+    for (int j = 0; j < EPL; ++j)
+      if (j < ln.nvalid) pos_row[ln.lo + j] = T(1);     // idle lane groups evaluate a harmless point
+  }
+  __syncwarp();
+  bool exhausted = !active;      // no more chains for this lane group
 
   T q[EPL], p[EPL], g[EPL], prime[EPL];
 #pragma unroll
@@ -222,6 +248,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
   for (int k = 0; k < kNutsDepthCap; ++k) n_stack[k] = 0;
 
   int phase = (active && a.n_steps > 0) ? NP_START : NP_DONE;
+  if (active && a.n_steps == 0) store_chain();
   uint32_t s = 0;          // transition of this launch
   uint32_t draw = 0;       // uniform draws of the current transition (Philox stream 2)
   int j_depth = 0, v = 1;
@@ -230,8 +257,6 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
   int nR = 0, n_alpha = 0;
   bool sR = true;
   T alpha_sum = T(0), logu = T(0), joint0 = T(0);
-  unsigned long long my_leapfrogs = 0, my_diverge = 0, my_depth = 0;
-
   auto next_unif = [&]() -> double {
     if (inject) {
       const double u = (i_unif < a.n_unif) ? a.inj_unif[chain * a.n_unif + i_unif] : 0.75;
@@ -245,6 +270,27 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
   };
 
   for (;;) {
+    // ---- 0. lane groups whose chain is finished take the next one from the queue
+    {
+      const bool need = (phase == NP_DONE) && !exhausted;
+      if (__any_sync(kFull, need)) {
+        unsigned long long nxt = 0;
+        if (need && ln.part == 0) nxt = atomicAdd(a.queue, 1ull);
+        nxt = __shfl_sync(kFull, nxt, ln.gbase);
+        if (need) {
+          if (nxt < (unsigned long long)a.n_chains) {
+            chain = (size_t)nxt;
+            load_chain();
+            s = 0;
+            if (a.n_steps > 0) phase = NP_START; else store_chain();
+          } else {
+            exhausted = true;
+          }
+        }
+        __syncwarp();
+      }
+      if (__all_sync(kFull, phase == NP_DONE && exhausted)) break;
+    }
     // ---- A. momentum for the chains that start a transition (generic_nuts.rs:759-762)
     const bool is_start = (phase == NP_START);
     const bool is_leaf = (phase == NP_LEAF);
@@ -320,7 +366,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       phase = NP_LEAF;
     } else if (is_leaf) {
       // leaf of build_tree (j == 0 branch, generic_nuts.rs:1185-1222)
-      ++my_leapfrogs;
+      ++my_leapfrogs; ++chain_leaps;
       nR = (logu < joint) ? 1 : 0;
       sR = (logu - T(1000)) < joint;
       if (!sR) ++my_diverge;
@@ -446,24 +492,12 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
           if (j < ln.nvalid) __stcs(a.out + (chain * a.out_n + (size_t)slot) * d + ln.lo + j, pos_row[ln.lo + j]);
       }
       ++s;
-      phase = (s < a.n_steps) ? NP_START : NP_DONE;
+      if (s < a.n_steps) phase = NP_START;
+      else { phase = NP_DONE; store_chain(); }
     }
-    if (__all_sync(kFull, phase == NP_DONE)) break;
   }
 
-  // ---- state back to HBM
-  __syncwarp();
-  for (int c = 0; c < chains_in_warp; ++c) {
-    const size_t ch = warp_first_chain + c;
-    if (ch >= a.n_chains) break;
-    for (int i = lane; i < a.d; i += 32) a.positions[ch * d + i] = warp_pos[(size_t)c * a.d_pad + i];
-  }
-  if (active && ln.part == 0) {
-    a.eps[chain] = eps; a.eps_bar[chain] = eps_bar; a.h_bar[chain] = h_bar;
-    if (inject) { a.inj_used[chain * 3] = i_norm; a.inj_used[chain * 3 + 1] = i_exp; a.inj_used[chain * 3 + 2] = i_unif; }
-    if (a.chain_leapfrogs) a.chain_leapfrogs[chain] += (long long)my_leapfrogs;
-  }
-  if (!(active && ln.part == 0)) { my_leapfrogs = 0; my_diverge = 0; my_depth = 0; }
+  if (ln.part != 0) { my_leapfrogs = 0; my_diverge = 0; my_depth = 0; }
   for (int o = 16; o > 0; o >>= 1) {
     my_leapfrogs += __shfl_xor_sync(kFull, my_leapfrogs, o);
     my_diverge += __shfl_xor_sync(kFull, my_diverge, o);
@@ -616,6 +650,7 @@ inline NutsArgs<T> make_nuts_args(const NutsLaunch& L) {
   a.chain_leapfrogs = L.chain_leapfrogs;
   a.inj_normals = L.inj_normals; a.n_norm = L.n_norm; a.inj_exp1 = L.inj_exp1; a.n_exp = L.n_exp;
   a.inj_unif = L.inj_unif; a.n_unif = L.n_unif; a.inj_used = L.inj_used;
+  a.queue = L.queue;
   return a;
 }
 
@@ -650,7 +685,20 @@ inline cudaError_t nuts_launch_one(const NutsLaunch& L, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  kern<<<blocks, kHmcBlock, smem, st>>>(a);
+  // persistent grid: as many CTAs as fit on the device at once (or fewer when there are fewer chains); the lane groups
+  // pull further chains from the queue, which starts at the number of groups handed out statically
+  int per_sm = 0, dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kHmcBlock, smem);
+  if (eo != cudaSuccess) return eo;
+  const unsigned resident = (unsigned)(per_sm > 0 ? per_sm : 1) * (unsigned)sms;
+  const unsigned grid = blocks < resident ? blocks : resident;
+  const unsigned long long first = (unsigned long long)grid * (kHmcBlock / L.lpc);
+  cudaError_t eq = cudaMemcpyAsync(L.queue, &first, sizeof first, cudaMemcpyHostToDevice, st);
+  if (eq != cudaSuccess) return eq;
+  cudaStreamSynchronize(st);   // `first` is a stack variable
+  kern<<<grid, kHmcBlock, smem, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -171,7 +171,7 @@ struct gmcmc_sampler {
   unsigned long long* d_nuts_used = nullptr;                     // [C][3]
   uint32_t nuts_m = 0, nuts_n_discard = 0;
   // counters
-  unsigned long long* d_counts = nullptr;  // [4]: accepts, divergences, grad_evals(NUTS), spare
+  unsigned long long* d_counts = nullptr;  // [8]: accepts, divergences, grad_evals(NUTS), depth sum, NUTS chain queue, spare
   uint64_t transitions = 0;
   uint64_t hmc_grad_evals = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -397,6 +397,7 @@ gmcmc_status nuts_launch(gmcmc_sampler* s, NutsLaunch& L) {
   L.inj_exp1 = s->d_nuts_inj[1]; L.n_exp = s->nuts_inj_n[1];
   L.inj_unif = s->d_nuts_inj[2]; L.n_unif = s->nuts_inj_n[2];
   L.inj_used = s->d_nuts_used;
+  L.queue = s->d_counts + 4;
   L.epl = s->epl; L.lpc = s->lpc;
   cudaError_t e = s->tgt->custom ? s->tgt->custom->launch_nuts(L, s->ctx->stream)
                   : (s->math == GMCMC_MATH_EXACT) ? launch_nuts_exact(L, s->ctx->stream) : launch_nuts_fast(L, s->ctx->stream);
@@ -896,8 +897,8 @@ static gmcmc_status sampler_common(gmcmc_ctx* ctx, gmcmc_target* tgt, size_t n_c
   const size_t bytes = n_chains * (size_t)s->dim * esize(s->dtype);
   bool ok = cudaMalloc(&s->d_pos, bytes) == cudaSuccess &&
             cudaMemcpy(s->d_pos, init_host, bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
-            cudaMalloc(&s->d_counts, 4 * sizeof(unsigned long long)) == cudaSuccess &&
-            cudaMemset(s->d_counts, 0, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMalloc(&s->d_counts, 8 * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMemset(s->d_counts, 0, 8 * sizeof(unsigned long long)) == cudaSuccess &&
             cudaEventCreate(&s->ev0) == cudaSuccess && cudaEventCreate(&s->ev1) == cudaSuccess;
   if (!ok) {
     gmcmc_status st = fail(GMCMC_ERR_CUDA, "sampler allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
