@@ -257,6 +257,17 @@ __device__ __forceinline__ T eval_target(TagDenseGauss, const T (&x)[EPL], T (&g
 constexpr int kMaxComp = 8;
 // The component loops are deliberately NOT unrolled (K is a runtime value): unrolling 8 components x EPL
 // coordinates made the NUTS kernel ~200 KB of code and instruction-fetch bound.
+// fast-math transcendental helpers: MUFU approximations in fast mode (f32), libdevice otherwise
+template <class T> __device__ __forceinline__ T fast_log(T x) {
+  if constexpr (!kExact && sizeof(T) == 4) return __logf(x); else return log(x);
+}
+template <class T> __device__ __forceinline__ T fast_exp(T x) {
+  if constexpr (!kExact && sizeof(T) == 4) return __expf(x); else return exp(x);
+}
+template <class T> __device__ __forceinline__ T fast_div(T a, T b) {
+  if constexpr (!kExact && sizeof(T) == 4) return __fdividef(a, b); else return a / b;
+}
+
 // this lane's slice of component k's mean: from the lane-padded shared-memory copy (vector loads) or from HBM / L1
 template <class T, int EPL>
 __device__ __forceinline__ void mixture_mean_slice(T (&m)[EPL], const TParams<T>& tp, const T* mu, int k, int d, const Lane& ln) {
@@ -308,13 +319,13 @@ __device__ __forceinline__ T eval_target(TagMixture, const T (&x)[EPL], T (&g)[E
       terms[j] = df * df;
     }
     const T sq = chain_sum<T, EPL>(terms, ln);
-    const T ak = log(w[k]) - T(0.5) * sq * inv_var;
+    const T ak = fast_log<T>(w[k]) - T(0.5) * sq * inv_var;
     a[k] = ak;
     amax = max(amax, ak);
   }
   T se = T(0);
 #pragma unroll 1
-  for (int k = 0; k < K; ++k) { const T e = exp(a[k] - amax); a[k] = e; se = se + e; }
+  for (int k = 0; k < K; ++k) { const T e = fast_exp<T>(a[k] - amax); a[k] = e; se = se + e; }
   T acc[EPL];
 #pragma unroll
   for (int j = 0; j < EPL; ++j) acc[j] = T(0);
@@ -322,7 +333,7 @@ __device__ __forceinline__ T eval_target(TagMixture, const T (&x)[EPL], T (&g)[E
   for (int k = 0; k < K; ++k) {
     T m[EPL];
     mixture_mean_slice<T, EPL>(m, tp, mu, k, d, ln);
-    const T rk = a[k] / se;
+    const T rk = fast_div<T>(a[k], se);
 #pragma unroll
     for (int j = 0; j < EPL; ++j) {
       const T dm = (!PADDED || j < ln.nvalid) ? (m[j] - x[j]) : T(0);
@@ -331,7 +342,7 @@ __device__ __forceinline__ T eval_target(TagMixture, const T (&x)[EPL], T (&g)[E
   }
 #pragma unroll
   for (int j = 0; j < EPL; ++j) g[j] = acc[j] * inv_var;
-  return amax + log(se);
+  return amax + fast_log<T>(se);
 }
 
 // Rosenbrock2D — distributions.rs:502-515 (one lane per chain, EPL == 2)

@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       nR = (logu < joint) ? 1 : 0;
       sR = (logu - T(1000)) < joint;
       if (!sR) ++my_diverge;
-      alpha_sum = alpha_sum + min(T(1), (T)exp(joint - joint0));
+      alpha_sum = alpha_sum + min(T(1), fast_exp<T>(joint - joint0));
       ++n_alpha;
 #pragma unroll
       for (int j = 0; j < EPL; ++j) prime[j] = q[j];
