@@ -121,17 +121,25 @@ def init_positions(rank, n_chains, dim, dtype=np.float32):
 # ------------------------------------------------------------------------------------------------
 # CPU legs (oracle "port": the C++ restatement of the reference algorithm, all host threads)
 # ------------------------------------------------------------------------------------------------
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers: ignore that)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_hmc_rate(target_seconds=12.0, chains=None):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     oracle_lib.build()
-    threads = oracle_lib.max_threads()
+    threads = host_threads()
     chains = chains or max(threads * 64, 2048)
     q0 = init_positions(0, chains, DIM)
-    secs, _, _ = oracle_lib.hmc_bench(oracle_lib.ROSENBROCK_ND, [], q0, STEP_SIZE, N_LEAPFROG, 1, seed=1)
+    secs, _, _ = oracle_lib.hmc_bench(oracle_lib.ROSENBROCK_ND, [], q0, STEP_SIZE, N_LEAPFROG, 1, seed=1, threads=threads)
     rate1 = chains * N_LEAPFROG / max(secs, 1e-9)
     n_steps = int(max(1, min(200000, target_seconds * rate1 / (chains * N_LEAPFROG))))
-    secs, _, _ = oracle_lib.hmc_bench(oracle_lib.ROSENBROCK_ND, [], q0, STEP_SIZE, N_LEAPFROG, n_steps, seed=2)
+    secs, _, _ = oracle_lib.hmc_bench(oracle_lib.ROSENBROCK_ND, [], q0, STEP_SIZE, N_LEAPFROG, n_steps, seed=2, threads=threads)
     rate = chains * n_steps * N_LEAPFROG / secs
     return rate, threads, "%d chains x %d transitions x L=%d, d=%d, f32 (%.1f s)" % (chains, n_steps, N_LEAPFROG, DIM, secs)
 
@@ -140,14 +148,14 @@ def cpu_mh_rate(target_seconds=12.0):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     oracle_lib.build()
-    threads = oracle_lib.max_threads()
+    threads = host_threads()
     chains = max(threads * 256, 8192)
     x0 = np.random.default_rng(0).standard_normal((chains, 2))
     params = [0.0, 0.0, 1.0, 0.0, 0.0, 1.0]
-    secs, _, _ = oracle_lib.mh_bench(oracle_lib.GAUSS2D, params, x0, 1.0, 20, seed=1, keep_samples=True)
+    secs, _, _ = oracle_lib.mh_bench(oracle_lib.GAUSS2D, params, x0, 1.0, 20, seed=1, threads=threads, keep_samples=True)
     rate1 = chains * 20 / max(secs, 1e-9)
     n_steps = int(max(1, min(1000, target_seconds * rate1 / chains)))
-    secs, _, _ = oracle_lib.mh_bench(oracle_lib.GAUSS2D, params, x0, 1.0, n_steps, seed=2, keep_samples=True)
+    secs, _, _ = oracle_lib.mh_bench(oracle_lib.GAUSS2D, params, x0, 1.0, n_steps, seed=2, threads=threads, keep_samples=True)
     return chains * n_steps / secs, threads, "%d chains x %d steps, f64, samples kept (%.1f s)" % (chains, n_steps, secs)
 
 
