@@ -120,6 +120,14 @@ def test_cfg1_rosenbrock3d_hmc_exact_mode_bit_exact(ctx, oracle, dtype):
     assert np.array_equal(out, ref["samples"][:, n_discard:, :])
     assert np.array_equal(s.positions(), ref["q"])
     assert 0.3 < diag["accepted"].mean() <= 1.0
+    # and against the committed golden fixture (tests/golden/oracle_cfg1.json, written by make_golden.py)
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_cfg1.json")))
+    key = "f32" if dtype == np.float32 else "f64"
+    assert np.array_equal(s.positions().astype(np.float64), np.asarray(gold[key]["final_positions"]))
+    assert diag["accepted"].sum(0).tolist() == gold[key]["accepted_per_chain"]
+    assert np.array_equal(out[:, -1, :].astype(np.float64), np.asarray(gold[key]["sample_399"]))
 
 
 @pytest.mark.parametrize("dtype,tol", [(np.float32, 1e-5), (np.float64, 1e-10)])
