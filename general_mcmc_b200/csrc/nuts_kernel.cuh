@@ -66,6 +66,11 @@ struct NutsArgs {
   const double* inj_unif; size_t n_unif;
   unsigned long long* inj_used;   // [C][3] consumption counters, in/out
   unsigned long long* queue;      // [1] next chain to hand out (initialised to the number of lane groups of the grid)
+  // diagonal mass matrix (MassMatrix::Diagonal, generic_nuts.rs:177-304): inv = 1 / var, sqrt = sqrt(var); null = identity
+  const T* mass_inv; const T* mass_sqrt;          // [C, d]
+  // warm-up position statistics (RunningCov, generic_nuts.rs:81-132), updated for collect_after < m < collect_before
+  T* run_mean; T* run_m2; unsigned int* run_n;    // [C, d], [C, d], [C]
+  uint32_t collect_after, collect_before;
 };
 
 enum NutsPhase : int { NP_START = 0, NP_LEAF = 1, NP_END = 2, NP_DONE = 3 };
@@ -205,6 +210,9 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
   unsigned long long i_norm = 0, i_exp = 0, i_unif = 0;
   const bool inject = a.inj_normals != nullptr;
   unsigned long long my_leapfrogs = 0, my_diverge = 0, my_depth = 0, chain_leaps = 0;
+  T minv[EPL], msqrt[EPL];         // this chain's diagonal mass (1 = identity: x * 1 is exact, so parity is untouched)
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) { minv[j] = T(1); msqrt[j] = T(1); }
 
   // per-chain state in / out (each lane moves its own slice of the position row)
   auto load_chain = [&]() {
@@ -220,6 +228,11 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
     }
     chain_leaps = 0;
     gchain = a.chain_offset + chain;
+    if (a.mass_inv) {
+#pragma unroll
+      for (int j = 0; j < EPL; ++j)
+        if (j < ln.nvalid) { minv[j] = a.mass_inv[chain * d + ln.lo + j]; msqrt[j] = a.mass_sqrt[chain * d + ln.lo + j]; }
+    }
   };
   auto store_chain = [&]() {
 #pragma unroll
@@ -318,9 +331,9 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
         for (int j = 0; j < EPL; ++j) pn[j] = (j < ln.nvalid) ? row[ln.lo + j] : T(0);
         __syncwarp();
       }
-      if (is_start) {
+      if (is_start) {   // sample_momentum, generic_nuts.rs:283-303: z * sqrt(var)
 #pragma unroll
-        for (int j = 0; j < EPL; ++j) { p[j] = pn[j]; q[j] = (j < ln.nvalid) ? pos_row[ln.lo + j] : T(1); }
+        for (int j = 0; j < EPL; ++j) { p[j] = pn[j] * msqrt[j]; q[j] = (j < ln.nvalid) ? pos_row[ln.lo + j] : T(1); }
       }
     }
 
@@ -331,7 +344,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
 #pragma unroll
       for (int j = 0; j < EPL; ++j) p[j] = p[j] + g[j] * he;
 #pragma unroll
-      for (int j = 0; j < EPL; ++j) q[j] = q[j] + p[j] * veps;
+      for (int j = 0; j < EPL; ++j) q[j] = q[j] + (minv[j] * p[j]) * veps;     // velocity = M^-1 p (apply_inv_mass)
     }
     // every chain is in the START, LEAF or DONE phase here, and a finished chain never reads g again: the
     // gradient is written in place
@@ -342,7 +355,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
     }
     T terms[EPL];
 #pragma unroll
-    for (int j = 0; j < EPL; ++j) terms[j] = p[j] * p[j];
+    for (int j = 0; j < EPL; ++j) terms[j] = p[j] * p[j] * minv[j];            // MassMatrix::kinetic :228-263
     const T ke = T(0.5) * chain_sum<T, EPL>(terms, ln);
     const T joint = logp - ke;
 
@@ -415,11 +428,13 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       const bool fwd = (v == 1);
       const T dm = chain_sum_fn<T, EPL>(ln, [&](int j) {
         const T df = fwd ? (q[j] - fq[j]) : (fq[j] - q[j]);
-        return (!PADDED || j < ln.nvalid) ? df * (fwd ? fp[j] : p[j]) : T(0);
+        const T mi = do_top ? minv[j] : T(1);
+        return (!PADDED || j < ln.nvalid) ? df * (mi * (fwd ? fp[j] : p[j])) : T(0);
       });
       const T dp = chain_sum_fn<T, EPL>(ln, [&](int j) {
         const T df = fwd ? (q[j] - fq[j]) : (fq[j] - q[j]);
-        return (!PADDED || j < ln.nvalid) ? df * (fwd ? p[j] : fp[j]) : T(0);
+        const T mi = do_top ? minv[j] : T(1);
+        return (!PADDED || j < ln.nvalid) ? df * (mi * (fwd ? p[j] : fp[j])) : T(0);
       });
       const bool crit = (dm >= T(0)) && (dp >= T(0));
       if (do_merge) {
@@ -484,6 +499,26 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
         eps_bar = exp((T(1) - eta) * log(eps_bar) + eta * log(eps));
       } else {
         eps = eps_bar;
+      }
+      if (a.run_mean && m <= a.n_discard && m > a.collect_after && m < a.collect_before) {
+        // RunningCov::update (generic_nuts.rs:105-114) on the position after this transition
+        const unsigned int n_new = a.run_n[chain] + 1u;
+        const T n_s = (T)n_new;
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+          if (j < ln.nvalid) {
+            const size_t idx = chain * d + ln.lo + j;
+            const T x = pos_row[ln.lo + j];
+            T mean = a.run_mean[idx];
+            const T delta = x - mean;
+            mean = mean + delta / n_s;
+            const T delta2 = x - mean;
+            a.run_mean[idx] = mean;
+            a.run_m2[idx] = a.run_m2[idx] + delta * delta2;
+          }
+        }
+        __syncwarp();
+        if (ln.part == 0) a.run_n[chain] = n_new;
       }
       const long long slot = (long long)m - a.rec_off;
       if (a.out && slot >= 0 && slot < (long long)a.out_n) {

@@ -343,30 +343,60 @@ struct NutsStream {
   double next_unif()   { if (i_unif >= n_unif) { exhausted = true; return 0.75; } return unif[i_unif++]; }
 };
 
+// MassMatrix::{Identity, Diagonal}, generic_nuts.rs:177-304.  `inv` empty = Identity.  (Dense is out of scope.)
 template <class T>
-inline T nuts_kinetic(const T* p, int d) {  // generic_nuts.rs:234-242 (Identity): half * sum(p*p)
+struct DiagMass {
+  std::vector<T> inv, sqrt_;
+  bool identity() const { return inv.empty(); }
+  // diagonal_from_var, generic_nuts.rs:196-206
+  static DiagMass from_var(std::vector<T> var, T jitter) {
+    DiagMass m;
+    m.inv.resize(var.size()); m.sqrt_.resize(var.size());
+    for (size_t i = 0; i < var.size(); ++i) {
+      T v = std::max(var[i], jitter);
+      m.inv[i] = T(1) / v;
+      m.sqrt_[i] = std::sqrt(v);
+    }
+    return m;
+  }
+};
+
+template <class T>
+inline T nuts_kinetic(const T* p, int d, const DiagMass<T>* mass = nullptr) {  // generic_nuts.rs:228-263
   T q = 0;
-  for (int i = 0; i < d; ++i) q = q + p[i] * p[i];
+  if (!mass || mass->identity()) for (int i = 0; i < d; ++i) q = q + p[i] * p[i];
+  else for (int i = 0; i < d; ++i) q = q + p[i] * p[i] * mass->inv[i];
   return T(0.5) * q;
 }
 
 template <class T>
-inline T nuts_leapfrog(const Target<T>& tgt, T* q, T* p, T* g, T eps) {  // generic_nuts.rs:1396-1418
+inline T nuts_leapfrog(const Target<T>& tgt, T* q, T* p, T* g, T eps, const DiagMass<T>* mass = nullptr) {  // generic_nuts.rs:1396-1418
   const int d = tgt.dim;
   const T half = T(0.5);
   add_scaled_assign(p, g, eps * half, d);
-  add_scaled_assign(q, p, eps, d);  // identity mass: velocity = momentum
+  if (!mass || mass->identity()) {
+    add_scaled_assign(q, p, eps, d);  // identity mass: velocity = momentum
+  } else {
+    std::vector<T> vel(d);
+    for (int i = 0; i < d; ++i) vel[i] = mass->inv[i] * p[i];   // apply_inv_mass
+    add_scaled_assign(q, vel.data(), eps, d);
+  }
   T logp = tgt.logp_and_grad(q, g);
   add_scaled_assign(p, g, eps * half, d);
   return logp;
 }
 
 template <class T>
-inline bool nuts_stop_criterion(const T* qm, const T* qp, const T* pm, const T* pp, int d) {
-  // generic_nuts.rs:1357-1378 (identity): diff = q+ - q- ; diff.v- >= 0 && diff.v+ >= 0
+inline bool nuts_stop_criterion(const T* qm, const T* qp, const T* pm, const T* pp, int d, const DiagMass<T>* mass = nullptr) {
+  // generic_nuts.rs:1357-1378: diff = q+ - q- ; diff.v- >= 0 && diff.v+ >= 0, v = M^-1 p
   T dm = 0, dp = 0;
-  for (int i = 0; i < d; ++i) { T df = qp[i] - qm[i]; dm = dm + df * pm[i]; }
-  for (int i = 0; i < d; ++i) { T df = qp[i] - qm[i]; dp = dp + df * pp[i]; }
+  if (!mass || mass->identity()) {
+    for (int i = 0; i < d; ++i) { T df = qp[i] - qm[i]; dm = dm + df * pm[i]; }
+    for (int i = 0; i < d; ++i) { T df = qp[i] - qm[i]; dp = dp + df * pp[i]; }
+  } else {
+    for (int i = 0; i < d; ++i) { T df = qp[i] - qm[i]; dm = dm + df * (mass->inv[i] * pm[i]); }
+    for (int i = 0; i < d; ++i) { T df = qp[i] - qm[i]; dp = dp + df * (mass->inv[i] * pp[i]); }
+  }
   return dm >= T(0) && dp >= T(0);
 }
 
@@ -385,14 +415,14 @@ struct TreeOut {
 template <class T>
 TreeOut<T> nuts_build_tree(const Target<T>& tgt, const std::vector<T>& q, const std::vector<T>& p,
                            const std::vector<T>& g, T logu, int v, int j, T eps, T joint_0,
-                           NutsStream& rng, size_t* leapfrogs) {
+                           NutsStream& rng, size_t* leapfrogs, const DiagMass<T>* mass = nullptr) {
   const int d = tgt.dim;
   if (j == 0) {
     TreeOut<T> o;
     std::vector<T> q1 = q, p1 = p, g1 = g;
-    T logp1 = nuts_leapfrog(tgt, q1.data(), p1.data(), g1.data(), (T)v * eps);  // :1185-1192
+    T logp1 = nuts_leapfrog(tgt, q1.data(), p1.data(), g1.data(), (T)v * eps, mass);  // :1185-1192
     if (leapfrogs) ++*leapfrogs;
-    T joint = logp1 - nuts_kinetic(p1.data(), d);                               // :1193
+    T joint = logp1 - nuts_kinetic(p1.data(), d, mass);                         // :1193
     o.n_prime = (logu < joint) ? 1 : 0;                                         // :1194
     o.s_prime = (logu - T(1000)) < joint;                                       // :1195
     o.q_minus = q1; o.q_plus = q1; o.p_minus = p1; o.p_plus = p1; o.g_minus = g1; o.g_plus = g1;
@@ -401,11 +431,11 @@ TreeOut<T> nuts_build_tree(const Target<T>& tgt, const std::vector<T>& q, const 
     o.n_alpha_prime = 1;
     return o;
   }
-  TreeOut<T> o = nuts_build_tree(tgt, q, p, g, logu, v, j - 1, eps, joint_0, rng, leapfrogs);  // :1238
+  TreeOut<T> o = nuts_build_tree(tgt, q, p, g, logu, v, j - 1, eps, joint_0, rng, leapfrogs, mass);  // :1238
   if (o.s_prime) {                                                                              // :1251
     TreeOut<T> o2 = (v == -1)
-        ? nuts_build_tree(tgt, o.q_minus, o.p_minus, o.g_minus, logu, v, j - 1, eps, joint_0, rng, leapfrogs)
-        : nuts_build_tree(tgt, o.q_plus, o.p_plus, o.g_plus, logu, v, j - 1, eps, joint_0, rng, leapfrogs);
+        ? nuts_build_tree(tgt, o.q_minus, o.p_minus, o.g_minus, logu, v, j - 1, eps, joint_0, rng, leapfrogs, mass)
+        : nuts_build_tree(tgt, o.q_plus, o.p_plus, o.g_plus, logu, v, j - 1, eps, joint_0, rng, leapfrogs, mass);
     if (v == -1) { o.q_minus = o2.q_minus; o.p_minus = o2.p_minus; o.g_minus = o2.g_minus; }
     else         { o.q_plus = o2.q_plus;   o.p_plus = o2.p_plus;   o.g_plus = o2.g_plus; }
     double u_build_tree = rng.next_unif();                                                      // :1305 (f64)
@@ -430,28 +460,28 @@ inline bool all_finite(const T* v, int d) {
 
 // find_reasonable_epsilon_with_mass, generic_nuts.rs:1025-1102 (identity mass)
 template <class T>
-T nuts_find_reasonable_epsilon(const Target<T>& tgt, const T* position, const T* mom) {
+T nuts_find_reasonable_epsilon(const Target<T>& tgt, const T* position, const T* mom, const DiagMass<T>* mass = nullptr) {
   const int d = tgt.dim;
   T epsilon = 1;
   const T half = T(0.5);
   std::vector<T> grad(d, T(0));
   T ulogp = tgt.logp_and_grad(position, grad.data());
   std::vector<T> q1(position, position + d), p1(mom, mom + d), g1 = grad;
-  T ulogp1 = nuts_leapfrog(tgt, q1.data(), p1.data(), g1.data(), epsilon);
+  T ulogp1 = nuts_leapfrog(tgt, q1.data(), p1.data(), g1.data(), epsilon, mass);
   T k = 1;
   while (!std::isfinite(ulogp1) || !all_finite(g1.data(), d)) {
     k = k * half;
     q1.assign(position, position + d); p1.assign(mom, mom + d); g1 = grad;
-    ulogp1 = nuts_leapfrog(tgt, q1.data(), p1.data(), g1.data(), epsilon * k);
+    ulogp1 = nuts_leapfrog(tgt, q1.data(), p1.data(), g1.data(), epsilon * k, mass);
   }
   epsilon = half * k * epsilon;
-  T lap = ulogp1 - ulogp - (nuts_kinetic(p1.data(), d) - nuts_kinetic(mom, d));
+  T lap = ulogp1 - ulogp - (nuts_kinetic(p1.data(), d, mass) - nuts_kinetic(mom, d, mass));
   T a = (lap > std::log(half)) ? T(1) : T(-1);
   while (a * lap > -a * std::log(T(2))) {
     epsilon = epsilon * std::pow(T(2), a);
     q1.assign(position, position + d); p1.assign(mom, mom + d); g1 = grad;
-    ulogp1 = nuts_leapfrog(tgt, q1.data(), p1.data(), g1.data(), epsilon);
-    lap = ulogp1 - ulogp - (nuts_kinetic(p1.data(), d) - nuts_kinetic(mom, d));
+    ulogp1 = nuts_leapfrog(tgt, q1.data(), p1.data(), g1.data(), epsilon, mass);
+    lap = ulogp1 - ulogp - (nuts_kinetic(p1.data(), d, mass) - nuts_kinetic(mom, d, mass));
   }
   return epsilon;
 }
@@ -471,6 +501,37 @@ struct NutsChain {
   T epsilon_bar = T(1);
   T h_bar = T(0);
   int max_depth = 0;  // 0 = uncapped (reference); >0 = cap added by BASELINE cfg5
+  // diagonal mass-matrix adaptation (NUTSMassMatrixConfig / MassMatrixWarmup / RunningCov, generic_nuts.rs:40-175)
+  bool mass_adapt = false;
+  size_t start_buffer = 75, end_buffer = 50, initial_window = 25;
+  double regularize = 0.05, jitter = 1e-6;
+  DiagMass<T> mass;
+  size_t next_window_end = 0, window_len = 0, run_n = 0;
+  std::vector<T> run_mean, run_m2;
+  size_t mass_updates = 0;
+  void enable_mass_adaptation(size_t sb, size_t eb, size_t iw, double reg, double jit) {
+    mass_adapt = true; start_buffer = sb; end_buffer = eb; initial_window = iw; regularize = reg; jitter = jit;
+    size_t sbm = std::max<size_t>(sb, 1);                 // MassMatrixWarmup::new, :141-150
+    window_len = std::max<size_t>(iw, 10);
+    next_window_end = sbm + window_len;
+    run_mean.assign(tgt.dim, T(0)); run_m2.assign(tgt.dim, T(0)); run_n = 0;
+  }
+  bool should_collect(size_t mm, size_t n_warm) const {   // :152-160
+    if (mm == 0 || mm > n_warm) return false;
+    if (mm <= start_buffer) return false;
+    size_t lim = n_warm > end_buffer ? n_warm - end_buffer : 0;
+    return mm < lim;
+  }
+  bool note_if_window_end(size_t mm, size_t n_warm) {     // :162-173
+    if (!should_collect(mm, n_warm)) return false;
+    size_t lim = n_warm > end_buffer ? n_warm - end_buffer : 0;
+    if (mm >= next_window_end || mm + 1 >= lim) {
+      next_window_end = next_window_end + window_len;
+      window_len = std::min<size_t>(window_len * 2, 400);
+      return true;
+    }
+    return false;
+  }
   // diagnostics of the last step
   size_t last_leapfrogs = 0;
   int last_depth = 0;
@@ -481,8 +542,10 @@ struct NutsChain {
     n_collect = n_collect_; n_discard = n_discard_; m = 0;
     std::vector<T> mom0(d);
     for (int i = 0; i < d; ++i) mom0[i] = (T)rng.next_normal();
+    if (!mass.identity()) for (int i = 0; i < d; ++i) mom0[i] = mom0[i] * mass.sqrt_[i];   // sample_momentum :283-303
+    if (mass_adapt) { run_n = 0; std::fill(run_mean.begin(), run_mean.end(), T(0)); std::fill(run_m2.begin(), run_m2.end(), T(0)); }
     if (std::abs(epsilon + T(1)) <= std::numeric_limits<T>::epsilon())
-      epsilon = nuts_find_reasonable_epsilon(tgt, position.data(), mom0.data());
+      epsilon = nuts_find_reasonable_epsilon(tgt, position.data(), mom0.data(), &mass);
     mu = std::log(T(10) * epsilon);
   }
 
@@ -491,9 +554,10 @@ struct NutsChain {
     m += 1;
     std::vector<T> mom0(d);
     for (int i = 0; i < d; ++i) mom0[i] = (T)rng.next_normal();                    // :761
+    if (!mass.identity()) for (int i = 0; i < d; ++i) mom0[i] = mom0[i] * mass.sqrt_[i];
     std::vector<T> grad(d, T(0));
     T logp = tgt.logp_and_grad(position.data(), grad.data());                     // :765
-    T joint = logp - nuts_kinetic(mom0.data(), d);                                // :766
+    T joint = logp - nuts_kinetic(mom0.data(), d, &mass);                         // :766
     T exp1_obs = (T)rng.next_exp1();                                              // :767
     T logu = joint - exp1_obs;                                                    // :768
     std::vector<T> qm = position, qp = position, pm = mom0, pp = mom0, gm = grad, gp = grad;
@@ -507,8 +571,8 @@ struct NutsChain {
       T u_run_1 = (T)rng.next_unif();
       int v = (u_run_1 < T(0.5)) ? 1 : -1;                                        // :784
       TreeOut<T> o = (v == -1)
-          ? nuts_build_tree(tgt, qm, pm, gm, logu, v, j, epsilon, joint, rng, &leap)
-          : nuts_build_tree(tgt, qp, pp, gp, logu, v, j, epsilon, joint, rng, &leap);
+          ? nuts_build_tree(tgt, qm, pm, gm, logu, v, j, epsilon, joint, rng, &leap, &mass)
+          : nuts_build_tree(tgt, qp, pp, gp, logu, v, j, epsilon, joint, rng, &leap, &mass);
       if (v == -1) { qm = o.q_minus; pm = o.p_minus; gm = o.g_minus; }
       else         { qp = o.q_plus;  pp = o.p_plus;  gp = o.g_plus; }
       alpha = o.alpha_prime; n_alpha = o.n_alpha_prime;
@@ -516,7 +580,7 @@ struct NutsChain {
       T u_run_2 = (T)rng.next_unif();                                             // :865
       if (o.s_prime && (u_run_2 < tmp)) position = o.q_prime;                     // :866-868
       n += o.n_prime;                                                             // :869
-      s = o.s_prime && nuts_stop_criterion(qm.data(), qp.data(), pm.data(), pp.data(), d);  // :871-878
+      s = o.s_prime && nuts_stop_criterion(qm.data(), qp.data(), pm.data(), pp.data(), d, &mass);  // :871-878
       j += 1;
       if (max_depth > 0 && j >= max_depth) s = false;  // cap: not in the reference
       if (rng.exhausted) break;
@@ -530,6 +594,33 @@ struct NutsChain {
       epsilon = std::exp(mu - std::sqrt(mm) / gamma * h_bar);
       eta = std::pow(mm, -kappa);
       epsilon_bar = std::exp((T(1) - eta) * std::log(epsilon_bar) + eta * std::log(epsilon));
+      if (mass_adapt && should_collect(m, n_discard)) {                             // :902-920
+        // RunningCov::update, :105-114
+        run_n += 1;
+        T n_s = (T)run_n;
+        for (int i = 0; i < d; ++i) {
+          T delta = position[i] - run_mean[i];
+          run_mean[i] = run_mean[i] + delta / n_s;
+          T delta2 = position[i] - run_mean[i];
+          run_m2[i] = run_m2[i] + delta * delta2;
+        }
+        if (note_if_window_end(m, n_discard) && run_n >= 5) {                       // maybe_update_mass_matrix :948-969
+          T n_denom = (T)(run_n - 1);
+          T reg = (T)regularize, omr = T(1) - reg;
+          T jit = (T)std::max(jitter, 1e-10);
+          std::vector<T> var(d);
+          for (int i = 0; i < d; ++i) var[i] = std::max(omr * (run_m2[i] / n_denom) + reg, jit);
+          mass = DiagMass<T>::from_var(var, jit);
+          mass_updates += 1;
+          std::vector<T> probe(d);
+          for (int i = 0; i < d; ++i) probe[i] = (T)rng.next_normal() * mass.sqrt_[i];
+          epsilon = nuts_find_reasonable_epsilon(tgt, position.data(), probe.data(), &mass);
+          mu = std::log(T(10) * epsilon);
+          epsilon_bar = epsilon;
+          h_bar = T(0);
+          run_n = 0; std::fill(run_mean.begin(), run_mean.end(), T(0)); std::fill(run_m2.begin(), run_m2.end(), T(0));
+        }
+      }
     } else {
       epsilon = epsilon_bar;
     }

@@ -100,7 +100,8 @@ void nuts_run(int kind, int dim, const double* params, size_t np, size_t C, T* q
               int max_depth, T eps_init /* <0 => find_reasonable_epsilon */, size_t n_collect,
               size_t n_discard, const double* normals, size_t n_norm, const double* exp1, size_t n_exp,
               const double* unif, size_t n_unif, T* samples, T* eps_final, long long* leapfrogs,
-              long long* used, int* exhausted) {
+              long long* used, int* exhausted, const double* mass_cfg /*null or [start_buffer, end_buffer, initial_window,
+              regularize, jitter]*/ = nullptr, T* mass_inv_out /*[C,d] or null*/ = nullptr, int n_runs = 1) {
   const size_t d = (size_t)dim;
 #pragma omp parallel for schedule(dynamic, 1)
   for (long long ci = 0; ci < (long long)C; ++ci) {
@@ -115,14 +116,18 @@ void nuts_run(int kind, int dim, const double* params, size_t np, size_t C, T* q
     rng.normals = normals + c * n_norm; rng.n_normals = n_norm;
     rng.exp1 = exp1 + c * n_exp; rng.n_exp1 = n_exp;
     rng.unif = unif + c * n_unif; rng.n_unif = n_unif;
-    ch.init_chain_state(n_collect, n_discard, rng);
-    size_t total = n_collect + n_discard;
+    if (mass_cfg) ch.enable_mass_adaptation((size_t)mass_cfg[0], (size_t)mass_cfg[1], (size_t)mass_cfg[2], mass_cfg[3], mass_cfg[4]);
     long long leap = 0;
-    for (size_t s = 0; s < total; ++s) {
-      if (s > 0) { ch.step(rng); leap += (long long)ch.last_leapfrogs; }
-      if (s >= n_discard && samples)
-        std::memcpy(samples + (c * n_collect + (s - n_discard)) * d, ch.position.data(), d * sizeof(T));
+    for (int run = 0; run < n_runs; ++run) {          // n_runs > 1: repeated run() calls on the same chain (state carries over)
+      ch.init_chain_state(n_collect, n_discard, rng);
+      size_t total = n_collect + n_discard;
+      for (size_t s = 0; s < total; ++s) {
+        if (s > 0) { ch.step(rng); leap += (long long)ch.last_leapfrogs; }
+        if (s >= n_discard && samples)
+          std::memcpy(samples + (c * n_collect + (s - n_discard)) * d, ch.position.data(), d * sizeof(T));
+      }
     }
+    if (mass_inv_out) for (size_t i = 0; i < d; ++i) mass_inv_out[c * d + i] = ch.mass.identity() ? T(1) : ch.mass.inv[i];
     std::memcpy(q + c * d, ch.position.data(), d * sizeof(T));
     if (eps_final) eps_final[c] = ch.epsilon;
     if (leapfrogs) leapfrogs[c] = leap;
@@ -254,6 +259,13 @@ void orc_nuts_run_f64(int kind, int dim, const double* params, size_t np, size_t
 }
 void orc_nuts_run_f32(int kind, int dim, const double* params, size_t np, size_t C, float* q, float target_accept, int max_depth, float eps_init, size_t n_collect, size_t n_discard, const double* normals, size_t n_norm, const double* exp1, size_t n_exp, const double* unif, size_t n_unif, float* samples, float* eps_final, long long* leapfrogs, long long* used, int* exhausted) {
   nuts_run<float>(kind, dim, params, np, C, q, target_accept, max_depth, eps_init, n_collect, n_discard, normals, n_norm, exp1, n_exp, unif, n_unif, samples, eps_final, leapfrogs, used, exhausted);
+}
+// with diagonal mass-matrix adaptation (GenericNUTS::new_with_mass_matrix, generic_nuts.rs:379-398)
+void orc_nuts_run_mass_f64(int kind, int dim, const double* params, size_t np, size_t C, double* q, double target_accept, int max_depth, double eps_init, size_t n_collect, size_t n_discard, const double* normals, size_t n_norm, const double* exp1, size_t n_exp, const double* unif, size_t n_unif, double* samples, double* eps_final, long long* leapfrogs, long long* used, int* exhausted, const double* mass_cfg, double* mass_inv_out) {
+  nuts_run<double>(kind, dim, params, np, C, q, target_accept, max_depth, eps_init, n_collect, n_discard, normals, n_norm, exp1, n_exp, unif, n_unif, samples, eps_final, leapfrogs, used, exhausted, mass_cfg, mass_inv_out);
+}
+void orc_nuts_run_mass_f32(int kind, int dim, const double* params, size_t np, size_t C, float* q, float target_accept, int max_depth, float eps_init, size_t n_collect, size_t n_discard, const double* normals, size_t n_norm, const double* exp1, size_t n_exp, const double* unif, size_t n_unif, float* samples, float* eps_final, long long* leapfrogs, long long* used, int* exhausted, const double* mass_cfg, float* mass_inv_out) {
+  nuts_run<float>(kind, dim, params, np, C, q, target_accept, max_depth, eps_init, n_collect, n_discard, normals, n_norm, exp1, n_exp, unif, n_unif, samples, eps_final, leapfrogs, used, exhausted, mass_cfg, mass_inv_out);
 }
 
 // ---- stats ----
