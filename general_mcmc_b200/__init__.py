@@ -6,7 +6,7 @@ build step can run), any call raises if it is missing.
 """
 from ._lib import GmcmcError, LIB_PATH, SYMBOLS, lib  # noqa: F401
 from .api import (  # noqa: F401
-    HMC, NUTS, BasicStats, Context, Counters, CustomTarget, DenseGaussian, DiffableGaussian2D, Gaussian2D, GaussianMixture,
+    HMC, NUTS, NUTSMassMatrixConfig, BasicStats, Context, Counters, CustomTarget, DenseGaussian, DiffableGaussian2D, Gaussian2D, GaussianMixture,
     IsotropicGaussian, MetropolisHastings, Rosenbrock2D, RosenbrockND, RunStats, default_context, init, init_det,
     init_with_seed, set_default_context, shard_chains, split_rhat_mean_ess, build_custom_target)
 

@@ -499,11 +499,29 @@ class MetropolisHastings(_Sampler):
         return self.set_seed(seed)
 
 
+class NUTSMassMatrixConfig:
+    """≙ NUTSMassMatrixConfig (generic_nuts.rs:40-78): warm-up mass-matrix adaptation of NUTS.  `adaptation` is
+    "none", "diagonal" (the reference default) or "dense" (not implemented: GMCMC_ERR_UNSUPPORTED)."""
+    _KINDS = {"none": 0, "diagonal": 1, "dense": 2}
+
+    def __init__(self, adaptation="diagonal", start_buffer=75, end_buffer=50, initial_window=25, regularize=0.05,
+                 jitter=1e-6):
+        if adaptation not in self._KINDS:
+            raise ValueError("adaptation must be one of %s" % sorted(self._KINDS))
+        self.adaptation, self.start_buffer, self.end_buffer = adaptation, int(start_buffer), int(end_buffer)
+        self.initial_window, self.regularize, self.jitter = int(initial_window), float(regularize), float(jitter)
+
+    @classmethod
+    def disabled(cls):
+        return cls("none", 0, 0, 0, 0.0, 0.0)
+
+
 class NUTS(_Sampler):
-    """≙ nuts::NUTS (nuts.rs:156-304) over GenericNUTS (generic_nuts.rs:370-557), identity mass."""
+    """≙ nuts::NUTS (nuts.rs:156-304) over GenericNUTS (generic_nuts.rs:370-557).  `mass_matrix` ≙
+    GenericNUTS::new_with_mass_matrix (generic_nuts.rs:379-398); None = identity mass (GenericNUTS::new)."""
 
     def __init__(self, target, initial_positions, target_accept_p, seed=None, ctx=None, chain_offset=0, dtype=None,
-                 max_depth=0, init_step_size=-1.0):
+                 max_depth=0, init_step_size=-1.0, mass_matrix=None):
         self.ctx = ctx or default_context()
         pos = _as_positions(initial_positions, dtype)
         self.n_chains, self.dim = pos.shape
@@ -518,6 +536,19 @@ class NUTS(_Sampler):
                                           L.ptr(pos), C.c_double(target_accept_p), C.c_uint32(max_depth),
                                           C.c_double(init_step_size), C.c_uint64(seed), C.byref(h)))
         self._h = h
+        if mass_matrix is not None and mass_matrix.adaptation != "none":
+            m = mass_matrix
+            L.check(L.lib().gmcmc_nuts_set_mass_adaptation(self._h, C.c_int(m._KINDS[m.adaptation]),
+                                                           C.c_size_t(m.start_buffer), C.c_size_t(m.end_buffer),
+                                                           C.c_size_t(m.initial_window), C.c_double(m.regularize),
+                                                           C.c_double(m.jitter)))
+
+    def mass_matrix(self):
+        """Per-chain diagonal inverse mass [chains, dim] and the number of warm-up updates applied so far."""
+        inv = np.empty((self.n_chains, self.dim), self.dtype)
+        n = C.c_uint64(0)
+        L.check(L.lib().gmcmc_nuts_mass_matrix(self._h, L.ptr(inv), C.byref(n)))
+        return inv, int(n.value)
 
     def state(self):
         """Per-chain step sizes, accumulated leapfrogs and (when streams were injected) consumed draws."""

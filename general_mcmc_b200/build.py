@@ -54,12 +54,24 @@ def _units():
     return units
 
 
-def _headers_mtime():
-    m = 0.0
-    for d in (CSRC, INCLUDE):
-        for f in os.listdir(d):
-            if f.endswith((".h", ".cuh", ".inc")):
-                m = max(m, os.path.getmtime(os.path.join(d, f)))
+_INC_RE = __import__("re").compile(r'^\s*#\s*include\s+"([^"]+)"', __import__("re").M)
+
+
+def _deps_mtime(src, _seen=None):
+    """Newest mtime of `src` and of every header it includes (transitively) from csrc/ or include/."""
+    seen = _seen if _seen is not None else set()
+    if src in seen or not os.path.exists(src):
+        return 0.0
+    seen.add(src)
+    m = os.path.getmtime(src)
+    with open(src) as f:
+        text = f.read()
+    for inc in _INC_RE.findall(text):
+        for d in (os.path.dirname(src), CSRC, INCLUDE):
+            cand = os.path.join(d, inc)
+            if os.path.exists(cand):
+                m = max(m, _deps_mtime(cand, seen))
+                break
     return m
 
 
@@ -67,14 +79,13 @@ def build(force=False, verbose=False, jobs=None):
     """Compile whatever is stale and link libgmcmc.so.  Returns the library path."""
     os.makedirs(BUILD, exist_ok=True)
     nvcc = _nvcc()
-    hdr = _headers_mtime()
     todo = []
     objs = []
     for src, obj, flags in _units():
         s = os.path.join(CSRC, src)
         o = os.path.join(BUILD, obj)
         objs.append(o)
-        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr):
+        if force or not os.path.exists(o) or os.path.getmtime(o) < _deps_mtime(s):
             todo.append([nvcc] + ARCH + COMMON + flags + ["-c", s, "-o", o])
 
     def run(cmd):

@@ -128,6 +128,12 @@ struct NutsLaunch {
   unsigned long long* inj_used;
   unsigned long long* queue;    // [1] device counter of the dynamic chain queue
   int epl, lpc;
+  // diagonal mass matrix (GenericNUTS::new_with_mass_matrix, generic_nuts.rs:379-398); null = identity
+  void* mass_inv; void* mass_sqrt;                       // [C, d] T: 1 / var, sqrt(var)
+  void* run_mean; void* run_m2;                          // RunningCov of the warm-up window, [C, d], [C, d]
+  uint32_t run_n_base;                                   // its sample count when the launch starts (same for every chain)
+  uint32_t collect_after, collect_before;                // positions are collected for collect_after < m < collect_before
+  int probe;              // with init_only: mass-matrix update probe (generic_nuts.rs:906-918) instead of init_chain_state
 };
 
 struct StatsLaunch {
@@ -151,7 +157,7 @@ struct StatsLaunch {
 };
 
 // custom-target plugins (gmcmc_custom_target.cuh): the launchers a plugin instantiates for its target
-constexpr int kCustomAbiVersion = 1;
+constexpr int kCustomAbiVersion = 2;
 constexpr int kTargetCustom = 7;      // TargetDesc.kind of a plugin target
 struct CustomTargetVTable {
   int abi_version;

@@ -320,6 +320,196 @@ __global__ void __launch_bounds__(kMhBlock, GM_MH_MINB) mh_run_kernel(const MhAr
   if (lane == 0 && n_accept) atomicAdd(a.accept_total, (unsigned long long)n_accept);
 }
 
+// ------------------------------------------------------------------------------------------------
+// K2 fast path: d == 2 (every 2-D target; BASELINE config 2), fast math mode, production (no injected
+// draws).  Same transition as mh_run_kernel; what differs is how the per-step cost is kept near the 16
+// bytes the step writes:
+//   * one Philox block per transition, computed one transition AHEAD (it does not depend on the chain
+//     state, so its 40 integer instructions fill the issue slots under the f64 dependency chain);
+//   * uniforms are built without int->float conversions: the top 23 bits of a word become the mantissa
+//     of a float in [1,2) (one LEA.HI), u = f - (1 - 2^-24) = (k + 1/2) 2^-23 in (0,1);
+//   * the accept test runs in the linear domain: e = ex2.approx(log_ratio * log2 e) against the 23-bit
+//     uniform, and only when |e - u| is inside the combined error bound (2^-24 truncation of u + MUFU /
+//     rounding error of e) is the full-width uniform built and `log_ratio > ln u` evaluated in T — the
+//     decision is always the full-precision one (metropolis_hastings.rs:313-316);
+//   * the f64 sample of a step is ONE 16-byte unit: it is staged with st.shared.v2 under an XOR swizzle
+//     (conflict-free for the per-chain writes and for the per-row reads) and flushed every GM_MH2_STEPS
+//     steps as LDS.128 + STG.128 pairs, 256 (16 steps) or 512 (32 steps) contiguous bytes per chain.
+// Measured on B200 (tools/mh_bench.cu, tools/microbench_write.cu): a write-only stream of 256-byte pieces
+// reaches 5.3 TB/s, of 512-byte pieces 6.6 TB/s, cudaMemset 7.4 TB/s; the kernel runs at 3.6 TB/s with either
+// staging depth, any occupancy from 12 to 32 warps per SM and any unroll factor: it is bound by instruction
+// dispatch (110 warp-instructions per step, 73 of them on half-rate pipes: Philox's 20 LOP3 + 20 IMAD.WIDE,
+// 13 FP64, selects), not by HBM — profiles/r1_mh_run2_kernel_full.txt.
+// ------------------------------------------------------------------------------------------------
+#ifndef GM_MH2_STEPS
+#define GM_MH2_STEPS 16
+#endif
+#ifndef GM_MH2_MINB
+#define GM_MH2_MINB 6
+#endif
+#ifndef GM_MH2_UNROLL
+#define GM_MH2_UNROLL 4
+#endif
+constexpr int kMh2Steps = GM_MH2_STEPS;   // steps staged per chain between flushes: 16 (256 B per chain) or 32 (512 B)
+constexpr int kMh2Unroll = GM_MH2_UNROLL;
+constexpr int kMh2Row = kMh2Steps * 16;   // bytes of one chain's stage row
+constexpr size_t kMh2Smem = (size_t)kMhBlock * kMh2Row;
+static_assert(kMh2Steps == 16 || kMh2Steps == 32, "the flush maps 32 lanes onto 16-byte units of one or two chains");
+
+__device__ __forceinline__ float mant_float(uint32_t w) { return __uint_as_float((w >> 9) + 0x3f800000u); }  // [1,2)
+
+template <class T, int KIND>
+__global__ void __launch_bounds__(kMhBlock, GM_MH2_MINB) mh_run2_kernel(const MhArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char stage[];   // kMhBlock rows of kMh2Row bytes
+
+  const size_t chain = (size_t)blockIdx.x * kMhBlock + threadIdx.x;
+  const bool active = chain < a.n_chains;
+  const unsigned long long gchain = a.chain_offset + chain;
+  const int lane = threadIdx.x & 31;
+  const int warp_row0 = threadIdx.x & ~31;
+  const size_t warp_first_chain = (size_t)blockIdx.x * kMhBlock + warp_row0;
+  const int warp_rows = a.n_chains > warp_first_chain
+                            ? (int)(a.n_chains - warp_first_chain < 32 ? a.n_chains - warp_first_chain : 32) : 0;
+  const PhiloxRoundKeys rk = philox_round_keys(a.key);
+
+  // shared-memory addresses (32-bit).  Unit (chain c, step t) of a warp lives at row c, 16-byte column t ^ (c & (S-1)):
+  // the 8 lanes of a quarter-warp then hit 8 different bank groups both when every chain writes its step-t unit and
+  // when a row is read back along t.
+  constexpr int kColMask = kMh2Steps - 1;
+  const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(stage) + (uint32_t)warp_row0 * kMh2Row;
+  uint32_t st_addr = stage_base + (uint32_t)lane * kMh2Row + ((uint32_t)(lane & kColMask) << 4);
+  asm volatile("mov.b32 %0, %0;" : "+r"(st_addr));   // opaque: keep it in a register instead of rematerialising it every step
+  // flush: one store instruction moves 512 contiguous bytes per chain (32 steps) or 2 x 256 (16 steps)
+  constexpr int kCpi = 32 / kMh2Steps;               // chains per flush instruction
+  const int f_sub = lane / kMh2Steps, f_t = lane & kColMask;
+
+  T x[2];
+  x[0] = active ? a.state[chain * 2 + 0] : T(0);
+  x[1] = active ? a.state[chain * 2 + 1] : T(0);
+  const MhInv<T> inv = mh_prepare<T, KIND>(a);
+  T lp_cur = mh_logp<T, 2, KIND, true>(a, inv, x);
+  unsigned int n_accept = 0;
+
+  // Software pipeline: the random inputs of transition s + 1 (Philox block -> Box-Muller pair, accept words) are
+  // produced while transition s runs its state-dependent f64 chain; they do not depend on the chain state.
+  float z0, z1; uint32_t wz, ww;
+  auto draw = [&](const uint32_t step) {
+    const uint4 r = philox4x32_10(philox_ctr(gchain, step, 0u, 0u), rk);
+    // proposal noise (distributions.rs:368-376): Box-Muller on words 0 and 1
+    const float u_rad = mant_float(r.x) - 0.99999994039535522461f;          // (k + 1/2) 2^-23
+    const float ang = fmaf(mant_float(r.y), 6.283185307179586f, -9.42477796076938f);   // [-pi, pi)
+    float rad, sn, cs;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(u_rad));
+    rad *= -1.3862943611198906f;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(rad));
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ang));
+    z0 = rad * cs; z1 = rad * sn; wz = r.z; ww = r.w;
+  };
+  draw(a.step_base);
+
+  auto transition = [&](const uint32_t s) {
+    const float c0 = z0, c1 = z1; const uint32_t cz = wz, cw = ww;
+    draw(a.step_base + s + 1u);
+    T xp[2];
+    xp[0] = x[0] + (T)c0 * a.prop_std;
+    xp[1] = x[1] + (T)c1 * a.prop_std;
+    // ---- log acceptance ratio (metropolis_hastings.rs:308-312); symmetric proposal: q_fwd == q_bwd bit-for-bit
+    const T lp_prop = mh_logp<T, 2, KIND, true>(a, inv, xp);
+    const T log_ratio = lp_prop - lp_cur;
+    // ---- accept iff log_ratio > ln u (strict; metropolis_hastings.rs:313-316), u from words 2 (and 3)
+    const float u_acc = mant_float(cz) - 0.99999994039535522461f;
+    const float lr32 = (float)log_ratio;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(lr32 * 1.4426950408889634f));
+    const float diff = e - u_acc;
+    const float tol = fmaf(e * (1.0f + fabsf(lr32)), 1e-6f, 5.9604644775390625e-08f);
+    bool accept;
+    if (fabsf(diff) > tol) {
+      accept = diff > 0.0f;
+    } else {
+      T u;
+      if constexpr (sizeof(T) == 8) u = u01d(cz, cw); else u = u01(cz);
+      accept = log_ratio > log(u);
+    }
+    x[0] = accept ? xp[0] : x[0];
+    x[1] = accept ? xp[1] : x[1];
+    lp_cur = accept ? lp_prop : lp_cur;
+    n_accept += accept ? 1u : 0u;
+  };
+
+  uint32_t s = 0;
+  const uint32_t n_skip = a.n_skip < a.n_steps ? a.n_skip : a.n_steps;
+  for (; s < n_skip; ++s) transition(s);                 // burn-in: nothing recorded
+  if (a.out) {
+    // this lane's flush destination: [chain = warp_first + f_sub (+kCpi per iteration), slot = out_t0 + f_t (+S per flush)]
+    double* out_lane = a.out + ((warp_first_chain + f_sub) * a.out_n + a.out_t0 + f_t) * 2;
+    const size_t pitch = a.out_n * 2 * kCpi;             // doubles between the chains of consecutive iterations
+    auto flush = [&](const int cnt) {
+      __syncwarp();
+      if (f_t < cnt) {
+        double* dst = out_lane;
+        if (warp_rows == 32) {
+#pragma unroll
+          for (int i = 0; i < 32 / kCpi; ++i) {
+            const int c = kCpi * i + f_sub;
+            const uint32_t addr = stage_base + (uint32_t)c * kMh2Row + ((uint32_t)(f_t ^ (c & kColMask)) << 4);
+            double v0, v1;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(addr));
+            __stcs(reinterpret_cast<double2*>(dst), make_double2(v0, v1));
+            dst += pitch;
+          }
+        } else {
+          for (int i = 0; i < 32 / kCpi; ++i) {
+            const int c = kCpi * i + f_sub;
+            if (c < warp_rows) {
+              const uint32_t addr = stage_base + (uint32_t)c * kMh2Row + ((uint32_t)(f_t ^ (c & kColMask)) << 4);
+              double v0, v1;
+              asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(addr));
+              __stcs(reinterpret_cast<double2*>(dst), make_double2(v0, v1));
+            }
+            dst += pitch;
+          }
+        }
+      }
+      __syncwarp();
+      out_lane += kMh2Steps * 2;
+    };
+    auto record = [&](const int t) {
+      asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(st_addr ^ ((uint32_t)t << 4)), "d"((double)x[0]), "d"((double)x[1]) : "memory");
+    };
+    while (a.n_steps - s >= (uint32_t)kMh2Steps) {
+#pragma unroll kMh2Unroll
+      for (int t = 0; t < kMh2Steps; ++t) { transition(s + t); record(t); }
+      s += kMh2Steps;
+      flush(kMh2Steps);
+    }
+    if (s < a.n_steps) {
+      int t = 0;
+      for (; s < a.n_steps; ++s, ++t) { transition(s); record(t); }
+      flush(t);
+    }
+  } else {
+    for (; s < a.n_steps; ++s) transition(s);
+  }
+
+  if (active) { a.state[chain * 2 + 0] = x[0]; a.state[chain * 2 + 1] = x[1]; }
+  if (!active) n_accept = 0;
+  for (int o = 16; o > 0; o >>= 1) n_accept += __shfl_xor_sync(0xffffffffu, n_accept, o);
+  if (lane == 0 && n_accept) atomicAdd(a.accept_total, (unsigned long long)n_accept);
+}
+
+template <class T, int KIND>
+inline cudaError_t mh_launch_run2(const MhArgs<T>& a, unsigned blocks, cudaStream_t st) {
+  auto kern = mh_run2_kernel<T, KIND>;
+  if (kMh2Smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMh2Smem);
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<blocks, kMhBlock, kMh2Smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 template <class T>
 inline MhArgs<T> make_mh_args(const MhLaunch& L) {
   MhArgs<T> a;
@@ -376,10 +566,12 @@ template <class T, int MAXD, int KIND, bool FULL>
 inline cudaError_t mh_launch_one(const MhLaunch& L, cudaStream_t st) {
   MhArgs<T> a = make_mh_args<T>(L);
   const unsigned blocks = (unsigned)((L.n_chains + kMhBlock - 1) / kMhBlock);
-  if (a.inj_normals || a.inj_lnu || a.diag_logratio)
+  if (a.inj_normals || a.inj_lnu || a.diag_logratio) {
     mh_run_kernel<T, MAXD, KIND, FULL, true><<<blocks, kMhBlock, 0, st>>>(a);
-  else
-    mh_run_kernel<T, MAXD, KIND, FULL, false><<<blocks, kMhBlock, 0, st>>>(a);
+  } else {
+    if constexpr (!kMhExact && MAXD == 2 && FULL) return mh_launch_run2<T, KIND>(a, blocks, st);
+    else mh_run_kernel<T, MAXD, KIND, FULL, false><<<blocks, kMhBlock, 0, st>>>(a);
+  }
   return cudaGetLastError();
 }
 

@@ -69,7 +69,8 @@ struct NutsArgs {
   // diagonal mass matrix (MassMatrix::Diagonal, generic_nuts.rs:177-304): inv = 1 / var, sqrt = sqrt(var); null = identity
   const T* mass_inv; const T* mass_sqrt;          // [C, d]
   // warm-up position statistics (RunningCov, generic_nuts.rs:81-132), updated for collect_after < m < collect_before
-  T* run_mean; T* run_m2; unsigned int* run_n;    // [C, d], [C, d], [C]
+  T* run_mean; T* run_m2;                         // [C, d], [C, d]
+  uint32_t run_n_base;                            // positions already in the statistics when this launch starts (same for every chain)
   uint32_t collect_after, collect_before;
 };
 
@@ -502,8 +503,9 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       }
       if (a.run_mean && m <= a.n_discard && m > a.collect_after && m < a.collect_before) {
         // RunningCov::update (generic_nuts.rs:105-114) on the position after this transition
-        const unsigned int n_new = a.run_n[chain] + 1u;
-        const T n_s = (T)n_new;
+        // every chain collects at the same transitions, so the count is a function of m alone (no device counter)
+        const uint32_t first_m = a.m_base > a.collect_after ? a.m_base : a.collect_after;
+        const T n_s = (T)(a.run_n_base + (m - first_m));
 #pragma unroll
         for (int j = 0; j < EPL; ++j) {
           if (j < ln.nvalid) {
@@ -517,8 +519,6 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
             a.run_m2[idx] = a.run_m2[idx] + delta * delta2;
           }
         }
-        __syncwarp();
-        if (ln.part == 0) a.run_n[chain] = n_new;
       }
       const long long slot = (long long)m - a.rec_off;
       if (a.out && slot >= 0 && slot < (long long)a.out_n) {
@@ -561,6 +561,13 @@ struct NutsInitArgs {
   T* eps; T* mu;
   const double* inj_normals; size_t n_norm;
   unsigned long long* inj_used;
+  // diagonal mass matrix: the momentum is z * sqrt(var) (sample_momentum, generic_nuts.rs:283-303); the step-size
+  // search itself runs with the identity mass, as the reference's find_reasonable_epsilon does (:1009-1023)
+  const T* mass_sqrt;
+  // probe = 1: the step-size reset after a mass-matrix update (generic_nuts.rs:906-918): always search, from a fresh
+  // momentum (Philox stream 3 of transition `step`), then mu = ln(10 eps), eps_bar = eps, h_bar = 0
+  int probe;
+  T* eps_bar; T* h_bar;
 };
 
 template <class T, int EPL, class TAG>
@@ -593,7 +600,7 @@ __global__ void __launch_bounds__(kHmcBlock, 2) nuts_init_kernel(const NutsInitA
     const int nblocks = (a.d + NPB - 1) / NPB;
     for (int b = ln.part; b < nblocks; b += a.lpc) {
       T z[NPB];
-      normals_from_block<kExact>(philox4x32_10(philox_ctr(gchain, a.step, 0u, (uint32_t)b), a.key), z);
+      normals_from_block<kExact>(philox4x32_10(philox_ctr(gchain, a.step, a.probe ? 3u : 0u, (uint32_t)b), a.key), z);
 #pragma unroll
       for (int k = 0; k < NPB; ++k)
         if (b * NPB + k < a.d_pad) row[b * NPB + k] = z[k];
@@ -603,8 +610,13 @@ __global__ void __launch_bounds__(kHmcBlock, 2) nuts_init_kernel(const NutsInitA
     for (int j = 0; j < EPL; ++j) mom[j] = (j < ln.nvalid) ? row[ln.lo + j] : T(0);
     __syncwarp();
   }
+  if (a.mass_sqrt) {
+#pragma unroll
+    for (int j = 0; j < EPL; ++j)
+      if (active && j < ln.nvalid) mom[j] = mom[j] * a.mass_sqrt[chain * d + ln.lo + j];
+  }
   T eps = active ? a.eps[chain] : T(1);
-  const bool need = active && (fabs(eps + T(1)) <= (sizeof(T) == 4 ? T(1.1920929e-07) : T(2.220446049250313e-16)));
+  const bool need = active && (a.probe || fabs(eps + T(1)) <= (sizeof(T) == 4 ? T(1.1920929e-07) : T(2.220446049250313e-16)));
 
   // find_reasonable_epsilon_with_mass, generic_nuts.rs:1025-1102 (identity mass).  stage 0: gradient at
   // the position; stage 1: halve until finite; stage 2: double / halve until the acceptance crosses 1/2.
@@ -662,6 +674,7 @@ __global__ void __launch_bounds__(kHmcBlock, 2) nuts_init_kernel(const NutsInitA
   if (active && ln.part == 0) {
     if (need) { eps = epsilon; a.eps[chain] = eps; }
     a.mu[chain] = log(T(10) * eps);
+    if (a.probe) { a.eps_bar[chain] = eps; a.h_bar[chain] = T(0); }
   }
 }
 
@@ -686,6 +699,9 @@ inline NutsArgs<T> make_nuts_args(const NutsLaunch& L) {
   a.inj_normals = L.inj_normals; a.n_norm = L.n_norm; a.inj_exp1 = L.inj_exp1; a.n_exp = L.n_exp;
   a.inj_unif = L.inj_unif; a.n_unif = L.n_unif; a.inj_used = L.inj_used;
   a.queue = L.queue;
+  a.mass_inv = (const T*)L.mass_inv; a.mass_sqrt = (const T*)L.mass_sqrt;
+  a.run_mean = (T*)L.run_mean; a.run_m2 = (T*)L.run_m2; a.run_n_base = L.run_n_base;
+  a.collect_after = L.collect_after; a.collect_before = L.collect_before;
   return a;
 }
 
@@ -703,6 +719,7 @@ inline cudaError_t nuts_launch_one(const NutsLaunch& L, cudaStream_t st) {
     a.d = L.tgt.dim; a.d_pad = d_pad; a.lpc = L.lpc;
     a.eps = (T*)L.eps; a.mu = (T*)L.mu;
     a.inj_normals = L.inj_normals; a.n_norm = L.n_norm; a.inj_used = L.inj_used;
+    a.mass_sqrt = (const T*)L.mass_sqrt; a.probe = L.probe; a.eps_bar = (T*)L.eps_bar; a.h_bar = (T*)L.h_bar;
     const size_t smem = (size_t)(kHmcBlock / L.lpc) * d_pad * sizeof(T);
     auto kern = nuts_init_kernel<T, EPL, TAG>;
     if (smem > 48 * 1024) {

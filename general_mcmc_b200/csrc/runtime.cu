@@ -170,6 +170,15 @@ struct gmcmc_sampler {
   size_t nuts_inj_n[3] = {0, 0, 0};
   unsigned long long* d_nuts_used = nullptr;                     // [C][3]
   uint32_t nuts_m = 0, nuts_n_discard = 0;
+  // NUTS diagonal mass-matrix adaptation (NUTSMassMatrixConfig / MassMatrixWarmup, generic_nuts.rs:40-175)
+  bool mass_adapt = false;
+  size_t mass_start_buffer = 75, mass_end_buffer = 50, mass_initial_window = 25;
+  double mass_regularize = 0.05, mass_jitter = 1e-6;
+  size_t mass_next_window_end = 0, mass_window_len = 0;   // window schedule: identical for every chain, kept on the host
+  size_t mass_run_n = 0;                                  // positions in the running covariance (same for every chain)
+  uint64_t mass_updates = 0;
+  void* d_mass_inv = nullptr; void* d_mass_sqrt = nullptr;          // [C, d] T
+  void* d_run_mean = nullptr; void* d_run_m2 = nullptr;
   // counters
   unsigned long long* d_counts = nullptr;  // [8]: accepts, divergences, grad_evals(NUTS), depth sum, NUTS chain queue, spare
   uint64_t transitions = 0;
@@ -399,11 +408,109 @@ gmcmc_status nuts_launch(gmcmc_sampler* s, NutsLaunch& L) {
   L.inj_used = s->d_nuts_used;
   L.queue = s->d_counts + 4;
   L.epl = s->epl; L.lpc = s->lpc;
+  if (s->mass_adapt) {
+    L.mass_inv = s->d_mass_inv; L.mass_sqrt = s->d_mass_sqrt;
+    L.run_mean = s->d_run_mean; L.run_m2 = s->d_run_m2;
+    L.collect_after = (uint32_t)s->mass_start_buffer;
+    L.collect_before = (uint32_t)(L.n_discard > s->mass_end_buffer ? L.n_discard - s->mass_end_buffer : 0);
+  }
   cudaError_t e = s->tgt->custom ? s->tgt->custom->launch_nuts(L, s->ctx->stream)
                   : (s->math == GMCMC_MATH_EXACT) ? launch_nuts_exact(L, s->ctx->stream) : launch_nuts_fast(L, s->ctx->stream);
   if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "NUTS kernel launch failed: %s", cudaGetErrorString(e));
   s->launches += 1;
   return GMCMC_OK;
+}
+
+// maybe_update_mass_matrix (generic_nuts.rs:948-969, Diagonal) + MassMatrix::diagonal_from_var (:196-206) for every
+// chain, then RunningCov::reset.  Explicit _rn intrinsics: no FMA contraction, so the result is bit-for-bit the
+// reference arithmetic  var = max((1 - reg) * (m2 / (n - 1)) + reg, jitter);  inv = 1 / var;  sqrt = sqrt(var).
+template <class T> __device__ __forceinline__ T mul_rn(T a, T b);
+template <> __device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
+template <> __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
+template <class T> __device__ __forceinline__ T add_rn(T a, T b);
+template <> __device__ __forceinline__ float add_rn<float>(float a, float b) { return __fadd_rn(a, b); }
+template <> __device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
+
+template <class T>
+__global__ void nuts_mass_update_kernel(size_t n_elems, unsigned int n, T* run_mean, T* run_m2, T* mass_inv, T* mass_sqrt,
+                                        T reg, T jitter) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_elems) return;
+  const T n_denom = (T)(n - 1u);
+  const T omr = T(1) - reg;
+  const T raw = run_m2[i] / n_denom;
+  T v = add_rn<T>(mul_rn<T>(omr, raw), reg);
+  v = v > jitter ? v : jitter;          // .max(jitter), twice in the reference (update + diagonal_from_var)
+  mass_inv[i] = T(1) / v;
+  mass_sqrt[i] = sqrt(v);
+  run_mean[i] = T(0);
+  run_m2[i] = T(0);
+}
+
+// MassMatrixWarmup::{should_collect, note_if_window_end} (generic_nuts.rs:152-173).  The schedule depends on m only,
+// so every chain reaches its window ends at the same transitions and the host keeps ONE copy of it.
+bool mass_should_collect(const gmcmc_sampler* s, size_t m, size_t n_warm) {
+  if (m == 0 || m > n_warm) return false;
+  if (m <= s->mass_start_buffer) return false;
+  return m < (n_warm > s->mass_end_buffer ? n_warm - s->mass_end_buffer : 0);
+}
+bool mass_note_if_window_end(gmcmc_sampler* s, size_t m, size_t n_warm) {
+  if (!mass_should_collect(s, m, n_warm)) return false;
+  const size_t lim = n_warm > s->mass_end_buffer ? n_warm - s->mass_end_buffer : 0;
+  if (m >= s->mass_next_window_end || m + 1 >= lim) {
+    s->mass_next_window_end += s->mass_window_len;
+    s->mass_window_len = std::min<size_t>(s->mass_window_len * 2, 400);
+    return true;
+  }
+  return false;
+}
+
+// Runs the transitions described by L (m = L.m_base + 1 .. L.m_base + L.n_steps).  Without mass-matrix adaptation
+// this is one launch.  With it, the launch is cut after every transition that ends an adaptation window
+// (generic_nuts.rs:897-921): the chains' running variances become the new diagonal mass matrix, a fresh momentum
+// probes a new step size and the dual-averaging state restarts, all on the device and in stream order.
+gmcmc_status nuts_advance(gmcmc_sampler* s, const NutsLaunch& L0) {
+  if (!s->mass_adapt) { NutsLaunch L = L0; return nuts_launch(s, L); }
+  const size_t n_warm = L0.n_discard;
+  uint32_t done = 0;
+  bool first = true;
+  size_t seg_n0 = s->mass_run_n;      // samples in the running covariance when the next segment starts
+  auto launch_segment = [&](uint32_t upto) -> gmcmc_status {   // transitions [done, upto) of L0
+    if (upto == done && !(first && L0.write_init)) return GMCMC_OK;
+    NutsLaunch L = L0;
+    L.step_base = L0.step_base + done; L.m_base = L0.m_base + done; L.n_steps = upto - done;
+    L.run_n_base = (uint32_t)seg_n0;
+    L.write_init = first ? L0.write_init : 0;
+    first = false;
+    done = upto;
+    return nuts_launch(s, L);
+  };
+  for (uint32_t k = 0; k < L0.n_steps; ++k) {
+    const size_t m = (size_t)L0.m_base + k + 1;
+    if (m > n_warm) break;
+    if (!mass_should_collect(s, m, n_warm)) continue;
+    s->mass_run_n += 1;
+    if (!mass_note_if_window_end(s, m, n_warm) || s->mass_run_n < 5) continue;
+    GM_TRY(launch_segment(k + 1));
+    const size_t nd = s->n_chains * (size_t)s->dim;
+    const unsigned blocks = (unsigned)((nd + 255) / 256);
+    const double jit = std::max(s->mass_jitter, 1e-10);
+    if (s->dtype == GMCMC_F32)
+      nuts_mass_update_kernel<float><<<blocks, 256, 0, s->ctx->stream>>>(nd, (unsigned int)s->mass_run_n, (float*)s->d_run_mean,
+          (float*)s->d_run_m2, (float*)s->d_mass_inv, (float*)s->d_mass_sqrt, (float)s->mass_regularize, (float)jit);
+    else
+      nuts_mass_update_kernel<double><<<blocks, 256, 0, s->ctx->stream>>>(nd, (unsigned int)s->mass_run_n, (double*)s->d_run_mean,
+          (double*)s->d_run_m2, (double*)s->d_mass_inv, (double*)s->d_mass_sqrt, s->mass_regularize, jit);
+    GM_CU(cudaGetLastError());
+    s->mass_run_n = 0;
+    seg_n0 = 0;
+    s->mass_updates += 1;
+    NutsLaunch P{};
+    P.init_only = 1; P.probe = 1;
+    P.step_base = L0.step_base + k;          // Philox stream 3 of the transition that ended the window
+    GM_TRY(nuts_launch(s, P));
+  }
+  return launch_segment(L0.n_steps);
 }
 
 // NUTS run: init_chain_state, then the transitions.  progress = false mirrors run() (generic_nuts.rs:667-682:
@@ -428,7 +535,14 @@ gmcmc_status nuts_run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard,
   L.rec_off = (long long)n_discard + (progress ? 1 : 0);
   L.write_init = (!progress && n_discard == 0 && n_collect > 0 && d_out) ? 1 : 0;
   L.out = d_out; L.out_n = n_collect;
-  if (n_steps > 0 || L.write_init) GM_TRY(nuts_launch(s, L));
+  if (s->mass_adapt) {
+    // init_chain_state resets the running covariance (generic_nuts.rs:741-743)
+    const size_t es = esize(s->dtype), nd = s->n_chains * (size_t)s->dim;
+    GM_CU(cudaMemsetAsync(s->d_run_mean, 0, nd * es, s->ctx->stream));
+    GM_CU(cudaMemsetAsync(s->d_run_m2, 0, nd * es, s->ctx->stream));
+    s->mass_run_n = 0;
+  }
+  if (n_steps > 0 || L.write_init) GM_TRY(nuts_advance(s, L));
   s->step_index += (uint32_t)n_steps;
   s->nuts_m = (uint32_t)n_steps;
   s->transitions += (uint64_t)n_steps * s->n_chains;
@@ -1027,6 +1141,7 @@ gmcmc_status gmcmc_sampler_destroy(gmcmc_sampler* s) {
   cudaFree(s->d_ws_edges); cudaFree(s->d_ws_first); cudaFree(s->d_ws_prime); cudaFree(s->d_chain_leapfrogs);
   for (double* p : s->d_nuts_inj) cudaFree(p);
   cudaFree(s->d_nuts_used);
+  cudaFree(s->d_mass_inv); cudaFree(s->d_mass_sqrt); cudaFree(s->d_run_mean); cudaFree(s->d_run_m2);
   cudaFree(s->d_inj_normals); cudaFree(s->d_inj_lnu);
   cudaFree(s->d_diag_logacc); cudaFree(s->d_diag_acc); cudaFree(s->d_diag_pq); cudaFree(s->d_diag_pp);
   if (s->ev0) cudaEventDestroy(s->ev0);
@@ -1139,6 +1254,55 @@ gmcmc_status gmcmc_nuts_inject(gmcmc_sampler* s, const double* normals, size_t n
   return GMCMC_OK;
 }
 
+gmcmc_status gmcmc_nuts_set_mass_adaptation(gmcmc_sampler* s, gmcmc_mass_adaptation kind, size_t start_buffer,
+                                            size_t end_buffer, size_t initial_window, double regularize, double jitter) {
+  GM_REQUIRE(s && s->type == S_NUTS, "gmcmc_nuts_set_mass_adaptation applies to NUTS samplers");
+  if (kind == GMCMC_MASS_DENSE)
+    return fail(GMCMC_ERR_UNSUPPORTED, "dense mass-matrix adaptation is not implemented (diagonal and none are)");
+  GM_REQUIRE(kind == GMCMC_MASS_NONE || kind == GMCMC_MASS_DIAGONAL, "unknown mass-matrix adaptation kind");
+  GM_REQUIRE(!s->tgt->custom, "mass-matrix adaptation is not available for plugin targets");
+  GM_CU(cudaSetDevice(s->ctx->device));
+  const size_t es = esize(s->dtype), C = s->n_chains, nd = C * (size_t)s->dim;
+  if (kind == GMCMC_MASS_NONE) {      // NUTSMassMatrixConfig::disabled(): identity mass, no warm-up statistics
+    s->mass_adapt = false;
+    return GMCMC_OK;
+  }
+  if (!s->d_mass_inv) {
+    bool ok = cudaMalloc(&s->d_mass_inv, nd * es) == cudaSuccess && cudaMalloc(&s->d_mass_sqrt, nd * es) == cudaSuccess &&
+              cudaMalloc(&s->d_run_mean, nd * es) == cudaSuccess && cudaMalloc(&s->d_run_m2, nd * es) == cudaSuccess;
+    if (!ok) return fail(GMCMC_ERR_CUDA, "out of device memory for the mass-matrix state");
+  }
+  const unsigned blocks = (unsigned)((nd + 255) / 256);
+  if (s->dtype == GMCMC_F32) {        // MassMatrix::identity
+    fill_kernel<float><<<blocks, 256, 0, s->ctx->stream>>>((float*)s->d_mass_inv, nd, 1.0f);
+    fill_kernel<float><<<blocks, 256, 0, s->ctx->stream>>>((float*)s->d_mass_sqrt, nd, 1.0f);
+  } else {
+    fill_kernel<double><<<blocks, 256, 0, s->ctx->stream>>>((double*)s->d_mass_inv, nd, 1.0);
+    fill_kernel<double><<<blocks, 256, 0, s->ctx->stream>>>((double*)s->d_mass_sqrt, nd, 1.0);
+  }
+  GM_CU(cudaGetLastError());
+  GM_CU(cudaMemsetAsync(s->d_run_mean, 0, nd * es, s->ctx->stream));
+  GM_CU(cudaMemsetAsync(s->d_run_m2, 0, nd * es, s->ctx->stream));
+  s->mass_adapt = true;
+  s->mass_start_buffer = start_buffer; s->mass_end_buffer = end_buffer; s->mass_initial_window = initial_window;
+  s->mass_regularize = regularize; s->mass_jitter = jitter;
+  s->mass_window_len = std::max<size_t>(initial_window, 10);                         // MassMatrixWarmup::new, :141-150
+  s->mass_next_window_end = std::max<size_t>(start_buffer, 1) + s->mass_window_len;
+  s->mass_run_n = 0; s->mass_updates = 0;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_nuts_mass_matrix(gmcmc_sampler* s, void* inv_mass_out, uint64_t* n_updates_out) {
+  GM_REQUIRE(s && s->type == S_NUTS, "gmcmc_nuts_mass_matrix applies to NUTS samplers");
+  GM_REQUIRE(s->mass_adapt, "mass-matrix adaptation is not enabled on this sampler");
+  GM_CU(cudaSetDevice(s->ctx->device));
+  GM_CU(cudaStreamSynchronize(s->ctx->stream));
+  if (inv_mass_out)
+    GM_CU(cudaMemcpy(inv_mass_out, s->d_mass_inv, s->n_chains * (size_t)s->dim * esize(s->dtype), cudaMemcpyDeviceToHost));
+  if (n_updates_out) *n_updates_out = s->mass_updates;
+  return GMCMC_OK;
+}
+
 gmcmc_status gmcmc_nuts_state(gmcmc_sampler* s, void* eps_out, long long* leapfrogs_out, unsigned long long* used_out) {
   GM_REQUIRE(s && s->type == S_NUTS, "gmcmc_nuts_state applies to NUTS samplers");
   GM_CU(cudaSetDevice(s->ctx->device));
@@ -1180,7 +1344,7 @@ gmcmc_status gmcmc_step(gmcmc_sampler* s) {
     NutsLaunch L{};
     L.step_base = s->step_index; L.n_steps = 1; L.m_base = s->nuts_m; L.n_discard = s->nuts_n_discard;
     L.rec_off = 0; L.out = nullptr; L.out_n = 0;
-    GM_TRY(nuts_launch(s, L));
+    GM_TRY(nuts_advance(s, L));
     s->step_index += 1; s->nuts_m += 1; s->transitions += s->n_chains;
     return GMCMC_OK;
   }

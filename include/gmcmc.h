@@ -29,6 +29,7 @@
  *             f64: block b -> elements 2b, 2b+1 (53-bit uniforms from (r0,r1) and (r2,r3));
  *   stream 1: block 0 -> accept uniform (r0 [f32] or (r0,r1) [f64]); NUTS: r2/r3 -> Exp(1) draw;
  *   stream 2: NUTS tree uniforms, block = draw index / 4 (see gmcmc_nuts_create).
+ *   stream 3: NUTS momentum probe after a mass-matrix update (see gmcmc_nuts_set_mass_adaptation).
  * Uniforms are in (0,1]:  f32 ((r>>8)+1)*2^-24,  f64 ((r64>>11)+1)*2^-53.
  */
 #ifndef GMCMC_H
@@ -173,6 +174,19 @@ gmcmc_status gmcmc_inject(gmcmc_sampler*, const void* normals, const void* ln_u,
  * exp1 [C, n_exp], unif [C, n_unif], all f64. */
 gmcmc_status gmcmc_nuts_inject(gmcmc_sampler*, const double* normals, size_t n_norm, const double* exp1,
                                size_t n_exp, const double* unif, size_t n_unif);
+/* Warm-up mass-matrix adaptation of NUTS.  ≙ GenericNUTS::new_with_mass_matrix(.., NUTSMassMatrixConfig)
+ * (generic_nuts.rs:40-78, 379-398); the defaults of NUTSMassMatrixConfig are start_buffer 75, end_buffer 50,
+ * initial_window 25, regularize 0.05, jitter 1e-6.  Call before the first run.  Each chain adapts its own
+ * diagonal inverse mass from the running variance of its warm-up positions over doubling windows
+ * (MassMatrixWarmup :134-175, RunningCov :81-132, maybe_update_mass_matrix :948-969); after every update a
+ * fresh momentum (Philox stream 3 of the transition that ended the window) probes a new step size and dual
+ * averaging restarts (:906-918).  GMCMC_MASS_DENSE returns GMCMC_ERR_UNSUPPORTED. */
+typedef enum { GMCMC_MASS_NONE = 0, GMCMC_MASS_DIAGONAL = 1, GMCMC_MASS_DENSE = 2 } gmcmc_mass_adaptation;
+gmcmc_status gmcmc_nuts_set_mass_adaptation(gmcmc_sampler*, gmcmc_mass_adaptation kind, size_t start_buffer,
+                                            size_t end_buffer, size_t initial_window, double regularize,
+                                            double jitter);
+/* Current diagonal inverse mass [C, dim] (sampler dtype; 1 = identity) and the number of updates so far. */
+gmcmc_status gmcmc_nuts_mass_matrix(gmcmc_sampler*, void* inv_mass_out, uint64_t* n_updates_out);
 /* NUTS per-chain state (tests / diagnostics): current step sizes [C] (sampler dtype), accumulated
  * leapfrogs [C], consumed injected draws [C][3] (normals, exp1, unif).  Any pointer may be NULL. */
 gmcmc_status gmcmc_nuts_state(gmcmc_sampler*, void* eps_out, long long* leapfrogs_out,

@@ -458,7 +458,8 @@ inline bool all_finite(const T* v, int d) {
   return true;
 }
 
-// find_reasonable_epsilon_with_mass, generic_nuts.rs:1025-1102 (identity mass)
+// find_reasonable_epsilon_with_mass, generic_nuts.rs:1025-1102.  Both reference call sites (:745, :911) go through
+// find_reasonable_epsilon (:1009-1023), which passes the IDENTITY mass even when the chain carries an adapted one.
 template <class T>
 T nuts_find_reasonable_epsilon(const Target<T>& tgt, const T* position, const T* mom, const DiagMass<T>* mass = nullptr) {
   const int d = tgt.dim;
@@ -545,7 +546,7 @@ struct NutsChain {
     if (!mass.identity()) for (int i = 0; i < d; ++i) mom0[i] = mom0[i] * mass.sqrt_[i];   // sample_momentum :283-303
     if (mass_adapt) { run_n = 0; std::fill(run_mean.begin(), run_mean.end(), T(0)); std::fill(run_m2.begin(), run_m2.end(), T(0)); }
     if (std::abs(epsilon + T(1)) <= std::numeric_limits<T>::epsilon())
-      epsilon = nuts_find_reasonable_epsilon(tgt, position.data(), mom0.data(), &mass);
+      epsilon = nuts_find_reasonable_epsilon(tgt, position.data(), mom0.data());   // :745 — identity mass (find_reasonable_epsilon :1009-1023)
     mu = std::log(T(10) * epsilon);
   }
 
@@ -614,7 +615,7 @@ struct NutsChain {
           mass_updates += 1;
           std::vector<T> probe(d);
           for (int i = 0; i < d; ++i) probe[i] = (T)rng.next_normal() * mass.sqrt_[i];
-          epsilon = nuts_find_reasonable_epsilon(tgt, position.data(), probe.data(), &mass);
+          epsilon = nuts_find_reasonable_epsilon(tgt, position.data(), probe.data());   // :911 — identity mass, as the reference
           mu = std::log(T(10) * epsilon);
           epsilon_bar = epsilon;
           h_bar = T(0);

@@ -165,8 +165,10 @@ def nuts_find_reasonable_epsilon(kind, params, q, p):
     return f(C.c_int(kind), C.c_int(q.size), ppar, np_, _p(q), _p(p))
 
 
-def nuts_run(kind, params, q0, target_accept, max_depth, eps_init, n_collect, n_discard, normals, exp1, unif):
-    """normals [C,nn], exp1 [C,ne], unif [C,nu] float64 streams (consumed in reference order)."""
+def nuts_run(kind, params, q0, target_accept, max_depth, eps_init, n_collect, n_discard, normals, exp1, unif,
+             mass_cfg=None):
+    """normals [C,nn], exp1 [C,ne], unif [C,nu] float64 streams (consumed in reference order).  mass_cfg =
+    (start_buffer, end_buffer, initial_window, regularize, jitter) enables diagonal mass-matrix adaptation."""
     q = np.array(q0, copy=True, order="C")
     dt = q.dtype
     Cn, d = q.shape
@@ -179,13 +181,19 @@ def nuts_run(kind, params, q0, target_accept, max_depth, eps_init, n_collect, n_
     used = np.zeros((Cn, 3), np.int64)
     exh = np.zeros(Cn, np.int32)
     par, ppar, np_ = _params(params)
-    f = getattr(lib(), "orc_nuts_run_" + _sfx(dt))
     ct = _ct(dt)
-    f(C.c_int(kind), C.c_int(d), ppar, np_, C.c_size_t(Cn), _p(q), ct(target_accept), C.c_int(max_depth),
-      ct(eps_init), C.c_size_t(n_collect), C.c_size_t(n_discard), _p(normals), C.c_size_t(normals.shape[1]),
-      _p(exp1), C.c_size_t(exp1.shape[1]), _p(unif), C.c_size_t(unif.shape[1]), _p(samples), _p(eps_f),
-      _p(leap), _p(used), _p(exh))
-    return dict(q=q, samples=samples, eps=eps_f, leapfrogs=leap, used=used, exhausted=exh)
+    args = [C.c_int(kind), C.c_int(d), ppar, np_, C.c_size_t(Cn), _p(q), ct(target_accept), C.c_int(max_depth),
+            ct(eps_init), C.c_size_t(n_collect), C.c_size_t(n_discard), _p(normals), C.c_size_t(normals.shape[1]),
+            _p(exp1), C.c_size_t(exp1.shape[1]), _p(unif), C.c_size_t(unif.shape[1]), _p(samples), _p(eps_f),
+            _p(leap), _p(used), _p(exh)]
+    mass_inv = None
+    if mass_cfg is None:
+        getattr(lib(), "orc_nuts_run_" + _sfx(dt))(*args)
+    else:
+        cfg = np.ascontiguousarray(mass_cfg, np.float64)
+        mass_inv = np.ones((Cn, d), dt)
+        getattr(lib(), "orc_nuts_run_mass_" + _sfx(dt))(*args, _p(cfg), _p(mass_inv))
+    return dict(q=q, samples=samples, eps=eps_f, leapfrogs=leap, used=used, exhausted=exh, mass_inv=mass_inv)
 
 
 def split_rhat_mean_ess(sample):

@@ -17,8 +17,10 @@ SO = os.path.join(HERE, "plugins", "banana.so")
 
 @pytest.fixture(scope="module")
 def banana():
-    hdr = os.path.join(os.path.dirname(HERE), "general_mcmc_b200", "csrc", "gmcmc_custom_target.cuh")
-    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
+    csrc = os.path.join(os.path.dirname(HERE), "general_mcmc_b200", "csrc")
+    newest = max([os.path.getmtime(SRC)] + [os.path.getmtime(os.path.join(csrc, f)) for f in os.listdir(csrc)
+                                            if f.endswith((".h", ".cuh", ".inc"))])
+    if not os.path.exists(SO) or os.path.getmtime(SO) < newest:   # the plugin embeds the kernels: any header change rebuilds it
         gm.build_custom_target(SRC, SO)
     return gm.CustomTarget(SO, 3, [1.5, 0.3])
 

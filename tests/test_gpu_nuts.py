@@ -140,3 +140,93 @@ def test_nuts_sharding_invariance(ctx):
     lo = gm.NUTS(tgt, q0[:72], 0.8, seed=42, ctx=ctx, max_depth=6, chain_offset=0).run(6, 4)
     hi = gm.NUTS(tgt, q0[72:], 0.8, seed=42, ctx=ctx, max_depth=6, chain_offset=72).run(6, 4)
     assert np.array_equal(full, np.concatenate([lo, hi]))
+
+
+@pytest.mark.parametrize("dtype,exact,n_discard,cfg,n_upd", [
+    (np.float64, True, 20, (1, 1, 10, 0.05, 1e-6), 2),
+    (np.float64, True, 40, (3, 2, 10, 0.05, 1e-6), 3),
+    (np.float32, True, 20, (1, 1, 10, 0.05, 1e-6), 2),
+    (np.float32, False, 20, (1, 1, 10, 0.05, 1e-6), 2),
+])
+def test_nuts_diagonal_mass_adaptation_matches_oracle(ctx, oracle, dtype, exact, n_discard, cfg, n_upd):
+    """GenericNUTS::new_with_mass_matrix (generic_nuts.rs:379-398), diagonal adaptation.  Window ends inside the
+    warm-up (m = 11, 18 for start_buffer 1 / end_buffer 1 / window 10 / 20 warm-up transitions; m = 13, 23, 37 for
+    3 / 2 / 10 / 40) each replace the mass matrix by the regularised running variance, probe a new step size from a
+    fresh momentum and restart dual averaging.  Same injected streams on both sides.  The step size goes through
+    exp / log / pow (device libm vs glibc, 1 ulp), and dual averaging feeds every rounding difference back into the
+    next trajectory: measured deviations grow about tenfold every few transitions with or without the mass matrix
+    (tools/diag_mass.py), so the bounds are on the per-chain MEDIAN error, with a loose cap on the worst chain."""
+    Cn, d, n_collect = 96, 5, 6
+    scales = np.array([0.3, 1.0, 3.0, 0.7, 2.0])
+    tgt = gm.DenseGaussian(np.zeros(d), cov=np.diag(scales ** 2))
+    rng = np.random.default_rng(21)
+    q0 = (rng.standard_normal((Cn, d)) * scales).astype(dtype)
+    normals, exp1, unif = _streams(Cn, d, n_collect + n_discard + 4, seed=23, n_unif=20000)
+    ref = oracle.nuts_run(tgt.kind, tgt.params(), q0, 0.8, 8, -1.0, n_collect, n_discard, normals, exp1, unif, mass_cfg=cfg)
+    assert not ref["exhausted"].any()
+    s = gm.NUTS(tgt, q0, 0.8, seed=1, ctx=ctx, max_depth=8,
+                mass_matrix=gm.NUTSMassMatrixConfig("diagonal", *cfg)).set_math_mode(exact)
+    s.inject_streams(normals, exp1, unif)
+    out = s.run(n_collect, n_discard)
+    st = s.state()
+    inv, n_updates = s.mass_matrix()
+    assert n_updates == n_upd
+    # normals consumed: d at init, d per transition, d per mass-matrix probe — on every chain, whatever its trees did
+    assert np.array_equal(st["used"][:, 0].astype(np.int64), ref["used"][:, 0])
+    assert (ref["used"][:, 0] == d * (1 + n_collect + n_discard - 1 + n_upd)).all()
+    same = (st["leapfrogs"] == ref["leapfrogs"])
+    assert same.mean() > (0.9 if dtype == np.float64 else 0.6)
+    err = (np.abs(inv[same] - ref["mass_inv"][same]) / ref["mass_inv"][same]).max(1)
+    med_tol, max_tol = (1e-8, 1e-3) if dtype == np.float64 else (2e-3, 0.5)
+    assert np.median(err) < med_tol and err.max() < max_tol
+    eps_err = np.abs(st["eps"][same] - ref["eps"][same]) / ref["eps"][same]
+    assert np.median(eps_err) < med_tol and eps_err.max() < max_tol
+    samp_err = np.abs(out[same] - ref["samples"][same]).reshape(same.sum(), -1).max(1)
+    assert np.median(samp_err) < 100 * med_tol
+    assert (inv > 0).all() and not np.allclose(inv, 1.0)       # the mass matrix did move away from the identity
+
+
+def test_nuts_mass_adaptation_philox_matches_oracle_distribution(ctx, oracle):
+    """Philox path with the reference's default windows (start 75 / end 50 / window 25), 300 warm-up transitions,
+    chains started in stationarity on an ill-conditioned diagonal Gaussian.  The identity-mass sampler keeps the
+    target variances.  The adapting sampler reproduces what the REFERENCE algorithm does, which is not what one would
+    hope for: the reference sets the mass to the variance (generic_nuts.rs:196-206: inv = 1 / var, p = z sqrt(var)),
+    searches the step size and tests sub-tree U-turns with the identity mass (:1009-1023, :1316) and the whole-tree
+    U-turn with the adapted one (:872), so its transition is no longer reversible and the large-scale coordinates
+    come out over-dispersed (CPU oracle: variance ratio ~1.9 on the widest coordinate).  Parity is the bar: the
+    GPU must show the oracle's distribution, bias included."""
+    Cn, d = 1024, 8
+    scales = np.logspace(-1, 1, d)
+    tgt = gm.DenseGaussian(np.zeros(d), cov=np.diag(scales ** 2))
+    q0 = (np.random.default_rng(5).standard_normal((Cn, d)) * scales).astype(np.float32)
+    r2 = np.random.default_rng(1)
+    Co = 512
+    streams = (r2.standard_normal((Co, d * 412)), r2.exponential(size=(Co, 402)), r2.random((Co, 400000)))
+    for name, cfg in [("identity", None), ("diagonal", (75, 50, 25, 0.05, 1e-6))]:
+        ref = oracle.nuts_run(tgt.kind, tgt.params(), q0[:Co], 0.8, 10, -1.0, 100, 300, *streams, mass_cfg=cfg)
+        assert not ref["exhausted"].any()
+        ratio_ref = ref["samples"].reshape(-1, d).astype(np.float64).var(0) / scales ** 2
+        mm = gm.NUTSMassMatrixConfig("diagonal", *cfg) if cfg else None
+        s = gm.NUTS(tgt, q0, 0.8, seed=11, ctx=ctx, max_depth=10, mass_matrix=mm)
+        out = s.run(100, 300)
+        ratio = out.reshape(-1, d).astype(np.float64).var(0) / scales ** 2
+        leap_gpu = s.counters().grad_evals / (Cn * 399.0)
+        leap_ref = ref["leapfrogs"].mean() / 399.0
+        assert np.allclose(ratio, ratio_ref, rtol=0.15), (name, ratio, ratio_ref)
+        assert abs(leap_gpu / leap_ref - 1.0) < 0.15, (name, leap_gpu, leap_ref)
+        if cfg is None:
+            assert np.allclose(ratio, 1.0, atol=0.06)
+        else:
+            assert ratio[-1] > 1.4 and ratio_ref[-1] > 1.4          # the reference's over-dispersion, reproduced
+            inv, n = s.mass_matrix()
+            assert n == 4 and np.all(np.isfinite(inv))
+            # mass = regularised within-window variance: same per-coordinate medians over chains as the oracle's
+            got = np.median(1.0 / inv.astype(np.float64), axis=0)
+            want = np.median(1.0 / ref["mass_inv"].astype(np.float64), axis=0)
+            assert np.allclose(got, want, rtol=0.25), (got, want)
+
+
+def test_nuts_dense_mass_adaptation_is_unsupported(ctx):
+    with pytest.raises(Exception):
+        gm.NUTS(gm.IsotropicGaussian(1.0, 3), np.zeros((4, 3), np.float32), 0.8, seed=1, ctx=ctx,
+                mass_matrix=gm.NUTSMassMatrixConfig("dense"))
