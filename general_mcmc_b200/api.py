@@ -310,6 +310,22 @@ def split_rhat_mean_ess(sample, ctx=None):
     return rhat, ess
 
 
+def tracker_stats(sample, ctx=None):
+    """≙ MultiChainTracker (stats.rs:199-339) stepped once per draw of `sample` [chains, draws, params]: returns
+    {"rhat": float32[p], "max_rhat": float, "p_accept": float} — the figures run_progress displays."""
+    ctx = ctx or default_context()
+    s = np.ascontiguousarray(sample)
+    if s.dtype not in (np.float32, np.float64):
+        s = s.astype(np.float64)
+    c, n, p = s.shape
+    rhat = np.empty(p, np.float32)
+    mx = C.c_float(0)
+    pa = C.c_float(0)
+    L.check(L.lib().gmcmc_tracker_stats(ctx._h, L.ptr(s), C.c_size_t(c), C.c_size_t(n), C.c_size_t(p),
+                                        L.dtype_code(s.dtype), 0, L.ptr(rhat), C.byref(mx), C.byref(pa)))
+    return {"rhat": rhat, "max_rhat": float(mx.value), "p_accept": float(pa.value)}
+
+
 @dataclass
 class Counters:
     transitions: int

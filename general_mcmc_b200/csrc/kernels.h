@@ -169,6 +169,8 @@ struct CustomTargetVTable {
 
 size_t stats_npad(size_t n);
 int stats_ppb(size_t N);
+cudaError_t launch_tracker(const void* samples, int dtype, size_t C, size_t n, int p, float* mean /*[C,p]*/, float* mean_sq /*[C,p]*/,
+                           float* rhat /*[p]*/, float* p_accept /*[1]*/, cudaStream_t st);   // K6, stats.cu
 int stats_groups(size_t N, size_t p, size_t C, int sm_count);   // chain groups of the accumulate kernel
 void stats_fill_twiddles(size_t N, float* host_tw);
 cudaError_t launch_stats_accumulate(const StatsLaunch&, cudaStream_t);

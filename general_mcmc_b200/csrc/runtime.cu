@@ -1559,6 +1559,32 @@ gmcmc_status gmcmc_split_rhat_ess(gmcmc_ctx* ctx, const void* samples, size_t C,
   return device_split_rhat_ess(ctx, d, C, n, p, dtype, rhat, nullptr, ess);
 }
 
+gmcmc_status gmcmc_tracker_stats(gmcmc_ctx* ctx, const void* samples, size_t C, size_t n, size_t p, gmcmc_dtype dtype,
+                                 int on_device, float* rhat, float* max_rhat, float* p_accept) {
+  GM_REQUIRE(ctx && samples, "null argument");
+  GM_REQUIRE(C >= 2 && n >= 2 && p >= 1, "the tracker R-hat needs C >= 2 chains and n >= 2 draws (got %zu, %zu)", C, n);
+  TempDevice tmp, mean, mean_sq, out;
+  const void* d = nullptr;
+  GM_TRY(stage_samples(ctx, samples, C * n * p * esize(dtype), on_device, &tmp, &d));
+  GM_CU(cudaMalloc(&mean.p, C * p * sizeof(float)));
+  GM_CU(cudaMalloc(&mean_sq.p, C * p * sizeof(float)));
+  GM_CU(cudaMalloc(&out.p, (p + 1) * sizeof(float)));
+  cudaError_t e = launch_tracker(d, dtype, C, n, (int)p, (float*)mean.p, (float*)mean_sq.p, (float*)out.p, (float*)out.p + p,
+                                 ctx->stream);
+  if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "tracker launch failed: %s", cudaGetErrorString(e));
+  std::vector<float> host(p + 1);
+  GM_CU(cudaMemcpyAsync(host.data(), out.p, (p + 1) * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CU(cudaStreamSynchronize(ctx->stream));
+  if (rhat) std::memcpy(rhat, host.data(), p * sizeof(float));
+  if (max_rhat) {   // MultiChainTracker::max_rhat: reduce(f32::max), which skips NaN operands
+    float mx = host[0];
+    for (size_t k = 1; k < p; ++k) mx = std::fmax(mx, host[k]);
+    *max_rhat = mx;
+  }
+  if (p_accept) *p_accept = host[p];
+  return GMCMC_OK;
+}
+
 gmcmc_status gmcmc_run_stats_from(gmcmc_ctx* ctx, const void* samples, size_t C, size_t n, size_t p, gmcmc_dtype dtype,
                                   int on_device, gmcmc_run_stats_t* out) {
   GM_REQUIRE(ctx && samples && out, "null argument");

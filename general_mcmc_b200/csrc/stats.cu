@@ -552,6 +552,112 @@ stats_finalize(const float* __restrict__ spec, const double* __restrict__ mom, d
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// K6 — progress tracker (MultiChainTracker, stats.rs:199-339) evaluated on the device from a [C, n, p] tensor of
+// draws: what the reference accumulates on the host after every step of run_progress (running mean / mean of
+// squares per chain and parameter, EMA acceptance rate, tracker R-hat) computed in one pass over the tensor.
+// ------------------------------------------------------------------------------------------------
+// One thread per (chain, parameter): the reference's f32 recurrences in the reference's order, no contraction
+// (stats.rs:249-255):  mean = (mean (n-1) + x) / n,  mean_sq = x^2 for n = 1, else (mean_sq (n-1) + x^2) / n.
+template <class TIN>
+__global__ void __launch_bounds__(256) tracker_moments_kernel(const TIN* __restrict__ x, size_t C, size_t n, int p,
+                                                              float* __restrict__ mean, float* __restrict__ mean_sq) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * (size_t)p) return;
+  const size_t c = i / (size_t)p;
+  const TIN* src = x + c * n * (size_t)p + (i - c * (size_t)p);
+  float m = 0.f, q = 0.f;
+#pragma unroll 8
+  for (size_t t = 0; t < n; ++t) {
+    const float v = (float)src[t * (size_t)p];
+    const float nf = (float)(t + 1), nm1 = __fadd_rn(nf, -1.0f);
+    const float vv = __fmul_rn(v, v);
+    m = __fdiv_rn(__fadd_rn(__fmul_rn(m, nm1), v), nf);
+    q = (t == 0) ? vv : __fdiv_rn(__fadd_rn(__fmul_rn(q, nm1), vv), nf);
+  }
+  mean[i] = m; mean_sq[i] = q;
+}
+
+// One CTA per parameter: within / between / var-hat / R-hat of MultiChainTracker::within_and_var (stats.rs:314-339);
+// the sums over chains are carried in f64 in a fixed order.
+__global__ void __launch_bounds__(256) tracker_rhat_kernel(const float* __restrict__ mean, const float* __restrict__ mean_sq,
+                                                           size_t C, size_t n, int p, float* __restrict__ rhat) {
+  __shared__ double red[256];
+  const int k = blockIdx.x;
+  auto block_sum = [&](double v) {
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+    const double r = red[0];
+    __syncthreads();
+    return r;
+  };
+  double s = 0.0;
+  for (size_t c = threadIdx.x; c < C; c += 256) s += (double)mean[c * p + k];
+  const float nc = (float)C, nf = (float)n;
+  const float mc = (float)(block_sum(s) / (double)C);
+  double b = 0.0, w = 0.0;
+  for (size_t c = threadIdx.x; c < C; c += 256) {
+    const float m1 = mean[c * p + k];
+    const float df = m1 - mc;
+    b += (double)(df * df);
+    w += (double)((mean_sq[c * p + k] - m1 * m1) * nf / (nf - 1.0f));
+  }
+  const double bs = block_sum(b), ws = block_sum(w);
+  if (threadIdx.x == 0) {
+    const float between = (float)bs * (nf / (nc - 1.0f));
+    const float within = (float)(ws / (double)C);
+    const float var = within * ((nf - 1.0f) / nf) + between * (1.0f / nf);
+    rhat[k] = sqrtf(var / within);
+  }
+}
+
+// EMA acceptance rate (stats.rs:257-265): p <- 0.99 p + 0.01 [row changed], folded over the chains of a step, step
+// after step, from p = 0 and last_state = 0.  Terms older than 4096 folds carry a weight below 0.99^4096 = 1e-18, so
+// folding the LAST 4096 (step, chain) pairs sequentially in f32 reproduces the full fold to the last bit.
+template <class TIN>
+__global__ void __launch_bounds__(1024) tracker_accept_kernel(const TIN* __restrict__ x, size_t C, size_t n, int p,
+                                                              float* __restrict__ p_accept) {
+  constexpr int W = 4096;
+  __shared__ unsigned char flag[W];
+  const size_t total = C * n;
+  const size_t first = total > (size_t)W ? total - W : 0;
+  const int cnt = (int)(total - first);
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const size_t kk = first + i;                 // fold index = t * C + c
+    const size_t t = kk / C, c = kk - t * C;
+    const TIN* cur = x + (c * n + t) * (size_t)p;
+    bool ne = false;
+    for (int j = 0; j < p; ++j) {
+      const float a = (float)cur[j];
+      const float b = t > 0 ? (float)cur[j - p] : 0.f;
+      ne = ne || (a != b);
+    }
+    flag[i] = ne ? 1 : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float pa = 0.f;
+    for (int i = 0; i < cnt; ++i) pa = __fadd_rn(__fmul_rn(1.0f - 0.01f, pa), __fmul_rn(0.01f, flag[i] ? 1.0f : 0.0f));
+    *p_accept = pa;
+  }
+}
+
+cudaError_t launch_tracker(const void* samples, int dtype, size_t C, size_t n, int p, float* mean, float* mean_sq,
+                           float* rhat, float* p_accept, cudaStream_t st) {
+  const size_t total = C * (size_t)p;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (dtype == 0) {
+    tracker_moments_kernel<float><<<blocks, 256, 0, st>>>((const float*)samples, C, n, p, mean, mean_sq);
+    tracker_accept_kernel<float><<<1, 1024, 0, st>>>((const float*)samples, C, n, p, p_accept);
+  } else {
+    tracker_moments_kernel<double><<<blocks, 256, 0, st>>>((const double*)samples, C, n, p, mean, mean_sq);
+    tracker_accept_kernel<double><<<1, 1024, 0, st>>>((const double*)samples, C, n, p, p_accept);
+  }
+  tracker_rhat_kernel<<<(unsigned)p, 256, 0, st>>>(mean, mean_sq, C, n, p, rhat);
+  return cudaGetLastError();
+}
+
 size_t stats_npad(size_t n) {
   const size_t half = n / 2;
   size_t N = 1;

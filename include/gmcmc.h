@@ -31,6 +31,9 @@
  *   stream 2: NUTS tree uniforms, block = draw index / 4 (see gmcmc_nuts_create).
  *   stream 3: NUTS momentum probe after a mass-matrix update (see gmcmc_nuts_set_mass_adaptation).
  * Uniforms are in (0,1]:  f32 ((r>>8)+1)*2^-24,  f64 ((r64>>11)+1)*2^-53.
+ * Fast-mode MH with dim == 2 takes everything for a transition from block 0 of stream 0: words 0 and 1 ->
+ * Box-Muller pair from the 23-bit uniforms ((r>>9)+1/2)*2^-23 (radius from word 0, angle from word 1), words
+ * 2-3 -> the accept uniform (the 53-bit / 24-bit value above; its leading 23 bits are tested first).
  */
 #ifndef GMCMC_H
 #define GMCMC_H
@@ -225,6 +228,14 @@ gmcmc_status gmcmc_split_rhat_ess(gmcmc_ctx*, const void* samples, size_t C, siz
 /* ≙ RunStats::from (stats.rs:383-394) */
 gmcmc_status gmcmc_run_stats_from(gmcmc_ctx*, const void* samples, size_t C, size_t n, size_t p,
                                   gmcmc_dtype dtype, int on_device, gmcmc_run_stats_t* out);
+
+/* Progress tracker.  ≙ MultiChainTracker::{new, step (once per draw), rhat, max_rhat, p_accept} (stats.rs:199-339):
+ * what run_progress shows while sampling — per-chain running mean / mean of squares (f32, the reference's
+ * recurrences), the EMA acceptance rate (alpha = 0.01, "row changed" test, folded over the chains of a step, step
+ * after step) and the tracker R-hat sqrt(var_hat / W) — evaluated on the device from the draws [C, n, p] collected
+ * so far.  rhat: host float[p]; max_rhat, p_accept: host scalars; any may be NULL.  Needs C >= 2, n >= 2. */
+gmcmc_status gmcmc_tracker_stats(gmcmc_ctx*, const void* samples, size_t C, size_t n, size_t p,
+                                 gmcmc_dtype dtype, int on_device, float* rhat, float* max_rhat, float* p_accept);
 
 /* raw Philox4x32-10 blocks computed on the device (contract check): ctr [n,4], key [2] -> out [n,4] */
 gmcmc_status gmcmc_philox_blocks(gmcmc_ctx*, const uint32_t* ctr_host, size_t n, const uint32_t* key,

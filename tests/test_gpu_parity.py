@@ -295,6 +295,24 @@ def test_split_rhat_ess_matches_oracle(ctx, oracle, c, n, p, rho):
     assert np.allclose(rhat64, rhat, rtol=1e-6) and np.allclose(ess64, ess, rtol=1e-6)
 
 
+@pytest.mark.parametrize("c,n,p,dtype", [(2, 2, 2, np.float32), (5, 40, 3, np.float32), (64, 300, 17, np.float64),
+                                          (6000, 9, 4, np.float32), (300, 500, 100, np.float32)])
+def test_tracker_stats_match_oracle(ctx, oracle, c, n, p, dtype):
+    """MultiChainTracker (stats.rs:199-339) on the device vs the oracle's host restatement (itself pinned by the
+    reference's tracker R-hat KAT, stats.rs:734-783): chains with rejected steps (repeated rows), so the EMA
+    acceptance rate is exercised; p_accept is bit-exact (same f32 fold), R-hat to f32 summation order."""
+    rng = np.random.default_rng(c * 7 + n)
+    x = _ar1(c, n, p, 0.6, seed=c + n).astype(dtype)
+    stay = rng.random((c, n)) < 0.35
+    for t in range(1, n):                      # a rejected proposal repeats the previous draw
+        x[stay[:, t], t] = x[stay[:, t], t - 1]
+    got = gm.tracker_stats(x, ctx)
+    rhat, pa = oracle.tracker_rhat(np.ascontiguousarray(x.transpose(1, 0, 2)))
+    assert got["p_accept"] == pa
+    assert np.allclose(got["rhat"], rhat, rtol=2e-4 if c > 1000 else 2e-5)
+    assert np.isclose(got["max_rhat"], rhat.max(), rtol=2e-4)
+
+
 def test_run_stats_struct_matches_oracle(ctx, oracle):
     x = _ar1(8, 600, 11, 0.6, seed=3)
     st = gm.RunStats.from_samples(x, ctx)

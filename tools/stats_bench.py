@@ -33,3 +33,16 @@ print("wall ms: min %.2f median %.2f max %.2f" % (times[0], times[len(times) // 
 gb = chains * n * p * 4 / 1e9
 print("K4 %d x %d x %d: %.2f ms wall (incl. buffer allocation and the host read-back), %.0f GB/s of sample reads; ess mean %.0f (iid: %d), rhat max %.5f"
       % (chains, n, p, best, gb / (best * 1e-3), ess.mean(), chains * n, rhat.max()))
+
+# K6: progress tracker over the same tensor
+mx = C.c_float(0)
+pa = C.c_float(0)
+tt = []
+for it in range(5):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    L.check(L.lib().gmcmc_tracker_stats(ctx._h, C.c_void_p(x.data_ptr()), C.c_size_t(chains), C.c_size_t(n), C.c_size_t(p),
+                                        L.F32, 1, L.ptr(rhat), C.byref(mx), C.byref(pa)))
+    ctx.synchronize()
+    tt.append((time.perf_counter() - t0) * 1e3)
+print("K6 tracker: %.2f ms wall, %.0f GB/s of sample reads; max_rhat %.5f p_accept %.4f" % (min(tt[1:]), gb / (min(tt[1:]) * 1e-3), mx.value, pa.value))
