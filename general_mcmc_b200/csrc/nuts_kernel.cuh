@@ -156,7 +156,9 @@ __device__ __forceinline__ T chain_sum_fn(const Lane& ln, F f) {
 #define GM_NUTS_MINB 3
 #endif
 
-template <class T, int EPL, class TAG, bool PADDED>
+// MASS: diagonal mass matrix + warm-up statistics compiled in (GenericNUTS::new_with_mass_matrix); the identity-mass
+// instantiation carries none of it (measured: the run-time test alone cost 16 % on BASELINE config 5).
+template <class T, int EPL, class TAG, bool PADDED, bool MASS>
 __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const NutsArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* smem = reinterpret_cast<T*>(smem_raw);
@@ -211,9 +213,9 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
   unsigned long long i_norm = 0, i_exp = 0, i_unif = 0;
   const bool inject = a.inj_normals != nullptr;
   unsigned long long my_leapfrogs = 0, my_diverge = 0, my_depth = 0, chain_leaps = 0;
-  T minv[EPL], msqrt[EPL];         // this chain's diagonal mass (1 = identity: x * 1 is exact, so parity is untouched)
-#pragma unroll
-  for (int j = 0; j < EPL; ++j) { minv[j] = T(1); msqrt[j] = T(1); }
+  // Diagonal mass matrix (MASS): its entries are re-read from global memory (L1-resident, coalesced) where they are
+  // used instead of living in 2 x EPL registers.
+  constexpr bool has_mass = MASS;
 
   // per-chain state in / out (each lane moves its own slice of the position row)
   auto load_chain = [&]() {
@@ -229,11 +231,6 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
     }
     chain_leaps = 0;
     gchain = a.chain_offset + chain;
-    if (a.mass_inv) {
-#pragma unroll
-      for (int j = 0; j < EPL; ++j)
-        if (j < ln.nvalid) { minv[j] = a.mass_inv[chain * d + ln.lo + j]; msqrt[j] = a.mass_sqrt[chain * d + ln.lo + j]; }
-    }
   };
   auto store_chain = [&]() {
 #pragma unroll
@@ -334,7 +331,12 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       }
       if (is_start) {   // sample_momentum, generic_nuts.rs:283-303: z * sqrt(var)
 #pragma unroll
-        for (int j = 0; j < EPL; ++j) { p[j] = pn[j] * msqrt[j]; q[j] = (j < ln.nvalid) ? pos_row[ln.lo + j] : T(1); }
+        for (int j = 0; j < EPL; ++j) { p[j] = pn[j]; q[j] = (j < ln.nvalid) ? pos_row[ln.lo + j] : T(1); }
+        if constexpr (has_mass) {
+#pragma unroll
+          for (int j = 0; j < EPL; ++j)
+            if (j < ln.nvalid) p[j] = pn[j] * a.mass_sqrt[chain * d + ln.lo + j];
+        }
       }
     }
 
@@ -345,7 +347,14 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
 #pragma unroll
       for (int j = 0; j < EPL; ++j) p[j] = p[j] + g[j] * he;
 #pragma unroll
-      for (int j = 0; j < EPL; ++j) q[j] = q[j] + (minv[j] * p[j]) * veps;     // velocity = M^-1 p (apply_inv_mass)
+      for (int j = 0; j < EPL; ++j) {
+        if constexpr (has_mass) {                                             // velocity = M^-1 p (apply_inv_mass)
+          const T mi = (j < ln.nvalid) ? a.mass_inv[chain * d + ln.lo + j] : T(1);
+          q[j] = q[j] + (mi * p[j]) * veps;
+        } else {
+          q[j] = q[j] + p[j] * veps;
+        }
+      }
     }
     // every chain is in the START, LEAF or DONE phase here, and a finished chain never reads g again: the
     // gradient is written in place
@@ -356,7 +365,10 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
     }
     T terms[EPL];
 #pragma unroll
-    for (int j = 0; j < EPL; ++j) terms[j] = p[j] * p[j] * minv[j];            // MassMatrix::kinetic :228-263
+    for (int j = 0; j < EPL; ++j) {                                              // MassMatrix::kinetic :228-263
+      if constexpr (has_mass) terms[j] = p[j] * p[j] * ((j < ln.nvalid) ? a.mass_inv[chain * d + ln.lo + j] : T(1));
+      else terms[j] = p[j] * p[j];
+    }
     const T ke = T(0.5) * chain_sum<T, EPL>(terms, ln);
     const T joint = logp - ke;
 
@@ -429,13 +441,13 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       const bool fwd = (v == 1);
       const T dm = chain_sum_fn<T, EPL>(ln, [&](int j) {
         const T df = fwd ? (q[j] - fq[j]) : (fq[j] - q[j]);
-        const T mi = do_top ? minv[j] : T(1);
-        return (!PADDED || j < ln.nvalid) ? df * (mi * (fwd ? fp[j] : p[j])) : T(0);
+        if (has_mass && do_top && j < ln.nvalid) return df * (a.mass_inv[chain * d + ln.lo + j] * (fwd ? fp[j] : p[j]));
+        return (!PADDED || j < ln.nvalid) ? df * (fwd ? fp[j] : p[j]) : T(0);
       });
       const T dp = chain_sum_fn<T, EPL>(ln, [&](int j) {
         const T df = fwd ? (q[j] - fq[j]) : (fq[j] - q[j]);
-        const T mi = do_top ? minv[j] : T(1);
-        return (!PADDED || j < ln.nvalid) ? df * (mi * (fwd ? p[j] : fp[j])) : T(0);
+        if (has_mass && do_top && j < ln.nvalid) return df * (a.mass_inv[chain * d + ln.lo + j] * (fwd ? p[j] : fp[j]));
+        return (!PADDED || j < ln.nvalid) ? df * (fwd ? p[j] : fp[j]) : T(0);
       });
       const bool crit = (dm >= T(0)) && (dp >= T(0));
       if (do_merge) {
@@ -501,7 +513,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       } else {
         eps = eps_bar;
       }
-      if (a.run_mean && m <= a.n_discard && m > a.collect_after && m < a.collect_before) {
+      if (MASS && a.run_mean && m <= a.n_discard && m > a.collect_after && m < a.collect_before) {
         // RunningCov::update (generic_nuts.rs:105-114) on the position after this transition
         // every chain collects at the same transitions, so the count is a function of m alone (no device counter)
         const uint32_t first_m = a.m_base > a.collect_after ? a.m_base : a.collect_after;
@@ -732,7 +744,9 @@ inline cudaError_t nuts_launch_one(const NutsLaunch& L, cudaStream_t st) {
   NutsArgs<T> a = make_nuts_args<T>(L);
   size_t smem = 2 * (size_t)(kHmcBlock / L.lpc) * d_pad * sizeof(T);
   if (std::is_same<TAG, TagMixture>::value) smem += (size_t)L.tgt.n_comp * L.lpc * Eplp<EPL>::value * sizeof(T);
-  auto kern = (L.epl * L.lpc == L.tgt.dim) ? nuts_run_kernel<T, EPL, TAG, false> : nuts_run_kernel<T, EPL, TAG, true>;
+  const bool exact_fit = (L.epl * L.lpc == L.tgt.dim);
+  auto kern = L.mass_inv ? (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, true> : nuts_run_kernel<T, EPL, TAG, true, true>)
+                         : (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, false> : nuts_run_kernel<T, EPL, TAG, true, false>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
