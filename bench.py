@@ -159,6 +159,17 @@ def cpu_mh_rate(target_seconds=12.0):
     return chains * n_steps / secs, threads, "%d chains x %d steps, f64, samples kept (%.1f s)" % (chains, n_steps, secs)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of each workload's dominant kernel, from the `ncu --set full`
+# captures summarised under profiles/ (same launch shapes as the bench: chains per GPU and transitions per launch below)
+DEFAULT_CHAINS = {"hmc_rosenbrock": 65536, "mh_gauss2d": 1048576, "hmc_dense": 65536, "nuts_mixture": 65536}
+NCU_TRAFFIC = {
+    "hmc_rosenbrock": {"bytes": 27.2e6 + 2.592e9, "launch": "65,536 chains x 100 transitions", "source": "profiles/r1_hmc_run_kernel_full.txt"},
+    "mh_gauss2d": {"bytes": 17.4e6 + 16.735e9, "launch": "1,048,576 chains x 1000 steps", "source": "profiles/r1_mh_run2_kernel_full.txt"},
+    "hmc_dense": {"bytes": 1.071e9 + 0.481e9, "launch": "one gradient GEMM of 65,536 chains, d = 1000", "source": "profiles/r1_dense_gemm_kick_full.txt"},
+    "nuts_mixture": {"bytes": 47.5e6 + 5.380e9, "launch": "65,536 chains x 200 transitions", "source": "profiles/r1_nuts_run_kernel_full.txt"},
+}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -367,7 +378,7 @@ def run_ours(args, rank, world, local):
         tfl = value / world * flop / 1e12
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"]) / 2.0
         roof = {"bound": "tensor", "kernel": "dense_gemm_kick_kernel (tcgen05.mma kind::tf32, 128x256x8)", "achieved": tfl,
-                "peak": peak, "unit": "TFLOP/s", "frac": tfl / peak, "traffic": None,
+                "peak": peak, "unit": "TFLOP/s", "frac": tfl / peak, "traffic": NCU_TRAFFIC[args.workload]["bytes"] if (chains == DEFAULT_CHAINS[args.workload] and args.dim in (0, 1000)) else None, "traffic_unit": "bytes per launch (ncu: %s, %s)" % (NCU_TRAFFIC[args.workload]["source"], NCU_TRAFFIC[args.workload]["launch"]),
                 "peak_source": "TF32 dense = half of the measured sustained bf16 peak (%s)" % pk["source"],
                 "algorithmic_flop_per_unit": flop, "executed_tensor_tflops": 3.0 * tfl * (1.0 + 1.0 / N_LEAPFROG),
                 "note": "3xTF32 error-compensated split (hi.hi + lo.hi + hi.lo): the tensor pipe executes 3x the "
@@ -378,7 +389,7 @@ def run_ours(args, rank, world, local):
         flop = (5 * 4 + 6) * DIM      # (5K + 6) d flop per leapfrog
         tfl = value / world * flop / 1e12
         roof = {"bound": "fp32", "kernel": "nuts_run_kernel<float,25,Mixture>", "achieved": tfl, "peak": fp32_peak.value,
-                "unit": "TFLOP/s", "frac": tfl / fp32_peak.value if fp32_peak.value else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": tfl / fp32_peak.value if fp32_peak.value else None, "traffic": NCU_TRAFFIC[args.workload]["bytes"] if (chains == DEFAULT_CHAINS[args.workload] and args.dim in (0, 1000)) else None, "traffic_unit": "bytes per launch (ncu: %s, %s)" % (NCU_TRAFFIC[args.workload]["source"], NCU_TRAFFIC[args.workload]["launch"]),
                 "peak_source": "FFMA micro-benchmark in this run", "algorithmic_flop_per_unit": flop,
                 "mean_leapfrogs_per_transition": unit_per_step / chains,
                 "note": "divergence-limited: chains of a warp build trees of different sizes (warp-level masking)"}
@@ -386,15 +397,15 @@ def run_ours(args, rank, world, local):
         ach = bytes_per_step * per_launch / (kernel_ms_per_launch * 1e-3) / 1e9 if len(plan) and plan[0] == per_launch else \
             bytes_per_step * args.steps / (ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "mh_run2_kernel<double, Gaussian2D>", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
-                "algorithmic_bytes_per_unit": 16, "note": "co-bound by instruction dispatch: 110 warp-instructions per chain-step, 73 on half-rate pipes (Philox4x32-10 = 20 LOP3 + 20 IMAD.WIDE, 13 FP64); a write-only stream of the same 256-byte pieces reaches 5.3 TB/s (tools/microbench_write.cu)"}
+                "frac": ach / pk["hbm_gbs"], "traffic": NCU_TRAFFIC[args.workload]["bytes"] if (chains == DEFAULT_CHAINS[args.workload] and args.dim in (0, 1000)) else None, "traffic_unit": "bytes per launch (ncu: %s, %s)" % (NCU_TRAFFIC[args.workload]["source"], NCU_TRAFFIC[args.workload]["launch"]), "peak_source": pk["source"],
+                "algorithmic_bytes_per_unit": 16, "note": "co-bound by instruction dispatch: 103 warp-instructions per chain-step, ~70 on half-rate pipes (Philox4x32-10 = 20 LOP3 + 20 IMAD.WIDE, 13 FP64); a write-only stream of the same 256-byte pieces reaches 5.3 TB/s (tools/microbench_write.cu)"}
     else:
         fp32_peak = C.c_double(0)
         L.check(lib.gmcmc_measure_fp32_peak(ctx._h, C.byref(fp32_peak)))
         tfl = value / world * FLOP_PER_GRAD_EVAL / 1e12
         hbm = bytes_per_step * args.steps / (ms * 1e-3) / 1e9
         roof = {"bound": "fp32", "kernel": "hmc_run_kernel<float,25,RosenbrockND>", "achieved": tfl, "peak": fp32_peak.value,
-                "unit": "TFLOP/s", "frac": tfl / fp32_peak.value if fp32_peak.value else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": tfl / fp32_peak.value if fp32_peak.value else None, "traffic": NCU_TRAFFIC[args.workload]["bytes"] if (chains == DEFAULT_CHAINS[args.workload] and args.dim in (0, 1000)) else None, "traffic_unit": "bytes per launch (ncu: %s, %s)" % (NCU_TRAFFIC[args.workload]["source"], NCU_TRAFFIC[args.workload]["launch"]),
                 "peak_source": "FFMA micro-benchmark in this run (gmcmc_measure_fp32_peak); nominal 148*128*2*%.3f GHz = %.1f"
                                % (pk["sm_max_mhz"] / 1e3, 148 * 128 * 2 * pk["sm_max_mhz"] / 1e6),
                 "algorithmic_flop_per_unit": FLOP_PER_GRAD_EVAL,

@@ -54,6 +54,7 @@ struct MhArgs {
   size_t n_chains;
   unsigned long long chain_offset;
   PhiloxKey key;
+  PhiloxRoundKeys rk;   // the ten round keys of `key`, computed on the host: read as constant-bank operands
   uint32_t step_base, n_steps, n_skip;
   T* state;
   double* out;
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(kMhBlock, GM_MH_MINB) mh_run_kernel(const MhAr
 // Measured on B200 (tools/mh_bench.cu, tools/microbench_write.cu): a write-only stream of 256-byte pieces
 // reaches 5.3 TB/s, of 512-byte pieces 6.6 TB/s, cudaMemset 7.4 TB/s; the kernel runs at 3.6 TB/s with either
 // staging depth, any occupancy from 12 to 32 warps per SM and any unroll factor: it is bound by instruction
-// dispatch (110 warp-instructions per step, 73 of them on half-rate pipes: Philox's 20 LOP3 + 20 IMAD.WIDE,
+// dispatch (103 warp-instructions per step, about 70 of them on half-rate pipes: Philox's 20 LOP3 + 20 IMAD.WIDE,
 // 13 FP64, selects), not by HBM — profiles/r1_mh_run2_kernel_full.txt.
 // ------------------------------------------------------------------------------------------------
 #ifndef GM_MH2_STEPS
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(kMhBlock, GM_MH2_MINB) mh_run2_kernel(const Mh
   const size_t warp_first_chain = (size_t)blockIdx.x * kMhBlock + warp_row0;
   const int warp_rows = a.n_chains > warp_first_chain
                             ? (int)(a.n_chains - warp_first_chain < 32 ? a.n_chains - warp_first_chain : 32) : 0;
-  const PhiloxRoundKeys rk = philox_round_keys(a.key);
+  const PhiloxRoundKeys& rk = a.rk;
 
   // shared-memory addresses (32-bit).  Unit (chain c, step t) of a warp lives at row c, 16-byte column t ^ (c & (S-1)):
   // the 8 lanes of a quarter-warp then hit 8 different bank groups both when every chain writes its step-t unit and
@@ -553,6 +554,7 @@ inline MhArgs<T> make_mh_args(const MhLaunch& L) {
   a.n_chains = L.n_chains;
   a.chain_offset = L.chain_offset;
   a.key = PhiloxKey{(uint32_t)L.seed, (uint32_t)(L.seed >> 32)};
+  a.rk = philox_round_keys(a.key);
   a.step_base = L.step_base; a.n_steps = L.n_steps; a.n_skip = L.n_skip;
   a.state = (T*)L.state;
   a.out = L.out; a.out_n = L.out_n; a.out_t0 = L.out_t0;
