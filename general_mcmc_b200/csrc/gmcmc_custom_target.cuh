@@ -4,7 +4,7 @@
 // (/root/reference/src/distributions.rs:67-90) as host closures differentiated by burn autodiff.  On the
 // device a custom target is a user-written `__device__` log-density-and-gradient function, compiled ahead of
 // time with nvcc into a small shared library that instantiates the same fused kernels (K1 trajectory kernel,
-// gradient evaluation, K5 NUTS) for it and exposes them through one C entry point:
+// gradient evaluation, K5 NUTS, K2 Metropolis-Hastings) for it and exposes them through one C entry point:
 //
 //   #include "gmcmc_custom_target.cuh"
 //   struct Banana {
@@ -23,6 +23,8 @@
 // (general_mcmc_b200.CustomTarget in Python).  One thread per chain, dim <= 32.
 #pragma once
 #include "nuts_kernel.cuh"   // pulls hmc_kernel.cuh
+#define GM_MH_NO_BUILTIN_LAUNCHERS
+#include "mh_kernel.cuh"     // K2 kernel template (MetropolisHastings with a custom Target)
 
 namespace gm {
 namespace GM_NS {
@@ -55,6 +57,32 @@ inline cudaError_t custom_launch_nuts(const NutsLaunch& L, cudaStream_t st) {
   return nuts_launch_one<double, U::dim, TagCustom<U>>(L, st);
 }
 
+// MetropolisHastings on a custom target (Target::unnorm_logp, distributions.rs:107-110): the K2 kernel with the
+// plugin's log density (the gradient its function also writes is dead code here and is removed by the compiler).
+template <class U>
+struct CustomLogp {
+  template <class T>
+  __device__ static __forceinline__ T logp(const T (&x)[U::dim], const T* params) {
+    T g[U::dim];
+    return U::template logp_grad<T>(x, g, params);
+  }
+};
+template <class T, class U>
+inline cudaError_t custom_mh_one(const MhLaunch& L, cudaStream_t st) {
+  MhArgs<T> a = make_mh_args<T>(L);
+  const unsigned blocks = (unsigned)((L.n_chains + kMhBlock - 1) / kMhBlock);
+  if (a.inj_normals || a.inj_lnu || a.diag_logratio)
+    mh_run_kernel<T, U::dim, kTargetCustom, true, true, CustomLogp<U>><<<blocks, kMhBlock, 0, st>>>(a);
+  else
+    mh_run_kernel<T, U::dim, kTargetCustom, true, false, CustomLogp<U>><<<blocks, kMhBlock, 0, st>>>(a);
+  return cudaGetLastError();
+}
+template <class U>
+inline cudaError_t custom_launch_mh(const MhLaunch& L, cudaStream_t st) {
+  if (L.tgt.dim != U::dim) return cudaErrorInvalidValue;
+  return L.tgt.dtype == 0 ? custom_mh_one<float, U>(L, st) : custom_mh_one<double, U>(L, st);
+}
+
 }  // namespace GM_NS
 }  // namespace gm
 
@@ -62,6 +90,7 @@ inline cudaError_t custom_launch_nuts(const NutsLaunch& L, cudaStream_t st) {
   static_assert(U::dim >= 1 && U::dim <= 32, "custom target dim must be 1..32");                            \
   extern "C" const gm::CustomTargetVTable* gmcmc_custom_entry(void) {                                      \
     static const gm::CustomTargetVTable vt = {gm::kCustomAbiVersion, U::dim, &gm::GM_NS::custom_launch_hmc<U>,      \
-                                              &gm::GM_NS::custom_launch_eval<U>, &gm::GM_NS::custom_launch_nuts<U>}; \
+                                              &gm::GM_NS::custom_launch_eval<U>, &gm::GM_NS::custom_launch_nuts<U>,  \
+                                              &gm::GM_NS::custom_launch_mh<U>};                                       \
     return &vt;                                                                                             \
   }

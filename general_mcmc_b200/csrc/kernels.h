@@ -157,7 +157,7 @@ struct StatsLaunch {
 };
 
 // custom-target plugins (gmcmc_custom_target.cuh): the launchers a plugin instantiates for its target
-constexpr int kCustomAbiVersion = 2;
+constexpr int kCustomAbiVersion = 3;
 constexpr int kTargetCustom = 7;      // TargetDesc.kind of a plugin target
 struct CustomTargetVTable {
   int abi_version;
@@ -165,6 +165,7 @@ struct CustomTargetVTable {
   cudaError_t (*launch_hmc)(const HmcLaunch&, cudaStream_t);
   cudaError_t (*launch_eval)(const EvalLaunch&, cudaStream_t);
   cudaError_t (*launch_nuts)(const NutsLaunch&, cudaStream_t);
+  cudaError_t (*launch_mh)(const MhLaunch&, cudaStream_t);
 };
 
 size_t stats_npad(size_t n);

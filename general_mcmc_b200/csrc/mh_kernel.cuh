@@ -21,6 +21,7 @@
 #include "philox.cuh"
 
 #include <cmath>
+#include <type_traits>
 
 #ifndef GM_EXACT
 #define GM_EXACT 0
@@ -56,6 +57,7 @@ struct MhArgs {
   PhiloxKey key;
   PhiloxRoundKeys rk;   // the ten round keys of `key`, computed on the host: read as constant-bank operands
   uint32_t step_base, n_steps, n_skip;
+  const T* dparams;     // device parameter block of a plugin target (gmcmc_custom_target.cuh), else null
   T* state;
   double* out;
   size_t out_n;
@@ -154,7 +156,9 @@ __device__ __forceinline__ T mh_logq(const MhArgs<T>& a, const T (&from)[MAXD], 
 
 // One launch = n_skip discarded transitions, then (n_steps - n_skip) recorded ones.  INSTR = the
 // instrumented variant used by the parity tests (injected normals / ln u, per-step diagnostics).
-template <class T, int MAXD, int KIND, bool FULL, bool INSTR>
+// LP = void: the built-in target KIND (mh_logp above).  Otherwise LP::logp<T>(x, params) is a plugin target's log density
+// (gmcmc_custom_target.cuh instantiates this kernel for it).
+template <class T, int MAXD, int KIND, bool FULL, bool INSTR, class LP = void>
 __global__ void __launch_bounds__(kMhBlock, GM_MH_MINB) mh_run_kernel(const MhArgs<T> a) {
   __shared__ double stage[kMhBlock * kStageStride];
 
@@ -179,7 +183,11 @@ __global__ void __launch_bounds__(kMhBlock, GM_MH_MINB) mh_run_kernel(const MhAr
 #pragma unroll
   for (int i = 0; i < MAXD; ++i) x[i] = (active && (FULL || i < d)) ? a.state[chain * d + i] : T(0);
   const MhInv<T> inv = mh_prepare<T, KIND>(a);
-  T lp_cur = mh_logp<T, MAXD, KIND, FULL>(a, inv, x);
+  auto logp_of = [&](const T (&v)[MAXD]) -> T {
+    if constexpr (std::is_void<LP>::value) return mh_logp<T, MAXD, KIND, FULL>(a, inv, v);
+    else return LP::template logp<T>(v, a.dparams);
+  };
+  T lp_cur = logp_of(x);
 
   unsigned int n_accept = 0;
   int staged = 0;                 // doubles currently in this chain's stage row
@@ -228,7 +236,7 @@ __global__ void __launch_bounds__(kMhBlock, GM_MH_MINB) mh_run_kernel(const MhAr
     for (int i = 0; i < MAXD; ++i) xp[i] = (FULL || i < d) ? (x[i] + z[i] * a.prop_std) : T(0);
 
     // ---- log acceptance ratio (metropolis_hastings.rs:308-312)
-    const T lp_prop = mh_logp<T, MAXD, KIND, FULL>(a, inv, xp);
+    const T lp_prop = logp_of(xp);
     T log_ratio;
     if constexpr (kMhExact) {
       const T q_fwd = mh_logq<T, MAXD, FULL>(a, x, xp);
@@ -551,6 +559,7 @@ inline MhArgs<T> make_mh_args(const MhLaunch& L) {
     volatile T h = nd * T(0.5);
     a.prop_logq_const = h * lg;
   }
+  a.dparams = (const T*)L.tgt.dparams;
   a.n_chains = L.n_chains;
   a.chain_offset = L.chain_offset;
   a.key = PhiloxKey{(uint32_t)L.seed, (uint32_t)(L.seed >> 32)};
@@ -608,6 +617,7 @@ inline cudaError_t mh_dispatch(const MhLaunch& L, cudaStream_t st) {
 
 }  // namespace GM_NS
 
+#ifndef GM_MH_NO_BUILTIN_LAUNCHERS   // plugins include this header for the kernel template only
 #if GM_EXACT
 cudaError_t launch_mh_exact(const MhLaunch& L, cudaStream_t st) {
   return L.tgt.dtype == 0 ? exact::mh_dispatch<float>(L, st) : exact::mh_dispatch<double>(L, st);
@@ -617,5 +627,6 @@ cudaError_t launch_mh_fast(const MhLaunch& L, cudaStream_t st) {
   return L.tgt.dtype == 0 ? fast::mh_dispatch<float>(L, st) : fast::mh_dispatch<double>(L, st);
 }
 #endif
+#endif  // GM_MH_NO_BUILTIN_LAUNCHERS
 
 }  // namespace gm

@@ -378,7 +378,8 @@ gmcmc_status mh_segment(gmcmc_sampler* s, size_t first, size_t count, size_t n_d
     L.diag_logratio = (char*)s->d_diag_logacc + inj_first * s->n_chains * es;
     L.diag_acc = s->d_diag_acc + inj_first * s->n_chains;
   }
-  cudaError_t e = (s->math == GMCMC_MATH_EXACT) ? launch_mh_exact(L, s->ctx->stream) : launch_mh_fast(L, s->ctx->stream);
+  cudaError_t e = s->tgt->custom ? s->tgt->custom->launch_mh(L, s->ctx->stream)
+                  : (s->math == GMCMC_MATH_EXACT) ? launch_mh_exact(L, s->ctx->stream) : launch_mh_fast(L, s->ctx->stream);
   if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "MH kernel launch failed: %s", cudaGetErrorString(e));
   s->launches += 1;
   return GMCMC_OK;
@@ -1066,8 +1067,7 @@ gmcmc_status gmcmc_mh_create(gmcmc_ctx* ctx, gmcmc_target* tgt, double proposal_
   GM_REQUIRE(tgt, "null target");
   GM_REQUIRE(proposal_std > 0.0, "proposal_std must be positive");
   const int k = tgt->desc.kind;
-  if (tgt->custom) return fail(GMCMC_ERR_UNSUPPORTED, "custom targets are available for HMC and NUTS");
-  if (!(k == 0 || k == 1 || k == 2 || k == 4 || k == 5) || tgt->desc.dim > 32)
+  if (!tgt->custom && (!(k == 0 || k == 1 || k == 2 || k == 4 || k == 5) || tgt->desc.dim > 32))
     return fail(GMCMC_ERR_UNSUPPORTED, "MH kernel supports targets ISO_GAUSS, GAUSS2D, DIFF_GAUSS2D, ROSENBROCK2D, ROSENBROCK_ND with dim <= 32");
   gmcmc_sampler* s = nullptr;
   GM_TRY(sampler_common(ctx, tgt, n_chains, chain_offset, init_host, seed, S_MH, &s));

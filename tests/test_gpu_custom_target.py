@@ -58,5 +58,41 @@ def test_custom_target_hmc_and_nuts_sample_it(banana):
     f2 = o2.reshape(-1, 3).astype(np.float64)
     assert np.isfinite(f2).all()
     assert abs(f2[:, 0].var() - 2.25) < 0.2 and abs(f2[:, 2].mean() - 1.0) < 0.03
-    with pytest.raises(gm.GmcmcError):
-        gm.MetropolisHastings(banana, gm.IsotropicGaussian(1.0), q0.astype(np.float64))
+
+
+@pytest.mark.parametrize("dtype,exact", [(np.float64, False), (np.float32, False), (np.float64, True)])
+def test_custom_target_metropolis_hastings(banana, dtype, exact):
+    """MetropolisHastings::new(target, proposal, ..) with a custom Target (distributions.rs:107-110): the K2 kernel
+    instantiated by the plugin for its log density.  Moments of the banana; per-step equivalence against a numpy
+    restatement of metropolis_hastings.rs:306-318 on injected draws."""
+    Cn = 4096
+    x0 = np.zeros((Cn, 3), dtype)
+    x0[:, 2] = 1.0
+    s = gm.MetropolisHastings(banana, gm.IsotropicGaussian(0.6), x0).seed(42).set_math_mode(exact)
+    out = s.run(1500, 500)
+    assert out.dtype == np.float64 and out.shape == (Cn, 1500, 3)
+    flat = out[:, ::10].reshape(-1, 3)
+    assert abs(flat[:, 0].var() - 2.25) < 0.12          # x0 ~ N(0, 1.5^2)
+    assert abs(flat[:, 1].mean() - 0.3 * 2.25) < 0.06   # E[x1] = b s^2
+    assert abs(flat[:, 2].mean() - 1.0) < 0.02 and abs(flat[:, 2].var() - 0.25) < 0.02
+    c = s.counters()
+    assert 0.2 < c.accepts / c.transitions < 0.7
+    # injected draws: the accept decisions and states follow the reference recurrence
+    Ci, n = 64, 12
+    rng = np.random.default_rng(1)
+    xi = rng.standard_normal((Ci, 3)).astype(dtype)
+    z = rng.standard_normal((n, Ci, 3)).astype(dtype)
+    lnu = np.log(rng.random((n, Ci))).astype(dtype)
+    t = gm.MetropolisHastings(banana, gm.IsotropicGaussian(0.6), xi).seed(1).set_math_mode(exact)
+    t.inject(z, lnu)
+    got = t.run(n, 0)
+    x = xi.astype(np.float64)
+    alive = np.ones(Ci, bool)                  # chains none of whose decisions sat on the rounding margin so far
+    tol = 1e-12 if dtype == np.float64 else 2e-5
+    for k in range(n):
+        xp = x + z[k].astype(np.float64) * 0.6
+        lr = _ref(xp)[0] - _ref(x)[0]
+        alive &= np.abs(lr - lnu[k]) > 1e-3
+        x = np.where((lr > lnu[k])[:, None], xp, x)
+        assert np.allclose(got[alive, k], x[alive], rtol=tol, atol=tol)
+    assert alive.sum() > Ci // 2
