@@ -6,9 +6,14 @@
 // (/root/reference/src/distributions.rs:265-291):  delta = x - mu ; z = delta . P ; logp = c - 1/2 sum(z * delta) ;
 // grad = -z.  z for all chains is a real [chains x d] . [d x d] GEMM per gradient evaluation.
 //
-// Precision: plain TF32 (10-bit mantissa) cannot meet the 1e-5 per-step bar, so both operands are split
-// x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi), and the accumulator receives hi.hi + lo.hi + hi.lo in
-// FP32 (TMEM): three tcgen05.mma.kind::tf32 per K-step.
+// Precision: plain TF32 / FP16 (11-bit significand) cannot meet the 1e-5 per-step bar, so both operands are split
+// x = hi + lo (22 bits) and the accumulator receives hi.hi + lo.hi + hi.lo in FP32 (TMEM): three MMAs per K-step.
+//   GM_TC_F16 = 1 (default): hi = half(x), lo = half(x - hi), tcgen05.mma.kind::f16 (K = 16 per instruction, twice
+//     the TF32 rate).  FP16 products are exact in FP32.  P is pre-scaled by a power of two so that its entries use
+//     the upper part of FP16's exponent range (the epilogue undoes it); delta = q - mu is O(1..10), and a low part
+//     that falls into the subnormals costs at most 2^-25 absolute.  Measured against the f64 oracle at d = 1000,
+//     L = 32: same error as the TF32 split (tests/test_gpu_dense_tc.py holds both to 2e-5); 7.5e7 -> 9.3e7 grad-evals/s.
+//   GM_TC_F16 = 0: hi = rna_tf32(x), lo = rna_tf32(x - hi), tcgen05.mma.kind::tf32 (K = 8).
 //
 // State: the trajectory runs in delta-space.  p [C, d] and delta [C, kpad] (two ping-pong buffers, padded columns
 // zero) are the only per-leapfrog HBM arrays: 16 bytes per coordinate per leapfrog.  One transition (fast math
@@ -19,15 +24,17 @@
 //   dense_accept_kernel    Hamiltonian, Metropolis accept, q <- delta + mu, sample row -> [chain, slot, :]
 //
 // dense_gemm_kick_kernel — one CTA per 128 chains, clusters of 2 CTAs, 15 warps:
-//   warp 0      TMA loads of the raw f32 delta tile [128 x 16] (ring of 4)
-//   warp 1      TMA loads of P_hi / P_lo [256 x 16]: each CTA of the cluster loads half of every tile and multicasts it
-//   warp 2      tcgen05.mma issue (one elected lane; 128 x 256 x 8, accumulators double-buffered over the 512 TMEM cols)
+//   warp 0      TMA loads of the raw f32 delta tile [128 x 32] (ring of 3; [128 x 16], ring of 4 in TF32 mode)
+//   warp 1      TMA loads of P_hi / P_lo [256 x 32 halves]: each CTA of the cluster loads half of every tile and multicasts it
+//   warp 2      tcgen05.mma issue (one elected lane; 128 x 256 x 16, accumulators double-buffered over the 512 TMEM cols)
 //   warps 3-6   split the raw tile into hi / lo operand tiles in shared memory (element-wise, so the TMA swizzle
 //               is preserved) — the split never touches HBM
 //   warps 7-14  epilogue: tcgen05.ld, transpose through shared memory, row-contiguous global updates
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -43,10 +50,16 @@ namespace {
 
 constexpr int kTileM = 128;      // chains per CTA
 constexpr int kTileN = 256;      // accumulator columns per MMA
-constexpr int kTileK = 16;       // floats per K stage: 64-byte rows, SWIZZLE_64B
-constexpr int kUmmaK = 8;        // tf32 elements per tcgen05.mma
+#ifndef GM_TC_F16
+#define GM_TC_F16 1              // 1: FP16 x 3 split (kind::f16, twice the TF32 MMA rate); 0: TF32 x 3 split (kind::tf32)
+#endif
+constexpr bool kF16 = (GM_TC_F16 != 0);
+// Operand rows are 64 bytes in both modes (SWIZZLE_64B): 32 halves or 16 tf32 words per K stage, two MMAs per stage.
+constexpr int kTileK = kF16 ? 32 : 16;   // elements per K stage
+constexpr int kUmmaK = kF16 ? 16 : 8;    // elements per tcgen05.mma
+constexpr int kOpElem = kF16 ? 2 : 4;    // bytes per operand element
 constexpr int kStages = 3;       // operand stages (A_hi, A_lo, P_hi, P_lo)
-constexpr int kRawStages = 4;    // raw delta tiles in flight ahead of the split
+constexpr int kRawStages = kF16 ? 3 : 4; // raw f32 delta tiles in flight ahead of the split (16 KB / 8 KB each)
 constexpr int kKPadUnit = 32;    // K is padded to a multiple of 32 floats in both layouts
 #ifndef GM_TC_CLUSTER
 #define GM_TC_CLUSTER 2          // CTAs per cluster sharing every P tile through TMA multicast (1 = no cluster)
@@ -56,10 +69,10 @@ constexpr int kEpiWarps = 8;        // two warps per TMEM lane quarter, interlea
 constexpr int kCvtWarps = 4;
 constexpr int kFirstCvtWarp = 3, kFirstEpiWarp = kFirstCvtWarp + kCvtWarps;
 constexpr int kGemmThreads = 32 * (kFirstEpiWarp + kEpiWarps);
-constexpr uint32_t kABytes = kTileM * kTileK * 4;   // 8 KB
-constexpr uint32_t kBBytes = kTileN * kTileK * 4;   // 16 KB
+constexpr uint32_t kABytes = kTileM * kTileK * kOpElem;   // 8 KB
+constexpr uint32_t kBBytes = kTileN * kTileK * kOpElem;   // 16 KB
 constexpr uint32_t kStageBytes = 2 * kABytes + 2 * kBBytes;   // 48 KB
-constexpr uint32_t kRawBytes = kABytes;
+constexpr uint32_t kRawBytes = kTileM * kTileK * 4;       // raw f32 tile: 16 KB (128-byte rows, SWIZZLE_128B) / 8 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -124,7 +137,11 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
+#if GM_TC_F16
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+#else
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+#endif
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -151,15 +168,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3fff);        // start address, bits [0,14)
   d |= (uint64_t)0 << 16;                            // leading byte offset (unused: K extent = one swizzle row)
-  constexpr uint32_t kRowBytes = kTileK * 4;         // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+  constexpr uint32_t kRowBytes = kTileK * kOpElem;   // 64: SWIZZLE_64B
   d |= (uint64_t)(((8 * kRowBytes) >> 4) & 0x3fff) << 32;   // stride byte offset between 8-row groups, bits [32,46)
   d |= (uint64_t)1 << 46;                            // descriptor version (sm_100), bits [46,48)
   d |= (uint64_t)4 << 61;                            // layout type SWIZZLE_64B, bits [61,64)
   return d;
 }
 
-// instruction descriptor: D f32, A/B tf32, both K-major, M = 128, N = 256
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+// instruction descriptor: D f32 (bits 4-5 = 1), A / B format (bits 7-9 / 10-12: 0 = f16, 2 = tf32), both K-major, M = 128, N = 256
+constexpr uint32_t kOpFmt = kF16 ? 0u : 2u;
+constexpr uint32_t kIdesc = (1u << 4) | (kOpFmt << 7) | (kOpFmt << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
@@ -176,6 +194,7 @@ struct GemmArgs {
   float coef;             // kick: p -= coef * z   (grad = -z)
   float drift_eps;
   float norm_const;
+  float zscale;           // the accumulator holds z / zscale (P is pre-scaled by a power of two in FP16 mode); coef carries it too
   float* logp_out;        // [C] or null: logp = c - 1/2 sum z * delta
   float* ke_out;          // [C] or null: 1/2 |p_new|^2
 };
@@ -242,7 +261,7 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
         mbar_expect_tx(&b_full[s], 2 * kBBytes);
         if constexpr (kCluster > 1) {
           const int half_rows = kTileN / kCluster;
-          const uint32_t off = crank * (uint32_t)(half_rows * kTileK * 4);
+          const uint32_t off = crank * (uint32_t)(half_rows * kTileK * kOpElem);
           tma_load_2d_mc(st + off, &map_bhi, &b_full[s], k * kTileK, n * kTileN + (int)crank * half_rows, kMask);
           tma_load_2d_mc(st + kBBytes + off, &map_blo, &b_full[s], k * kTileK, n * kTileN + (int)crank * half_rows, kMask);
         } else {
@@ -271,7 +290,7 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
           const uint64_t d_bhi = umma_desc(st + 2 * kABytes), d_blo = umma_desc(st + 2 * kABytes + kBBytes);
 #pragma unroll
           for (int kk = 0; kk < kTileK / kUmmaK; ++kk) {
-            const uint64_t adv = (uint64_t)((kk * kUmmaK * 4) >> 4);   // 32 bytes per K step inside the swizzle row
+            const uint64_t adv = (uint64_t)((kk * kUmmaK * kOpElem) >> 4);   // 32 bytes per K step inside the swizzle row
             tc_mma_tf32(tmem_d, d_alo + adv, d_bhi + adv, kIdesc, (k | kk) ? 1u : 0u);   // small terms first
             tc_mma_tf32(tmem_d, d_ahi + adv, d_blo + adv, kIdesc, 1u);
             tc_mma_tf32(tmem_d, d_ahi + adv, d_bhi + adv, kIdesc, 1u);
@@ -283,12 +302,39 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
       }
     }
   } else if (warp < kFirstEpiWarp) {
-    // ===== operand split: raw f32 tile -> hi = rna_tf32(x), lo = rna_tf32(x - hi), same (swizzled) byte offsets
+    // ===== operand split.  TF32 mode: raw f32 tile -> hi = rna_tf32(x), lo = rna_tf32(x - hi) at the same (swizzled) byte
+    // offsets.  FP16 mode: hi = half(x), lo = half(x - hi); the raw tile has 128-byte rows under SWIZZLE_128B (16-byte
+    // chunk c of row r sits at chunk c ^ (r & 7)), the operand tiles 64-byte rows under SWIZZLE_64B (chunk c of row r at
+    // c ^ ((r >> 1) & 3)); a thread turns 8 consecutive floats of a row into one 16-byte chunk of each operand tile.
     const int t = (warp - kFirstCvtWarp) * 32 + lane;          // 0..127
     for (int it = 0; it < n_iters; ++it) {
       const int r = it % kRawStages, s = it % kStages;
       mbar_wait(&raw_full[r], (uint32_t)(it / kRawStages) & 1u);
       mbar_wait(&empty[s], ((uint32_t)(it / kStages) & 1u) ^ 1u);
+#if GM_TC_F16
+      const unsigned char* src = raw_base + (size_t)r * kRawBytes;
+      unsigned char* dhi = base + (size_t)s * kStageBytes;
+      unsigned char* dlo = dhi + kABytes;
+#pragma unroll
+      for (int i = 0; i < (kTileM * 4) / (32 * kCvtWarps); ++i) {
+        const int u = t + i * 32 * kCvtWarps;
+        const int row = u >> 2, oc = u & 3, sw = row & 7;
+        const float4 x0 = *reinterpret_cast<const float4*>(src + row * 128 + (((2 * oc) ^ sw) << 4));
+        const float4 x1 = *reinterpret_cast<const float4*>(src + row * 128 + (((2 * oc + 1) ^ sw) << 4));
+        const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __half h0 = __float2half_rn(xs[2 * e]), h1 = __float2half_rn(xs[2 * e + 1]);
+          const __half l0 = __float2half_rn(xs[2 * e] - __half2float(h0)), l1 = __float2half_rn(xs[2 * e + 1] - __half2float(h1));
+          hw[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          lw[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        }
+        const int so = row * 64 + ((oc ^ ((row >> 1) & 3)) << 4);
+        *reinterpret_cast<uint4*>(dhi + so) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(dlo + so) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+#else
       const float4* src = reinterpret_cast<const float4*>(raw_base + (size_t)r * kRawBytes);
       float4* dhi = reinterpret_cast<float4*>(base + (size_t)s * kStageBytes);
       float4* dlo = reinterpret_cast<float4*>(base + (size_t)s * kStageBytes + kABytes);
@@ -301,6 +347,7 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
         dhi[t + i * 32 * kCvtWarps] = h;
         dlo[t + i * 32 * kCvtWarps] = l;
       }
+#endif
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
       __syncwarp();
       if (lane == 0) { mbar_arrive(&a_full[s]); mbar_arrive(&raw_empty[r]); }
@@ -384,7 +431,7 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
         for (int w = 0; w < kEpiWarps; ++w) {
           if (((w + kFirstEpiWarp) & 3) == q4) { qsum += tr_base[(size_t)w * 16 * 33 + lane]; ksum += tr_base[(size_t)w * 16 * 33 + 32 + lane]; }
         }
-        if (a.logp_out) a.logp_out[row0 + lane] = a.norm_const - 0.5f * qsum;
+        if (a.logp_out) a.logp_out[row0 + lane] = a.norm_const - 0.5f * (a.zscale * qsum);
         if (a.ke_out) a.ke_out[row0 + lane] = 0.5f * ksum;
       }
     }
@@ -493,16 +540,19 @@ EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-// 2-D f32 tensor [rows, cols] (cols contiguous), box [box_rows, kTileK floats], SWIZZLE_64B
-bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// 2-D tensor [rows, cols] (cols contiguous) of f32 (elem = 4) or f16 (elem = 2), box [box_rows, kTileK elements]; the
+// swizzle width equals the box row: 64 bytes (operands; raw tile in TF32 mode) or 128 bytes (raw f32 tile in FP16 mode)
+bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, int elem) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return false;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 4};
+  cuuint64_t strides[1] = {cols * (cuuint64_t)elem};
   cuuint32_t box[2] = {(cuuint32_t)kTileK, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  const bool wide = (kTileK * elem == 128);
+  return enc(m, elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 inline float host_tf32_rna(float x) {
@@ -521,7 +571,9 @@ inline float host_tf32_rna(float x) {
 struct DenseTc {
   int d = 0, kpad = 0, npad = 0;
   size_t n_chains = 0;
-  float *p = nullptr, *dl[2] = {nullptr, nullptr}, *b_hi = nullptr, *b_lo = nullptr, *mu = nullptr;
+  float *p = nullptr, *dl[2] = {nullptr, nullptr}, *mu = nullptr;
+  void *b_hi = nullptr, *b_lo = nullptr;   // P split into hi / lo operand arrays [npad, kpad]: tf32-in-f32 or f16
+  float zscale = 1.f;                      // 1 / (power-of-two scale applied to P before the FP16 split)
   float *logp0 = nullptr, *logp1 = nullptr, *ke0 = nullptr, *ke1 = nullptr;
   float norm_const = 0.f;
   CUtensorMap map_dl[2], map_bhi, map_blo;
@@ -548,27 +600,51 @@ DenseTc* dense_tc_create(size_t n_chains, int d, const double* params, const cha
   bool ok = cudaMalloc(&t->p, C * d * 4) == cudaSuccess &&
             cudaMalloc(&t->dl[0], C * (size_t)t->kpad * 4) == cudaSuccess && cudaMalloc(&t->dl[1], C * (size_t)t->kpad * 4) == cudaSuccess &&
             cudaMemset(t->dl[1], 0, C * (size_t)t->kpad * 4) == cudaSuccess &&
-            cudaMalloc(&t->b_hi, (size_t)t->npad * t->kpad * 4) == cudaSuccess && cudaMalloc(&t->b_lo, (size_t)t->npad * t->kpad * 4) == cudaSuccess &&
+            cudaMalloc(&t->b_hi, (size_t)t->npad * t->kpad * kOpElem) == cudaSuccess && cudaMalloc(&t->b_lo, (size_t)t->npad * t->kpad * kOpElem) == cudaSuccess &&
             cudaMalloc(&t->mu, (size_t)d * 4) == cudaSuccess && cudaMalloc(&t->logp0, C * 4) == cudaSuccess &&
             cudaMalloc(&t->logp1, C * 4) == cudaSuccess && cudaMalloc(&t->ke0, C * 4) == cudaSuccess && cudaMalloc(&t->ke1, C * 4) == cudaSuccess;
   if (!ok) { *err = e_alloc; dense_tc_destroy(t); return nullptr; }
   // B operand: rows = output column n, cols = k (K-major); P symmetric so B[n][k] = P[k][n] = P[n][k]
-  std::vector<float> bh((size_t)t->npad * t->kpad, 0.f), bl((size_t)t->npad * t->kpad, 0.f), mu(d);
+  std::vector<float> mu(d);
   for (int i = 0; i < d; ++i) mu[i] = (float)params[i];
-  for (int n = 0; n < d; ++n)
-    for (int k = 0; k < d; ++k) {
-      const float v = (float)params[(size_t)d + (size_t)k * d + n];
-      const float hi = host_tf32_rna(v);
-      bh[(size_t)n * t->kpad + k] = hi;
-      bl[(size_t)n * t->kpad + k] = host_tf32_rna(v - hi);
-    }
-  ok = cudaMemcpy(t->b_hi, bh.data(), bh.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
-       cudaMemcpy(t->b_lo, bl.data(), bl.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
-       cudaMemcpy(t->mu, mu.data(), (size_t)d * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+  const size_t nel = (size_t)t->npad * t->kpad;
+  if (kF16) {
+    // FP16 has 5 exponent bits: P is scaled by a power of two so that its largest entry sits near 2^12 (hi never
+    // overflows, lo = P s - hi stays normal down to entries 2^-14 times smaller); the epilogue undoes the scale.
+    double amax = 0.0;
+    for (size_t i = 0; i < (size_t)d * d; ++i) amax = std::max(amax, std::fabs(params[(size_t)d + i]));
+    int e = 0;
+    if (amax > 0.0) e = 12 - (int)std::ceil(std::log2(amax));
+    e = std::max(-24, std::min(24, e));
+    const float sc = std::ldexp(1.0f, e);
+    t->zscale = std::ldexp(1.0f, -e);
+    std::vector<__half> bh(nel, __float2half_rn(0.f)), bl(nel, __float2half_rn(0.f));
+    for (int n = 0; n < d; ++n)
+      for (int k = 0; k < d; ++k) {
+        const float v = (float)params[(size_t)d + (size_t)k * d + n] * sc;
+        const __half hi = __float2half_rn(v);
+        bh[(size_t)n * t->kpad + k] = hi;
+        bl[(size_t)n * t->kpad + k] = __float2half_rn(v - __half2float(hi));
+      }
+    ok = cudaMemcpy(t->b_hi, bh.data(), nel * 2, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(t->b_lo, bl.data(), nel * 2, cudaMemcpyHostToDevice) == cudaSuccess;
+  } else {
+    std::vector<float> bh(nel, 0.f), bl(nel, 0.f);
+    for (int n = 0; n < d; ++n)
+      for (int k = 0; k < d; ++k) {
+        const float v = (float)params[(size_t)d + (size_t)k * d + n];
+        const float hi = host_tf32_rna(v);
+        bh[(size_t)n * t->kpad + k] = hi;
+        bl[(size_t)n * t->kpad + k] = host_tf32_rna(v - hi);
+      }
+    ok = cudaMemcpy(t->b_hi, bh.data(), nel * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(t->b_lo, bl.data(), nel * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+  }
+  ok = ok && cudaMemcpy(t->mu, mu.data(), (size_t)d * 4, cudaMemcpyHostToDevice) == cudaSuccess;
   if (!ok) { *err = e_alloc; dense_tc_destroy(t); return nullptr; }
-  ok = make_map(&t->map_dl[0], t->dl[0], C, (uint64_t)t->kpad, kTileM) && make_map(&t->map_dl[1], t->dl[1], C, (uint64_t)t->kpad, kTileM) &&
-       make_map(&t->map_bhi, t->b_hi, (uint64_t)t->npad, (uint64_t)t->kpad, kTileN / kCluster) &&
-       make_map(&t->map_blo, t->b_lo, (uint64_t)t->npad, (uint64_t)t->kpad, kTileN / kCluster);
+  ok = make_map(&t->map_dl[0], t->dl[0], C, (uint64_t)t->kpad, kTileM, 4) && make_map(&t->map_dl[1], t->dl[1], C, (uint64_t)t->kpad, kTileM, 4) &&
+       make_map(&t->map_bhi, t->b_hi, (uint64_t)t->npad, (uint64_t)t->kpad, kTileN / kCluster, kOpElem) &&
+       make_map(&t->map_blo, t->b_lo, (uint64_t)t->npad, (uint64_t)t->kpad, kTileN / kCluster, kOpElem);
   if (!ok) { *err = e_map; dense_tc_destroy(t); return nullptr; }
   t->smem = (size_t)kStages * kStageBytes + (size_t)kRawStages * kRawBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ +
             (size_t)kEpiWarps * 16 * 33 * 4 /*epilogue transpose*/;
@@ -585,7 +661,7 @@ static cudaError_t gemm_kick(DenseTc* t, int buf, float coef, float drift_eps, f
   GemmArgs g;
   g.d = t->d; g.kpad = t->kpad; g.npad = t->npad; g.n_chains = t->n_chains;
   g.p = t->p; g.dl = t->dl[buf]; g.dl_next = drift_eps != 0.f ? t->dl[buf ^ 1] : nullptr;
-  g.coef = coef; g.drift_eps = drift_eps; g.norm_const = t->norm_const;
+  g.coef = coef * t->zscale; g.drift_eps = drift_eps; g.norm_const = t->norm_const; g.zscale = t->zscale;
   g.logp_out = logp_out; g.ke_out = ke_out;
   unsigned blocks = (unsigned)((t->n_chains + kTileM - 1) / kTileM);
   blocks = (blocks + kCluster - 1) / kCluster * kCluster;   // whole clusters; a surplus CTA only feeds the multicast
