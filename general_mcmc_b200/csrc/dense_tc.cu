@@ -12,7 +12,8 @@
 //     the TF32 rate).  FP16 products are exact in FP32.  P is pre-scaled by a power of two so that its entries use
 //     the upper part of FP16's exponent range (the epilogue undoes it); delta = q - mu is O(1..10), and a low part
 //     that falls into the subnormals costs at most 2^-25 absolute.  Measured against the f64 oracle at d = 1000,
-//     L = 32: same error as the TF32 split (tests/test_gpu_dense_tc.py holds both to 2e-5); 7.5e7 -> 9.3e7 grad-evals/s.
+//     L = 32: same error as the TF32 split (tests/test_gpu_dense_tc.py holds both to 2e-5); 7.5e7 -> 9.3e7 grad-evals/s
+//     (1.1e8 with the persistent unit schedule below).
 //   GM_TC_F16 = 0: hi = rna_tf32(x), lo = rna_tf32(x - hi), tcgen05.mma.kind::tf32 (K = 8).
 //
 // State: the trajectory runs in delta-space.  p [C, d] and delta [C, kpad] (two ping-pong buffers, padded columns
@@ -195,6 +196,7 @@ struct GemmArgs {
   float drift_eps;
   float norm_const;
   float zscale;           // the accumulator holds z / zscale (P is pre-scaled by a power of two in FP16 mode); coef carries it too
+  int persist;            // 1: the grid is a set of persistent clusters walking (row-tile group, column chunk) units (no row sums)
   float* logp_out;        // [C] or null: logp = c - 1/2 sum z * delta
   float* ke_out;          // [C] or null: 1/2 |p_new|^2
 };
@@ -217,10 +219,24 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
   float* tr_base = reinterpret_cast<float*>(raw_base + (size_t)kRawStages * kRawBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kTileM;
   const int n_chunks = a.npad / kTileN;
   const int k_chunks = a.kpad / kTileK;
-  const int n_iters = n_chunks * k_chunks;
+  // Work units = (group of kCluster adjacent row tiles, column chunk), chunk fastest.  persist = 0: cluster c owns group c
+  // and walks its n_chunks units (needed at the trajectory ends, where the row sums run over all columns).  persist = 1:
+  // the grid is one cluster per SM pair; cluster c takes units c, c + W, c + 2W, ... — 512 row tiles on 148 SMs are 3.46
+  // waves of whole tiles but 13.8 rounds of units.
+  const int cluster_id = (int)blockIdx.x / kCluster, n_clusters = (int)gridDim.x / kCluster;
+  const int my_rank = (int)blockIdx.x - cluster_id * kCluster;
+  const int n_groups = (int)((a.n_chains + (size_t)kTileM * kCluster - 1) / ((size_t)kTileM * kCluster));
+  const int n_units_all = n_groups * n_chunks;
+  const int n_units = a.persist ? (cluster_id < n_units_all ? (n_units_all - cluster_id + n_clusters - 1) / n_clusters : 0) : n_chunks;
+  auto unit_of = [&](int j, int& m0, int& n) {
+    const int u = a.persist ? cluster_id + j * n_clusters : cluster_id * n_chunks + j;
+    const int grp = u / n_chunks;
+    n = u - grp * n_chunks;
+    m0 = (grp * kCluster + my_rank) * kTileM;
+  };
+  const int n_iters = n_units * k_chunks;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&a_full[i], kCvtWarps); mbar_init(&empty[i], kCluster); }
@@ -247,6 +263,8 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
         const int r = it % kRawStages;
         mbar_wait(&raw_empty[r], ((uint32_t)(it / kRawStages) & 1u) ^ 1u);
         mbar_expect_tx(&raw_full[r], kRawBytes);
+        int m0, n;
+        unit_of(it / k_chunks, m0, n);
         tma_load_2d(raw_base + (size_t)r * kRawBytes, &map_dl, &raw_full[r], (it % k_chunks) * kTileK, m0);
       }
     }
@@ -255,7 +273,9 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
       // ===== P tiles: my half of every tile, multicast to the cluster
       for (int it = 0; it < n_iters; ++it) {
         const int s = it % kStages;
-        const int n = it / k_chunks, k = it % k_chunks;
+        const int k = it % k_chunks;
+        int m0, n;
+        unit_of(it / k_chunks, m0, n);
         mbar_wait(&empty[s], ((uint32_t)(it / kStages) & 1u) ^ 1u);
         unsigned char* st = base + (size_t)s * kStageBytes + 2 * kABytes;
         mbar_expect_tx(&b_full[s], 2 * kBBytes);
@@ -274,9 +294,9 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
     if (lane == 0) {
       // ===== MMA issuer
       int it = 0;
-      for (int n = 0; n < n_chunks; ++n) {
-        const int acc = n & 1;
-        mbar_wait(&tempty[acc], (uint32_t)((n >> 1) & 1) ^ 1u);
+      for (int j = 0; j < n_units; ++j) {
+        const int acc = j & 1;
+        mbar_wait(&tempty[acc], (uint32_t)((j >> 1) & 1) ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kTileN);
         for (int k = 0; k < k_chunks; ++k, ++it) {
@@ -362,12 +382,16 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
     // the kEpiWarps / 4 warps that share a quarter interleave over the 32-column blocks
     int cb_first = 0;
     for (int w = kFirstEpiWarp; w < warp; ++w) cb_first += ((w & 3) == q4) ? 1 : 0;
-    const size_t row0 = (size_t)m0 + (size_t)q4 * 32;
-    const int nrows = row0 < a.n_chains ? (int)((a.n_chains - row0) < 32 ? (a.n_chains - row0) : 32) : 0;
-    float quad = 0.f, ke = 0.f;                  // lane r holds the sums of row r
-    for (int n = 0; n < n_chunks; ++n) {
-      const int acc = n & 1;
-      mbar_wait(&tfull[acc], (uint32_t)((n >> 1) & 1));
+    size_t row0 = 0;
+    int nrows = 0;
+    float quad = 0.f, ke = 0.f;                  // lane r holds the sums of row r (persist = 0: one row tile per CTA)
+    for (int j = 0; j < n_units; ++j) {
+      int m0, n;
+      unit_of(j, m0, n);
+      row0 = (size_t)m0 + (size_t)q4 * 32;
+      nrows = row0 < a.n_chains ? (int)((a.n_chains - row0) < 32 ? (a.n_chains - row0) : 32) : 0;
+      const int acc = j & 1;
+      mbar_wait(&tfull[acc], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
 #pragma unroll 1
       for (int cb = cb_first; cb < kTileN / 32; cb += kEpiWarps / 4) {
@@ -574,6 +598,7 @@ struct DenseTc {
   float *p = nullptr, *dl[2] = {nullptr, nullptr}, *mu = nullptr;
   void *b_hi = nullptr, *b_lo = nullptr;   // P split into hi / lo operand arrays [npad, kpad]: tf32-in-f32 or f16
   float zscale = 1.f;                      // 1 / (power-of-two scale applied to P before the FP16 split)
+  int sms = 0;                             // SMs of the device (persistent grid size)
   float *logp0 = nullptr, *logp1 = nullptr, *ke0 = nullptr, *ke1 = nullptr;
   float norm_const = 0.f;
   CUtensorMap map_dl[2], map_bhi, map_blo;
@@ -593,6 +618,7 @@ DenseTc* dense_tc_create(size_t n_chains, int d, const double* params, const cha
   static const char* e_map = "dense tensor-core path: cuTensorMapEncodeTiled unavailable or failed";
   DenseTc* t = new DenseTc();
   t->d = d; t->n_chains = n_chains;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&t->sms, cudaDevAttrMultiProcessorCount, dev); }
   t->kpad = ((d + kKPadUnit - 1) / kKPadUnit) * kKPadUnit;
   t->npad = ((d + kTileN - 1) / kTileN) * kTileN;
   t->norm_const = (float)params[(size_t)d + (size_t)d * d];
@@ -665,6 +691,9 @@ static cudaError_t gemm_kick(DenseTc* t, int buf, float coef, float drift_eps, f
   g.logp_out = logp_out; g.ke_out = ke_out;
   unsigned blocks = (unsigned)((t->n_chains + kTileM - 1) / kTileM);
   blocks = (blocks + kCluster - 1) / kCluster * kCluster;   // whole clusters; a surplus CTA only feeds the multicast
+  // no row sums wanted (every launch but the two trajectory ends): persistent clusters over (row-tile group, chunk) units
+  g.persist = (!logp_out && !ke_out && t->sms > 0 && blocks > (unsigned)t->sms) ? 1 : 0;
+  if (g.persist) blocks = (unsigned)(t->sms / kCluster) * kCluster;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = t->smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
