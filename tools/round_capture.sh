@@ -23,4 +23,6 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 timeout 200 ncu --set full --import-source on --clock-control none -k regex:stats_accumulate_warp -s 1 -c 1 -o $out/r1_full_stats_warp -f python tools/stats_bench.py > $out/ncu_stats.log 2>&1
 timeout 200 ncu --set full --import-source on --clock-control none -k regex:mh_run2 -s 2 -c 1 -o $out/r1_full_mh2 -f python bench.py --workload mh_gauss2d --steps 2000 --warmup 1000 --no-cpu > $out/ncu_mh2.log 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:nuts_run_kernel -s 1 -c 1 -o $out/r1_full_nuts -f python bench.py --workload nuts_mixture --steps 200 --warmup 20 --no-cpu > $out/ncu_nuts.log 2>&1
-ls -la $out/*.ncu-rep | tail -5
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:dense_gemm_kick -s 40 -c 1 -o $out/r1_full_dense -f python bench.py --workload hmc_dense --steps 4 --warmup 3 --no-cpu > $out/ncu_dense.log 2>&1
+timeout 200 ncu --set full --import-source on --clock-control none -k regex:hmc_run_kernel -s 101 -c 1 -o $out/r1_full_hmc -f python bench.py --steps 300 --warmup 100 --no-cpu --no-ess > $out/ncu_hmc.log 2>&1
+ls -la $out/*.ncu-rep | tail -6
