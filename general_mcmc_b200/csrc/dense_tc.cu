@@ -59,8 +59,14 @@ constexpr bool kF16 = (GM_TC_F16 != 0);
 constexpr int kTileK = kF16 ? 32 : 16;   // elements per K stage
 constexpr int kUmmaK = kF16 ? 16 : 8;    // elements per tcgen05.mma
 constexpr int kOpElem = kF16 ? 2 : 4;    // bytes per operand element
-constexpr int kStages = 3;       // operand stages (A_hi, A_lo, P_hi, P_lo)
-constexpr int kRawStages = kF16 ? 3 : 4; // raw f32 delta tiles in flight ahead of the split (16 KB / 8 KB each)
+#ifndef GM_TC_STAGES
+#define GM_TC_STAGES 3
+#endif
+#ifndef GM_TC_RAW_STAGES
+#define GM_TC_RAW_STAGES (GM_TC_F16 ? 3 : 4)
+#endif
+constexpr int kStages = GM_TC_STAGES;         // operand stages (A_hi, A_lo, P_hi, P_lo)
+constexpr int kRawStages = GM_TC_RAW_STAGES;  // raw f32 delta tiles in flight ahead of the split (16 KB / 8 KB each)
 constexpr int kKPadUnit = 32;    // K is padded to a multiple of 32 floats in both layouts
 #ifndef GM_TC_CLUSTER
 #define GM_TC_CLUSTER 2          // CTAs per cluster sharing every P tile through TMA multicast (1 = no cluster)
@@ -345,10 +351,12 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
         uint32_t hw[4], lw[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const __half h0 = __float2half_rn(xs[2 * e]), h1 = __float2half_rn(xs[2 * e + 1]);
-          const __half l0 = __float2half_rn(xs[2 * e] - __half2float(h0)), l1 = __float2half_rn(xs[2 * e + 1] - __half2float(h1));
-          hw[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-          lw[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+          // packed conversions (F2FP.F16.F32.PACK_AB: one FMA-pipe instruction per pair, not the quarter-rate XU F2F)
+          const __half2 h = __floats2half2_rn(xs[2 * e], xs[2 * e + 1]);
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn(xs[2 * e] - hf.x, xs[2 * e + 1] - hf.y);
+          hw[e] = *reinterpret_cast<const uint32_t*>(&h);
+          lw[e] = *reinterpret_cast<const uint32_t*>(&l);
         }
         const int so = row * 64 + ((oc ^ ((row >> 1) & 3)) << 4);
         *reinterpret_cast<uint4*>(dhi + so) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -399,6 +407,9 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
         tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * kTileN + cb * 32), z);
         const int c0 = n * kTileN + cb * 32;
         if (c0 >= a.d) continue;                 // padded columns (warp-uniform)
+#ifdef GM_TC_EXPERIMENT_NOEPI
+        if (z[0] != 123456.f) continue;          // timing experiment only: drain TMEM, skip the update
+#endif
         const int col = c0 + lane;
         const bool col_ok = col < a.d;
 #pragma unroll 1
@@ -409,27 +420,43 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
             for (int c = 0; c < 32; ++c) tr[(lane & 15) * 33 + c] = z[c];
           }
           __syncwarp();
+          // block pointers once per 16 rows; the rows then advance by d / kpad elements
+          float* p_blk = a.p + (row0 + rb) * (size_t)a.d + col;
+          const float* dl_blk = a.dl + (row0 + rb) * (size_t)a.kpad + col;
+          const uint32_t d32 = (uint32_t)a.d, k32 = (uint32_t)a.kpad;
           float pv[16], dv[16];
+          if (a.dl_next && !a.logp_out && !a.ke_out && nrows == 32 && c0 + 32 <= a.d) {
+            // fast path (every launch but the trajectory ends, every full 16 x 32 block): no bounds tests, no row sums
+            float* dn_blk = a.dl_next + (row0 + rb) * (size_t)a.kpad + col;
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) { pv[rr] = __ldcs(p_blk + rr * d32); dv[rr] = dl_blk[rr * k32]; }
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) {
+              const float pn = fmaf(-a.coef, tr[rr * 33 + lane], pv[rr]);
+              __stcs(p_blk + rr * d32, pn);
+              dn_blk[rr * k32] = fmaf(a.drift_eps, pn, dv[rr]);
+            }
+            continue;
+          }
 #pragma unroll
           for (int rr = 0; rr < 16; ++rr) {
             const int r = rb + rr;
             pv[rr] = 0.f; dv[rr] = 0.f;
             if (r < nrows && col_ok) {
-              pv[rr] = __ldcs(a.p + (row0 + r) * (size_t)a.d + col);
-              dv[rr] = a.dl[(row0 + r) * (size_t)a.kpad + col];
+              pv[rr] = __ldcs(p_blk + rr * d32);
+              dv[rr] = dl_blk[rr * k32];
             }
           }
 #pragma unroll
           for (int rr = 0; rr < 16; ++rr) {
             const int r = rb + rr;
             if (r < nrows) {
-              const size_t row = row0 + r;
               const float zv = tr[rr * 33 + lane];
               float pn = 0.f;
               if (col_ok) {
                 pn = fmaf(-a.coef, zv, pv[rr]);
-                __stcs(a.p + row * (size_t)a.d + col, pn);
-                if (a.dl_next) a.dl_next[row * (size_t)a.kpad + col] = fmaf(a.drift_eps, pn, dv[rr]);
+                __stcs(p_blk + rr * d32, pn);
+                if (a.dl_next) a.dl_next[(row0 + r) * (size_t)a.kpad + col] = fmaf(a.drift_eps, pn, dv[rr]);
               }
               if (a.logp_out || a.ke_out) {          // trajectory ends only: row sums over the 32 columns
                 float s1 = zv * dv[rr], s2 = pn * pn;
