@@ -407,8 +407,8 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
         tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * kTileN + cb * 32), z);
         const int c0 = n * kTileN + cb * 32;
         if (c0 >= a.d) continue;                 // padded columns (warp-uniform)
-#ifdef GM_TC_EXPERIMENT_NOEPI
-        if (z[0] != 123456.f) continue;          // timing experiment only: drain TMEM, skip the update
+#ifdef GM_TC_EXPERIMENT_NOEPI   // timing experiments (wrong results): -DGM_TC_EXPERIMENT_NOEPI / _NOLOAD / _NOSTORE, see DESIGN.md K3
+        if (z[0] != 123456.f) continue;
 #endif
         const int col = c0 + lane;
         const bool col_ok = col < a.d;
@@ -429,12 +429,20 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
             // fast path (every launch but the trajectory ends, every full 16 x 32 block): no bounds tests, no row sums
             float* dn_blk = a.dl_next + (row0 + rb) * (size_t)a.kpad + col;
 #pragma unroll
+#ifdef GM_TC_EXPERIMENT_NOLOAD
+            for (int rr = 0; rr < 16; ++rr) { pv[rr] = 1.f; dv[rr] = 2.f; }
+#else
             for (int rr = 0; rr < 16; ++rr) { pv[rr] = __ldcs(p_blk + rr * d32); dv[rr] = dl_blk[rr * k32]; }
+#endif
 #pragma unroll
             for (int rr = 0; rr < 16; ++rr) {
               const float pn = fmaf(-a.coef, tr[rr * 33 + lane], pv[rr]);
+#ifdef GM_TC_EXPERIMENT_NOSTORE
+              if (pn == 123456.f) { __stcs(p_blk + rr * d32, pn); dn_blk[rr * k32] = fmaf(a.drift_eps, pn, dv[rr]); }
+#else
               __stcs(p_blk + rr * d32, pn);
               dn_blk[rr * k32] = fmaf(a.drift_eps, pn, dv[rr]);
+#endif
             }
             continue;
           }
