@@ -165,7 +165,7 @@ DEFAULT_CHAINS = {"hmc_rosenbrock": 65536, "mh_gauss2d": 1048576, "hmc_dense": 6
 NCU_TRAFFIC = {
     "hmc_rosenbrock": {"bytes": 27.2e6 + 2.592e9, "launch": "65,536 chains x 100 transitions", "source": "profiles/r1_hmc_run_kernel_full.txt"},
     "mh_gauss2d": {"bytes": 17.4e6 + 16.735e9, "launch": "1,048,576 chains x 1000 steps", "source": "profiles/r1_mh_run2_kernel_full.txt"},
-    "hmc_dense": {"bytes": 0.674e9 + 0.472e9, "launch": "one persistent-schedule gradient GEMM of 65,536 chains, d = 1000", "source": "profiles/r1_dense_gemm_kick_full.txt"},
+    "hmc_dense": {"bytes": 0.666e9 + 0.479e9, "launch": "one persistent-schedule gradient GEMM of 65,536 chains, d = 1000", "source": "profiles/r1_dense_gemm_kick_full.txt"},
     "nuts_mixture": {"bytes": 47.5e6 + 5.380e9, "launch": "65,536 chains x 200 transitions", "source": "profiles/r1_nuts_run_kernel_full.txt"},
 }
 
