@@ -164,7 +164,7 @@ def cpu_mh_rate(target_seconds=12.0):
 DEFAULT_CHAINS = {"hmc_rosenbrock": 65536, "mh_gauss2d": 1048576, "hmc_dense": 65536, "nuts_mixture": 65536}
 NCU_TRAFFIC = {
     "hmc_rosenbrock": {"bytes": 27.2e6 + 2.592e9, "launch": "65,536 chains x 100 transitions", "source": "profiles/r1_hmc_run_kernel_full.txt"},
-    "mh_gauss2d": {"bytes": 17.4e6 + 16.735e9, "launch": "1,048,576 chains x 1000 steps", "source": "profiles/r1_mh_run2_kernel_full.txt"},
+    "mh_gauss2d": {"bytes": 17.1e6 + 16.735e9, "launch": "1,048,576 chains x 1000 steps", "source": "profiles/r1_mh_run2_kernel_full.txt"},
     "hmc_dense": {"bytes": 0.666e9 + 0.479e9, "launch": "one persistent-schedule gradient GEMM of 65,536 chains, d = 1000", "source": "profiles/r1_dense_gemm_kick_full.txt"},
     "nuts_mixture": {"bytes": 47.5e6 + 5.380e9, "launch": "65,536 chains x 200 transitions", "source": "profiles/r1_nuts_run_kernel_full.txt"},
 }
@@ -399,7 +399,7 @@ def run_ours(args, rank, world, local):
             bytes_per_step * args.steps / (ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "mh_run2_kernel<double, Gaussian2D>", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / pk["hbm_gbs"], "traffic": NCU_TRAFFIC[args.workload]["bytes"] if (chains == DEFAULT_CHAINS[args.workload] and args.dim in (0, 1000)) else None, "traffic_unit": "bytes per launch (ncu: %s, %s)" % (NCU_TRAFFIC[args.workload]["source"], NCU_TRAFFIC[args.workload]["launch"]), "peak_source": pk["source"],
-                "algorithmic_bytes_per_unit": 16, "note": "co-bound by instruction dispatch: 103 warp-instructions per chain-step, ~70 on half-rate pipes (Philox4x32-10 = 20 LOP3 + 20 IMAD.WIDE, 13 FP64); a write-only stream of the same 256-byte pieces reaches 5.3 TB/s (tools/microbench_write.cu)"}
+                "algorithmic_bytes_per_unit": 16, "note": "co-bound by instruction dispatch (Philox4x32-10 LOP3 / IMAD.WIDE, 13 FP64 and the selects sit on half-rate pipes; one Philox block feeds two transitions); a write-only stream of the same 256-byte pieces reaches 5.3 TB/s (tools/microbench_write.cu)"}
     else:
         fp32_peak = C.c_double(0)
         L.check(lib.gmcmc_measure_fp32_peak(ctx._h, C.byref(fp32_peak)))

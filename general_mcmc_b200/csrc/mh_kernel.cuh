@@ -333,14 +333,12 @@ __global__ void __launch_bounds__(kMhBlock, GM_MH_MINB) mh_run_kernel(const MhAr
 // K2 fast path: d == 2 (every 2-D target; BASELINE config 2), fast math mode, production (no injected
 // draws).  Same transition as mh_run_kernel; what differs is how the per-step cost is kept near the 16
 // bytes the step writes:
-//   * one Philox block per transition, computed one transition AHEAD (it does not depend on the chain
-//     state, so its 40 integer instructions fill the issue slots under the f64 dependency chain);
-//   * uniforms are built without int->float conversions: the top 23 bits of a word become the mantissa
-//     of a float in [1,2) (one LEA.HI), u = f - (1 - 2^-24) = (k + 1/2) 2^-23 in (0,1);
-//   * the accept test runs in the linear domain: e = ex2.approx(log_ratio * log2 e) against the 23-bit
-//     uniform, and only when |e - u| is inside the combined error bound (2^-24 truncation of u + MUFU /
-//     rounding error of e) is the full-width uniform built and `log_ratio > ln u` evaluated in T — the
-//     decision is always the full-precision one (metropolis_hastings.rs:313-316);
+//   * one Philox block per TWO transitions (20-bit radius / angle uniforms, a 23-bit accept uniform: 64 bits per
+//     transition), the inputs of transition s + 1 produced while transition s runs its f64 dependency chain;
+//   * uniforms are built without int->float conversions: bits become the mantissa of a float in [1,2);
+//   * the accept test runs in the linear domain: e = ex2.approx(log_ratio * log2 e) against the uniform, and only
+//     when |e - u| is inside the error bound of e (MUFU + argument rounding) is `log_ratio > ln u` evaluated in T
+//     with the same uniform — the decision is always the full-precision one (metropolis_hastings.rs:313-316);
 //   * the f64 sample of a step is ONE 16-byte unit: it is staged with st.shared.v2 under an XOR swizzle
 //     (conflict-free for the per-chain writes and for the per-row reads) and flushed every GM_MH2_STEPS
 //     steps as LDS.128 + STG.128 pairs, 256 (16 steps) or 512 (32 steps) contiguous bytes per chain.
@@ -357,7 +355,7 @@ __global__ void __launch_bounds__(kMhBlock, GM_MH_MINB) mh_run_kernel(const MhAr
 #define GM_MH2_MINB 6
 #endif
 #ifndef GM_MH2_UNROLL
-#define GM_MH2_UNROLL 4
+#define GM_MH2_UNROLL 8
 #endif
 constexpr int kMh2Steps = GM_MH2_STEPS;   // steps staged per chain between flushes: 16 (256 B per chain) or 32 (512 B)
 constexpr int kMh2Unroll = GM_MH2_UNROLL;
@@ -365,11 +363,10 @@ constexpr int kMh2Row = kMh2Steps * 16;   // bytes of one chain's stage row
 constexpr size_t kMh2Smem = (size_t)kMhBlock * kMh2Row;
 static_assert(kMh2Steps == 16 || kMh2Steps == 32, "the flush maps 32 lanes onto 16-byte units of one or two chains");
 
-__device__ __forceinline__ float mant_float(uint32_t w) { return __uint_as_float((w >> 9) + 0x3f800000u); }  // [1,2)
 
 template <class T, int KIND>
 __global__ void __launch_bounds__(kMhBlock, GM_MH2_MINB) mh_run2_kernel(const MhArgs<T> a) {
-  extern __shared__ __align__(16) unsigned char stage[];   // kMhBlock rows of kMh2Row bytes
+  extern __shared__ __align__(1024) unsigned char stage[];   // kMhBlock rows of kMh2Row bytes (row-aligned: the flush XORs address bits)
 
   const size_t chain = (size_t)blockIdx.x * kMhBlock + threadIdx.x;
   const bool active = chain < a.n_chains;
@@ -399,47 +396,67 @@ __global__ void __launch_bounds__(kMhBlock, GM_MH2_MINB) mh_run2_kernel(const Mh
   T lp_cur = mh_logp<T, 2, KIND, true>(a, inv, x);
   unsigned int n_accept = 0;
 
-  // Software pipeline: the random inputs of transition s + 1 (Philox block -> Box-Muller pair, accept words) are
-  // produced while transition s runs its state-dependent f64 chain; they do not depend on the chain state.
-  float z0, z1; uint32_t wz, ww;
-  auto draw = [&](const uint32_t step) {
-    const uint4 r = philox4x32_10(philox_ctr(gchain, step, 0u, 0u), rk);
-    // proposal noise (distributions.rs:368-376): Box-Muller on words 0 and 1
-    const float u_rad = mant_float(r.x) - 0.99999994039535522461f;          // (k + 1/2) 2^-23
-    const float ang = fmaf(mant_float(r.y), 6.283185307179586f, -9.42477796076938f);   // [-pi, pi)
+  // Random inputs.  ONE Philox block feeds TWO transitions (Philox4x32-10 is 40 of the kernel's ~100 instructions per
+  // step): transition t (absolute index) takes words (0, 1) of block t >> 1 when t is even, words (2, 3) when odd.  Of a
+  // word pair (w0, w1): bits 31..12 of w0 -> radius uniform (k + 1/2) 2^-20, bits 31..12 of w1 -> angle
+  // 2 pi (k + 1/2) 2^-20 - pi (a grid that maps onto itself under z -> -z, so the proposal stays exactly symmetric),
+  // the low 12 + 11 bits -> the accept uniform (k + 1/2) 2^-23, which IS the uniform of this mode (no hidden bits).
+  // The inputs of transition s + 1 are produced while transition s runs its state-dependent f64 chain.
+  float z0, z1, ua;
+  uint32_t sv0 = 0u, sv1 = 0u;      // words (2, 3) of the current block: the odd transition's pair
+  auto derive = [&](const uint32_t w0, const uint32_t w1) {
+    // proposal noise (distributions.rs:368-376): Box-Muller
+    const float u_rad = __uint_as_float(((w0 >> 9) & 0x007ffff8u) | 0x3f800000u) - 0.999999523162841796875f;   // f - (1 - 2^-21)
+    const float ang = fmaf(__uint_as_float(((w1 >> 9) & 0x007ffff8u) | 0x3f800000u), 6.283185307179586f, -9.424774964f);  // -3 pi + pi 2^-20
     float rad, sn, cs;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(u_rad));
     rad *= -1.3862943611198906f;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(rad));
     asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
     asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ang));
-    z0 = rad * cs; z1 = rad * sn; wz = r.z; ww = r.w;
+    z0 = rad * cs; z1 = rad * sn;
+    ua = __uint_as_float(((w0 & 0xfffu) << 11) | (w1 & 0x7ffu) | 0x3f800000u) - 0.99999994039535522461f;     // (k + 1/2) 2^-23
   };
-  draw(a.step_base);
+  // MODE 1: t is even (new block); 0: t is odd (saved words); 2: decided at run time (burn-in and tail loops)
+  auto draw = [&](auto mode, const uint32_t t) {
+    constexpr int MODE = decltype(mode)::value;
+    uint32_t w0 = sv0, w1 = sv1;
+    if (MODE == 1 || (MODE == 2 && (t & 1u) == 0u)) {
+      const uint4 r = philox4x32_10(philox_ctr(gchain, t >> 1, 0u, 0u), rk);
+      w0 = r.x; w1 = r.y; sv0 = r.z; sv1 = r.w;
+    }
+    derive(w0, w1);
+  };
+  using Saved = std::integral_constant<int, 0>;
+  using Fresh = std::integral_constant<int, 1>;
+  using Either = std::integral_constant<int, 2>;
+  {
+    const uint4 r = philox4x32_10(philox_ctr(gchain, a.step_base >> 1, 0u, 0u), rk);
+    sv0 = r.z; sv1 = r.w;
+    if (a.step_base & 1u) derive(r.z, r.w); else derive(r.x, r.y);
+  }
 
-  auto transition = [&](const uint32_t s) {
-    const float c0 = z0, c1 = z1; const uint32_t cz = wz, cw = ww;
-    draw(a.step_base + s + 1u);
+  auto transition = [&](const uint32_t s, auto next_mode) {     // next_mode: how transition s + 1 gets its word pair
+    const float c0 = z0, c1 = z1, cu = ua;
+    draw(next_mode, a.step_base + s + 1u);
     T xp[2];
     xp[0] = x[0] + (T)c0 * a.prop_std;
     xp[1] = x[1] + (T)c1 * a.prop_std;
     // ---- log acceptance ratio (metropolis_hastings.rs:308-312); symmetric proposal: q_fwd == q_bwd bit-for-bit
     const T lp_prop = mh_logp<T, 2, KIND, true>(a, inv, xp);
     const T log_ratio = lp_prop - lp_cur;
-    // ---- accept iff log_ratio > ln u (strict; metropolis_hastings.rs:313-316), u from words 2 (and 3)
-    const float u_acc = mant_float(cz) - 0.99999994039535522461f;
+    // ---- accept iff log_ratio > ln u (strict; metropolis_hastings.rs:313-316).  Linear-domain test first; inside the
+    // error bound of e (MUFU + rounding of its argument) the comparison is redone in T with the very same uniform.
     const float lr32 = (float)log_ratio;
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(lr32 * 1.4426950408889634f));
-    const float diff = e - u_acc;
-    const float tol = fmaf(e * (1.0f + fabsf(lr32)), 1e-6f, 5.9604644775390625e-08f);
+    const float diff = e - cu;
+    const float tol = e * (1.0f + fabsf(lr32)) * 1e-6f;
     bool accept;
     if (fabsf(diff) > tol) {
       accept = diff > 0.0f;
     } else {
-      T u;
-      if constexpr (sizeof(T) == 8) u = u01d(cz, cw); else u = u01(cz);
-      accept = log_ratio > log(u);
+      accept = log_ratio > log((T)cu);
     }
     x[0] = accept ? xp[0] : x[0];
     x[1] = accept ? xp[1] : x[1];
@@ -449,7 +466,7 @@ __global__ void __launch_bounds__(kMhBlock, GM_MH2_MINB) mh_run2_kernel(const Mh
 
   uint32_t s = 0;
   const uint32_t n_skip = a.n_skip < a.n_steps ? a.n_skip : a.n_steps;
-  for (; s < n_skip; ++s) transition(s);                 // burn-in: nothing recorded
+  for (; s < n_skip; ++s) transition(s, Either{});       // burn-in: nothing recorded
   if (a.out) {
     // this lane's flush destination: [chain = warp_first + f_sub (+kCpi per iteration), slot = out_t0 + f_t (+S per flush)]
     double* out_lane = a.out + ((warp_first_chain + f_sub) * a.out_n + a.out_t0 + f_t) * 2;
@@ -459,10 +476,12 @@ __global__ void __launch_bounds__(kMhBlock, GM_MH2_MINB) mh_run2_kernel(const Mh
       if (f_t < cnt) {
         double* dst = out_lane;
         if (warp_rows == 32) {
+          // chain c = kCpi i + f_sub: c & mask = ((kCpi i) & mask) ^ f_sub (f_sub only occupies the bit kCpi i leaves free), so
+          // the swizzled address is one XOR of a per-lane base with a compile-time constant, plus a compile-time row offset
+          const uint32_t lane_base = stage_base + (uint32_t)f_sub * kMh2Row + ((uint32_t)(f_t ^ f_sub) << 4);
 #pragma unroll
           for (int i = 0; i < 32 / kCpi; ++i) {
-            const int c = kCpi * i + f_sub;
-            const uint32_t addr = stage_base + (uint32_t)c * kMh2Row + ((uint32_t)(f_t ^ (c & kColMask)) << 4);
+            const uint32_t addr = (lane_base ^ ((uint32_t)((kCpi * i) & kColMask) << 4)) + (uint32_t)(kCpi * i) * kMh2Row;
             double v0, v1;
             asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(addr));
             __stcs(reinterpret_cast<double2*>(dst), make_double2(v0, v1));
@@ -487,19 +506,27 @@ __global__ void __launch_bounds__(kMhBlock, GM_MH2_MINB) mh_run2_kernel(const Mh
     auto record = [&](const int t) {
       asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(st_addr ^ ((uint32_t)t << 4)), "d"((double)x[0]), "d"((double)x[1]) : "memory");
     };
+    // groups of kMh2Steps recorded transitions; the parity of the absolute index is the same at every group start, so
+    // inside a group it is a compile-time fact which transitions open a new Philox block
+    const bool start_even = ((a.step_base + s) & 1u) == 0u;
     while (a.n_steps - s >= (uint32_t)kMh2Steps) {
-#pragma unroll kMh2Unroll
-      for (int t = 0; t < kMh2Steps; ++t) { transition(s + t); record(t); }
+      if (start_even) {
+#pragma unroll kMh2Unroll / 2
+        for (int t = 0; t < kMh2Steps; t += 2) { transition(s + t, Saved{}); record(t); transition(s + t + 1, Fresh{}); record(t + 1); }
+      } else {
+#pragma unroll kMh2Unroll / 2
+        for (int t = 0; t < kMh2Steps; t += 2) { transition(s + t, Fresh{}); record(t); transition(s + t + 1, Saved{}); record(t + 1); }
+      }
       s += kMh2Steps;
       flush(kMh2Steps);
     }
     if (s < a.n_steps) {
       int t = 0;
-      for (; s < a.n_steps; ++s, ++t) { transition(s); record(t); }
+      for (; s < a.n_steps; ++s, ++t) { transition(s, Either{}); record(t); }
       flush(t);
     }
   } else {
-    for (; s < a.n_steps; ++s) transition(s);
+    for (; s < a.n_steps; ++s) transition(s, Either{});
   }
 
   if (active) { a.state[chain * 2 + 0] = x[0]; a.state[chain * 2 + 1] = x[1]; }

@@ -31,9 +31,12 @@
  *   stream 2: NUTS tree uniforms, block = draw index / 4 (see gmcmc_nuts_create).
  *   stream 3: NUTS momentum probe after a mass-matrix update (see gmcmc_nuts_set_mass_adaptation).
  * Uniforms are in (0,1]:  f32 ((r>>8)+1)*2^-24,  f64 ((r64>>11)+1)*2^-53.
- * Fast-mode MH with dim == 2 takes everything for a transition from block 0 of stream 0: words 0 and 1 ->
- * Box-Muller pair from the 23-bit uniforms ((r>>9)+1/2)*2^-23 (radius from word 0, angle from word 1), words
- * 2-3 -> the accept uniform (the 53-bit / 24-bit value above; its leading 23 bits are tested first).
+ * Fast-mode MH with dim == 2 feeds TWO transitions from one block of stream 0 (Philox4x32-10 is 40 of the kernel's
+ * ~90 instructions per step): with t the absolute transition index, the counter word "transition_index" is t >> 1,
+ * and transition t takes words (0, 1) when t is even, words (2, 3) when odd.  Of its word pair (w0, w1): bits 31..12
+ * of w0 -> radius uniform (k + 1/2) 2^-20, bits 31..12 of w1 -> angle 2 pi (k + 1/2) 2^-20 - pi (the grid maps onto
+ * itself under z -> -z: the proposal stays exactly symmetric), ((w0 & 0xfff) << 11) | (w1 & 0x7ff) -> the accept
+ * uniform (k + 1/2) 2^-23, which is the whole uniform of this mode.  Exact mode keeps the layout above.
  */
 #ifndef GMCMC_H
 #define GMCMC_H
