@@ -186,11 +186,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 constexpr uint32_t kOpFmt = kF16 ? 0u : 2u;
 constexpr uint32_t kIdesc = (1u << 4) | (kOpFmt << 7) | (kOpFmt << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 
+#if !GM_TC_F16
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+#endif
 
 struct GemmArgs {
   int d, kpad, npad;
