@@ -343,10 +343,10 @@ __global__ void __launch_bounds__(kMhBlock, GM_MH_MINB) mh_run_kernel(const MhAr
 //     (conflict-free for the per-chain writes and for the per-row reads) and flushed every GM_MH2_STEPS
 //     steps as LDS.128 + STG.128 pairs, 256 (16 steps) or 512 (32 steps) contiguous bytes per chain.
 // Measured on B200 (tools/mh_bench.cu, tools/microbench_write.cu): a write-only stream of 256-byte pieces
-// reaches 5.3 TB/s, of 512-byte pieces 6.6 TB/s, cudaMemset 7.4 TB/s; the kernel runs at 3.6 TB/s with either
-// staging depth, any occupancy from 12 to 32 warps per SM and any unroll factor: it is bound by instruction
-// dispatch (103 warp-instructions per step, about 70 of them on half-rate pipes: Philox's 20 LOP3 + 20 IMAD.WIDE,
-// 13 FP64, selects), not by HBM — profiles/r1_mh_run2_kernel_full.txt.
+// reaches 5.3 TB/s, of 512-byte pieces 6.6 TB/s, cudaMemset 7.4 TB/s; the kernel writes 4.6 TB/s (3.65 ms per
+// 1000 steps of 1,048,576 chains, 70 % of the measured copy bandwidth) with either staging depth and any occupancy
+// from 12 to 32 warps per SM: it is bound by instruction dispatch (89 warp-instructions per step, most of them on
+// half-rate pipes: Philox's LOP3 / IMAD.WIDE, 13 FP64, selects), not by HBM — profiles/r1_mh_run2_kernel_full.txt.
 // ------------------------------------------------------------------------------------------------
 #ifndef GM_MH2_STEPS
 #define GM_MH2_STEPS 16
