@@ -236,7 +236,9 @@ gmcmc_status gmcmc_run_stats_from(gmcmc_ctx*, const void* samples, size_t C, siz
  * what run_progress shows while sampling — per-chain running mean / mean of squares (f32, the reference's
  * recurrences), the EMA acceptance rate (alpha = 0.01, "row changed" test, folded over the chains of a step, step
  * after step) and the tracker R-hat sqrt(var_hat / W) — evaluated on the device from the draws [C, n, p] collected
- * so far.  rhat: host float[p]; max_rhat, p_accept: host scalars; any may be NULL.  Needs C >= 2, n >= 2. */
+ * so far.  rhat: host float[p]; max_rhat, p_accept: host scalars; any may be NULL.  Needs C >= 2, n >= 2.  With a
+ * distributed context the figures cover THIS rank's chains (a progress display, not a diagnostic: use
+ * gmcmc_split_rhat_ess / gmcmc_run_stats_from for the all-ranks R-hat and ESS). */
 gmcmc_status gmcmc_tracker_stats(gmcmc_ctx*, const void* samples, size_t C, size_t n, size_t p,
                                  gmcmc_dtype dtype, int on_device, float* rhat, float* max_rhat, float* p_accept);
 
