@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kMhBlock, GM_MH_MINB) mh_run_kernel(const MhAr
   double* out_lane = a.out ? a.out + (warp_first_chain * a.out_n + a.out_t0) * (size_t)d + lane : nullptr;
   const double* stage_lane = stage + warp_row0 * kStageStride + lane;
   double* const stage_row = stage + threadIdx.x * kStageStride;
-  const PhiloxRoundKeys rk = philox_round_keys(a.key);
+  const PhiloxRoundKeys& rk = a.rk;   // host-computed round keys: constant-bank operands
 
   T x[MAXD];
 #pragma unroll
