@@ -309,19 +309,60 @@ __device__ __forceinline__ T eval_target(TagMixture, const T (&x)[EPL], T (&g)[E
   const T* mu = tp.dp + K;
   T a[kMaxComp];          // dynamically indexed: lives in (L1-resident) local memory
   T amax = -INFINITY;
-#pragma unroll 1
-  for (int k = 0; k < K; ++k) {
-    T m[EPL], terms[EPL];
-    mixture_mean_slice<T, EPL>(m, tp, mu, k, d, ln);
+  bool packed = false;
+#ifndef GM_MIX_NO_PACKED_REDUCE
+  if constexpr (!kExact) packed = (K == 4 && ln.lpc >= 4);   // fast math mode only: the summation order changes
+#endif
+  if (packed) {
+    // Four components, chains spread over >= 4 lanes: the four per-lane partial sums are reduced together by a
+    // transpose-reduce (2 + 1 shuffles leave one component per lane, log2(lpc) - 2 finish it, 1 + 2 gather the four
+    // totals back) — 8 shuffles in 7 dependent steps at lpc = 16 instead of 4 x 4 in sequence.
+    T sk[4];
 #pragma unroll
-    for (int j = 0; j < EPL; ++j) {
-      const T df = (!PADDED || j < ln.nvalid) ? (x[j] - m[j]) : T(0);
-      terms[j] = df * df;
+    for (int k = 0; k < 4; ++k) {
+      T m[EPL];
+      mixture_mean_slice<T, EPL>(m, tp, mu, k, d, ln);
+      T acc0 = T(0), acc1 = T(0);
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) {
+        const T df = (!PADDED || j < ln.nvalid) ? (x[j] - m[j]) : T(0);
+        if (j & 1) acc1 = fma(df, df, acc1); else acc0 = fma(df, df, acc0);
+      }
+      sk[k] = acc0 + acc1;
     }
-    const T sq = chain_sum<T, EPL>(terms, ln);
-    const T ak = fast_log<T>(w[k]) - T(0.5) * sq * inv_var;
-    a[k] = ak;
-    amax = max(amax, ak);
+    const int ln32 = (int)(threadIdx.x & 31u);
+    const bool b0 = (ln32 & 1) != 0, b1 = (ln32 & 2) != 0;
+    T keep0 = b0 ? sk[2] : sk[0], keep1 = b0 ? sk[3] : sk[1];
+    keep0 += __shfl_xor_sync(kFull, b0 ? sk[0] : sk[2], 1);
+    keep1 += __shfl_xor_sync(kFull, b0 ? sk[1] : sk[3], 1);
+    T keep = b1 ? keep1 : keep0;
+    keep += __shfl_xor_sync(kFull, b1 ? keep0 : keep1, 2);          // this lane now owns component 2 b0 + b1
+    for (int o = 4; o < ln.lpc; o <<= 1) keep += __shfl_xor_sync(kFull, keep, o);
+    const T other = __shfl_xor_sync(kFull, keep, 2);
+    const T q0 = b1 ? other : keep, q1 = b1 ? keep : other;        // components 2 b0, 2 b0 + 1
+    const T o0 = __shfl_xor_sync(kFull, q0, 1), o1 = __shfl_xor_sync(kFull, q1, 1);
+    sk[0] = b0 ? o0 : q0; sk[1] = b0 ? o1 : q1; sk[2] = b0 ? q0 : o0; sk[3] = b0 ? q1 : o1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const T ak = fast_log<T>(w[k]) - T(0.5) * sk[k] * inv_var;
+      a[k] = ak;
+      amax = max(amax, ak);
+    }
+  } else {
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+      T m[EPL], terms[EPL];
+      mixture_mean_slice<T, EPL>(m, tp, mu, k, d, ln);
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) {
+        const T df = (!PADDED || j < ln.nvalid) ? (x[j] - m[j]) : T(0);
+        terms[j] = df * df;
+      }
+      const T sq = chain_sum<T, EPL>(terms, ln);
+      const T ak = fast_log<T>(w[k]) - T(0.5) * sq * inv_var;
+      a[k] = ak;
+      amax = max(amax, ak);
+    }
   }
   T se = T(0);
 #pragma unroll 1
