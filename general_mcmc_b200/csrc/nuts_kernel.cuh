@@ -152,6 +152,30 @@ __device__ __forceinline__ T chain_sum_fn(const Lane& ln, F f) {
   }
 }
 
+// two such sums at once: in fast mode their butterfly steps interleave (half the dependent shuffle latency); exact mode
+// keeps the two sequential lane-ordered sums
+template <class T, int EPL, class F1, class F2>
+__device__ __forceinline__ void chain_sum_fn2(const Lane& ln, F1 f1, F2 f2, T& out1, T& out2) {
+  if constexpr (kExact) {
+    out1 = chain_sum_fn<T, EPL>(ln, f1);
+    out2 = chain_sum_fn<T, EPL>(ln, f2);
+  } else {
+    T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0), b0 = T(0), b1 = T(0), b2 = T(0), b3 = T(0);
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      const T t = f1(j), u = f2(j);
+      if ((j & 3) == 0) { a0 += t; b0 += u; } else if ((j & 3) == 1) { a1 += t; b1 += u; }
+      else if ((j & 3) == 2) { a2 += t; b2 += u; } else { a3 += t; b3 += u; }
+    }
+    T s1 = (a0 + a1) + (a2 + a3), s2 = (b0 + b1) + (b2 + b3);
+    for (int o = ln.lpc >> 1; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(kFull, s1, o);
+      s2 += __shfl_xor_sync(kFull, s2, o);
+    }
+    out1 = s1; out2 = s2;
+  }
+}
+
 #ifndef GM_NUTS_MINB
 #define GM_NUTS_MINB 3
 #endif
@@ -439,16 +463,16 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       load_slice<T, EPL>(fp, src_p, ln, do_merge || do_top, T(0));
       // stop_criterion (generic_nuts.rs:1357-1378, identity mass): diff = q+ - q- ; diff.p- >= 0 && diff.p+ >= 0
       const bool fwd = (v == 1);
-      const T dm = chain_sum_fn<T, EPL>(ln, [&](int j) {
+      T dm, dp;
+      chain_sum_fn2<T, EPL>(ln, [&](int j) {
         const T df = fwd ? (q[j] - fq[j]) : (fq[j] - q[j]);
         if (has_mass && do_top && j < ln.nvalid) return df * (a.mass_inv[chain * d + ln.lo + j] * (fwd ? fp[j] : p[j]));
         return (!PADDED || j < ln.nvalid) ? df * (fwd ? fp[j] : p[j]) : T(0);
-      });
-      const T dp = chain_sum_fn<T, EPL>(ln, [&](int j) {
+      }, [&](int j) {
         const T df = fwd ? (q[j] - fq[j]) : (fq[j] - q[j]);
         if (has_mass && do_top && j < ln.nvalid) return df * (a.mass_inv[chain * d + ln.lo + j] * (fwd ? p[j] : fp[j]));
         return (!PADDED || j < ln.nvalid) ? df * (fwd ? p[j] : fp[j]) : T(0);
-      });
+      }, dm, dp);
       const bool crit = (dm >= T(0)) && (dp >= T(0));
       if (do_merge) {
         // generic_nuts.rs:1305-1323
