@@ -115,6 +115,8 @@ class _Target:
         """≙ BatchedHamiltonianTarget::logp_and_grad (batched_hmc.rs:18-22) on host arrays [n, dim]."""
         ctx = ctx or default_context()
         x = np.ascontiguousarray(x)
+        if self.dim is None:
+            self.dim = int(x.shape[1])
         h = self._create(ctx, x.dtype)
         try:
             lp = np.empty(x.shape[0], x.dtype)
@@ -356,6 +358,7 @@ def _as_positions(initial, dtype=None):
 class _Sampler:
     _h = None
     _out_dtype = None
+    _n_inj = 0
 
     def _info(self):
         return self.n_chains, self.dim
@@ -400,6 +403,14 @@ class _Sampler:
         L.check(L.lib().gmcmc_run_device(self._h, C.c_size_t(n_collect), C.c_size_t(n_discard), C.byref(p)))
         return p.value
 
+    def reserve(self, n_collect):
+        """Sizes the device sample buffer for up to n_collect draws per chain ahead of the run (0 frees it)."""
+        L.check(L.lib().gmcmc_reserve_samples(self._h, C.c_size_t(n_collect)))
+
+    def close(self):
+        """Frees the sampler's device memory now (≙ drop)."""
+        self._destroy()
+
     def step(self):
         L.check(L.lib().gmcmc_step(self._h))
 
@@ -434,6 +445,8 @@ class _Sampler:
 
     def diagnostics(self):
         n = self._n_inj
+        if n == 0:   # let the library report "no injected transitions recorded"
+            L.check(L.lib().gmcmc_read_diagnostics(self._h, None, None, None, None))
         la = np.empty((n, self.n_chains), self.dtype)
         acc = np.empty((n, self.n_chains), np.uint8)
         hmc = isinstance(self, HMC)
@@ -513,6 +526,18 @@ class MetropolisHastings(_Sampler):
 
     def seed(self, seed):  # metropolis_hastings.rs:189-197
         return self.set_seed(seed)
+
+    def record(self, n_steps):
+        """Test hook (gmcmc_mh_record): the next n_steps transitions of the production 2-D fast kernel record their
+        log ratio / decision (diagnostics()) and the draws they used (draws())."""
+        L.check(L.lib().gmcmc_mh_record(self._h, C.c_size_t(n_steps)))
+        self._n_inj = int(n_steps)
+
+    def draws(self):
+        """float32 [n_steps, n_chains, 3]: proposal noise z0, z1 and the accept uniform of the recorded transitions."""
+        out = np.empty((self._n_inj, self.n_chains, 3), np.float32)
+        L.check(L.lib().gmcmc_mh_read_draws(self._h, L.ptr(out)))
+        return out
 
 
 class NUTSMassMatrixConfig:

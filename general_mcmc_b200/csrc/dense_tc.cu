@@ -10,8 +10,11 @@
 // x = hi + lo (22 bits) and the accumulator receives hi.hi + lo.hi + hi.lo in FP32 (TMEM): three MMAs per K-step.
 //   GM_TC_F16 = 1 (default): hi = half(x), lo = half(x - hi), tcgen05.mma.kind::f16 (K = 16 per instruction, twice
 //     the TF32 rate).  FP16 products are exact in FP32.  P is pre-scaled by a power of two so that its entries use
-//     the upper part of FP16's exponent range (the epilogue undoes it); delta = q - mu is O(1..10), and a low part
-//     that falls into the subnormals costs at most 2^-25 absolute.  Measured against the f64 oracle at d = 1000,
+//     the upper part of FP16's exponent range (the epilogue undoes it); delta = q - mu is scaled likewise, per
+//     transition, by the power of two that puts max |delta| of the batch at 2^8 (dense_begin_kernel reduces the maximum,
+//     dense_scale_kernel turns it into the scale the GEMM launches read), so targets of any variance scale (1e-8 ..
+//     1e+10) stay inside FP16's range with 2^7 headroom for the trajectory; a low part that falls into the subnormals
+//     costs at most 2^-32 of max |delta|.  Measured against the f64 oracle at d = 1000,
 //     L = 32: same error as the TF32 split (tests/test_gpu_dense_tc.py holds both to 2e-5); 7.5e7 -> 9.3e7 grad-evals/s
 //     (1.1e8 with the persistent unit schedule below).
 //   GM_TC_F16 = 0: hi = rna_tf32(x), lo = rna_tf32(x - hi), tcgen05.mma.kind::tf32 (K = 8).
@@ -203,7 +206,8 @@ struct GemmArgs {
   float coef;             // kick: p -= coef * z   (grad = -z)
   float drift_eps;
   float norm_const;
-  float zscale;           // the accumulator holds z / zscale (P is pre-scaled by a power of two in FP16 mode); coef carries it too
+  float zscale;           // the accumulator holds z / (zscale * dscale[1]): P is pre-scaled by a power of two in FP16 mode
+  const float* dscale;    // device [2]: power-of-two scale applied to delta before the FP16 split, and its inverse
   int persist;            // 1: the grid is a set of persistent clusters walking (row-tile group, column chunk) units (no row sums)
   float* logp_out;        // [C] or null: logp = c - 1/2 sum z * delta
   float* ke_out;          // [C] or null: 1/2 |p_new|^2
@@ -335,6 +339,8 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
     // chunk c of row r sits at chunk c ^ (r & 7)), the operand tiles 64-byte rows under SWIZZLE_64B (chunk c of row r at
     // c ^ ((r >> 1) & 3)); a thread turns 8 consecutive floats of a row into one 16-byte chunk of each operand tile.
     const int t = (warp - kFirstCvtWarp) * 32 + lane;          // 0..127
+    const float dl_scale = kF16 ? a.dscale[0] : 1.f;
+    (void)dl_scale;
     for (int it = 0; it < n_iters; ++it) {
       const int r = it % kRawStages, s = it % kStages;
       mbar_wait(&raw_full[r], (uint32_t)(it / kRawStages) & 1u);
@@ -343,13 +349,14 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
       const unsigned char* src = raw_base + (size_t)r * kRawBytes;
       unsigned char* dhi = base + (size_t)s * kStageBytes;
       unsigned char* dlo = dhi + kABytes;
+      const float sa = dl_scale;
 #pragma unroll
       for (int i = 0; i < (kTileM * 4) / (32 * kCvtWarps); ++i) {
         const int u = t + i * 32 * kCvtWarps;
         const int row = u >> 2, oc = u & 3, sw = row & 7;
         const float4 x0 = *reinterpret_cast<const float4*>(src + row * 128 + (((2 * oc) ^ sw) << 4));
         const float4 x1 = *reinterpret_cast<const float4*>(src + row * 128 + (((2 * oc + 1) ^ sw) << 4));
-        const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        const float xs[8] = {x0.x * sa, x0.y * sa, x0.z * sa, x0.w * sa, x1.x * sa, x1.y * sa, x1.z * sa, x1.w * sa};
         uint32_t hw[4], lw[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -388,6 +395,8 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
     // line per warp instruction for p and delta.
     const int ew = warp - kFirstEpiWarp;
     const int q4 = warp & 3;                     // TMEM lane quarter this warp may access
+    const float zs = kF16 ? a.zscale * a.dscale[1] : a.zscale;   // z = zs * accumulator
+    const float coef = a.coef * zs;
     float* tr = tr_base + (size_t)ew * 16 * 33;
     // the kEpiWarps / 4 warps that share a quarter interleave over the 32-column blocks
     int cb_first = 0;
@@ -438,7 +447,7 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
 #endif
 #pragma unroll
             for (int rr = 0; rr < 16; ++rr) {
-              const float pn = fmaf(-a.coef, tr[rr * 33 + lane], pv[rr]);
+              const float pn = fmaf(-coef, tr[rr * 33 + lane], pv[rr]);
 #ifdef GM_TC_EXPERIMENT_NOSTORE
               if (pn == 123456.f) { __stcs(p_blk + rr * d32, pn); dn_blk[rr * k32] = fmaf(a.drift_eps, pn, dv[rr]); }
 #else
@@ -464,7 +473,7 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
               const float zv = tr[rr * 33 + lane];
               float pn = 0.f;
               if (col_ok) {
-                pn = fmaf(-a.coef, zv, pv[rr]);
+                pn = fmaf(-coef, zv, pv[rr]);
                 __stcs(p_blk + rr * d32, pn);
                 if (a.dl_next) a.dl_next[(row0 + r) * (size_t)a.kpad + col] = fmaf(a.drift_eps, pn, dv[rr]);
               }
@@ -492,7 +501,7 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
         for (int w = 0; w < kEpiWarps; ++w) {
           if (((w + kFirstEpiWarp) & 3) == q4) { qsum += tr_base[(size_t)w * 16 * 33 + lane]; ksum += tr_base[(size_t)w * 16 * 33 + 32 + lane]; }
         }
-        if (a.logp_out) a.logp_out[row0 + lane] = a.norm_const - 0.5f * (a.zscale * qsum);
+        if (a.logp_out) a.logp_out[row0 + lane] = a.norm_const - 0.5f * (zs * qsum);
         if (a.ke_out) a.ke_out[row0 + lane] = 0.5f * ksum;
       }
     }
@@ -512,6 +521,7 @@ struct BeginArgs {
   unsigned long long chain_offset; PhiloxKey key; uint32_t step;
   const float* q; float* p; const float* mu; float* dl; float* ke0;
   const float* inj_normals;   // [C, d] for this transition or null
+  unsigned int* dmax_bits;    // [1] max |delta| of the batch as float bits (non-negative floats order like unsigned ints)
 };
 
 // one warp per chain: momentum, ke0, delta = q - mu (padded columns zero)
@@ -520,7 +530,7 @@ __global__ void __launch_bounds__(256) dense_begin_kernel(const BeginArgs a) {
   const int lane = threadIdx.x & 31;
   if (chain >= a.n_chains) return;
   const unsigned long long gchain = a.chain_offset + chain;
-  float ke = 0.f;
+  float ke = 0.f, dmax = 0.f;
   for (int b = lane; b * 4 < a.kpad; b += 32) {
     float z[4] = {0.f, 0.f, 0.f, 0.f};
     if (b * 4 < a.d) {
@@ -539,12 +549,36 @@ __global__ void __launch_bounds__(256) dense_begin_kernel(const BeginArgs a) {
         a.p[chain * a.d + c] = z[k];
         ke += z[k] * z[k];
         dl[k] = a.q[chain * a.d + c] - a.mu[c];
+        const float ad = fabsf(dl[k]);
+        if (ad < INFINITY) dmax = fmaxf(dmax, ad);
       }
     }
     *reinterpret_cast<float4*>(a.dl + chain * a.kpad + b * 4) = make_float4(dl[0], dl[1], dl[2], dl[3]);
   }
-  for (int o = 16; o > 0; o >>= 1) ke += __shfl_xor_sync(0xffffffffu, ke, o);
-  if (lane == 0) a.ke0[chain] = 0.5f * ke;
+  for (int o = 16; o > 0; o >>= 1) {
+    ke += __shfl_xor_sync(0xffffffffu, ke, o);
+    dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  }
+  if (lane == 0) {
+    a.ke0[chain] = 0.5f * ke;
+    if (a.dmax_bits && dmax > 0.f) atomicMax(a.dmax_bits, __float_as_uint(dmax));
+  }
+}
+
+// max |delta| of the batch -> the power-of-two operand scale of this transition's GEMMs (2^8 / max, rounded down to a power
+// of two: 2^7 headroom below FP16's largest finite value for the trajectory); resets the maximum for the next transition
+__global__ void dense_scale_kernel(unsigned int* dmax_bits, float* dscale) {
+  const float m = __uint_as_float(*dmax_bits);
+  int e = 0;
+  if (m > 0.f && m < INFINITY) {
+    int ex;
+    frexpf(m, &ex);              // m = f * 2^ex, f in [0.5, 1)
+    e = 8 - ex;
+  }
+  e = e < -100 ? -100 : (e > 100 ? 100 : e);
+  dscale[0] = ldexpf(1.f, e);
+  dscale[1] = ldexpf(1.f, -e);
+  *dmax_bits = 0u;
 }
 
 struct AcceptArgs {
@@ -635,6 +669,8 @@ struct DenseTc {
   float *p = nullptr, *dl[2] = {nullptr, nullptr}, *mu = nullptr;
   void *b_hi = nullptr, *b_lo = nullptr;   // P split into hi / lo operand arrays [npad, kpad]: tf32-in-f32 or f16
   float zscale = 1.f;                      // 1 / (power-of-two scale applied to P before the FP16 split)
+  float* dscale = nullptr;                 // device [2]: power-of-two scale of delta for this transition, and its inverse
+  unsigned int* dmax_bits = nullptr;       // device [1]: max |delta| of the batch (float bits)
   int sms = 0;                             // SMs of the device (persistent grid size)
   float *logp0 = nullptr, *logp1 = nullptr, *ke0 = nullptr, *ke1 = nullptr;
   float norm_const = 0.f;
@@ -646,6 +682,7 @@ void dense_tc_destroy(DenseTc* t) {
   if (!t) return;
   cudaFree(t->p); cudaFree(t->dl[0]); cudaFree(t->dl[1]); cudaFree(t->b_hi); cudaFree(t->b_lo); cudaFree(t->mu);
   cudaFree(t->logp0); cudaFree(t->logp1); cudaFree(t->ke0); cudaFree(t->ke1);
+  cudaFree(t->dscale); cudaFree(t->dmax_bits);
   delete t;
 }
 
@@ -665,7 +702,9 @@ DenseTc* dense_tc_create(size_t n_chains, int d, const double* params, const cha
             cudaMemset(t->dl[1], 0, C * (size_t)t->kpad * 4) == cudaSuccess &&
             cudaMalloc(&t->b_hi, (size_t)t->npad * t->kpad * kOpElem) == cudaSuccess && cudaMalloc(&t->b_lo, (size_t)t->npad * t->kpad * kOpElem) == cudaSuccess &&
             cudaMalloc(&t->mu, (size_t)d * 4) == cudaSuccess && cudaMalloc(&t->logp0, C * 4) == cudaSuccess &&
-            cudaMalloc(&t->logp1, C * 4) == cudaSuccess && cudaMalloc(&t->ke0, C * 4) == cudaSuccess && cudaMalloc(&t->ke1, C * 4) == cudaSuccess;
+            cudaMalloc(&t->logp1, C * 4) == cudaSuccess && cudaMalloc(&t->ke0, C * 4) == cudaSuccess && cudaMalloc(&t->ke1, C * 4) == cudaSuccess &&
+            cudaMalloc(&t->dscale, 8) == cudaSuccess && cudaMalloc(&t->dmax_bits, 4) == cudaSuccess &&
+            cudaMemset(t->dmax_bits, 0, 4) == cudaSuccess;
   if (!ok) { *err = e_alloc; dense_tc_destroy(t); return nullptr; }
   // B operand: rows = output column n, cols = k (K-major); P symmetric so B[n][k] = P[k][n] = P[n][k]
   std::vector<float> mu(d);
@@ -678,7 +717,7 @@ DenseTc* dense_tc_create(size_t n_chains, int d, const double* params, const cha
     for (size_t i = 0; i < (size_t)d * d; ++i) amax = std::max(amax, std::fabs(params[(size_t)d + i]));
     int e = 0;
     if (amax > 0.0) e = 12 - (int)std::ceil(std::log2(amax));
-    e = std::max(-24, std::min(24, e));
+    e = std::max(-100, std::min(100, e));
     const float sc = std::ldexp(1.0f, e);
     t->zscale = std::ldexp(1.0f, -e);
     std::vector<__half> bh(nel, __float2half_rn(0.f)), bl(nel, __float2half_rn(0.f));
@@ -724,7 +763,7 @@ static cudaError_t gemm_kick(DenseTc* t, int buf, float coef, float drift_eps, f
   GemmArgs g;
   g.d = t->d; g.kpad = t->kpad; g.npad = t->npad; g.n_chains = t->n_chains;
   g.p = t->p; g.dl = t->dl[buf]; g.dl_next = drift_eps != 0.f ? t->dl[buf ^ 1] : nullptr;
-  g.coef = coef * t->zscale; g.drift_eps = drift_eps; g.norm_const = t->norm_const; g.zscale = t->zscale;
+  g.coef = coef; g.drift_eps = drift_eps; g.norm_const = t->norm_const; g.zscale = t->zscale; g.dscale = t->dscale;
   g.logp_out = logp_out; g.ke_out = ke_out;
   unsigned blocks = (unsigned)((t->n_chains + kTileM - 1) / kTileM);
   blocks = (blocks + kCluster - 1) / kCluster * kCluster;   // whole clusters; a surplus CTA only feeds the multicast
@@ -750,8 +789,10 @@ int dense_tc_transition(DenseTc* t, const DenseTcStep& S, cudaStream_t st) {
   b.key = PhiloxKey{(uint32_t)S.seed, (uint32_t)(S.seed >> 32)}; b.step = S.step;
   b.q = (const float*)S.q; b.p = t->p; b.mu = t->mu; b.dl = t->dl[0]; b.ke0 = t->ke0;
   b.inj_normals = (const float*)S.inj_normals;
+  b.dmax_bits = t->dmax_bits;
   dense_begin_kernel<<<wblocks, 256, 0, st>>>(b);
-  ++launches;
+  dense_scale_kernel<<<1, 1, 0, st>>>(t->dmax_bits, t->dscale);
+  launches += 2;
   const float eps = (float)S.eps, half = 0.5f * eps;
   // GEMM 0: gradient at the current point (log density, first half kick, drift of leapfrog 1);
   // GEMM l (1 <= l < L): kick eps + drift of leapfrog l + 1;  GEMM L: last half kick, log density, kinetic energy

@@ -83,6 +83,7 @@ struct MhLaunch {
   const void* inj_lnu;      // [n, C] T
   void* diag_logratio;      // [n, C] T
   uint8_t* diag_acc;        // [n, C]
+  float* diag_draws;        // [n, C, 3] draws used by the 2-D fast kernel (gmcmc_mh_record), or null
 };
 
 // K3: dense-Gaussian HMC with the gradient GEMM on tcgen05 (dense_tc.cu)
@@ -121,6 +122,7 @@ struct NutsLaunch {
   void* ws_edges; void* ws_first; void* ws_prime;
   int cap;
   unsigned long long* leapfrog_total; unsigned long long* diverge_total; unsigned long long* depth_total;
+  unsigned long long* accept_total;
   long long* chain_leapfrogs;
   const double* inj_normals; size_t n_norm;
   const double* inj_exp1; size_t n_exp;

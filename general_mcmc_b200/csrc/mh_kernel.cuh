@@ -67,6 +67,7 @@ struct MhArgs {
   const T* inj_lnu;
   T* diag_logratio;
   uint8_t* diag_acc;
+  float* diag_draws;    // [n, C, 3] (z0, z1, accept uniform) actually used by mh_run2_kernel<.., REC = true>, else null
 };
 
 // Target::unnorm_logp for the MH path (distributions.rs:107-110): log density only.
@@ -364,7 +365,9 @@ constexpr size_t kMh2Smem = (size_t)kMhBlock * kMh2Row;
 static_assert(kMh2Steps == 16 || kMh2Steps == 32, "the flush maps 32 lanes onto 16-byte units of one or two chains");
 
 
-template <class T, int KIND>
+// REC = true: the same kernel with per-step stores of what it drew and decided (proposal noise, accept uniform, log
+// ratio, decision) for the per-step parity test against the oracle (gmcmc_mh_record); no arithmetic differs.
+template <class T, int KIND, bool REC = false>
 __global__ void __launch_bounds__(kMhBlock, GM_MH2_MINB) mh_run2_kernel(const MhArgs<T> a) {
   extern __shared__ __align__(1024) unsigned char stage[];   // kMhBlock rows of kMh2Row bytes (row-aligned: the flush XORs address bits)
 
@@ -462,6 +465,14 @@ __global__ void __launch_bounds__(kMhBlock, GM_MH2_MINB) mh_run2_kernel(const Mh
     x[1] = accept ? xp[1] : x[1];
     lp_cur = accept ? lp_prop : lp_cur;
     n_accept += accept ? 1u : 0u;
+    if constexpr (REC) {
+      if (active) {
+        const size_t idx = (size_t)s * a.n_chains + chain;
+        a.diag_draws[idx * 3 + 0] = c0; a.diag_draws[idx * 3 + 1] = c1; a.diag_draws[idx * 3 + 2] = cu;
+        a.diag_logratio[idx] = log_ratio;
+        a.diag_acc[idx] = accept ? 1 : 0;
+      }
+    }
   };
 
   uint32_t s = 0;
@@ -535,9 +546,9 @@ __global__ void __launch_bounds__(kMhBlock, GM_MH2_MINB) mh_run2_kernel(const Mh
   if (lane == 0 && n_accept) atomicAdd(a.accept_total, (unsigned long long)n_accept);
 }
 
-template <class T, int KIND>
+template <class T, int KIND, bool REC = false>
 inline cudaError_t mh_launch_run2(const MhArgs<T>& a, unsigned blocks, cudaStream_t st) {
-  auto kern = mh_run2_kernel<T, KIND>;
+  auto kern = mh_run2_kernel<T, KIND, REC>;
   if (kMh2Smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMh2Smem);
     if (e != cudaSuccess) return e;
@@ -596,7 +607,7 @@ inline MhArgs<T> make_mh_args(const MhLaunch& L) {
   a.out = L.out; a.out_n = L.out_n; a.out_t0 = L.out_t0;
   a.accept_total = L.accept_total;
   a.inj_normals = (const T*)L.inj_normals; a.inj_lnu = (const T*)L.inj_lnu;
-  a.diag_logratio = (T*)L.diag_logratio; a.diag_acc = L.diag_acc;
+  a.diag_logratio = (T*)L.diag_logratio; a.diag_acc = L.diag_acc; a.diag_draws = L.diag_draws;
   return a;
 }
 
@@ -604,7 +615,10 @@ template <class T, int MAXD, int KIND, bool FULL>
 inline cudaError_t mh_launch_one(const MhLaunch& L, cudaStream_t st) {
   MhArgs<T> a = make_mh_args<T>(L);
   const unsigned blocks = (unsigned)((L.n_chains + kMhBlock - 1) / kMhBlock);
-  if (a.inj_normals || a.inj_lnu || a.diag_logratio) {
+  if (a.diag_draws) {   // gmcmc_mh_record: the production 2-D fast kernel, instrumented
+    if constexpr (!kMhExact && MAXD == 2 && FULL) return mh_launch_run2<T, KIND, true>(a, blocks, st);
+    else return cudaErrorInvalidValue;
+  } else if (a.inj_normals || a.inj_lnu || a.diag_logratio) {
     mh_run_kernel<T, MAXD, KIND, FULL, true><<<blocks, kMhBlock, 0, st>>>(a);
   } else {
     if constexpr (!kMhExact && MAXD == 2 && FULL) return mh_launch_run2<T, KIND>(a, blocks, st);

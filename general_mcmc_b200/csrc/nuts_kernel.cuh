@@ -59,6 +59,7 @@ struct NutsArgs {
   unsigned long long* leapfrog_total;
   unsigned long long* diverge_total;
   unsigned long long* depth_total;
+  unsigned long long* accept_total;   // transitions that moved the chain (a subtree proposal was accepted, :866-868)
   long long* chain_leapfrogs;   // [C] accumulated (may be null)
   // injected per-chain streams (parity tests); null -> Philox
   const double* inj_normals; size_t n_norm;
@@ -237,6 +238,8 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
   unsigned long long i_norm = 0, i_exp = 0, i_unif = 0;
   const bool inject = a.inj_normals != nullptr;
   unsigned long long my_leapfrogs = 0, my_diverge = 0, my_depth = 0, chain_leaps = 0;
+  unsigned int my_moved = 0;
+  bool moved = false;      // the current transition accepted at least one subtree proposal
   // Diagonal mass matrix (MASS): its entries are re-read from global memory (L1-resident, coalesced) where they are
   // used instead of living in 2 x EPL registers.
   constexpr bool has_mass = MASS;
@@ -409,7 +412,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       logu = joint0 - e1;
       store_slice<T, EPL>(e_qm, q, ln, true); store_slice<T, EPL>(e_pm, p, ln, true); store_slice<T, EPL>(e_gm, g, ln, true);
       store_slice<T, EPL>(e_qp, q, ln, true); store_slice<T, EPL>(e_pp, p, ln, true); store_slice<T, EPL>(e_gp, g, ln, true);
-      j_depth = 0; n_tot = 1; draw = 0;
+      j_depth = 0; n_tot = 1; draw = 0; moved = false;
       const T u1 = (T)next_unif();             // :783-784
       v = (u1 < T(0.5)) ? 1 : -1;
       leaf_i = 0; alpha_sum = T(0); n_alpha = 0;
@@ -500,6 +503,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
 #pragma unroll
           for (int j = 0; j < EPL; ++j)
             if (j < ln.nvalid) pos_row[ln.lo + j] = prime[j];
+          moved = true;
         }
         n_tot += nR;
         bool cont = sR && crit;
@@ -527,6 +531,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
     if (phase == NP_END) {
       const uint32_t m = a.m_base + s + 1;
       my_depth += (unsigned long long)j_depth;
+      my_moved += moved ? 1u : 0u;
       T eta = T(1) / (T)(m + 10u);
       h_bar = (T(1) - eta) * h_bar + eta * (a.target_accept - alpha_sum / (T)n_alpha);
       if (m <= a.n_discard) {
@@ -568,13 +573,15 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
     }
   }
 
-  if (ln.part != 0) { my_leapfrogs = 0; my_diverge = 0; my_depth = 0; }
+  if (ln.part != 0) { my_leapfrogs = 0; my_diverge = 0; my_depth = 0; my_moved = 0; }
   for (int o = 16; o > 0; o >>= 1) {
     my_leapfrogs += __shfl_xor_sync(kFull, my_leapfrogs, o);
     my_diverge += __shfl_xor_sync(kFull, my_diverge, o);
     my_depth += __shfl_xor_sync(kFull, my_depth, o);
+    my_moved += __shfl_xor_sync(kFull, my_moved, o);
   }
   if (lane == 0) {
+    if (my_moved && a.accept_total) atomicAdd(a.accept_total, (unsigned long long)my_moved);
     if (my_leapfrogs) atomicAdd(a.leapfrog_total, my_leapfrogs);
     if (my_diverge) atomicAdd(a.diverge_total, my_diverge);
     if (my_depth) atomicAdd(a.depth_total, my_depth);
@@ -731,6 +738,7 @@ inline NutsArgs<T> make_nuts_args(const NutsLaunch& L) {
   a.max_depth = L.max_depth;
   a.ws_edges = (T*)L.ws_edges; a.ws_first = (T*)L.ws_first; a.ws_prime = (T*)L.ws_prime; a.cap = L.cap;
   a.leapfrog_total = L.leapfrog_total; a.diverge_total = L.diverge_total; a.depth_total = L.depth_total;
+  a.accept_total = L.accept_total;
   a.chain_leapfrogs = L.chain_leapfrogs;
   a.inj_normals = L.inj_normals; a.n_norm = L.n_norm; a.inj_exp1 = L.inj_exp1; a.n_exp = L.n_exp;
   a.inj_unif = L.inj_unif; a.n_unif = L.n_unif; a.inj_used = L.inj_used;

@@ -112,6 +112,7 @@ struct gmcmc_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t aux_stream = nullptr;   // side stream of the pooled dual-averaging chain (reduce -> all-reduce -> update)
   int rank = 0, world = 1;
   void* comm = nullptr;
   int sm_count = 148;
@@ -148,7 +149,7 @@ struct gmcmc_sampler {
   // HMC
   double step_size = 0.0;
   uint32_t n_leapfrog = 0;
-  void* d_eps = nullptr;       // [1] T (shared step size)
+  void* d_eps = nullptr;       // [2] T (shared step size; two slots: pooled warm-up transition t reads slot t & 1)
   bool eps_device_only = false; // the current step size was produced on the device and not yet read back
   DenseTc* dense_tc = nullptr;  // tensor-core path of the dense Gaussian (f32, fast mode, fixed step size)
   gmcmc_adapt_mode adapt = GMCMC_ADAPT_NONE;
@@ -156,8 +157,10 @@ struct gmcmc_sampler {
   void* d_da[4] = {nullptr, nullptr, nullptr, nullptr};   // per-chain: eps, eps_bar, h_bar, mu  (T [C])
   uint32_t da_m = 0;           // adaptation iterations consumed so far
   PooledDa* d_pooled = nullptr;
-  double* d_alpha_part = nullptr;
+  double* d_alpha_part = nullptr;  // [2][n_alpha_part]: transition t of a pooled warm-up writes half t & 1
   size_t n_alpha_part = 0;
+  cudaEvent_t ev_kern[4] = {nullptr, nullptr, nullptr, nullptr};   // pooled warm-up: transition t done / update t done
+  cudaEvent_t ev_upd[4] = {nullptr, nullptr, nullptr, nullptr};
   double* d_alpha_sum = nullptr;   // [2]: sum alpha, chain count (all-reduced together)
   // MH
   double prop_std = 1.0;
@@ -198,6 +201,9 @@ struct gmcmc_sampler {
   uint8_t* d_diag_acc = nullptr;
   void* d_diag_pq = nullptr;
   void* d_diag_pp = nullptr;
+  // gmcmc_mh_record: per-step record of the production 2-D fast MH kernel
+  size_t rec_steps = 0;       // pending recorded transitions
+  float* d_diag_draws = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -288,10 +294,11 @@ inline int out_dtype_of(const gmcmc_sampler* s) { return s->type == S_MH ? (int)
 
 gmcmc_status set_eps_device(gmcmc_sampler* s, double eps) {
   if (s->dtype == GMCMC_F32) {
-    float v = (float)eps;
-    GM_CU(cudaMemcpyAsync(s->d_eps, &v, 4, cudaMemcpyHostToDevice, s->ctx->stream));
+    float v[2] = {(float)eps, (float)eps};
+    GM_CU(cudaMemcpyAsync(s->d_eps, v, 8, cudaMemcpyHostToDevice, s->ctx->stream));
   } else {
-    GM_CU(cudaMemcpyAsync(s->d_eps, &eps, 8, cudaMemcpyHostToDevice, s->ctx->stream));
+    double v[2] = {eps, eps};
+    GM_CU(cudaMemcpyAsync(s->d_eps, v, 16, cudaMemcpyHostToDevice, s->ctx->stream));
   }
   GM_CU(cudaStreamSynchronize(s->ctx->stream));  // the source is a stack variable
   return GMCMC_OK;
@@ -306,7 +313,7 @@ gmcmc_status all_reduce(gmcmc_ctx* ctx, void* buf, size_t count, int nccl_dtype)
 // One launch of the HMC trajectory kernel covering run-local transitions [first, first + count).
 gmcmc_status hmc_segment(gmcmc_sampler* s, size_t first, size_t count, size_t n_discard, size_t n_collect,
                          void* out, bool use_injection, size_t inj_first, bool want_alpha, bool per_chain_da,
-                         uint32_t da_n_adapt) {
+                         uint32_t da_n_adapt, int slot = 0) {
   if (count == 0) return GMCMC_OK;
   HmcLaunch L{};
   GM_TRY(make_target_desc(s->tgt, &L.tgt));
@@ -317,7 +324,7 @@ gmcmc_status hmc_segment(gmcmc_sampler* s, size_t first, size_t count, size_t n_
   L.positions = s->d_pos;
   // fixed step size known on the host: pass it by value (constant-bank operand of the drift/kick FMAs)
   const bool eps_on_host = !want_alpha && !per_chain_da && !s->eps_device_only;
-  L.eps = eps_on_host ? nullptr : s->d_eps;
+  L.eps = eps_on_host ? nullptr : (const void*)((const char*)s->d_eps + (size_t)slot * esize(s->dtype));
   L.eps_val = s->step_size;
   L.eps_stride = 0;
   L.n_leapfrog = s->n_leapfrog;
@@ -329,7 +336,7 @@ gmcmc_status hmc_segment(gmcmc_sampler* s, size_t first, size_t count, size_t n_
   L.out_t0 = (uint32_t)(first >= n_discard ? first - n_discard : 0);
   L.accept_total = s->d_counts + 0;
   L.diverge_total = s->d_counts + 1;
-  L.alpha_part = want_alpha ? s->d_alpha_part : nullptr;
+  L.alpha_part = want_alpha ? s->d_alpha_part + (size_t)slot * s->n_alpha_part : nullptr;
   if (per_chain_da) {
     L.da_eps = s->d_da[0]; L.da_eps_bar = s->d_da[1]; L.da_h_bar = s->d_da[2]; L.da_mu = s->d_da[3];
     L.da_m_base = s->da_m + (uint32_t)first;
@@ -354,7 +361,7 @@ gmcmc_status hmc_segment(gmcmc_sampler* s, size_t first, size_t count, size_t n_
 }
 
 gmcmc_status mh_segment(gmcmc_sampler* s, size_t first, size_t count, size_t n_discard, size_t n_collect, void* out,
-                        bool use_injection, size_t inj_first) {
+                        bool use_injection, size_t inj_first, bool record = false) {
   if (count == 0) return GMCMC_OK;
   MhLaunch L{};
   GM_TRY(make_target_desc(s->tgt, &L.tgt));
@@ -377,6 +384,11 @@ gmcmc_status mh_segment(gmcmc_sampler* s, size_t first, size_t count, size_t n_d
     L.inj_lnu = (const char*)s->d_inj_lnu + inj_first * s->n_chains * es;
     L.diag_logratio = (char*)s->d_diag_logacc + inj_first * s->n_chains * es;
     L.diag_acc = s->d_diag_acc + inj_first * s->n_chains;
+  }
+  if (record) {
+    L.diag_logratio = (char*)s->d_diag_logacc + inj_first * s->n_chains * es;
+    L.diag_acc = s->d_diag_acc + inj_first * s->n_chains;
+    L.diag_draws = s->d_diag_draws + inj_first * s->n_chains * 3;
   }
   cudaError_t e = s->tgt->custom ? s->tgt->custom->launch_mh(L, s->ctx->stream)
                   : (s->math == GMCMC_MATH_EXACT) ? launch_mh_exact(L, s->ctx->stream) : launch_mh_fast(L, s->ctx->stream);
@@ -402,6 +414,7 @@ gmcmc_status nuts_launch(gmcmc_sampler* s, NutsLaunch& L) {
   L.max_depth = (int)s->max_depth;
   L.ws_edges = s->d_ws_edges; L.ws_first = s->d_ws_first; L.ws_prime = s->d_ws_prime; L.cap = kNutsDepthCapHost;
   L.leapfrog_total = s->d_counts + 2; L.diverge_total = s->d_counts + 1; L.depth_total = s->d_counts + 3;
+  L.accept_total = s->d_counts + 0;
   L.chain_leapfrogs = s->d_chain_leapfrogs;
   L.inj_normals = s->d_nuts_inj[0]; L.n_norm = s->nuts_inj_n[0];
   L.inj_exp1 = s->d_nuts_inj[1]; L.n_exp = s->nuts_inj_n[1];
@@ -560,7 +573,12 @@ gmcmc_status run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void
   const size_t inj = std::min(s->inj_steps, total);
   const size_t inj_first = s->diag_steps - s->inj_steps;  // offset of the first unconsumed injected transition
 
-  if (s->type == S_MH) {
+  if (s->type == S_MH && s->rec_steps > 0) {
+    const size_t rec = std::min(s->rec_steps, total);
+    GM_TRY(mh_segment(s, 0, rec, n_discard, n_collect, d_out, false, s->diag_steps - s->rec_steps, true));
+    GM_TRY(mh_segment(s, rec, total - rec, n_discard, n_collect, d_out, false, 0));
+    s->rec_steps -= rec;
+  } else if (s->type == S_MH) {
     GM_TRY(mh_segment(s, 0, inj, n_discard, n_collect, d_out, true, inj_first));
     GM_TRY(mh_segment(s, inj, total - inj, n_discard, n_collect, d_out, false, 0));
   } else if (s->type == S_HMC && s->dense_tc && s->math == GMCMC_MATH_FAST && s->adapt == GMCMC_ADAPT_NONE) {
@@ -589,18 +607,32 @@ gmcmc_status run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void
   } else if (s->type == S_HMC) {
     if (s->adapt == GMCMC_ADAPT_POOLED && n_discard > 0) {
       GM_REQUIRE(inj == 0, "injection cannot be combined with pooled adaptation");
-      // one transition per launch during warm-up: kernel -> fixed-order reduce -> (NCCL all-reduce) -> update
+      // One transition per launch during warm-up.  The dual-averaging chain of transition t (fixed-order reduce of the
+      // per-warp acceptance partials -> NCCL all-reduce over the ranks -> update) runs on a side stream WHILE transition
+      // t + 1 runs: the step size is one transition lagged (transition t uses the update of transition t - 2), so the
+      // collective's latency is off the critical path.  Step sizes and partials are double-buffered by t & 1.
+      cudaStream_t aux = ctx->aux_stream;
       for (size_t t = 0; t < n_discard; ++t) {
-        GM_TRY(hmc_segment(s, t, 1, n_discard, n_collect, nullptr, false, 0, true, false, 0));
-        alpha_reduce_kernel<<<1, 256, 0, ctx->stream>>>(s->d_alpha_part, s->n_alpha_part, (double)s->n_chains, s->d_alpha_sum);
-        GM_TRY(all_reduce(ctx, s->d_alpha_sum, 2, kNcclFloat64));
+        const int slot = (int)(t & 1), e = (int)(t & 3);
+        if (t >= 2) GM_CU(cudaStreamWaitEvent(ctx->stream, s->ev_upd[(t - 2) & 3], 0));   // eps slot + partial buffer free
+        GM_TRY(hmc_segment(s, t, 1, n_discard, n_collect, nullptr, false, 0, true, false, 0, slot));
+        GM_CU(cudaEventRecord(s->ev_kern[e], ctx->stream));
+        GM_CU(cudaStreamWaitEvent(aux, s->ev_kern[e], 0));
+        alpha_reduce_kernel<<<1, 256, 0, aux>>>(s->d_alpha_part + (size_t)slot * s->n_alpha_part, s->n_alpha_part,
+                                                (double)s->n_chains, s->d_alpha_sum);
+        if (ctx->world > 1) GM_NCCL(nccl_api().AllReduce(s->d_alpha_sum, s->d_alpha_sum, 2, kNcclFloat64, kNcclSum, ctx->comm, aux));
         const int last = (t + 1 == n_discard) ? 1 : 0;
+        void* eps_slot = (char*)s->d_eps + (size_t)slot * esize(s->dtype);
         if (s->dtype == GMCMC_F32)
-          pooled_da_update_kernel<float><<<1, 1, 0, ctx->stream>>>(s->d_pooled, s->d_alpha_sum, s->target_accept, last, (float*)s->d_eps);
+          pooled_da_update_kernel<float><<<1, 1, 0, aux>>>(s->d_pooled, s->d_alpha_sum, s->target_accept, last, (float*)eps_slot);
         else
-          pooled_da_update_kernel<double><<<1, 1, 0, ctx->stream>>>(s->d_pooled, s->d_alpha_sum, s->target_accept, last, (double*)s->d_eps);
+          pooled_da_update_kernel<double><<<1, 1, 0, aux>>>(s->d_pooled, s->d_alpha_sum, s->target_accept, last, (double*)eps_slot);
+        GM_CU(cudaEventRecord(s->ev_upd[e], aux));
         s->launches += 2;
       }
+      // the collection launch needs the final step size: join the side stream
+      GM_CU(cudaStreamWaitEvent(ctx->stream, s->ev_upd[(n_discard - 1) & 3], 0));
+      if (n_discard >= 2) GM_CU(cudaStreamWaitEvent(ctx->stream, s->ev_upd[(n_discard - 2) & 3], 0));
       GM_CU(cudaGetLastError());
       s->da_m += (uint32_t)n_discard;
       {
@@ -609,6 +641,7 @@ gmcmc_status run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void
         GM_CU(cudaMemcpyAsync(&h, s->d_pooled, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
         GM_CU(cudaStreamSynchronize(ctx->stream));
         s->step_size = (s->dtype == GMCMC_F32) ? (double)(float)h.eps : h.eps;
+        GM_TRY(set_eps_device(s, s->step_size));     // both slots = the adapted step size
       }
       GM_TRY(hmc_segment(s, n_discard, n_collect, n_discard, n_collect, d_out, false, 0, false, false, 0));
     } else {
@@ -646,6 +679,7 @@ gmcmc_status convert_on_device(gmcmc_ctx* ctx, const void* in, int in_dtype, voi
 }
 
 // ---- statistics ---------------------------------------------------------------------------------
+constexpr size_t kStatsMaxPadded = 16384;   // longest padded series the in-kernel FFT takes (n <= 16385 draws)
 struct StatsBuffers {
   void* tw = nullptr; float* part_spec = nullptr; double* part_mom = nullptr; float* spec = nullptr;
   double* mom = nullptr; float* out = nullptr;
@@ -661,7 +695,7 @@ gmcmc_status device_split_rhat_ess(gmcmc_ctx* ctx, const void* d_samples, size_t
   StatsLaunch S{};
   S.samples = d_samples; S.dtype = dtype; S.C = C; S.n = n; S.p = (int)p;
   S.N = stats_npad(n);
-  if (S.N > 16384) return fail(GMCMC_ERR_UNSUPPORTED, "series of %zu draws exceed the in-kernel FFT (max 16384 padded)", n);
+  if (S.N > kStatsMaxPadded) return fail(GMCMC_ERR_UNSUPPORTED, "series of %zu draws exceed the in-kernel FFT (max %zu padded)", n, (size_t)kStatsMaxPadded);
   S.log2n = 0;
   while (((size_t)1 << S.log2n) < S.N) ++S.log2n;
   S.ppb = stats_ppb(S.N);
@@ -773,7 +807,8 @@ gmcmc_status gmcmc_ctx_create_dist(int device, int rank, int world, const void* 
   gmcmc_ctx* c = new gmcmc_ctx();
   c->device = device; c->rank = rank; c->world = world; c->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete c;
     return fail(GMCMC_ERR_CUDA, "stream creation failed");
   }
@@ -796,6 +831,7 @@ gmcmc_status gmcmc_ctx_destroy(gmcmc_ctx* c) {
   if (c->comm) nccl_api().CommDestroy(c->comm);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   delete c;
   return GMCMC_OK;
 }
@@ -1035,10 +1071,13 @@ gmcmc_status gmcmc_hmc_create(gmcmc_ctx* ctx, gmcmc_target* tgt, size_t n_chains
   GM_TRY(sampler_common(ctx, tgt, n_chains, chain_offset, init_host, seed, S_HMC, &s));
   s->epl = epl; s->lpc = lpc; s->step_size = step_size; s->n_leapfrog = n_leapfrog;
   s->n_alpha_part = (n_chains * (size_t)lpc + 31) / 32;
-  bool ok = cudaMalloc(&s->d_eps, 8) == cudaSuccess &&
-            cudaMalloc((void**)&s->d_alpha_part, s->n_alpha_part * sizeof(double)) == cudaSuccess &&
+  bool ok = cudaMalloc(&s->d_eps, 16) == cudaSuccess &&
+            cudaMalloc((void**)&s->d_alpha_part, 2 * s->n_alpha_part * sizeof(double)) == cudaSuccess &&
             cudaMalloc((void**)&s->d_alpha_sum, 2 * sizeof(double)) == cudaSuccess &&
             cudaMalloc((void**)&s->d_pooled, sizeof(PooledDa)) == cudaSuccess;
+  for (int i = 0; i < 4 && ok; ++i)
+    ok = cudaEventCreateWithFlags(&s->ev_kern[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&s->ev_upd[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     gmcmc_status st = fail(GMCMC_ERR_CUDA, "sampler allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     gmcmc_sampler_destroy(s);
@@ -1142,8 +1181,11 @@ gmcmc_status gmcmc_sampler_destroy(gmcmc_sampler* s) {
   cudaFree(s->d_mass_inv); cudaFree(s->d_mass_sqrt); cudaFree(s->d_run_mean); cudaFree(s->d_run_m2);
   cudaFree(s->d_inj_normals); cudaFree(s->d_inj_lnu);
   cudaFree(s->d_diag_logacc); cudaFree(s->d_diag_acc); cudaFree(s->d_diag_pq); cudaFree(s->d_diag_pp);
+  cudaFree(s->d_diag_draws);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
+  for (cudaEvent_t e : s->ev_kern) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : s->ev_upd) if (e) cudaEventDestroy(e);
   gmcmc_target_destroy(s->tgt);
   delete s;
   return GMCMC_OK;
@@ -1214,6 +1256,7 @@ gmcmc_status gmcmc_inject(gmcmc_sampler* s, const void* normals, const void* ln_
   cudaFree(s->d_diag_logacc); cudaFree(s->d_diag_acc); cudaFree(s->d_diag_pq); cudaFree(s->d_diag_pp);
   s->d_inj_normals = s->d_inj_lnu = s->d_diag_logacc = s->d_diag_pq = s->d_diag_pp = nullptr;
   s->d_diag_acc = nullptr;
+  cudaFree(s->d_diag_draws); s->d_diag_draws = nullptr; s->rec_steps = 0;
   s->inj_steps = s->diag_steps = 0;
   const size_t es = esize(s->dtype), C = s->n_chains, d = (size_t)s->dim;
   GM_CU(cudaMalloc(&s->d_inj_normals, n_steps * C * d * es));
@@ -1228,6 +1271,36 @@ gmcmc_status gmcmc_inject(gmcmc_sampler* s, const void* normals, const void* ln_
   GM_CU(cudaMemcpy(s->d_inj_normals, normals, n_steps * C * d * es, cudaMemcpyHostToDevice));
   GM_CU(cudaMemcpy(s->d_inj_lnu, ln_u, n_steps * C * es, cudaMemcpyHostToDevice));
   s->inj_steps = s->diag_steps = n_steps;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_mh_record(gmcmc_sampler* s, size_t n_steps) {
+  GM_REQUIRE(s && s->type == S_MH, "gmcmc_mh_record applies to MH samplers");
+  GM_REQUIRE(n_steps >= 1, "n_steps must be >= 1");
+  if (s->dim != 2 || s->math != GMCMC_MATH_FAST || s->tgt->custom)
+    return fail(GMCMC_ERR_UNSUPPORTED, "gmcmc_mh_record instruments the 2-D fast-mode kernel (dim 2, GMCMC_MATH_FAST, built-in target)");
+  GM_CU(cudaSetDevice(s->ctx->device));
+  GM_CU(cudaStreamSynchronize(s->ctx->stream));
+  cudaFree(s->d_inj_normals); cudaFree(s->d_inj_lnu);
+  cudaFree(s->d_diag_logacc); cudaFree(s->d_diag_acc); cudaFree(s->d_diag_pq); cudaFree(s->d_diag_pp); cudaFree(s->d_diag_draws);
+  s->d_inj_normals = s->d_inj_lnu = s->d_diag_logacc = s->d_diag_pq = s->d_diag_pp = nullptr;
+  s->d_diag_acc = nullptr; s->d_diag_draws = nullptr;
+  s->inj_steps = s->diag_steps = s->rec_steps = 0;
+  const size_t es = esize(s->dtype), C = s->n_chains;
+  GM_CU(cudaMalloc(&s->d_diag_logacc, n_steps * C * es));
+  GM_CU(cudaMalloc((void**)&s->d_diag_acc, n_steps * C));
+  GM_CU(cudaMemset(s->d_diag_acc, 0, n_steps * C));
+  GM_CU(cudaMalloc((void**)&s->d_diag_draws, n_steps * C * 3 * sizeof(float)));
+  s->rec_steps = s->diag_steps = n_steps;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_mh_read_draws(gmcmc_sampler* s, float* draws_out) {
+  GM_REQUIRE(s && draws_out, "null argument");
+  if (!s->d_diag_draws || s->diag_steps == 0) return fail(GMCMC_ERR_STATE, "no recorded transitions (gmcmc_mh_record)");
+  GM_CU(cudaSetDevice(s->ctx->device));
+  GM_CU(cudaStreamSynchronize(s->ctx->stream));
+  GM_CU(cudaMemcpy(draws_out, s->d_diag_draws, s->diag_steps * s->n_chains * 3 * sizeof(float), cudaMemcpyDeviceToHost));
   return GMCMC_OK;
 }
 
@@ -1349,6 +1422,17 @@ gmcmc_status gmcmc_step(gmcmc_sampler* s) {
   return run_into(s, 0, 1, nullptr);
 }
 
+gmcmc_status gmcmc_reserve_samples(gmcmc_sampler* s, size_t n_collect) {
+  GM_REQUIRE(s, "null sampler");
+  GM_CU(cudaSetDevice(s->ctx->device));
+  GM_CU(cudaStreamSynchronize(s->ctx->stream));
+  if (n_collect == 0) {
+    if (s->d_samples) { cudaFree(s->d_samples); s->d_samples = nullptr; s->samples_cap = 0; }
+    return GMCMC_OK;
+  }
+  return ensure_samples(s, s->n_chains * n_collect * (size_t)s->dim * esize(out_dtype_of(s)));
+}
+
 gmcmc_status gmcmc_run_device(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void** out_dev) {
   GM_REQUIRE(s, "null sampler");
   GM_CU(cudaSetDevice(s->ctx->device));
@@ -1363,7 +1447,7 @@ gmcmc_status gmcmc_run_device(gmcmc_sampler* s, size_t n_collect, size_t n_disca
 // device->host copy of the previous chunk (copy stream + events).  Plain runs only (no injection, no adaptation
 // in flight, same dtype), HMC (register kernels) and MH.
 static bool can_pipeline(const gmcmc_sampler* s, size_t n_collect, gmcmc_dtype out_dtype) {
-  if (n_collect == 0 || s->inj_steps > 0 || (int)out_dtype != out_dtype_of(s)) return false;
+  if (n_collect == 0 || s->inj_steps > 0 || s->rec_steps > 0 || (int)out_dtype != out_dtype_of(s)) return false;
   if (s->type == S_MH) return s->n_chains >= 65536;
   if (s->type == S_HMC) return s->adapt == GMCMC_ADAPT_NONE && !(s->dense_tc && s->math == GMCMC_MATH_FAST) && s->n_chains >= 16384;
   return false;
@@ -1441,6 +1525,13 @@ gmcmc_status gmcmc_run(gmcmc_sampler* s, size_t n_collect, size_t n_discard, voi
 gmcmc_status gmcmc_run_stats(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void* out_host_or_null,
                              gmcmc_dtype out_dtype, gmcmc_run_stats_t* stats) {
   GM_REQUIRE(s && stats, "null argument");
+  // the limits of the device statistics are checked BEFORE any transition is taken: a failing call leaves the sampler
+  // (state, transition counter, counters) untouched
+  GM_REQUIRE(n_collect >= 4, "run_stats needs n_collect >= 4 draws for split R-hat / ESS (got %zu)", n_collect);
+  if (stats_npad(n_collect) > kStatsMaxPadded)
+    return fail(GMCMC_ERR_UNSUPPORTED, "run_stats: %zu draws per chain exceed the in-kernel FFT (padded length %zu > %zu); "
+                "collect with gmcmc_run / gmcmc_run_device and thin, or use at most %zu draws", n_collect, stats_npad(n_collect),
+                (size_t)kStatsMaxPadded, (size_t)kStatsMaxPadded + 1);
   void* d = nullptr;
   GM_CU(cudaSetDevice(s->ctx->device));
   GM_TRY(ensure_samples(s, s->n_chains * n_collect * (size_t)s->dim * esize(out_dtype_of(s))));

@@ -2,8 +2,7 @@
 
 Chains shard contiguously over ranks (api.shard_chains); the data path has no collective.  The tiny
 cross-chain reductions (pooled dual averaging, R-hat moments, summed power spectrum) run inside
-libgmcmc.so over its own NCCL communicator, whose unique id is exchanged here.  The numpy helpers at the
-bottom restate the moment combination of collective A2 so the N > 1 logic is testable on CPU (gloo).
+libgmcmc.so over its own NCCL communicator, whose unique id is exchanged here.
 """
 import os
 
@@ -54,6 +53,32 @@ def all_reduce_sum(a):
     return t.cpu().numpy()
 
 
+def chain_checksums(samples):
+    """One 64-bit checksum per chain of a [chains, n, d] sample tensor (sum of the raw bit patterns, wrapping):
+    what ranks exchange to verify that a sharded run reproduces the unsharded chains bit for bit."""
+    a = np.ascontiguousarray(samples)
+    bits = a.view(np.uint32 if a.dtype == np.float32 else np.uint64).reshape(a.shape[0], -1).astype(np.uint64)
+    w = (np.arange(bits.shape[1], dtype=np.uint64) * np.uint64(2654435761) + np.uint64(1))
+    return (bits * w).sum(axis=1, dtype=np.uint64)
+
+
+def pin_rank_to_local_cores(local_rank, ranks_on_node):
+    """Binds this process to its share of the host cores (contiguous slice of the allowed set) so that the ranks of
+    one node do not migrate over each other's cores while they drive PCIe copies; returns the cores kept."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return None
+    n = max(1, int(ranks_on_node))
+    per = max(1, len(allowed) // n)
+    mine = allowed[(local_rank % n) * per:(local_rank % n + 1) * per] or allowed
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        return None
+    return mine
+
+
 def make_context(device=None):
     """Context for this rank: initialises torch.distributed (NCCL) when WORLD_SIZE > 1 and hands the NCCL
     unique id of libgmcmc's own communicator to every rank."""
@@ -69,27 +94,3 @@ def make_context(device=None):
         dist.init_process_group("nccl", device_id=torch.device("cuda", device))
     nid = broadcast_bytes(api.Context.nccl_unique_id() if rank == 0 else None, 128, src=0)
     return api.Context(device, rank, world, nid)
-
-
-# ---- collective A2 restated on the host (what stats_accumulate / stats_finalize do on the device) ----
-def rhat_moment_partials(samples):
-    """[sum of split-chain means, sum of their squares, sum of within variances, chains] per parameter,
-    stats.rs:419-504 with the chain split (splitcat)."""
-    s = np.asarray(samples, np.float64)
-    c, n, p = s.shape
-    half = n // 2
-    halves = np.concatenate([s[:, :half], s[:, n - half:]], axis=0)
-    m = halves.mean(axis=1)
-    w = ((halves - m[:, None, :]) ** 2).mean(axis=1)
-    return np.stack([m.sum(0), (m * m).sum(0), w.sum(0), np.full(p, float(c))])
-
-
-def rhat_from_moments(tot, n):
-    sm, sm2, sw, c = tot
-    half = n // 2
-    c2 = 2.0 * c
-    om = sm / c2
-    b = (sm2 - c2 * om * om) * (half / (c2 - 1.0))
-    w = sw / c2
-    v = (half - 1.0) / half * w + b / half
-    return np.sqrt(w / v)          # reference orientation, stats.rs:452-454

@@ -98,7 +98,7 @@ typedef struct {
 
 typedef struct {
   uint64_t transitions;  /* chain-transitions taken by this rank since creation */
-  uint64_t accepts;      /* accepted proposals (this rank) */
+  uint64_t accepts;      /* accepted proposals (this rank); NUTS: transitions that accepted a subtree proposal */
   uint64_t grad_evals;   /* algorithmic gradient evaluations: HMC L per transition; NUTS leapfrogs taken */
   uint64_t divergences;  /* non-finite log-accept (HMC) / s' = false by energy (NUTS) */
   double step_size;      /* current (pooled or mean per-chain) step size */
@@ -176,6 +176,13 @@ gmcmc_status gmcmc_set_step_size(gmcmc_sampler*, double step_size);
  * instead of Philox.  HMC: normals [n_steps, n_chains, dim], ln_u [n_steps, n_chains].
  * MH: same shapes (normals = proposal noise).  NUTS: see gmcmc_nuts_inject. */
 gmcmc_status gmcmc_inject(gmcmc_sampler*, const void* normals, const void* ln_u, size_t n_steps);
+/* Test hook for the production 2-D fast-mode MH kernel (which draws from Philox only): the next `n_steps`
+ * transitions run through that same kernel and record, per step and chain, the log ratio and the decision (read
+ * with gmcmc_read_diagnostics) and the proposal noise / accept uniform it actually used (gmcmc_mh_read_draws:
+ * float [n_steps, n_chains, 3] = z0, z1, u).  Feeding those draws to the reference's MHMarkovChain::step
+ * (metropolis_hastings.rs:306-318) must reproduce the chain. */
+gmcmc_status gmcmc_mh_record(gmcmc_sampler*, size_t n_steps);
+gmcmc_status gmcmc_mh_read_draws(gmcmc_sampler*, float* draws_out);
 /* NUTS: per-chain streams in the reference's draw order: normals [C, n_norm],
  * exp1 [C, n_exp], unif [C, n_unif], all f64. */
 gmcmc_status gmcmc_nuts_inject(gmcmc_sampler*, const double* normals, size_t n_norm, const double* exp1,
@@ -211,8 +218,14 @@ gmcmc_status gmcmc_run(gmcmc_sampler*, size_t n_collect, size_t n_discard, void*
 /* ≙ BatchedGenericHMC::run_positions (batched_hmc.rs:115-123): samples stay on the device.
  * *out_dev: library-owned [C, n_collect, dim] (sampler dtype; f64 for MH). */
 gmcmc_status gmcmc_run_device(gmcmc_sampler*, size_t n_collect, size_t n_discard, void** out_dev);
+/* Sizes the library-owned device sample buffer for runs of up to n_collect draws per chain now (a multi-GB
+ * cudaMalloc) instead of inside the first gmcmc_run_device / gmcmc_run_stats that needs it.  n_collect = 0 frees it. */
+gmcmc_status gmcmc_reserve_samples(gmcmc_sampler*, size_t n_collect);
 /* ≙ run_progress (hmc.rs:245-306, core.rs:251-403, generic_nuts.rs:414-548) without the terminal UI:
- * samples (optional, may be NULL) + RunStats computed on the device over ALL ranks' chains. */
+ * samples (optional, may be NULL) + RunStats computed on the device over ALL ranks' chains.
+ * Limits of the device statistics (checked before any transition is taken, so a refused call leaves the sampler
+ * untouched): 4 <= n_collect <= 16385 (padded FFT length <= 16384) — GMCMC_ERR_INVALID / GMCMC_ERR_UNSUPPORTED
+ * otherwise.  The same limits apply to gmcmc_split_rhat_ess / gmcmc_run_stats_from. */
 gmcmc_status gmcmc_run_stats(gmcmc_sampler*, size_t n_collect, size_t n_discard, void* out_host_or_null,
                              gmcmc_dtype out_dtype, gmcmc_run_stats_t* stats);
 gmcmc_status gmcmc_positions(gmcmc_sampler*, void* out_host); /* ≙ positions() hmc.rs:318 */

@@ -268,6 +268,14 @@ void orc_nuts_run_mass_f32(int kind, int dim, const double* params, size_t np, s
   nuts_run<float>(kind, dim, params, np, C, q, target_accept, max_depth, eps_init, n_collect, n_discard, normals, n_norm, exp1, n_exp, unif, n_unif, samples, eps_final, leapfrogs, used, exhausted, mass_cfg, mass_inv_out);
 }
 
+// ---- mass matrix (MassMatrix::diagonal_from_var / kinetic / inv_mul, generic_nuts.rs:196-206, 228-281) ----
+// Reference KAT generic_nuts.rs:1427-1440: var = [4, 9], p = [2, 3] -> kinetic = 1.0, inv_mul = [0.5, 1/3].
+double orc_diag_mass_kinetic_inv_mul_f64(const double* var, int d, double jitter, const double* p, double* inv_mul_out) {
+  DiagMass<double> m = DiagMass<double>::from_var(std::vector<double>(var, var + d), jitter);
+  for (int i = 0; i < d; ++i) inv_mul_out[i] = m.inv[i] * p[i];   // inv_mul, :265-281
+  return nuts_kinetic<double>(p, d, &m);
+}
+
 // ---- stats ----
 void orc_split_rhat_mean_ess(const float* sample, size_t c, size_t n, size_t p, float* rhat, float* ess_out) { split_rhat_mean_ess(sample, c, n, p, rhat, ess_out); }
 void orc_autocov_bf(const float* x, size_t n, size_t d, float* out) { autocov_bf(x, n, d, out); }
@@ -291,6 +299,13 @@ void orc_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out) 
 double orc_hmc_bench_f32(int kind, int dim, const double* params, size_t np, size_t C, float* q, float eps, int L, size_t n_steps, uint64_t seed, int threads, float* samples) { return hmc_bench<float>(kind, dim, params, np, C, q, eps, L, n_steps, seed, threads, samples); }
 double orc_hmc_bench_f64(int kind, int dim, const double* params, size_t np, size_t C, double* q, double eps, int L, size_t n_steps, uint64_t seed, int threads, double* samples) { return hmc_bench<double>(kind, dim, params, np, C, q, eps, L, n_steps, seed, threads, samples); }
 double orc_mh_bench_f64(int kind, int dim, const double* params, size_t np, double prop_std, size_t C, double* x, size_t n_steps, uint64_t seed, int threads, double* samples) { return mh_bench<double>(kind, dim, params, np, prop_std, C, x, n_steps, seed, threads, samples); }
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -51,6 +51,7 @@ def lib(fast=False):
         L.orc_hmc_bench_f64.restype = C.c_double
         L.orc_mh_bench_f64.restype = C.c_double
         L.orc_max_threads.restype = C.c_int
+        L.orc_diag_mass_kinetic_inv_mul_f64.restype = C.c_double
         _libs[key] = L
     return _libs[key]
 
@@ -166,7 +167,7 @@ def nuts_find_reasonable_epsilon(kind, params, q, p):
 
 
 def nuts_run(kind, params, q0, target_accept, max_depth, eps_init, n_collect, n_discard, normals, exp1, unif,
-             mass_cfg=None):
+             mass_cfg=None, fast=False):
     """normals [C,nn], exp1 [C,ne], unif [C,nu] float64 streams (consumed in reference order).  mass_cfg =
     (start_buffer, end_buffer, initial_window, regularize, jitter) enables diagonal mass-matrix adaptation."""
     q = np.array(q0, copy=True, order="C")
@@ -188,12 +189,21 @@ def nuts_run(kind, params, q0, target_accept, max_depth, eps_init, n_collect, n_
             _p(leap), _p(used), _p(exh)]
     mass_inv = None
     if mass_cfg is None:
-        getattr(lib(), "orc_nuts_run_" + _sfx(dt))(*args)
+        getattr(lib(fast), "orc_nuts_run_" + _sfx(dt))(*args)
     else:
         cfg = np.ascontiguousarray(mass_cfg, np.float64)
         mass_inv = np.ones((Cn, d), dt)
-        getattr(lib(), "orc_nuts_run_mass_" + _sfx(dt))(*args, _p(cfg), _p(mass_inv))
+        getattr(lib(fast), "orc_nuts_run_mass_" + _sfx(dt))(*args, _p(cfg), _p(mass_inv))
     return dict(q=q, samples=samples, eps=eps_f, leapfrogs=leap, used=used, exhausted=exh, mass_inv=mass_inv)
+
+
+def diag_mass_kinetic_inv_mul(var, p, jitter=1e-12):
+    """MassMatrix::diagonal_from_var(var, jitter) -> (kinetic(p), inv_mul(p)) (generic_nuts.rs:196-281)."""
+    var = np.ascontiguousarray(var, np.float64)
+    p = np.ascontiguousarray(p, np.float64)
+    out = np.zeros_like(p)
+    ke = lib().orc_diag_mass_kinetic_inv_mul_f64(_p(var), C.c_int(var.size), C.c_double(jitter), _p(p), _p(out))
+    return ke, out
 
 
 def split_rhat_mean_ess(sample):
@@ -259,6 +269,10 @@ def mh_bench(kind, params, x0, prop_std, n_steps, seed=42, threads=0, keep_sampl
                                            C.c_size_t(Cn), _p(x), C.c_size_t(n_steps), C.c_uint64(seed),
                                            C.c_int(threads), _p(samples))
     return secs, x, samples
+
+
+def set_threads(n, fast=True):
+    lib(fast).orc_set_threads(C.c_int(n))
 
 
 def max_threads():

@@ -68,6 +68,37 @@ def test_dense_tc_per_step_equivalence(ctx, oracle, d, Cn, L, eps):
     assert np.array_equal(out[~acc, 0], q0[~acc])
 
 
+@pytest.mark.parametrize("scale", [1e-8, 1.0, 1e10], ids=["cov1e-8", "cov1", "cov1e+10"])
+def test_dense_tc_any_variance_scale(ctx, oracle, scale):
+    """The FP16 x 3 operand split must not depend on the target's units: delta = q - mu is scaled per transition by a
+    power of two (as P is at set-up), so covariance scales of 1e-8 and 1e+10 (|delta| ~ 1e-4 and ~ 1e+5, beyond FP16's
+    normal range without the scale) meet the same relative bar as O(1) targets."""
+    d, Cn, L = 128, 256, 8
+    rng = np.random.default_rng(5)
+    qm, _ = np.linalg.qr(rng.standard_normal((d, d)))
+    lam = np.logspace(-1, 1, d) * scale
+    tgt = gm.DenseGaussian(rng.standard_normal(d) * np.sqrt(scale), cov=(qm * lam) @ qm.T)
+    eps = 0.05 * np.sqrt(scale)
+    q0 = (tgt.mean + rng.standard_normal((Cn, d)) * np.sqrt(scale)).astype(np.float32)
+    # with eps ~ sqrt(scale) the dynamics are scale-free: momenta stay N(0, 1) (kinetic and potential energy are O(1))
+    mom = rng.standard_normal((1, Cn, d)).astype(np.float32)
+    ln_u = np.log(rng.random((1, Cn))).astype(np.float32)
+    params32 = np.asarray(tgt.params(), np.float32).astype(np.float64)
+    ref = oracle.hmc_run(tgt.kind, params32, q0.astype(np.float64), np.float64(np.float32(eps)), L,
+                         mom.astype(np.float64), ln_u.astype(np.float64), want_traj=True)
+    s = gm.HMC(tgt, q0, eps, L, seed=1, ctx=ctx)
+    s.inject(mom, ln_u)
+    s.run(1, 0)
+    diag = s.diagnostics()
+    assert np.isfinite(diag["prop_q"]).all() and np.isfinite(diag["log_accept"]).all()
+    dq = ref["prop_q"] - q0.astype(np.float64)[None]
+    err_q = np.max(np.abs(diag["prop_q"] - ref["prop_q"])) / max(np.abs(dq).max(), np.abs(q0 - tgt.mean).max())
+    err_p = np.max(np.abs(diag["prop_p"] - ref["prop_p"])) / np.abs(ref["prop_p"]).max()
+    print("cov scale %g: rel err q %.2e p %.2e, accept %.2f" % (scale, err_q, err_p, diag["accepted"].mean()))
+    assert err_q <= 1e-5 and err_p <= 1e-5
+    assert diag["accepted"].mean() > 0.3
+
+
 def test_dense_tc_matches_register_kernel_and_distribution(ctx):
     """Same Philox streams as K1: the tensor-core path and the register path (GMCMC_DENSE_TC=0 is the env switch;
     here the exact-mode sampler uses K1) produce the same chains up to the 3xTF32 rounding, and recover the target

@@ -230,3 +230,104 @@ def test_nuts_dense_mass_adaptation_is_unsupported(ctx):
     with pytest.raises(Exception):
         gm.NUTS(gm.IsotropicGaussian(1.0, 3), np.zeros((4, 3), np.float32), 0.8, seed=1, ctx=ctx,
                 mass_matrix=gm.NUTSMassMatrixConfig("dense"))
+
+
+# -------------------------------------------------------------------------------------------------
+# BASELINE config 5: NUTS on the 100-D, 4-component isotropic Gaussian mixture.  d = 100 runs at the production
+# decomposition (8 coordinates x 16 lanes per chain): mixture means staged in shared memory, and in fast mode the
+# packed transpose-reduce of the four components' partial sums.
+# -------------------------------------------------------------------------------------------------
+def _mixture(d=100, K=4):
+    mu = np.stack([(k - 1.5) * (2.0 / np.sqrt(d)) * np.ones(d) for k in range(K)])
+    return gm.GaussianMixture(np.full(K, 1.0 / K), mu, 1.0)
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+def test_nuts_cfg5_mixture_first_transition_matches_oracle(ctx, oracle, dtype, exact):
+    """generic_nuts.rs:755-925 on the cfg5 target.  run(2, 0) = init_chain_state (find_reasonable_epsilon, powers of
+    two) + ONE transition with that step size, no dual averaging in the trajectory: the only non-IEEE operations are the
+    mixture's exp / log (device libm or MUFU vs glibc), so tree shapes agree except where a slice / U-turn decision sits
+    on a rounding boundary, and the matching chains agree to rounding."""
+    Cn, d = 96, 100
+    tgt = _mixture(d)
+    rng = np.random.default_rng(31)
+    q0 = rng.standard_normal((Cn, d)).astype(dtype)
+    normals, exp1, unif = _streams(Cn, d, 2, seed=37, n_unif=4000)
+    ref = oracle.nuts_run(tgt.kind, tgt.params(), q0, 0.8, 10, -1.0, 2, 0, normals, exp1, unif)
+    assert not ref["exhausted"].any()
+    s = gm.NUTS(tgt, q0, 0.8, seed=1, ctx=ctx, max_depth=10).set_math_mode(exact)
+    assert (s.dim, s.n_chains) == (100, Cn)
+    s.inject_streams(normals, exp1, unif)
+    out = s.run(2, 0)
+    st = s.state()
+    same = (st["leapfrogs"] == ref["leapfrogs"])
+    tol = (1e-5 if not exact else 2e-6) if dtype == np.float32 else (1e-10 if not exact else 1e-12)
+    err = np.abs(out[same].astype(np.float64) - ref["samples"][same].astype(np.float64)).max() if same.any() else 0.0
+    print("cfg5 mixture %s %s: same trees %.3f, mean leapfrogs %.1f, max |dx| %.2e" % (
+        dtype.__name__, "exact" if exact else "fast", same.mean(), ref["leapfrogs"].mean(), err))
+    assert np.array_equal(out[:, 0, :], q0)
+    assert same.mean() >= 0.95
+    assert np.array_equal(st["eps"][same], ref["eps"][same])          # eps_bar = 1 after a transition without warm-up
+    assert np.array_equal(st["used"][same].astype(np.int64), ref["used"][same])
+    assert err <= tol * (1.0 + np.abs(ref["samples"]).max())
+    assert ref["leapfrogs"].mean() > 6                                  # non-trivial trees
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+def test_nuts_cfg5_mixture_with_adaptation_matches_oracle(ctx, oracle, exact):
+    """Warm-up + collection on the cfg5 target, f32, injected streams, as test_nuts_with_adaptation_matches_oracle."""
+    Cn, d, n_collect, n_discard = 128, 100, 3, 5
+    tgt = _mixture(d)
+    rng = np.random.default_rng(41)
+    q0 = rng.standard_normal((Cn, d)).astype(np.float32)
+    normals, exp1, unif = _streams(Cn, d, n_collect + n_discard, seed=43, n_unif=20000)
+    ref = oracle.nuts_run(tgt.kind, tgt.params(), q0, 0.8, 10, -1.0, n_collect, n_discard, normals, exp1, unif)
+    assert not ref["exhausted"].any()
+    s = gm.NUTS(tgt, q0, 0.8, seed=1, ctx=ctx, max_depth=10).set_math_mode(exact)
+    s.inject_streams(normals, exp1, unif)
+    out = s.run(n_collect, n_discard)
+    st = s.state()
+    same = (st["leapfrogs"] == ref["leapfrogs"])
+    err = np.abs(out[same] - ref["samples"][same]).reshape(same.sum(), -1).max(1)
+    eps_err = np.abs(st["eps"][same] - ref["eps"][same]) / ref["eps"][same]
+    print("cfg5 mixture adapt %s: same trees %.3f, mean leapfrogs/transition %.1f, median |dx| %.2e, median eps err %.2e" % (
+        "exact" if exact else "fast", same.mean(), ref["leapfrogs"].mean() / (n_collect + n_discard - 1), np.median(err),
+        np.median(eps_err)))
+    assert same.mean() > 0.8
+    assert np.median(err) < 2e-4 and np.median(eps_err) < 1e-4
+
+
+def test_nuts_cfg5_mixture_distribution(ctx):
+    """Philox path at the bench shape (d = 100, K = 4, depth <= 10, target accept 0.8): the chain projected on the
+    direction of the component means is the 1-D mixture of N(-3,1), N(-1,1), N(1,1), N(3,1) (mean 0, variance 6), every
+    orthogonal direction is N(0,1); mode occupancies from the normal CDF; split R-hat < 1.01 (north star)."""
+    from math import erf, sqrt
+    Cn, d = 8192, 100
+    tgt = _mixture(d)
+    q0 = np.random.default_rng(51).standard_normal((Cn, d)).astype(np.float32)
+    s = gm.NUTS(tgt, q0, 0.8, seed=42, ctx=ctx, max_depth=10)
+    out, st = s.run_progress(300, 200)
+    assert np.isfinite(out).all()
+    u = np.ones(d) / np.sqrt(d)
+    t = out.astype(np.float64) @ u                       # [C, n]
+    flat = t.ravel()
+    Phi = lambda z: 0.5 * (1.0 + erf(z / sqrt(2.0)))
+    modes = np.array([-3.0, -1.0, 1.0, 3.0])
+    edges = [-np.inf, -2.0, 0.0, 2.0, np.inf]
+    want = np.array([np.mean([Phi(edges[i + 1] - m) - Phi(edges[i] - m) for m in modes]) for i in range(4)])
+    got = np.array([np.mean((flat >= edges[i]) & (flat < edges[i + 1])) for i in range(4)])
+    resid = out.astype(np.float64) - t[..., None] * u
+    var_orth = (resid ** 2).sum(-1).mean() / (d - 1)
+    c = s.counters()
+    print("cfg5 mixture distribution: occupancy", got, "want", want, "mean %.3f var %.3f var_orth %.4f rhat max %.4f "
+          "ess min %.0f accept %.3f eps %.3f leapfrogs/transition %.1f" % (
+              flat.mean(), flat.var(), var_orth, st.rhat_std.max, st.ess.min, c.accept_rate, c.step_size,
+              c.grad_evals / c.transitions))
+    assert np.allclose(got, want, atol=0.01)
+    assert abs(flat.mean()) < 0.05 and abs(flat.var() / 6.0 - 1.0) < 0.03
+    assert abs(var_orth - 1.0) < 0.01
+    per_coord = out.reshape(-1, d).astype(np.float64).var(0)
+    assert np.allclose(per_coord, 1.0 + 5.0 * 4.0 / d, rtol=0.05)
+    assert st.rhat_std.max < 1.01
+    assert 0.5 < c.accept_rate <= 1.0 and c.divergences == 0

@@ -56,6 +56,13 @@ def test_nuts_run_1_0_returns_initial_point():
     np.testing.assert_allclose(r["samples"][0, 0], [0.0, 1.0], rtol=1e-5, atol=1e-6)
 
 
+def test_diagonal_mass_matrix_kat():
+    # /root/reference/src/generic_nuts.rs:1427-1440 (diagonal_mass_matrix_kinetic_and_inv_mul_are_consistent)
+    ke, out = O.diag_mass_kinetic_inv_mul([4.0, 9.0], [2.0, 3.0], jitter=1e-12)
+    assert abs(ke - 1.0) < 1e-12
+    assert abs(out[0] - 0.5) < 1e-12 and abs(out[1] - 1.0 / 3.0) < 1e-12
+
+
 def test_nuts_chain_runs_finite():
     # nuts.rs:603-665 (test_chain_2/3, test_run_1): finite, |x| < 100
     rng = np.random.default_rng(1)
