@@ -117,6 +117,7 @@ struct TParams {          // per-launch target parameters in T
   T sp[kMaxScalarParams];
   const T* dp;            // device block (dense Gaussian: mu[d], P[d*d], nc; mixture: w[K], mu[K*d])
   const T* smem_mu;       // mixture means staged in shared memory, lane-padded [K][lpc][roundup(EPL, 4)], or null
+  const T* smem_logw;     // mixture log weights staged in shared memory [K], or null
   int n_comp;
   // derived for DiffableGaussian2D (distributions.rs:229-253)
   T inv_cov[2][2];
@@ -342,12 +343,36 @@ __device__ __forceinline__ T eval_target(TagMixture, const T (&x)[EPL], T (&g)[E
     const T q0 = b1 ? other : keep, q1 = b1 ? keep : other;        // components 2 b0, 2 b0 + 1
     const T o0 = __shfl_xor_sync(kFull, q0, 1), o1 = __shfl_xor_sync(kFull, q1, 1);
     sk[0] = b0 ? o0 : q0; sk[1] = b0 ? o1 : q1; sk[2] = b0 ? q0 : o0; sk[3] = b0 ? q1 : o1;
+    // K = 4 stays in registers and fully unrolled from here on (no local-memory array, no component loops)
+    T ak[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const T ak = fast_log<T>(w[k]) - T(0.5) * sk[k] * inv_var;
-      a[k] = ak;
-      amax = max(amax, ak);
+      const T lw = tp.smem_logw ? tp.smem_logw[k] : fast_log<T>(w[k]);
+      ak[k] = lw - T(0.5) * sk[k] * inv_var;
     }
+    const T am = max(max(ak[0], ak[1]), max(ak[2], ak[3]));
+    T ek[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ek[k] = fast_exp<T>(ak[k] - am);
+    const T se4 = (ek[0] + ek[1]) + (ek[2] + ek[3]);
+    const T inv_se = fast_div<T>(T(1), se4);
+    T acc4[EPL];
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) acc4[j] = T(0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      T m[EPL];
+      mixture_mean_slice<T, EPL>(m, tp, mu, k, d, ln);
+      const T rk = ek[k] * inv_se;
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) {
+        const T dm = (!PADDED || j < ln.nvalid) ? (m[j] - x[j]) : T(0);
+        acc4[j] = fma(rk, dm, acc4[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) g[j] = acc4[j] * inv_var;
+    return am + fast_log<T>(se4);
   } else {
 #pragma unroll 1
     for (int k = 0; k < K; ++k) {
@@ -359,7 +384,8 @@ __device__ __forceinline__ T eval_target(TagMixture, const T (&x)[EPL], T (&g)[E
         terms[j] = df * df;
       }
       const T sq = chain_sum<T, EPL>(terms, ln);
-      const T ak = fast_log<T>(w[k]) - T(0.5) * sq * inv_var;
+      const T lw = tp.smem_logw ? tp.smem_logw[k] : fast_log<T>(w[k]);
+      const T ak = lw - T(0.5) * sq * inv_var;
       a[k] = ak;
       amax = max(amax, ak);
     }
@@ -525,6 +551,7 @@ __host__ inline TParams<T> make_tparams(const TargetDesc& td) {
   for (int i = 0; i < kMaxScalarParams; ++i) tp.sp[i] = (T)td.sp[i];
   tp.dp = (const T*)td.dparams;
   tp.smem_mu = nullptr;
+  tp.smem_logw = nullptr;
   tp.n_comp = td.n_comp;
   tp.inv_cov[0][0] = tp.inv_cov[0][1] = tp.inv_cov[1][0] = tp.inv_cov[1][1] = T(0);
   tp.norm_const = T(0);
@@ -571,7 +598,7 @@ struct HmcArgs {
   uint32_t out_t0;
   unsigned long long* accept_total;
   unsigned long long* diverge_total;
-  double* alpha_part;   // [warps of the grid] per-warp sum of min(1, exp(log_accept)) or null
+  double* alpha_part;   // [n_steps][warps of the grid] per-transition, per-warp sums of min(1, exp(log_accept)), or null
   T* da_eps; T* da_eps_bar; T* da_h_bar; T* da_mu;
   uint32_t da_m_base, da_n_adapt;
   T da_delta;
@@ -688,7 +715,6 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
   }
 
   unsigned int n_accept = 0, n_diverge = 0;
-  double alpha_acc = 0.0;
   // log density of the current point, carried from transition to transition: it is the same function
   // of the same position the reference re-evaluates (batched_hmc.rs:138), hence bit-identical
   T logp_cur = T(0);
@@ -789,7 +815,13 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
     if (active && ln.part == 0) {
       n_accept += accept ? 1u : 0u;
       n_diverge += finite ? 0u : 1u;
-      alpha_acc += (double)alpha;
+    }
+    if (a.alpha_part) {
+      // acceptance statistic of THIS transition, summed over the warp's chains in a fixed order (xor tree: the same
+      // value on every lane), one partial per (transition, warp): the pooled dual-averaging input (collective A1)
+      double al = (active && ln.part == 0) ? (double)alpha : 0.0;
+      for (int o = 16; o > 0; o >>= 1) al += __shfl_xor_sync(kFull, al, o);
+      if (lane == 0) a.alpha_part[(size_t)s * ((size_t)gridDim.x * (kHmcBlock / 32)) + ((size_t)(blockIdx.x * blockDim.x + threadIdx.x) >> 5)] = al;
     }
 
     if (a.diag_logacc && active) {
@@ -838,12 +870,10 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
   for (int o = 16; o > 0; o >>= 1) {
     n_accept += __shfl_xor_sync(kFull, n_accept, o);
     n_diverge += __shfl_xor_sync(kFull, n_diverge, o);
-    alpha_acc += __shfl_xor_sync(kFull, alpha_acc, o);   // xor tree: same value on every lane, fixed order
   }
   if (lane == 0) {
     if (n_accept) atomicAdd(a.accept_total, (unsigned long long)n_accept);
     if (n_diverge) atomicAdd(a.diverge_total, (unsigned long long)n_diverge);
-    if (a.alpha_part) a.alpha_part[(size_t)(blockIdx.x * blockDim.x + threadIdx.x) >> 5] = alpha_acc;
   }
 }
 

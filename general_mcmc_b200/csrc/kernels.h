@@ -40,7 +40,7 @@ struct HmcLaunch {
   // statistics
   unsigned long long* accept_total;  // [1]
   unsigned long long* diverge_total; // [1]
-  double* alpha_part;                // [ceil(C*lpc/32)] per-warp sums of min(1, exp(log_accept)) over the launch, or null
+  double* alpha_part;                // [n_steps][warps of the grid] per-transition, per-warp sums of min(1, exp(log_accept)), or null
   // per-chain dual averaging (GMCMC_ADAPT_PER_CHAIN), all T [C]; null otherwise
   void* da_eps; void* da_eps_bar; void* da_h_bar; void* da_mu;
   uint32_t da_m_base;    // adaptation iteration of the first transition of this launch (1-based m = base + s + 1)

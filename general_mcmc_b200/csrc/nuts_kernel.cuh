@@ -181,58 +181,102 @@ __device__ __forceinline__ void chain_sum_fn2(const Lane& ln, F1 f1, F2 f2, T& o
 #define GM_NUTS_MINB 3
 #endif
 
+// Targets whose padded slots (coordinates past the end of the chain in a non exact-fit decomposition) may simply hold
+// zeros: a zero position / momentum there contributes exact zeros to every sum and receives a zero gradient, so the
+// trajectory code needs no per-coordinate masks (which cost ~20 % of the NUTS kernel's instructions at d = 100 = 8 x 16 - 28).
+template <class TAG> struct PadSafe { static constexpr bool value = false; };
+template <> struct PadSafe<TagIsoGauss> { static constexpr bool value = true; };
+template <> struct PadSafe<TagMixture> { static constexpr bool value = true; };
+
+// unmasked slice moves for lane-padded vectors (padded slots hold harmless values by construction)
+template <class T, int EPL>
+__device__ __forceinline__ void load_slice_raw(T (&dst)[EPL], const T* src, const Lane& ln) {
+  using V = typename VecOf<T>::type;
+  constexpr int VN = VecOf<T>::n;
+  constexpr int EPLP = Eplp<EPL>::value;
+  const V* s = reinterpret_cast<const V*>(src + (size_t)ln.part * EPLP);
+#pragma unroll
+  for (int i = 0; i < EPLP / VN; ++i) {
+    if (i * VN < EPL) {
+      const V v = s[i];
+      if constexpr (VN == 4) {
+        dst[i * 4] = v.x;
+        if (i * 4 + 1 < EPL) dst[i * 4 + 1 < EPL ? i * 4 + 1 : 0] = v.y;
+        if (i * 4 + 2 < EPL) dst[i * 4 + 2 < EPL ? i * 4 + 2 : 0] = v.z;
+        if (i * 4 + 3 < EPL) dst[i * 4 + 3 < EPL ? i * 4 + 3 : 0] = v.w;
+      } else {
+        dst[i * 2] = v.x;
+        if (i * 2 + 1 < EPL) dst[i * 2 + 1 < EPL ? i * 2 + 1 : 0] = v.y;
+      }
+    }
+  }
+}
+
+// Hot per-chain vectors kept in shared memory (lane-padded, wd elements each): the two trajectory edges' (q, p) — the
+// other end of the whole-trajectory U-turn test and the restart point of a direction flip — and the (q, p) of the last
+// even leaf, which is the first leaf of the left subtree of EVERY level-0 merge (half of all merges).  Deeper merges
+// (level k >= 1: one per 2^(k+1) leaves) read their first leaf from the global workspace.
+enum NutsHot : int { H_QM = 0, H_PM = 1, H_QP = 2, H_PP = 3, H_LQ = 4, H_LP = 5, H_COUNT = 6 };
+
 // MASS: diagonal mass matrix + warm-up statistics compiled in (GenericNUTS::new_with_mass_matrix); the identity-mass
 // instantiation carries none of it (measured: the run-time test alone cost 16 % on BASELINE config 5).
-template <class T, int EPL, class TAG, bool PADDED, bool MASS>
+// LPC: lanes per chain as a compile-time constant (0 = run-time a.lpc): the shuffle trees unroll.
+template <class T, int EPL, class TAG, bool PADDED, bool MASS, int LPC>
 __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const NutsArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* smem = reinterpret_cast<T*>(smem_raw);
+  constexpr bool EP = PADDED && !PadSafe<TAG>::value;     // per-coordinate masks needed in the trajectory arithmetic
+  constexpr int EPLP = Eplp<EPL>::value;
+  const T pad_q = PadSafe<TAG>::value ? T(0) : T(1);      // position value of padded slots / idle lane groups
 
   // Lane groups are persistent workers: group `slot` starts with chain `slot` and, whenever its chain has finished
   // all its transitions, takes the next chain from a global queue — tree sizes are heavy-tailed (a few chains build
   // 20x larger trees), so a static chain -> lane-group assignment would leave most of the GPU waiting for them.
+  const int lpc = LPC > 0 ? LPC : a.lpc;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const Lane ln = make_lane<EPL>(tid, a.lpc, a.d);
-  const size_t slot_id = (size_t)(tid / a.lpc);      // workspace row of this lane group
+  const Lane ln = make_lane<EPL>(tid, lpc, a.d);
+  const size_t slot_id = (size_t)(tid / lpc);      // workspace row of this lane group
   size_t chain = slot_id;
   bool active = chain < a.n_chains;
   const int lane = threadIdx.x & 31;
-  const int chains_in_warp = 32 / a.lpc;
-  const int chain_in_warp = lane / a.lpc;
+  const int chains_in_warp = 32 / lpc;
+  const int chain_in_warp = lane / lpc;
   const size_t warp_elems = (size_t)chains_in_warp * a.d_pad;
   T* warp_pos = smem + (size_t)(threadIdx.x >> 5) * 2 * warp_elems;
   T* pos_row = warp_pos + (size_t)chain_in_warp * a.d_pad;
   T* row = warp_pos + warp_elems + (size_t)chain_in_warp * a.d_pad;
   unsigned long long gchain = a.chain_offset + chain;
   const size_t d = (size_t)a.d;
-  const size_t wd = (size_t)a.lpc * Eplp<EPL>::value;   // lane-padded workspace vector length
+  const size_t wd = (size_t)lpc * EPLP;   // lane-padded workspace vector length
   const size_t cw = slot_id;
 
-  T* e_qm = a.ws_edges + (cw * 6 + 0) * wd;
-  T* e_pm = a.ws_edges + (cw * 6 + 1) * wd;
-  T* e_gm = a.ws_edges + (cw * 6 + 2) * wd;
-  T* e_qp = a.ws_edges + (cw * 6 + 3) * wd;
-  T* e_pp = a.ws_edges + (cw * 6 + 4) * wd;
+  T* e_gm = a.ws_edges + (cw * 6 + 2) * wd;     // edge gradients: only read back on a direction flip
   T* e_gp = a.ws_edges + (cw * 6 + 5) * wd;
   T* w_first = a.ws_first + cw * (size_t)a.cap * 2 * wd;
   T* w_prime = a.ws_prime + cw * (size_t)a.cap * wd;
 
-  // mixture: component means staged once per CTA in shared memory, lane-padded for vector loads
+  size_t smem_off = (size_t)(kHmcBlock >> 5) * 2 * warp_elems;
+  smem_off = (smem_off + 3) / 4 * 4;
+  // mixture: component means and log weights staged once per CTA in shared memory, lane-padded for vector loads
   TParams<T> tp = a.tp;
   if constexpr (std::is_same<TAG, TagMixture>::value) {
-    constexpr int EPLP = Eplp<EPL>::value;
-    T* smu = smem + (size_t)(kHmcBlock >> 5) * 2 * warp_elems;
+    T* smu = smem + smem_off;
     const int K = a.tp.n_comp;
     const T* gmu = a.tp.dp + K;
-    for (int i = threadIdx.x; i < K * a.lpc * EPLP; i += blockDim.x) {
-      const int k = i / (a.lpc * EPLP), rem = i - k * (a.lpc * EPLP);
+    for (int i = threadIdx.x; i < K * lpc * EPLP; i += blockDim.x) {
+      const int k = i / (lpc * EPLP), rem = i - k * (lpc * EPLP);
       const int part = rem / EPLP, j = rem - part * EPLP;
       const int col = part * EPL + j;
       smu[i] = (j < EPL && col < a.d) ? gmu[(size_t)k * a.d + col] : T(0);
     }
+    T* slw = smu + (size_t)K * lpc * EPLP;
+    if ((int)threadIdx.x < K) slw[threadIdx.x] = fast_log<T>(a.tp.dp[threadIdx.x]);
     tp.smem_mu = smu;
-    __syncthreads();
+    tp.smem_logw = slw;
+    smem_off += ((size_t)K * lpc * EPLP + kMaxComp + 3) / 4 * 4;
   }
+  T* hot = smem + smem_off + (size_t)(threadIdx.x / lpc) * H_COUNT * wd;
+  __syncthreads();
 
   T eps = T(1), eps_bar = T(1), h_bar = T(0), mu = T(0);
   unsigned long long i_norm = 0, i_exp = 0, i_unif = 0;
@@ -273,14 +317,22 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
   else {
 #pragma unroll
     for (int j = 0; j < EPL; ++j)
-      if (j < ln.nvalid) pos_row[ln.lo + j] = T(1);     // idle lane groups evaluate a harmless point
+      if (j < ln.nvalid) pos_row[ln.lo + j] = pad_q;     // idle lane groups evaluate a harmless point
   }
   __syncwarp();
   bool exhausted = !active;      // no more chains for this lane group
 
   T q[EPL], p[EPL], g[EPL], prime[EPL];
 #pragma unroll
-  for (int j = 0; j < EPL; ++j) { q[j] = T(1); p[j] = T(0); g[j] = T(0); prime[j] = T(1); }
+  for (int j = 0; j < EPL; ++j) { q[j] = pad_q; p[j] = T(0); g[j] = T(0); prime[j] = pad_q; }
+  {
+    // the hot vectors are read unconditionally by the merge loop (lanes that do not merge ignore the result): defined values
+    T zero[EPL];
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) zero[j] = T(0);
+#pragma unroll
+    for (int h = 0; h < H_COUNT; ++h) store_slice<T, EPL>(hot + (size_t)h * wd, zero, ln, true);
+  }
   int n_stack[kNutsDepthCap];
 #pragma unroll
   for (int k = 0; k < kNutsDepthCap; ++k) n_stack[k] = 0;
@@ -289,6 +341,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
   if (active && a.n_steps == 0) store_chain();
   uint32_t s = 0;          // transition of this launch
   uint32_t draw = 0;       // uniform draws of the current transition (Philox stream 2)
+  uint32_t sv_z = 0, sv_w = 0;   // second half of the current Philox block of stream 2 (odd draws)
   int j_depth = 0, v = 1;
   unsigned int leaf_i = 0; // leaf index within the current subtree build
   long long n_tot = 1;
@@ -301,8 +354,15 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       ++i_unif;
       return u;
     }
-    const uint4 r = philox4x32_10(philox_ctr(gchain, a.step_base + s, 2u, draw >> 1), a.key);
-    const double u = (draw & 1u) ? u01d(r.z, r.w) : u01d(r.x, r.y);
+    // one Philox block per two draws: words (x, y) for the even draw, (z, w) kept for the odd one
+    double u;
+    if ((draw & 1u) == 0u) {
+      const uint4 r = philox4x32_10(philox_ctr(gchain, a.step_base + s, 2u, draw >> 1), a.key);
+      u = u01d(r.x, r.y);
+      sv_z = r.z; sv_w = r.w;
+    } else {
+      u = u01d(sv_z, sv_w);
+    }
     ++draw;
     return u;
   };
@@ -344,7 +404,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       } else {
         constexpr int NPB = NormalsPerBlock<T>::value;
         const int nblocks = (a.d + NPB - 1) / NPB;
-        for (int b = ln.part; b < nblocks; b += a.lpc) {
+        for (int b = ln.part; b < nblocks; b += lpc) {
           T z[NPB];
           normals_from_block<kExact>(philox4x32_10(philox_ctr(gchain, a.step_base + s, 0u, (uint32_t)b), a.key), z);
 #pragma unroll
@@ -358,7 +418,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       }
       if (is_start) {   // sample_momentum, generic_nuts.rs:283-303: z * sqrt(var)
 #pragma unroll
-        for (int j = 0; j < EPL; ++j) { p[j] = pn[j]; q[j] = (j < ln.nvalid) ? pos_row[ln.lo + j] : T(1); }
+        for (int j = 0; j < EPL; ++j) { p[j] = pn[j]; q[j] = (j < ln.nvalid) ? pos_row[ln.lo + j] : pad_q; }
         if constexpr (has_mass) {
 #pragma unroll
           for (int j = 0; j < EPL; ++j)
@@ -385,7 +445,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
     }
     // every chain is in the START, LEAF or DONE phase here, and a finished chain never reads g again: the
     // gradient is written in place
-    const T logp = eval_target<T, EPL, PADDED, true>(TAG{}, q, g, ln, tp, row);
+    const T logp = eval_target<T, EPL, EP, true>(TAG{}, q, g, ln, tp, row);
     if (is_leaf) {
 #pragma unroll
       for (int j = 0; j < EPL; ++j) p[j] = p[j] + g[j] * he;
@@ -410,8 +470,9 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
         e1 = (T)(-log(u01d(r.z, r.w)));
       }
       logu = joint0 - e1;
-      store_slice<T, EPL>(e_qm, q, ln, true); store_slice<T, EPL>(e_pm, p, ln, true); store_slice<T, EPL>(e_gm, g, ln, true);
-      store_slice<T, EPL>(e_qp, q, ln, true); store_slice<T, EPL>(e_pp, p, ln, true); store_slice<T, EPL>(e_gp, g, ln, true);
+      store_slice<T, EPL>(hot + (size_t)H_QM * wd, q, ln, true); store_slice<T, EPL>(hot + (size_t)H_PM * wd, p, ln, true);
+      store_slice<T, EPL>(hot + (size_t)H_QP * wd, q, ln, true); store_slice<T, EPL>(hot + (size_t)H_PP * wd, p, ln, true);
+      store_slice<T, EPL>(e_gm, g, ln, true); store_slice<T, EPL>(e_gp, g, ln, true);
       j_depth = 0; n_tot = 1; draw = 0; moved = false;
       const T u1 = (T)next_unif();             // :783-784
       v = (u1 < T(0.5)) ? 1 : -1;
@@ -428,12 +489,19 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
 #pragma unroll
       for (int j = 0; j < EPL; ++j) prime[j] = q[j];
       if ((leaf_i & 1u) == 0u) {
-        const int slot = __popc(leaf_i >> 1);
-        store_slice<T, EPL>(w_first + ((size_t)slot * 2 + 0) * wd, q, ln, true);
-        store_slice<T, EPL>(w_first + ((size_t)slot * 2 + 1) * wd, p, ln, true);
+        // an even leaf is the first leaf of the left subtree of the next level-0 merge (shared memory) and, when its
+        // index is a multiple of 4, of later merges at levels >= 1 (global workspace, stack slot popcount(c >> 1))
+        store_slice<T, EPL>(hot + (size_t)H_LQ * wd, q, ln, true);
+        store_slice<T, EPL>(hot + (size_t)H_LP * wd, p, ln, true);
+        if ((leaf_i & 3u) == 0u) {
+          const int slot = __popc(leaf_i >> 1);
+          store_slice<T, EPL>(w_first + ((size_t)slot * 2 + 0) * wd, q, ln, true);
+          store_slice<T, EPL>(w_first + ((size_t)slot * 2 + 1) * wd, p, ln, true);
+        }
       }
       in_merge = true;
     }
+    __syncwarp();     // the slices written above are read back (by the same lanes) through a different pointer type below
 
     // ---- C. merges with the pending left subtrees, then the top-level step of the doubling
     int k = 0;
@@ -449,32 +517,33 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
           ++leaf_i;
         }                                                      // else: failed subtree passed up through a left child
       }
-      // the other end of the U-turn test: first leaf of the left subtree (merge) / the other trajectory edge (top)
+      // the other end of the U-turn test: first leaf of the left subtree (merge) / the other trajectory edge (top).
+      // Lanes that do neither read the (always defined) last-even-leaf vectors and ignore the result.
       T fq[EPL], fp[EPL];
-      const T* src_q = e_qm;
-      const T* src_p = e_pm;
-      if (do_merge) {
+      const T* src_q = hot + (size_t)H_LQ * wd;
+      const T* src_p = hot + (size_t)H_LP * wd;
+      if (do_merge && k > 0) {
         const unsigned int start = (leaf_i >> (k + 1)) << (k + 1);
         const int slot = __popc(start >> 1);
         src_q = w_first + ((size_t)slot * 2 + 0) * wd;
         src_p = w_first + ((size_t)slot * 2 + 1) * wd;
       } else if (do_top) {
-        src_q = (v == 1) ? e_qm : e_qp;
-        src_p = (v == 1) ? e_pm : e_pp;
+        src_q = hot + (size_t)((v == 1) ? H_QM : H_QP) * wd;
+        src_p = hot + (size_t)((v == 1) ? H_PM : H_PP) * wd;
       }
-      load_slice<T, EPL>(fq, src_q, ln, do_merge || do_top, T(0));
-      load_slice<T, EPL>(fp, src_p, ln, do_merge || do_top, T(0));
+      load_slice_raw<T, EPL>(fq, src_q, ln);
+      load_slice_raw<T, EPL>(fp, src_p, ln);
       // stop_criterion (generic_nuts.rs:1357-1378, identity mass): diff = q+ - q- ; diff.p- >= 0 && diff.p+ >= 0
       const bool fwd = (v == 1);
       T dm, dp;
       chain_sum_fn2<T, EPL>(ln, [&](int j) {
         const T df = fwd ? (q[j] - fq[j]) : (fq[j] - q[j]);
         if (has_mass && do_top && j < ln.nvalid) return df * (a.mass_inv[chain * d + ln.lo + j] * (fwd ? fp[j] : p[j]));
-        return (!PADDED || j < ln.nvalid) ? df * (fwd ? fp[j] : p[j]) : T(0);
+        return (!EP || j < ln.nvalid) ? df * (fwd ? fp[j] : p[j]) : T(0);
       }, [&](int j) {
         const T df = fwd ? (q[j] - fq[j]) : (fq[j] - q[j]);
         if (has_mass && do_top && j < ln.nvalid) return df * (a.mass_inv[chain * d + ln.lo + j] * (fwd ? p[j] : fp[j]));
-        return (!PADDED || j < ln.nvalid) ? df * (fwd ? p[j] : fp[j]) : T(0);
+        return (!EP || j < ln.nvalid) ? df * (fwd ? p[j] : fp[j]) : T(0);
       }, dm, dp);
       const bool crit = (dm >= T(0)) && (dp >= T(0));
       if (do_merge) {
@@ -487,15 +556,16 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
 #pragma unroll
             for (int j = 0; j < EPL; ++j) prime[j] = fq[j];
           } else {
-            load_slice<T, EPL>(prime, w_prime + (size_t)k * wd, ln, true, T(1));
+            load_slice_raw<T, EPL>(prime, w_prime + (size_t)k * wd, ln);
           }
         }
         nR += nL;
         sR = sR && crit;
       } else if (do_top) {
         // generic_nuts.rs:803-880: new edge, accept the subtree's proposal, trajectory-level U-turn test
-        if (v == 1) { store_slice<T, EPL>(e_qp, q, ln, true); store_slice<T, EPL>(e_pp, p, ln, true); store_slice<T, EPL>(e_gp, g, ln, true); }
-        else { store_slice<T, EPL>(e_qm, q, ln, true); store_slice<T, EPL>(e_pm, p, ln, true); store_slice<T, EPL>(e_gm, g, ln, true); }
+        store_slice<T, EPL>(hot + (size_t)((v == 1) ? H_QP : H_QM) * wd, q, ln, true);
+        store_slice<T, EPL>(hot + (size_t)((v == 1) ? H_PP : H_PM) * wd, p, ln, true);
+        store_slice<T, EPL>((v == 1) ? e_gp : e_gm, g, ln, true);
         const T ratio = (T)nR / (T)n_tot;
         const T tmp = ratio < T(1) ? ratio : T(1);
         const T u2 = (T)next_unif();
@@ -514,9 +584,9 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
           const T u1 = (T)next_unif();
           const int vn = (u1 < T(0.5)) ? 1 : -1;
           if (vn != v) {
-            load_slice<T, EPL>(q, vn == 1 ? e_qp : e_qm, ln, true, T(1));
-            load_slice<T, EPL>(p, vn == 1 ? e_pp : e_pm, ln, true, T(0));
-            load_slice<T, EPL>(g, vn == 1 ? e_gp : e_gm, ln, true, T(0));
+            load_slice_raw<T, EPL>(q, hot + (size_t)((vn == 1) ? H_QP : H_QM) * wd, ln);
+            load_slice_raw<T, EPL>(p, hot + (size_t)((vn == 1) ? H_PP : H_PM) * wd, ln);
+            load_slice_raw<T, EPL>(g, vn == 1 ? e_gp : e_gm, ln);
           }
           v = vn;
           leaf_i = 0; alpha_sum = T(0); n_alpha = 0;
@@ -774,11 +844,19 @@ inline cudaError_t nuts_launch_one(const NutsLaunch& L, cudaStream_t st) {
     return cudaGetLastError();
   }
   NutsArgs<T> a = make_nuts_args<T>(L);
-  size_t smem = 2 * (size_t)(kHmcBlock / L.lpc) * d_pad * sizeof(T);
-  if (std::is_same<TAG, TagMixture>::value) smem += (size_t)L.tgt.n_comp * L.lpc * Eplp<EPL>::value * sizeof(T);
+  // shared memory (elements of T): position + scratch rows, [mixture means + log weights], hot per-chain vectors
+  size_t smem_el = ((size_t)(kHmcBlock >> 5) * 2 * (32 / L.lpc) * d_pad + 3) / 4 * 4;
+  if (std::is_same<TAG, TagMixture>::value) smem_el += ((size_t)L.tgt.n_comp * L.lpc * Eplp<EPL>::value + kMaxComp + 3) / 4 * 4;
+  smem_el += (size_t)kHmcBlock * H_COUNT * Eplp<EPL>::value;
+  const size_t smem = smem_el * sizeof(T);
   const bool exact_fit = (L.epl * L.lpc == L.tgt.dim);
-  auto kern = L.mass_inv ? (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, true> : nuts_run_kernel<T, EPL, TAG, true, true>)
-                         : (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, false> : nuts_run_kernel<T, EPL, TAG, true, false>);
+  // lanes per chain as a compile-time constant for the wide 8-coordinate layout (d = 65 .. 128: BASELINE config 5)
+  constexpr int kLpcFixed = (EPL == 8) ? 16 : 0;
+  const bool fixed = kLpcFixed > 0 && L.lpc == kLpcFixed;
+  auto kern = fixed ? (L.mass_inv ? (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, true, kLpcFixed> : nuts_run_kernel<T, EPL, TAG, true, true, kLpcFixed>)
+                                  : (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, false, kLpcFixed> : nuts_run_kernel<T, EPL, TAG, true, false, kLpcFixed>))
+                    : (L.mass_inv ? (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, true, 0> : nuts_run_kernel<T, EPL, TAG, true, true, 0>)
+                                  : (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, false, 0> : nuts_run_kernel<T, EPL, TAG, true, false, 0>));
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

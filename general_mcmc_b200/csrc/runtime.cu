@@ -157,8 +157,9 @@ struct gmcmc_sampler {
   void* d_da[4] = {nullptr, nullptr, nullptr, nullptr};   // per-chain: eps, eps_bar, h_bar, mu  (T [C])
   uint32_t da_m = 0;           // adaptation iterations consumed so far
   PooledDa* d_pooled = nullptr;
-  double* d_alpha_part = nullptr;  // [2][n_alpha_part]: transition t of a pooled warm-up writes half t & 1
+  double* d_alpha_part = nullptr;  // [2][pooled_window][n_alpha_part]: window j of a pooled warm-up writes half j & 1
   size_t n_alpha_part = 0;
+  size_t pooled_window = 8;        // warm-up transitions per launch / per collective in GMCMC_ADAPT_POOLED
   cudaEvent_t ev_kern[4] = {nullptr, nullptr, nullptr, nullptr};   // pooled warm-up: transition t done / update t done
   cudaEvent_t ev_upd[4] = {nullptr, nullptr, nullptr, nullptr};
   double* d_alpha_sum = nullptr;   // [2]: sum alpha, chain count (all-reduced together)
@@ -227,10 +228,12 @@ __global__ void fill_kernel(T* p, size_t n, T v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
-// fixed-order sum of the per-warp acceptance partials of one adaptation transition -> out[0]; out[1] = chains
-__global__ void __launch_bounds__(256) alpha_reduce_kernel(const double* __restrict__ part, size_t n, double chains,
-                                                           double* __restrict__ out) {
+// fixed-order sum of the per-warp acceptance partials of adaptation transition blockIdx.x -> out[2 b]; out[2 b + 1] = chains
+__global__ void __launch_bounds__(256) alpha_reduce_kernel(const double* __restrict__ part_all, size_t n, double chains,
+                                                           double* __restrict__ out_all) {
   __shared__ double sh[256];
+  const double* part = part_all + (size_t)blockIdx.x * n;
+  double* out = out_all + 2 * (size_t)blockIdx.x;
   double s = 0.0;
   for (size_t i = threadIdx.x; i < n; i += 256) s += part[i];
   sh[threadIdx.x] = s;
@@ -245,16 +248,19 @@ __global__ void __launch_bounds__(256) alpha_reduce_kernel(const double* __restr
 // Pooled dual averaging (Hoffman & Gelman Alg. 5 with the constants of generic_nuts.rs:638-641, 882-924),
 // driven by the mean acceptance statistic over ALL chains of all ranks.  One thread; f64.
 template <class T>
-__global__ void pooled_da_update_kernel(PooledDa* st, const double* __restrict__ alpha_sum /*[2]*/, double delta,
-                                        int last, T* __restrict__ eps_out) {
+__global__ void pooled_da_update_kernel(PooledDa* st, const double* __restrict__ alpha_sum /*[n_updates][2]*/, int n_updates,
+                                        double delta, int last, T* __restrict__ eps_out) {
   const double gamma = 0.05, t0 = 10.0, kappa = 0.75;
-  const double alpha = alpha_sum[0] / alpha_sum[1];
-  const double m = st->m + 1.0;
-  double eta = 1.0 / (m + t0);
-  const double h_bar = (1.0 - eta) * st->h_bar + eta * (delta - alpha);
-  double eps = exp(st->mu - sqrt(m) / gamma * h_bar);
-  eta = pow(m, -kappa);
-  const double log_eps_bar = (1.0 - eta) * st->log_eps_bar + eta * log(eps);
+  double m = st->m, h_bar = st->h_bar, log_eps_bar = st->log_eps_bar, eps = st->eps;
+  for (int u = 0; u < n_updates; ++u) {      // one dual-averaging iteration per warm-up transition of the window
+    const double alpha = alpha_sum[2 * u] / alpha_sum[2 * u + 1];
+    m += 1.0;
+    double eta = 1.0 / (m + t0);
+    h_bar = (1.0 - eta) * h_bar + eta * (delta - alpha);
+    eps = exp(st->mu - sqrt(m) / gamma * h_bar);
+    eta = pow(m, -kappa);
+    log_eps_bar = (1.0 - eta) * log_eps_bar + eta * log(eps);
+  }
   if (last) eps = exp(log_eps_bar);
   st->m = m; st->h_bar = h_bar; st->log_eps_bar = log_eps_bar; st->eps = eps;
   *eps_out = (T)eps;
@@ -336,7 +342,7 @@ gmcmc_status hmc_segment(gmcmc_sampler* s, size_t first, size_t count, size_t n_
   L.out_t0 = (uint32_t)(first >= n_discard ? first - n_discard : 0);
   L.accept_total = s->d_counts + 0;
   L.diverge_total = s->d_counts + 1;
-  L.alpha_part = want_alpha ? s->d_alpha_part + (size_t)slot * s->n_alpha_part : nullptr;
+  L.alpha_part = want_alpha ? s->d_alpha_part + (size_t)slot * s->pooled_window * s->n_alpha_part : nullptr;
   if (per_chain_da) {
     L.da_eps = s->d_da[0]; L.da_eps_bar = s->d_da[1]; L.da_h_bar = s->d_da[2]; L.da_mu = s->d_da[3];
     L.da_m_base = s->da_m + (uint32_t)first;
@@ -607,32 +613,37 @@ gmcmc_status run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void
   } else if (s->type == S_HMC) {
     if (s->adapt == GMCMC_ADAPT_POOLED && n_discard > 0) {
       GM_REQUIRE(inj == 0, "injection cannot be combined with pooled adaptation");
-      // One transition per launch during warm-up.  The dual-averaging chain of transition t (fixed-order reduce of the
-      // per-warp acceptance partials -> NCCL all-reduce over the ranks -> update) runs on a side stream WHILE transition
-      // t + 1 runs: the step size is one transition lagged (transition t uses the update of transition t - 2), so the
-      // collective's latency is off the critical path.  Step sizes and partials are double-buffered by t & 1.
+      // Warm-up in windows of W transitions per launch (W = kPooledWindow).  The kernel leaves one acceptance partial per
+      // (transition, warp); the dual-averaging chain of window j (fixed-order reduce per transition -> ONE NCCL all-reduce of
+      // the window's 2 W doubles over the ranks -> W dual-averaging iterations, one per transition) runs on a side stream
+      // WHILE window j + 1 runs, and its step size is the one window j + 2 uses.  The collective and the per-launch fixed
+      // costs (state load / store, kernel ramp) are paid once per window and are off the critical path.  Step sizes and
+      // partial buffers are double-buffered by j & 1.
       cudaStream_t aux = ctx->aux_stream;
-      for (size_t t = 0; t < n_discard; ++t) {
-        const int slot = (int)(t & 1), e = (int)(t & 3);
-        if (t >= 2) GM_CU(cudaStreamWaitEvent(ctx->stream, s->ev_upd[(t - 2) & 3], 0));   // eps slot + partial buffer free
-        GM_TRY(hmc_segment(s, t, 1, n_discard, n_collect, nullptr, false, 0, true, false, 0, slot));
+      const size_t W = s->pooled_window;
+      size_t j = 0;
+      for (size_t t = 0; t < n_discard; t += W, ++j) {
+        const size_t w = std::min(W, n_discard - t);
+        const int slot = (int)(j & 1), e = (int)(j & 3);
+        if (j >= 2) GM_CU(cudaStreamWaitEvent(ctx->stream, s->ev_upd[(j - 2) & 3], 0));   // eps slot + partial buffer free
+        GM_TRY(hmc_segment(s, t, w, n_discard, n_collect, nullptr, false, 0, true, false, 0, slot));
         GM_CU(cudaEventRecord(s->ev_kern[e], ctx->stream));
         GM_CU(cudaStreamWaitEvent(aux, s->ev_kern[e], 0));
-        alpha_reduce_kernel<<<1, 256, 0, aux>>>(s->d_alpha_part + (size_t)slot * s->n_alpha_part, s->n_alpha_part,
-                                                (double)s->n_chains, s->d_alpha_sum);
-        if (ctx->world > 1) GM_NCCL(nccl_api().AllReduce(s->d_alpha_sum, s->d_alpha_sum, 2, kNcclFloat64, kNcclSum, ctx->comm, aux));
-        const int last = (t + 1 == n_discard) ? 1 : 0;
+        alpha_reduce_kernel<<<(unsigned)w, 256, 0, aux>>>(s->d_alpha_part + (size_t)slot * W * s->n_alpha_part, s->n_alpha_part,
+                                                          (double)s->n_chains, s->d_alpha_sum);
+        if (ctx->world > 1) GM_NCCL(nccl_api().AllReduce(s->d_alpha_sum, s->d_alpha_sum, 2 * w, kNcclFloat64, kNcclSum, ctx->comm, aux));
+        const int last = (t + w == n_discard) ? 1 : 0;
         void* eps_slot = (char*)s->d_eps + (size_t)slot * esize(s->dtype);
         if (s->dtype == GMCMC_F32)
-          pooled_da_update_kernel<float><<<1, 1, 0, aux>>>(s->d_pooled, s->d_alpha_sum, s->target_accept, last, (float*)eps_slot);
+          pooled_da_update_kernel<float><<<1, 1, 0, aux>>>(s->d_pooled, s->d_alpha_sum, (int)w, s->target_accept, last, (float*)eps_slot);
         else
-          pooled_da_update_kernel<double><<<1, 1, 0, aux>>>(s->d_pooled, s->d_alpha_sum, s->target_accept, last, (double*)eps_slot);
+          pooled_da_update_kernel<double><<<1, 1, 0, aux>>>(s->d_pooled, s->d_alpha_sum, (int)w, s->target_accept, last, (double*)eps_slot);
         GM_CU(cudaEventRecord(s->ev_upd[e], aux));
         s->launches += 2;
       }
       // the collection launch needs the final step size: join the side stream
-      GM_CU(cudaStreamWaitEvent(ctx->stream, s->ev_upd[(n_discard - 1) & 3], 0));
-      if (n_discard >= 2) GM_CU(cudaStreamWaitEvent(ctx->stream, s->ev_upd[(n_discard - 2) & 3], 0));
+      GM_CU(cudaStreamWaitEvent(ctx->stream, s->ev_upd[(j - 1) & 3], 0));
+      if (j >= 2) GM_CU(cudaStreamWaitEvent(ctx->stream, s->ev_upd[(j - 2) & 3], 0));
       GM_CU(cudaGetLastError());
       s->da_m += (uint32_t)n_discard;
       {
@@ -1070,10 +1081,15 @@ gmcmc_status gmcmc_hmc_create(gmcmc_ctx* ctx, gmcmc_target* tgt, size_t n_chains
   gmcmc_sampler* s = nullptr;
   GM_TRY(sampler_common(ctx, tgt, n_chains, chain_offset, init_host, seed, S_HMC, &s));
   s->epl = epl; s->lpc = lpc; s->step_size = step_size; s->n_leapfrog = n_leapfrog;
-  s->n_alpha_part = (n_chains * (size_t)lpc + 31) / 32;
+  // the kernel writes one partial per warp of its GRID (whole CTAs of kHmcBlock threads)
+  s->n_alpha_part = ((n_chains * (size_t)lpc + kHmcBlock - 1) / kHmcBlock) * (kHmcBlock / 32);
+  if (const char* w_env = std::getenv("GMCMC_POOLED_WINDOW")) {
+    const int w = std::atoi(w_env);
+    if (w >= 1 && w <= 64) s->pooled_window = (size_t)w;
+  }
   bool ok = cudaMalloc(&s->d_eps, 16) == cudaSuccess &&
-            cudaMalloc((void**)&s->d_alpha_part, 2 * s->n_alpha_part * sizeof(double)) == cudaSuccess &&
-            cudaMalloc((void**)&s->d_alpha_sum, 2 * sizeof(double)) == cudaSuccess &&
+            cudaMalloc((void**)&s->d_alpha_part, 2 * s->pooled_window * s->n_alpha_part * sizeof(double)) == cudaSuccess &&
+            cudaMalloc((void**)&s->d_alpha_sum, 2 * s->pooled_window * sizeof(double)) == cudaSuccess &&
             cudaMalloc((void**)&s->d_pooled, sizeof(PooledDa)) == cudaSuccess;
   for (int i = 0; i < 4 && ok; ++i)
     ok = cudaEventCreateWithFlags(&s->ev_kern[i], cudaEventDisableTiming) == cudaSuccess &&
