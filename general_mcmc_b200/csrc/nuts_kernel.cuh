@@ -276,6 +276,8 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
     smem_off += ((size_t)K * lpc * EPLP + kMaxComp + 3) / 4 * 4;
   }
   T* hot = smem + smem_off + (size_t)(threadIdx.x / lpc) * H_COUNT * wd;
+  // uniform ring of this chain: 2 lpc doubles (kHmcBlock * 2 doubles per CTA), after the hot vectors
+  double* s_unif = reinterpret_cast<double*>(smem + smem_off + (size_t)kHmcBlock * H_COUNT * EPLP) + (size_t)(threadIdx.x / lpc) * 2 * lpc;
   __syncthreads();
 
   T eps = T(1), eps_bar = T(1), h_bar = T(0), mu = T(0);
@@ -341,30 +343,33 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
   if (active && a.n_steps == 0) store_chain();
   uint32_t s = 0;          // transition of this launch
   uint32_t draw = 0;       // uniform draws of the current transition (Philox stream 2)
-  uint32_t sv_z = 0, sv_w = 0;   // second half of the current Philox block of stream 2 (odd draws)
   int j_depth = 0, v = 1;
   unsigned int leaf_i = 0; // leaf index within the current subtree build
   long long n_tot = 1;
   int nR = 0, n_alpha = 0;
   bool sR = true;
   T alpha_sum = T(0), logu = T(0), joint0 = T(0);
+  // Tree uniforms (Philox stream 2: draw i = words (x, y) [i even] or (z, w) [i odd] of block i >> 1).  The lanes of a
+  // chain generate lpc blocks = 2 lpc draws at once — Philox costs the same ~70 warp-instructions for one block as for
+  // one block per lane — into a shared-memory ring; the draws in between are one shared-memory read.
+  const unsigned chain_mask = (lpc >= 32) ? kFull : (((1u << lpc) - 1u) << ln.gbase);
+  const uint32_t u_per = 2u * (uint32_t)lpc;
   auto next_unif = [&]() -> double {
     if (inject) {
       const double u = (i_unif < a.n_unif) ? a.inj_unif[chain * a.n_unif + i_unif] : 0.75;
       ++i_unif;
       return u;
     }
-    // one Philox block per two draws: words (x, y) for the even draw, (z, w) kept for the odd one
-    double u;
-    if ((draw & 1u) == 0u) {
-      const uint4 r = philox4x32_10(philox_ctr(gchain, a.step_base + s, 2u, draw >> 1), a.key);
-      u = u01d(r.x, r.y);
-      sv_z = r.z; sv_w = r.w;
-    } else {
-      u = u01d(sv_z, sv_w);
+    const uint32_t idx = draw & (u_per - 1u);
+    if (idx == 0u) {
+      __syncwarp(chain_mask);
+      const uint4 r = philox4x32_10(philox_ctr(gchain, a.step_base + s, 2u, (draw >> 1) + (uint32_t)ln.part), a.key);
+      s_unif[2 * ln.part] = u01d(r.x, r.y);
+      s_unif[2 * ln.part + 1] = u01d(r.z, r.w);
+      __syncwarp(chain_mask);
     }
     ++draw;
-    return u;
+    return s_unif[idx];
   };
 
   for (;;) {
@@ -467,7 +472,8 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       if (inject) { e1 = (T)((i_exp < a.n_exp) ? a.inj_exp1[chain * a.n_exp + i_exp] : 1.0); ++i_exp; }
       else {
         const uint4 r = philox4x32_10(philox_ctr(gchain, a.step_base + s, 1u, 0u), a.key);
-        e1 = (T)(-log(u01d(r.z, r.w)));
+        if constexpr (!kExact && sizeof(T) == 4) e1 = -__logf(u01(r.z));   // fast mode, f32: the 24 leading bits of word 2
+        else e1 = (T)(-log(u01d(r.z, r.w)));
       }
       logu = joint0 - e1;
       store_slice<T, EPL>(hot + (size_t)H_QM * wd, q, ln, true); store_slice<T, EPL>(hot + (size_t)H_PM * wd, p, ln, true);
@@ -534,24 +540,31 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       load_slice_raw<T, EPL>(fq, src_q, ln);
       load_slice_raw<T, EPL>(fp, src_p, ln);
       // stop_criterion (generic_nuts.rs:1357-1378, identity mass): diff = q+ - q- ; diff.p- >= 0 && diff.p+ >= 0
+      // With diff = q - f (current leaf minus the loaded end), r1 = diff . v(f), r2 = diff . v(current):
+      //   forward  (v = +1: f is the minus end): (q+ - q-) . v- = r1, (q+ - q-) . v+ = r2  -> both >= 0
+      //   backward (v = -1: f is the plus end):  (q+ - q-) = -diff: . v- = -r2, . v+ = -r1  -> both r <= 0
+      // (negation is exact and commutes with rounding, so the sums are bit-identical to the reference's order)
       const bool fwd = (v == 1);
-      T dm, dp;
+      T r1, r2;
       chain_sum_fn2<T, EPL>(ln, [&](int j) {
-        const T df = fwd ? (q[j] - fq[j]) : (fq[j] - q[j]);
-        if (has_mass && do_top && j < ln.nvalid) return df * (a.mass_inv[chain * d + ln.lo + j] * (fwd ? fp[j] : p[j]));
-        return (!EP || j < ln.nvalid) ? df * (fwd ? fp[j] : p[j]) : T(0);
+        const T df = q[j] - fq[j];
+        if (has_mass && do_top && j < ln.nvalid) return df * (a.mass_inv[chain * d + ln.lo + j] * fp[j]);
+        return (!EP || j < ln.nvalid) ? df * fp[j] : T(0);
       }, [&](int j) {
-        const T df = fwd ? (q[j] - fq[j]) : (fq[j] - q[j]);
-        if (has_mass && do_top && j < ln.nvalid) return df * (a.mass_inv[chain * d + ln.lo + j] * (fwd ? p[j] : fp[j]));
-        return (!EP || j < ln.nvalid) ? df * (fwd ? p[j] : fp[j]) : T(0);
-      }, dm, dp);
-      const bool crit = (dm >= T(0)) && (dp >= T(0));
+        const T df = q[j] - fq[j];
+        if (has_mass && do_top && j < ln.nvalid) return df * (a.mass_inv[chain * d + ln.lo + j] * p[j]);
+        return (!EP || j < ln.nvalid) ? df * p[j] : T(0);
+      }, r1, r2);
+      const bool crit = fwd ? ((r1 >= T(0)) && (r2 >= T(0))) : ((r1 <= T(0)) && (r2 <= T(0)));
       if (do_merge) {
         // generic_nuts.rs:1305-1323
         const double u = next_unif();
         const int nL = n_stack[k];
         const int den = (nL + nR) > 1 ? (nL + nR) : 1;
-        if (!(u < ((double)nR / (double)den))) {
+        bool take_right;
+        if constexpr (kExact) take_right = u < ((double)nR / (double)den);
+        else take_right = u * (double)den < (double)nR;       // same test without the f64 division
+        if (!take_right) {
           if (k == 0) {
 #pragma unroll
             for (int j = 0; j < EPL; ++j) prime[j] = fq[j];
@@ -607,7 +620,8 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       if (m <= a.n_discard) {
         const T mm = (T)m;
         eps = exp(mu - sqrt(mm) / T(0.05) * h_bar);
-        eta = pow(mm, -T(0.75));
+        if constexpr (!kExact && sizeof(T) == 4) eta = rsqrtf(mm) * rsqrtf(sqrtf(mm));   // m^(-3/4)
+        else eta = pow(mm, -T(0.75));
         eps_bar = exp((T(1) - eta) * log(eps_bar) + eta * log(eps));
       } else {
         eps = eps_bar;
@@ -848,7 +862,7 @@ inline cudaError_t nuts_launch_one(const NutsLaunch& L, cudaStream_t st) {
   size_t smem_el = ((size_t)(kHmcBlock >> 5) * 2 * (32 / L.lpc) * d_pad + 3) / 4 * 4;
   if (std::is_same<TAG, TagMixture>::value) smem_el += ((size_t)L.tgt.n_comp * L.lpc * Eplp<EPL>::value + kMaxComp + 3) / 4 * 4;
   smem_el += (size_t)kHmcBlock * H_COUNT * Eplp<EPL>::value;
-  const size_t smem = smem_el * sizeof(T);
+  const size_t smem = smem_el * sizeof(T) + (size_t)kHmcBlock * 2 * sizeof(double);   // + the tree-uniform rings
   const bool exact_fit = (L.epl * L.lpc == L.tgt.dim);
   // lanes per chain as a compile-time constant for the wide 8-coordinate layout (d = 65 .. 128: BASELINE config 5)
   constexpr int kLpcFixed = (EPL == 8) ? 16 : 0;

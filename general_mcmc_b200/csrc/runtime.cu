@@ -248,19 +248,21 @@ __global__ void __launch_bounds__(256) alpha_reduce_kernel(const double* __restr
 // Pooled dual averaging (Hoffman & Gelman Alg. 5 with the constants of generic_nuts.rs:638-641, 882-924),
 // driven by the mean acceptance statistic over ALL chains of all ranks.  One thread; f64.
 template <class T>
-__global__ void pooled_da_update_kernel(PooledDa* st, const double* __restrict__ alpha_sum /*[n_updates][2]*/, int n_updates,
+__global__ void pooled_da_update_kernel(PooledDa* st, const double* __restrict__ alpha_sum /*[n_win][2]*/, int n_win,
                                         double delta, int last, T* __restrict__ eps_out) {
+  // ONE dual-averaging iteration per window, driven by the mean acceptance statistic over the window's transitions and
+  // all chains of all ranks (every transition of a window ran at the same step size: they are replicates of one
+  // measurement, and feeding them as separate iterations would multiply the gain of the early, aggressive updates)
   const double gamma = 0.05, t0 = 10.0, kappa = 0.75;
-  double m = st->m, h_bar = st->h_bar, log_eps_bar = st->log_eps_bar, eps = st->eps;
-  for (int u = 0; u < n_updates; ++u) {      // one dual-averaging iteration per warm-up transition of the window
-    const double alpha = alpha_sum[2 * u] / alpha_sum[2 * u + 1];
-    m += 1.0;
-    double eta = 1.0 / (m + t0);
-    h_bar = (1.0 - eta) * h_bar + eta * (delta - alpha);
-    eps = exp(st->mu - sqrt(m) / gamma * h_bar);
-    eta = pow(m, -kappa);
-    log_eps_bar = (1.0 - eta) * log_eps_bar + eta * log(eps);
-  }
+  double sa = 0.0, sc = 0.0;
+  for (int u = 0; u < n_win; ++u) { sa += alpha_sum[2 * u]; sc += alpha_sum[2 * u + 1]; }
+  const double alpha = sa / sc;
+  const double m = st->m + 1.0;
+  double eta = 1.0 / (m + t0);
+  const double h_bar = (1.0 - eta) * st->h_bar + eta * (delta - alpha);
+  double eps = exp(st->mu - sqrt(m) / gamma * h_bar);
+  eta = pow(m, -kappa);
+  const double log_eps_bar = (1.0 - eta) * st->log_eps_bar + eta * log(eps);
   if (last) eps = exp(log_eps_bar);
   st->m = m; st->h_bar = h_bar; st->log_eps_bar = log_eps_bar; st->eps = eps;
   *eps_out = (T)eps;
@@ -613,17 +615,20 @@ gmcmc_status run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void
   } else if (s->type == S_HMC) {
     if (s->adapt == GMCMC_ADAPT_POOLED && n_discard > 0) {
       GM_REQUIRE(inj == 0, "injection cannot be combined with pooled adaptation");
-      // Warm-up in windows of W transitions per launch (W = kPooledWindow).  The kernel leaves one acceptance partial per
-      // (transition, warp); the dual-averaging chain of window j (fixed-order reduce per transition -> ONE NCCL all-reduce of
-      // the window's 2 W doubles over the ranks -> W dual-averaging iterations, one per transition) runs on a side stream
-      // WHILE window j + 1 runs, and its step size is the one window j + 2 uses.  The collective and the per-launch fixed
-      // costs (state load / store, kernel ramp) are paid once per window and are off the critical path.  Step sizes and
-      // partial buffers are double-buffered by j & 1.
+      // Warm-up in windows of w transitions per launch.  The kernel leaves one acceptance partial per (transition, warp);
+      // the dual-averaging chain of window j (fixed-order reduce per transition -> ONE NCCL all-reduce of the window's 2 w
+      // doubles over the ranks -> one dual-averaging iteration on the window's mean acceptance statistic) runs on a side
+      // stream WHILE window j + 1 runs, and its step size is the one window j + 2 uses: the collective and the update are
+      // off the critical path.  Windows start at one transition (the early iterations move the step size by large
+      // factors) and double every 16 windows up to pooled_window (the per-launch fixed costs — state load / store,
+      // kernel ramp — are then paid once per 8 transitions).  Step sizes and partial buffers are double-buffered by j & 1.
       cudaStream_t aux = ctx->aux_stream;
       const size_t W = s->pooled_window;
       size_t j = 0;
-      for (size_t t = 0; t < n_discard; t += W, ++j) {
-        const size_t w = std::min(W, n_discard - t);
+      for (size_t t = 0; t < n_discard; ++j) {
+        static const bool fixed_w = std::getenv("GMCMC_POOLED_FIXED") != nullptr;   // tuning: constant windows
+        size_t w = fixed_w ? W : ((size_t)1 << std::min<size_t>((s->da_m + j) / 16, 6));
+        w = std::min(std::min(w, W), n_discard - t);
         const int slot = (int)(j & 1), e = (int)(j & 3);
         if (j >= 2) GM_CU(cudaStreamWaitEvent(ctx->stream, s->ev_upd[(j - 2) & 3], 0));   // eps slot + partial buffer free
         GM_TRY(hmc_segment(s, t, w, n_discard, n_collect, nullptr, false, 0, true, false, 0, slot));
@@ -632,7 +637,8 @@ gmcmc_status run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void
         alpha_reduce_kernel<<<(unsigned)w, 256, 0, aux>>>(s->d_alpha_part + (size_t)slot * W * s->n_alpha_part, s->n_alpha_part,
                                                           (double)s->n_chains, s->d_alpha_sum);
         if (ctx->world > 1) GM_NCCL(nccl_api().AllReduce(s->d_alpha_sum, s->d_alpha_sum, 2 * w, kNcclFloat64, kNcclSum, ctx->comm, aux));
-        const int last = (t + w == n_discard) ? 1 : 0;
+        t += w;
+        const int last = (t == n_discard) ? 1 : 0;
         void* eps_slot = (char*)s->d_eps + (size_t)slot * esize(s->dtype);
         if (s->dtype == GMCMC_F32)
           pooled_da_update_kernel<float><<<1, 1, 0, aux>>>(s->d_pooled, s->d_alpha_sum, (int)w, s->target_accept, last, (float*)eps_slot);
@@ -641,11 +647,11 @@ gmcmc_status run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void
         GM_CU(cudaEventRecord(s->ev_upd[e], aux));
         s->launches += 2;
       }
+      s->da_m += (uint32_t)j;      // dual-averaging iterations so far (= windows)
       // the collection launch needs the final step size: join the side stream
       GM_CU(cudaStreamWaitEvent(ctx->stream, s->ev_upd[(j - 1) & 3], 0));
       if (j >= 2) GM_CU(cudaStreamWaitEvent(ctx->stream, s->ev_upd[(j - 2) & 3], 0));
       GM_CU(cudaGetLastError());
-      s->da_m += (uint32_t)n_discard;
       {
         // adapted step size back to the host once (8 bytes): the collection launch takes it by value
         PooledDa h;

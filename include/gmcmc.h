@@ -27,7 +27,8 @@
  *   stream 0: N(0,1) draws for the momentum (HMC/NUTS) or the proposal noise (MH);
  *             f32: block b -> elements 4b..4b+3 (Box–Muller on (r0,r1) and (r2,r3));
  *             f64: block b -> elements 2b, 2b+1 (53-bit uniforms from (r0,r1) and (r2,r3));
- *   stream 1: block 0 -> accept uniform (r0 [f32] or (r0,r1) [f64]); NUTS: r2/r3 -> Exp(1) draw;
+ *   stream 1: block 0 -> accept uniform (r0 [f32] or (r0,r1) [f64]); NUTS: r2/r3 -> Exp(1) draw (-ln of the 53-bit
+ *             uniform; f32 samplers in fast math mode: -ln of the 24-bit uniform of r2);
  *   stream 2: NUTS tree uniforms, block = draw index / 4 (see gmcmc_nuts_create).
  *   stream 3: NUTS momentum probe after a mass-matrix update (see gmcmc_nuts_set_mass_adaptation).
  * Uniforms are in (0,1]:  f32 ((r>>8)+1)*2^-24,  f64 ((r64>>11)+1)*2^-53.
