@@ -115,7 +115,7 @@ __device__ __forceinline__ T chain_max(T v, const Lane& ln) {
 template <class T>
 struct TParams {          // per-launch target parameters in T
   T sp[kMaxScalarParams];
-  const T* dp;            // device block (dense Gaussian: mu[d], P[d*d], nc; mixture: w[K], mu[K*d])
+  const T* dp;            // device block (dense Gaussian: mu[d], P[d*d], nc; mixture: w[K], mu[K*d], ln w[K])
   const T* smem_mu;       // mixture means staged in shared memory, lane-padded [K][lpc][roundup(EPL, 4)], or null
   const T* smem_logw;     // mixture log weights staged in shared memory [K], or null
   int n_comp;
@@ -306,8 +306,8 @@ __device__ __forceinline__ T eval_target(TagMixture, const T (&x)[EPL], T (&g)[E
   const int d = ln.d;
   const T sigma = tp.sp[1];
   const T inv_var = T(1) / (sigma * sigma);
-  const T* w = tp.dp;
   const T* mu = tp.dp + K;
+  const T* logw = tp.smem_logw ? tp.smem_logw : (tp.dp + K + (size_t)K * d);   // ln w[K], host-computed (runtime.cu)
   T a[kMaxComp];          // dynamically indexed: lives in (L1-resident) local memory
   T amax = -INFINITY;
   bool packed = false;
@@ -347,8 +347,7 @@ __device__ __forceinline__ T eval_target(TagMixture, const T (&x)[EPL], T (&g)[E
     T ak[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const T lw = tp.smem_logw ? tp.smem_logw[k] : fast_log<T>(w[k]);
-      ak[k] = lw - T(0.5) * sk[k] * inv_var;
+      ak[k] = logw[k] - T(0.5) * sk[k] * inv_var;
     }
     const T am = max(max(ak[0], ak[1]), max(ak[2], ak[3]));
     T ek[4];
@@ -384,8 +383,7 @@ __device__ __forceinline__ T eval_target(TagMixture, const T (&x)[EPL], T (&g)[E
         terms[j] = df * df;
       }
       const T sq = chain_sum<T, EPL>(terms, ln);
-      const T lw = tp.smem_logw ? tp.smem_logw[k] : fast_log<T>(w[k]);
-      const T ak = lw - T(0.5) * sq * inv_var;
+      const T ak = logw[k] - T(0.5) * sq * inv_var;
       a[k] = ak;
       amax = max(amax, ak);
     }

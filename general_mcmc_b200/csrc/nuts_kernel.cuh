@@ -178,7 +178,7 @@ __device__ __forceinline__ void chain_sum_fn2(const Lane& ln, F1 f1, F2 f2, T& o
 }
 
 #ifndef GM_NUTS_MINB
-#define GM_NUTS_MINB 3
+#define GM_NUTS_MINB 4   // 128 registers per thread: no spills, one more CTA per SM to hide the serial per-pass latency (+6 %)
 #endif
 
 // Targets whose padded slots (coordinates past the end of the chain in a non exact-fit decomposition) may simply hold
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
   T* row = warp_pos + warp_elems + (size_t)chain_in_warp * a.d_pad;
   unsigned long long gchain = a.chain_offset + chain;
   const size_t d = (size_t)a.d;
-  const size_t wd = (size_t)lpc * EPLP;   // lane-padded workspace vector length
+  const unsigned wd = (unsigned)lpc * EPLP;   // lane-padded workspace vector length (32-bit offset arithmetic)
   const size_t cw = slot_id;
 
   T* e_gm = a.ws_edges + (cw * 6 + 2) * wd;     // edge gradients: only read back on a direction flip
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       smu[i] = (j < EPL && col < a.d) ? gmu[(size_t)k * a.d + col] : T(0);
     }
     T* slw = smu + (size_t)K * lpc * EPLP;
-    if ((int)threadIdx.x < K) slw[threadIdx.x] = fast_log<T>(a.tp.dp[threadIdx.x]);
+    if ((int)threadIdx.x < K) slw[threadIdx.x] = a.tp.dp[K + (size_t)K * a.d + threadIdx.x];
     tp.smem_mu = smu;
     tp.smem_logw = slw;
     smem_off += ((size_t)K * lpc * EPLP + kMaxComp + 3) / 4 * 4;
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
 #pragma unroll
     for (int j = 0; j < EPL; ++j) zero[j] = T(0);
 #pragma unroll
-    for (int h = 0; h < H_COUNT; ++h) store_slice<T, EPL>(hot + (size_t)h * wd, zero, ln, true);
+    for (int h = 0; h < H_COUNT; ++h) store_slice<T, EPL>(hot + (unsigned)h * wd, zero, ln, true);
   }
   int n_stack[kNutsDepthCap];
 #pragma unroll
@@ -476,8 +476,8 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
         else e1 = (T)(-log(u01d(r.z, r.w)));
       }
       logu = joint0 - e1;
-      store_slice<T, EPL>(hot + (size_t)H_QM * wd, q, ln, true); store_slice<T, EPL>(hot + (size_t)H_PM * wd, p, ln, true);
-      store_slice<T, EPL>(hot + (size_t)H_QP * wd, q, ln, true); store_slice<T, EPL>(hot + (size_t)H_PP * wd, p, ln, true);
+      store_slice<T, EPL>(hot + H_QM * wd, q, ln, true); store_slice<T, EPL>(hot + H_PM * wd, p, ln, true);
+      store_slice<T, EPL>(hot + H_QP * wd, q, ln, true); store_slice<T, EPL>(hot + H_PP * wd, p, ln, true);
       store_slice<T, EPL>(e_gm, g, ln, true); store_slice<T, EPL>(e_gp, g, ln, true);
       j_depth = 0; n_tot = 1; draw = 0; moved = false;
       const T u1 = (T)next_unif();             // :783-784
@@ -497,12 +497,12 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       if ((leaf_i & 1u) == 0u) {
         // an even leaf is the first leaf of the left subtree of the next level-0 merge (shared memory) and, when its
         // index is a multiple of 4, of later merges at levels >= 1 (global workspace, stack slot popcount(c >> 1))
-        store_slice<T, EPL>(hot + (size_t)H_LQ * wd, q, ln, true);
-        store_slice<T, EPL>(hot + (size_t)H_LP * wd, p, ln, true);
+        store_slice<T, EPL>(hot + H_LQ * wd, q, ln, true);
+        store_slice<T, EPL>(hot + H_LP * wd, p, ln, true);
         if ((leaf_i & 3u) == 0u) {
           const int slot = __popc(leaf_i >> 1);
-          store_slice<T, EPL>(w_first + ((size_t)slot * 2 + 0) * wd, q, ln, true);
-          store_slice<T, EPL>(w_first + ((size_t)slot * 2 + 1) * wd, p, ln, true);
+          store_slice<T, EPL>(w_first + (unsigned)(slot * 2) * wd, q, ln, true);
+          store_slice<T, EPL>(w_first + (unsigned)(slot * 2 + 1) * wd, p, ln, true);
         }
       }
       in_merge = true;
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
         else if ((leaf_i >> k) & 1u) do_merge = true;          // pending left sibling at level k
         else if (sR) {                                         // becomes the pending left subtree of level k
           n_stack[k] = nR;
-          if (k >= 1) store_slice<T, EPL>(w_prime + (size_t)k * wd, prime, ln, true);
+          if (k >= 1) store_slice<T, EPL>(w_prime + (unsigned)k * wd, prime, ln, true);
           in_merge = false;
           ++leaf_i;
         }                                                      // else: failed subtree passed up through a left child
@@ -526,16 +526,16 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       // the other end of the U-turn test: first leaf of the left subtree (merge) / the other trajectory edge (top).
       // Lanes that do neither read the (always defined) last-even-leaf vectors and ignore the result.
       T fq[EPL], fp[EPL];
-      const T* src_q = hot + (size_t)H_LQ * wd;
-      const T* src_p = hot + (size_t)H_LP * wd;
+      const T* src_q = hot + H_LQ * wd;
+      const T* src_p = hot + H_LP * wd;
       if (do_merge && k > 0) {
         const unsigned int start = (leaf_i >> (k + 1)) << (k + 1);
         const int slot = __popc(start >> 1);
-        src_q = w_first + ((size_t)slot * 2 + 0) * wd;
-        src_p = w_first + ((size_t)slot * 2 + 1) * wd;
+        src_q = w_first + (unsigned)(slot * 2) * wd;
+        src_p = w_first + (unsigned)(slot * 2 + 1) * wd;
       } else if (do_top) {
-        src_q = hot + (size_t)((v == 1) ? H_QM : H_QP) * wd;
-        src_p = hot + (size_t)((v == 1) ? H_PM : H_PP) * wd;
+        src_q = hot + (unsigned)((v == 1) ? H_QM : H_QP) * wd;
+        src_p = hot + (unsigned)((v == 1) ? H_PM : H_PP) * wd;
       }
       load_slice_raw<T, EPL>(fq, src_q, ln);
       load_slice_raw<T, EPL>(fp, src_p, ln);
@@ -569,15 +569,15 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
 #pragma unroll
             for (int j = 0; j < EPL; ++j) prime[j] = fq[j];
           } else {
-            load_slice_raw<T, EPL>(prime, w_prime + (size_t)k * wd, ln);
+            load_slice_raw<T, EPL>(prime, w_prime + (unsigned)k * wd, ln);
           }
         }
         nR += nL;
         sR = sR && crit;
       } else if (do_top) {
         // generic_nuts.rs:803-880: new edge, accept the subtree's proposal, trajectory-level U-turn test
-        store_slice<T, EPL>(hot + (size_t)((v == 1) ? H_QP : H_QM) * wd, q, ln, true);
-        store_slice<T, EPL>(hot + (size_t)((v == 1) ? H_PP : H_PM) * wd, p, ln, true);
+        store_slice<T, EPL>(hot + (unsigned)((v == 1) ? H_QP : H_QM) * wd, q, ln, true);
+        store_slice<T, EPL>(hot + (unsigned)((v == 1) ? H_PP : H_PM) * wd, p, ln, true);
         store_slice<T, EPL>((v == 1) ? e_gp : e_gm, g, ln, true);
         const T ratio = (T)nR / (T)n_tot;
         const T tmp = ratio < T(1) ? ratio : T(1);
@@ -597,8 +597,8 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
           const T u1 = (T)next_unif();
           const int vn = (u1 < T(0.5)) ? 1 : -1;
           if (vn != v) {
-            load_slice_raw<T, EPL>(q, hot + (size_t)((vn == 1) ? H_QP : H_QM) * wd, ln);
-            load_slice_raw<T, EPL>(p, hot + (size_t)((vn == 1) ? H_PP : H_PM) * wd, ln);
+            load_slice_raw<T, EPL>(q, hot + (unsigned)((vn == 1) ? H_QP : H_QM) * wd, ln);
+            load_slice_raw<T, EPL>(p, hot + (unsigned)((vn == 1) ? H_PP : H_PM) * wd, ln);
             load_slice_raw<T, EPL>(g, vn == 1 ? e_gp : e_gm, ln);
           }
           v = vn;
@@ -892,15 +892,13 @@ inline cudaError_t nuts_launch_one(const NutsLaunch& L, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-// EPL menu of the NUTS kernels: {2 (2-D targets), 4, 8, 25 (f32 only), 13 (f64 only)}
+// EPL menu of the NUTS kernels: {2 (2-D targets), 4, 8, 13, 25 (f32 only)}
 template <class T, class TAG>
 inline cudaError_t nuts_dispatch(const NutsLaunch& L, cudaStream_t st) {
   switch (L.epl) {
     case 4: return nuts_launch_one<T, 4, TAG>(L, st);
     case 8: return nuts_launch_one<T, 8, TAG>(L, st);
-    case 13:
-      if constexpr (sizeof(T) == 8) return nuts_launch_one<T, 13, TAG>(L, st);
-      else return cudaErrorInvalidValue;
+    case 13: return nuts_launch_one<T, 13, TAG>(L, st);
     case 25:
       if constexpr (sizeof(T) == 4) return nuts_launch_one<T, 25, TAG>(L, st);
       else return cudaErrorInvalidValue;

@@ -941,7 +941,7 @@ gmcmc_status gmcmc_target_create(gmcmc_ctx* ctx, gmcmc_target_kind kind, gmcmc_d
       if (n_params < 2) { delete t; return fail(GMCMC_ERR_INVALID, "mixture params: [K, sigma, w[K], mu[K*d]]"); }
       const int K = (int)params[0];
       if (K < 1 || K > 8) { delete t; return fail(GMCMC_ERR_INVALID, "mixture components must be 1..8"); }
-      need = 2 + (size_t)K + (size_t)K * dim; dev_off = 2; dev_len = need - 2; d.n_comp = K;
+      need = 2 + (size_t)K + (size_t)K * dim; dev_off = 2; dev_len = need - 2 + (size_t)K; d.n_comp = K;   // + ln w[K]
       break;
     }
     default: delete t; return fail(GMCMC_ERR_INVALID, "unknown target kind %d", (int)kind);
@@ -955,9 +955,15 @@ gmcmc_status gmcmc_target_create(gmcmc_ctx* ctx, gmcmc_target_kind kind, gmcmc_d
   if (dev_len) {
     const size_t es = esize(dtype);
     std::vector<char> host(dev_len * es);
-    for (size_t i = 0; i < dev_len; ++i) {
+    const size_t n_copy = (kind == GMCMC_TARGET_GAUSS_MIXTURE) ? dev_len - (size_t)d.n_comp : dev_len;
+    for (size_t i = 0; i < n_copy; ++i) {
       if (dtype == GMCMC_F32) ((float*)host.data())[i] = (float)params[dev_off + i];
       else ((double*)host.data())[i] = params[dev_off + i];
+    }
+    // mixture: the log weights, evaluated once on the host in the sampler dtype (the value every log-density call adds)
+    for (size_t k = n_copy; k < dev_len; ++k) {
+      if (dtype == GMCMC_F32) ((float*)host.data())[k] = std::log((float)params[dev_off + (k - n_copy)]);
+      else ((double*)host.data())[k] = std::log(params[dev_off + (k - n_copy)]);
     }
     if (cudaMalloc(&t->dparams, dev_len * es) != cudaSuccess ||
         cudaMemcpy(t->dparams, host.data(), dev_len * es, cudaMemcpyHostToDevice) != cudaSuccess) {
