@@ -693,11 +693,35 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
   const size_t warp_first_chain = (size_t)((tid & ~31) / a.lpc);
   const unsigned long long gchain = a.chain_offset + chain;
 
-  // current positions -> shared rows (coalesced); chains past the end get a harmless point
-  for (int c = 0; c < chains_in_warp; ++c) {
-    const size_t ch = warp_first_chain + c;
-    for (int i = lane; i < a.d_pad; i += 32)
-      warp_pos[(size_t)c * a.d_pad + i] = (ch < a.n_chains && i < a.d) ? a.positions[ch * a.d + i] : T(1);
+  // current positions -> shared rows.  The warp's chains are one contiguous run of the [C, d] array: it is read as a flat
+  // list with 8 loads in flight per lane (a dependent load -> store loop over the rows cost ~15 us of HBM latency per CTA,
+  // more than a whole transition, which is what made short launches 2.3x as expensive per transition); rows of chains past
+  // the end and padding columns get a harmless point.
+  {
+    const size_t live_chains = a.n_chains > warp_first_chain ? a.n_chains - warp_first_chain : 0;
+    const int nch = live_chains < (size_t)chains_in_warp ? (int)live_chains : chains_in_warp;
+    const int total = nch * a.d;
+    const T* src = a.positions + warp_first_chain * (size_t)a.d;
+    if (a.d_pad != a.d || nch < chains_in_warp)
+      for (int i = lane; i < (int)warp_elems; i += 32) warp_pos[i] = T(1);
+    __syncwarp();
+    constexpr int UN = 8;
+    for (int base = 0; base < total; base += 32 * UN) {
+      T v[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int idx = base + lane + 32 * u;
+        v[u] = idx < total ? __ldg(src + idx) : T(1);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int idx = base + lane + 32 * u;
+        if (idx < total) {
+          const int c = idx / a.d;
+          warp_pos[(size_t)c * a.d_pad + (idx - c * a.d)] = v[u];
+        }
+      }
+    }
   }
   __syncwarp();
 
@@ -855,11 +879,17 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
     }
   }
 
-  // ---- state back to HBM
-  for (int c = 0; c < chains_in_warp; ++c) {
-    const size_t ch = warp_first_chain + c;
-    if (ch >= a.n_chains) break;
-    for (int i = lane; i < a.d; i += 32) a.positions[ch * a.d + i] = warp_pos[(size_t)c * a.d_pad + i];
+  // ---- state back to HBM (the same flat list)
+  {
+    const size_t live_chains = a.n_chains > warp_first_chain ? a.n_chains - warp_first_chain : 0;
+    const int nch = live_chains < (size_t)chains_in_warp ? (int)live_chains : chains_in_warp;
+    const int total = nch * a.d;
+    T* dst = a.positions + warp_first_chain * (size_t)a.d;
+#pragma unroll 4
+    for (int idx = lane; idx < total; idx += 32) {
+      const int c = idx / a.d;
+      dst[idx] = warp_pos[(size_t)c * a.d_pad + (idx - c * a.d)];
+    }
   }
   if (active && per_chain_da && ln.part == 0) {
     a.da_eps[chain] = eps; a.da_eps_bar[chain] = da_eps_bar; a.da_h_bar[chain] = da_h_bar;
