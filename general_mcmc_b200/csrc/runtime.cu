@@ -159,7 +159,7 @@ struct gmcmc_sampler {
   PooledDa* d_pooled = nullptr;
   double* d_alpha_part = nullptr;  // [2][pooled_window][n_alpha_part]: window j of a pooled warm-up writes half j & 1
   size_t n_alpha_part = 0;
-  size_t pooled_window = 16;       // longest warm-up window (transitions per launch / per collective) in GMCMC_ADAPT_POOLED
+  size_t pooled_window = 8;        // longest warm-up window (transitions per launch / per collective) in GMCMC_ADAPT_POOLED
   cudaEvent_t ev_kern[4] = {nullptr, nullptr, nullptr, nullptr};   // pooled warm-up: transition t done / update t done
   cudaEvent_t ev_upd[4] = {nullptr, nullptr, nullptr, nullptr};
   double* d_alpha_sum = nullptr;   // [2]: sum alpha, chain count (all-reduced together)
@@ -621,7 +621,7 @@ gmcmc_status run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void
       // stream WHILE window j + 1 runs, and its step size is the one window j + 2 uses: the collective and the update are
       // off the critical path.  Windows start at one transition (the early iterations move the step size by large
       // factors) and double every 8 windows up to pooled_window (the per-launch fixed costs — state load / store,
-      // kernel ramp — are then paid once per 16 transitions).  Step sizes and partial buffers are double-buffered by j & 1.
+      // kernel ramp — are then paid once per 8 transitions: measured 1.04-1.13x the sampling cost per transition).  Step sizes and partial buffers are double-buffered by j & 1.
       cudaStream_t aux = ctx->aux_stream;
       const size_t W = s->pooled_window;
       size_t j = 0;
