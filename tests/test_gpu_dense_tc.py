@@ -31,15 +31,14 @@ def test_dense_tc_per_step_equivalence(ctx, oracle, d, Cn, L, eps):
     q0 = rng.standard_normal((Cn, d)).astype(np.float32)
     mom = rng.standard_normal((1, Cn, d)).astype(np.float32)
     ln_u = np.log(rng.random((1, Cn))).astype(np.float32)
-    # truth: the oracle in f64 on the same f32 inputs and the same f32-rounded parameters; the f32 oracle (the
-    # reference's own f32 arithmetic: sequential 1000-term f32 sums) is itself ~1e-5 away from it at d = 1000,
-    # so the bar is: within 1e-5 relative, or at least as close to the truth as 1.5x the f32 reference is
+    # truth: the oracle in f64 on the same f32 inputs and the same f32-rounded parameters (the f32 oracle — the reference's own
+    # f32 arithmetic, sequential 1000-term f32 sums — is itself ~4e-6 away from it at d = 1000, L = 32; printed for scale)
     params32 = np.asarray(tgt.params(), np.float32).astype(np.float64)
     ref = oracle.hmc_run(tgt.kind, params32, q0.astype(np.float64), np.float64(np.float32(eps)), L,
                          mom.astype(np.float64), ln_u.astype(np.float64), want_traj=True)
     ref32 = oracle.hmc_run(tgt.kind, tgt.params(), q0, eps, L, mom, ln_u, want_traj=True)
-    floor_q = 1.5 * np.max(np.abs(ref32["prop_q"] - ref["prop_q"]))
-    floor_p = 1.5 * np.max(np.abs(ref32["prop_p"] - ref["prop_p"]))
+    f32_q = np.max(np.abs(ref32["prop_q"] - ref["prop_q"]))
+    f32_p = np.max(np.abs(ref32["prop_p"] - ref["prop_p"]))
     s = gm.HMC(tgt, q0, eps, L, seed=1, ctx=ctx)
     s.inject(mom, ln_u)
     out = s.run(1, 0)
@@ -49,14 +48,12 @@ def test_dense_tc_per_step_equivalence(ctx, oracle, d, Cn, L, eps):
     err_q = np.max(np.abs(diag["prop_q"] - ref["prop_q"]))
     err_p = np.max(np.abs(diag["prop_p"] - ref["prop_p"]))
     print("d=%d L=%d: GPU err q %.2e p %.2e (rel %.2e %.2e); f32 reference err q %.2e p %.2e" % (
-        d, L, err_q, err_p, err_q / scale_q, err_p / scale_p, floor_q / 1.5, floor_p / 1.5))
-    # Bar: rel 1e-5 (north star).  At d = 1000, L = 32 the momentum error measures 1.25e-5: the residual is the
-    # tensor-core accumulator itself (125 x 3 chained tcgen05.mma accumulations per output, each rounded toward
-    # zero in TMEM), not the 3xTF32 operand split (rounding the low parts instead of truncating them changes
-    # nothing).  That configuration is held to 2e-5 and reported in DESIGN.md.
-    tol = 2e-5 if d * L >= 32000 else 1e-5
-    assert err_q <= max(tol * scale_q, floor_q)
-    assert err_p <= max(tol * scale_p, floor_p)
+        d, L, err_q, err_p, err_q / scale_q, err_p / scale_p, f32_q, f32_p))
+    # Bar: rel 1e-5 over L leapfrog steps (north star), at every shape including d = 1000, L = 32 (measured 4.6e-6 / 6.4e-6
+    # since delta is scaled into FP16's normal range per transition: its low parts no longer fall into the subnormals)
+    tol = 1e-5
+    assert err_q <= tol * scale_q
+    assert err_p <= tol * scale_p
     escale = np.abs(ref["logp_cur"][0]) + np.abs(ref["logp_prop"][0]) + 0.5 * (mom[0].astype(np.float64) ** 2).sum(-1) + 1.0
     err = np.abs(diag["log_accept"][0].astype(np.float64) - ref["log_accept"][0])
     assert np.all(err <= 4e-5 * escale), (err / escale).max()
@@ -66,6 +63,34 @@ def test_dense_tc_per_step_equivalence(ctx, oracle, d, Cn, L, eps):
     acc = diag["accepted"][0].astype(bool)
     assert np.array_equal(out[acc, 0], diag["prop_q"][0][acc])
     assert np.array_equal(out[~acc, 0], q0[~acc])
+
+
+def test_dense_tc_bench_grid_persistent_units(ctx, oracle):
+    """The bench shape's code path: d = 1000 with more row tiles (321, the last one ragged) than SMs, so the L - 1 middle
+    launches run the persistent (row-tile group, column chunk) schedule.  Every chain runs on the GPU; a spread of chains
+    (first / middle / last ragged tile included) is checked against the f64 oracle to the 1e-5 bar."""
+    d, Cn, L, eps = 1000, 41000, 8, 0.05
+    tgt = _dense(d)
+    rng = np.random.default_rng(17)
+    q0 = rng.standard_normal((Cn, d)).astype(np.float32)
+    mom = rng.standard_normal((1, Cn, d)).astype(np.float32)
+    ln_u = np.log(rng.random((1, Cn))).astype(np.float32)
+    s = gm.HMC(tgt, q0, eps, L, seed=1, ctx=ctx)
+    s.inject(mom, ln_u)
+    out = s.run(1, 0)
+    diag = s.diagnostics()
+    idx = np.unique(np.concatenate([np.arange(0, Cn, 131), np.arange(Cn - 40, Cn), np.arange(20480, 20480 + 40)]))
+    params32 = np.asarray(tgt.params(), np.float32).astype(np.float64)
+    ref = oracle.hmc_run(tgt.kind, params32, q0[idx].astype(np.float64), np.float64(np.float32(eps)), L,
+                         mom[:, idx].astype(np.float64), ln_u[:, idx].astype(np.float64), want_traj=True)
+    err_q = np.abs(diag["prop_q"][0][idx] - ref["prop_q"][0]).max() / np.abs(ref["prop_q"]).max()
+    err_p = np.abs(diag["prop_p"][0][idx] - ref["prop_p"][0]).max() / np.abs(ref["prop_p"]).max()
+    print("bench grid d=%d C=%d L=%d (%d chains checked): rel err q %.2e p %.2e" % (d, Cn, L, idx.size, err_q, err_p))
+    assert err_q <= 1e-5 and err_p <= 1e-5
+    assert np.isfinite(out).all()
+    escale = np.abs(ref["logp_cur"][0]) + np.abs(ref["logp_prop"][0]) + 0.5 * (mom[0][idx].astype(np.float64) ** 2).sum(-1) + 1.0
+    safe = np.abs(ref["log_accept"][0] - ln_u[0][idx]) > 4e-5 * escale
+    assert np.array_equal(diag["accepted"][0][idx][safe], ref["accepted"][0][safe])
 
 
 @pytest.mark.parametrize("scale", [1e-8, 1.0, 1e10], ids=["cov1e-8", "cov1", "cov1e+10"])
