@@ -75,6 +75,9 @@ constexpr int kKPadUnit = 32;    // K is padded to a multiple of 32 floats in bo
 #define GM_TC_CLUSTER 2          // CTAs per cluster sharing every P tile through TMA multicast (1 = no cluster)
 #endif
 constexpr int kCluster = GM_TC_CLUSTER;
+#ifndef GM_TC_EPI_PREFETCH
+#define GM_TC_EPI_PREFETCH 0
+#endif
 #ifndef GM_TC_EPI_WARPS
 #define GM_TC_EPI_WARPS 8
 #endif
@@ -420,6 +423,38 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
       row0 = (size_t)m0 + (size_t)q4 * 32;
       nrows = row0 < a.n_chains ? (int)((a.n_chains - row0) < 32 ? (a.n_chains - row0) : 32) : 0;
       const int acc = j & 1;
+      // Fast blocks (every launch but the trajectory ends, every full 32 x 32 block of a d % 4 == 0 target): no bounds tests,
+      // no row sums, 128-bit global accesses — a lane owns 4 consecutive columns of 4 rows per 16-row half, one warp instruction
+      // moves four whole 128-byte lines.  (GM_TC_EPI_PREFETCH = 1 keeps the p / delta loads of the NEXT half in flight while the
+      // current half is transposed, updated and stored — measured SLOWER, 17.9 vs 16.4 ms per transition: the registers it
+      // takes spill, and the epilogue is not short of loads in flight: tensor pipe 57 %, L1 52 %, crossbar 40 %, DRAM 33 %, at
+      // a power-limited 1.54 GHz, nothing saturated.)
+      const bool unit_fast = a.dl_next && !a.logp_out && !a.ke_out && nrows == 32 && (a.d & 3) == 0;
+      auto blk_fast = [&](int cb) { return unit_fast && cb < kTileN / 32 && n * kTileN + cb * 32 + 32 <= a.d; };
+      const int sub = lane >> 3, ch = lane & 7;
+      const uint32_t d4 = 4u * (uint32_t)a.d, k4 = 4u * (uint32_t)a.kpad;
+      auto issue = [&](int cb, int rb, float4 (&pv4)[4], float4 (&dv4)[4]) {
+        const size_t r_first = row0 + rb + sub;
+        const int cc = n * kTileN + cb * 32 + 4 * ch;
+        const float* p_ptr = a.p + r_first * (size_t)a.d + cc;
+        const float* dl_ptr = a.dl + r_first * (size_t)a.kpad + cc;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+#ifdef GM_TC_EXPERIMENT_NOLOAD
+          pv4[jj] = make_float4(1.f, 1.f, 1.f, 1.f); dv4[jj] = make_float4(2.f, 2.f, 2.f, 2.f);
+#else
+          pv4[jj] = __ldcs(reinterpret_cast<const float4*>(p_ptr + jj * d4));
+          dv4[jj] = *reinterpret_cast<const float4*>(dl_ptr + jj * k4);
+#endif
+        }
+      };
+      float4 pA[4], dA[4], pB[4], dB[4];
+#if GM_TC_EPI_PREFETCH
+      bool preA = blk_fast(cb_first);
+      if (preA) issue(cb_first, 0, pA, dA);
+#else
+      bool preA = false;
+#endif
       mbar_wait(&tfull[acc], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
 #pragma unroll 1
@@ -433,6 +468,56 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
 #endif
         const int col = c0 + lane;
         const bool col_ok = col < a.d;
+        if (blk_fast(cb)) {
+          // one 16-row half: transpose staging (row L of the half as eight 16-byte chunks, chunk i at position i ^ (L & 7):
+          // conflict-free for the row-wise writes and for the 4-rows-by-8-chunks reads), kick, next drift, stores
+          auto half = [&](int rb, const float4 (&pv4)[4], const float4 (&dv4)[4]) {
+            __syncwarp();
+            if ((lane & 16) == rb) {
+              const int L = lane & 15;
+              float4* trow = reinterpret_cast<float4*>(tr + L * 32);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) trow[i ^ (L & 7)] = make_float4(z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]);
+            }
+            __syncwarp();
+            const size_t r_first = row0 + rb + sub;
+            float* p_ptr = a.p + r_first * (size_t)a.d + c0 + 4 * ch;
+            float* dn_ptr = a.dl_next + r_first * (size_t)a.kpad + c0 + 4 * ch;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int r = 4 * jj + sub;
+              const float4 zv = *reinterpret_cast<const float4*>(tr + r * 32 + ((ch ^ (r & 7)) << 2));
+              float4 pn, dn;
+              pn.x = fmaf(-coef, zv.x, pv4[jj].x); pn.y = fmaf(-coef, zv.y, pv4[jj].y);
+              pn.z = fmaf(-coef, zv.z, pv4[jj].z); pn.w = fmaf(-coef, zv.w, pv4[jj].w);
+              dn.x = fmaf(a.drift_eps, pn.x, dv4[jj].x); dn.y = fmaf(a.drift_eps, pn.y, dv4[jj].y);
+              dn.z = fmaf(a.drift_eps, pn.z, dv4[jj].z); dn.w = fmaf(a.drift_eps, pn.w, dv4[jj].w);
+#ifdef GM_TC_EXPERIMENT_NOSTORE
+              if (pn.x == 123456.f)
+#endif
+              {
+                __stcs(reinterpret_cast<float4*>(p_ptr + jj * d4), pn);
+                *reinterpret_cast<float4*>(dn_ptr + jj * k4) = dn;
+              }
+            }
+          };
+#if GM_TC_EPI_PREFETCH
+          if (!preA) issue(cb, 0, pA, dA);
+          issue(cb, 16, pB, dB);                         // second half in flight under the first
+          half(0, pA, dA);
+          const int cbn = cb + kEpiWarps / 4;
+          preA = blk_fast(cbn);
+          if (preA) issue(cbn, 0, pA, dA);               // next block's first half in flight under the second
+          half(16, pB, dB);
+#else
+          issue(cb, 0, pA, dA);
+          half(0, pA, dA);
+          issue(cb, 16, pB, dB);
+          half(16, pB, dB);
+#endif
+          continue;
+        }
+        preA = false;
 #pragma unroll 1
         for (int rb = 0; rb < 32; rb += 16) {
           __syncwarp();
@@ -446,27 +531,6 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
           const float* dl_blk = a.dl + (row0 + rb) * (size_t)a.kpad + col;
           const uint32_t d32 = (uint32_t)a.d, k32 = (uint32_t)a.kpad;
           float pv[16], dv[16];
-          if (a.dl_next && !a.logp_out && !a.ke_out && nrows == 32 && c0 + 32 <= a.d) {
-            // fast path (every launch but the trajectory ends, every full 16 x 32 block): no bounds tests, no row sums
-            float* dn_blk = a.dl_next + (row0 + rb) * (size_t)a.kpad + col;
-#pragma unroll
-#ifdef GM_TC_EXPERIMENT_NOLOAD
-            for (int rr = 0; rr < 16; ++rr) { pv[rr] = 1.f; dv[rr] = 2.f; }
-#else
-            for (int rr = 0; rr < 16; ++rr) { pv[rr] = __ldcs(p_blk + rr * d32); dv[rr] = dl_blk[rr * k32]; }
-#endif
-#pragma unroll
-            for (int rr = 0; rr < 16; ++rr) {
-              const float pn = fmaf(-coef, tr[rr * 33 + lane], pv[rr]);
-#ifdef GM_TC_EXPERIMENT_NOSTORE
-              if (pn == 123456.f) { __stcs(p_blk + rr * d32, pn); dn_blk[rr * k32] = fmaf(a.drift_eps, pn, dv[rr]); }
-#else
-              __stcs(p_blk + rr * d32, pn);
-              dn_blk[rr * k32] = fmaf(a.drift_eps, pn, dv[rr]);
-#endif
-            }
-            continue;
-          }
 #pragma unroll
           for (int rr = 0; rr < 16; ++rr) {
             const int r = rb + rr;

@@ -12,7 +12,7 @@ except Exception as e:
     print(sys.argv[1], "unreadable", e)
 PY
 done
-for v in "" _k1m4 _k1m5; do GMCMC_LIB=$PWD/general_mcmc_b200/libgmcmc$v.so timeout 120 python tools/k1_rate.py; done
+for v in ""; do GMCMC_LIB=$PWD/general_mcmc_b200/libgmcmc$v.so timeout 120 python tools/k1_rate.py; done
 timeout 300 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:dense_gemm_kick -s 40 -c 3 --csv --log-file $out/r2_dense_counters.csv python bench.py --workload hmc_dense --steps 4 --warmup 3 --no-cpu > $out/ncu_dense_q.log 2>&1
 python - <<'PY'
 import csv
