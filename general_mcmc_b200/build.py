@@ -49,7 +49,7 @@ def _units():
         if os.path.exists(os.path.join(CSRC, extra)):
             flags = ["--fmad=false"] if extra.endswith("_exact.cu") else []
             units.append((extra, extra[:-3] + ".o", flags))
-    for src in ("stats.cu", "dispatch.cu", "runtime.cu"):
+    for src in ("stats.cu", "export.cu", "dispatch.cu", "runtime.cu"):
         units.append((src, src[:-3] + ".o", []))
     return units
 

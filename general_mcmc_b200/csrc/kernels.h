@@ -170,6 +170,10 @@ struct CustomTargetVTable {
   cudaError_t (*launch_mh)(const MhLaunch&, cudaStream_t);
 };
 
+// export.cu: columns [kbase, kbase + d) of [C, n, ld] samples -> chain:u32 [rows], observation:u32 [rows], dims:f64 [d][rows]
+cudaError_t launch_export_columns(const void* samples, int dtype, size_t C, size_t n, int ld, int kbase, int d, int obs_major,
+                                  unsigned int chain_base, unsigned int* chain_col, unsigned int* obs_col, double* dims, cudaStream_t st);
+
 size_t stats_npad(size_t n);
 int stats_ppb(size_t N);
 cudaError_t launch_tracker(const void* samples, int dtype, size_t C, size_t n, int p, float* mean /*[C,p]*/, float* mean_sq /*[C,p]*/,

@@ -1713,6 +1713,41 @@ gmcmc_status gmcmc_run_stats_from(gmcmc_ctx* ctx, const void* samples, size_t C,
   return stats_on_device(ctx, d, C, n, p, dtype, out);
 }
 
+gmcmc_status gmcmc_export_columns(gmcmc_ctx* ctx, const void* samples, size_t C, size_t n, size_t d, gmcmc_dtype dtype,
+                                  int on_device, gmcmc_row_order order, uint32_t chain_base, uint32_t* chain_out,
+                                  uint32_t* obs_out, double* dims_out) {
+  GM_REQUIRE(ctx && (samples || C * n * d == 0), "null argument");
+  GM_REQUIRE(order == GMCMC_ROWS_CHAIN_MAJOR || order == GMCMC_ROWS_OBS_MAJOR, "bad row order");
+  GM_REQUIRE(dtype == GMCMC_F32 || dtype == GMCMC_F64, "bad dtype");
+  const size_t rows = C * n;
+  if (rows == 0) return GMCMC_OK;
+  GM_REQUIRE(rows < 0xffffffffull && d < 0x7fffffffull, "too many rows for u32 index columns");
+  GM_CU(cudaSetDevice(ctx->device));
+  TempDevice tmp, dc, doo, dd;
+  const void* dsrc = nullptr;
+  GM_TRY(stage_samples(ctx, samples, rows * d * esize(dtype), on_device, &tmp, &dsrc));
+  if (chain_out) GM_CU(cudaMalloc(&dc.p, rows * sizeof(uint32_t)));
+  if (obs_out) GM_CU(cudaMalloc(&doo.p, rows * sizeof(uint32_t)));
+  // the dimension columns are produced in slabs of whole columns so that the f64 staging buffer stays below ~1 GB
+  const size_t max_cols = (dims_out && d > 0) ? std::max<size_t>(1, std::min<size_t>(d, ((size_t)1 << 30) / (rows * sizeof(double)))) : 0;
+  if (max_cols) GM_CU(cudaMalloc(&dd.p, max_cols * rows * sizeof(double)));
+  bool first = true;
+  for (size_t k0 = 0; first || k0 < (max_cols ? d : 0); k0 += std::max<size_t>(max_cols, 1)) {
+    const size_t nk = max_cols ? std::min(max_cols, d - k0) : 0;
+    cudaError_t e = launch_export_columns(dsrc, dtype, C, n, (int)d, (int)k0, (int)nk, (int)order, chain_base,
+                                          first ? (unsigned int*)dc.p : nullptr, first ? (unsigned int*)doo.p : nullptr,
+                                          (double*)dd.p, ctx->stream);
+    if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "export kernel launch failed: %s", cudaGetErrorString(e));
+    if (nk > 0)
+      GM_CU(cudaMemcpyAsync(dims_out + k0 * rows, dd.p, nk * rows * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GM_CU(cudaStreamSynchronize(ctx->stream));
+    first = false;
+  }
+  if (chain_out) GM_CU(cudaMemcpy(chain_out, dc.p, rows * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (obs_out) GM_CU(cudaMemcpy(obs_out, doo.p, rows * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return GMCMC_OK;
+}
+
 gmcmc_status gmcmc_philox_blocks(gmcmc_ctx* ctx, const uint32_t* ctr_host, size_t n, const uint32_t* key, uint32_t* out_host) {
   GM_REQUIRE(ctx && ctr_host && key && out_host, "null argument");
   if (n == 0) return GMCMC_OK;

@@ -256,6 +256,19 @@ gmcmc_status gmcmc_run_stats_from(gmcmc_ctx*, const void* samples, size_t C, siz
 gmcmc_status gmcmc_tracker_stats(gmcmc_ctx*, const void* samples, size_t C, size_t n, size_t p,
                                  gmcmc_dtype dtype, int on_device, float* rhat, float* max_rhat, float* p_accept);
 
+/* Column export of a sample tensor, ≙ the column builders of io::csv::save_csv / save_csv_tensor (io/csv.rs:47-147),
+ * io::arrow::save_arrow (io/arrow.rs:53-117), io::parquet::save_parquet / save_parquet_tensor (io/parquet.rs:49-222):
+ * one row per (chain, observation) pair with columns chain:u32, observation:u32, dim_0 .. dim_{d-1}:f64.
+ * GMCMC_ROWS_CHAIN_MAJOR: chain outer, observation inner (save_csv, save_arrow, save_parquet);
+ * GMCMC_ROWS_OBS_MAJOR:   observation outer, chain inner (save_parquet_tensor's [obs, chain, dim] order, parquet.rs:166-176).
+ * samples: [C, n, d] of `dtype`, device (on_device = 1, e.g. the pointer gmcmc_run_device returned) or host.  The
+ * transpose and the widening to f64 run on the device.  chain_out / obs_out: host u32 [C n] (chain values start at
+ * chain_base: the rank's chain offset); dims_out: host f64 [d][C n] (column k contiguous).  Any output may be NULL. */
+typedef enum { GMCMC_ROWS_CHAIN_MAJOR = 0, GMCMC_ROWS_OBS_MAJOR = 1 } gmcmc_row_order;
+gmcmc_status gmcmc_export_columns(gmcmc_ctx*, const void* samples, size_t C, size_t n, size_t d, gmcmc_dtype dtype,
+                                  int on_device, gmcmc_row_order order, uint32_t chain_base, uint32_t* chain_out,
+                                  uint32_t* obs_out, double* dims_out);
+
 /* raw Philox4x32-10 blocks computed on the device (contract check): ctr [n,4], key [2] -> out [n,4] */
 gmcmc_status gmcmc_philox_blocks(gmcmc_ctx*, const uint32_t* ctr_host, size_t n, const uint32_t* key,
                                  uint32_t* out_host);
