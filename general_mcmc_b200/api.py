@@ -217,6 +217,34 @@ class GaussianMixture(_Target):
         return np.concatenate([[self.weights.size, self.sigma], self.weights, self.means.ravel()])
 
 
+class PoissonTarget:
+    """Discrete target of tests/metrohast_poisson_test.rs:18-50: unnorm_logp(k) = k ln(lambda) - lambda - ln(k!)."""
+    int_kind = 0
+
+    def __init__(self, lam):
+        self.lam = float(lam)
+
+    def params(self):
+        return [self.lam]
+
+
+class BinomialTarget:
+    """Discrete target of tests/metrohast_poisson_test.rs:195-222: Binomial(n, p) on {0, .., n}."""
+    int_kind = 1
+
+    def __init__(self, n, p):
+        self.n, self.p = int(n), float(p)
+
+    def params(self):
+        return [float(self.n), self.p]
+
+
+class RandomWalkProposal:
+    """The +-1 random walk of the reference's discrete tests (PoissonRandomWalk / BinomialRandomWalk,
+    tests/metrohast_poisson_test.rs:52-90, 224-252): each coordinate moves up or down with probability 1/2, clamped to
+    the target's support; logp(from, to) = ln 0.5."""
+
+
 class CustomTarget(_Target):
     """A user-written device target compiled ahead of time into a plugin (csrc/gmcmc_custom_target.cuh);
     ≙ implementing GradientTarget / BatchedGradientTarget (distributions.rs:67-90) in the reference."""
@@ -420,7 +448,8 @@ class _Sampler:
         return out
 
     def set_positions(self, positions):
-        a = _as_positions(positions, self.dtype)
+        a = (np.ascontiguousarray(positions, np.int32) if getattr(self, "_discrete", False)
+             else _as_positions(positions, self.dtype))
         assert a.shape == (self.n_chains, self.dim)
         L.check(L.lib().gmcmc_set_positions(self._h, L.ptr(a)))
         self.ctx.synchronize()
@@ -447,7 +476,7 @@ class _Sampler:
         n = self._n_inj
         if n == 0:   # let the library report "no injected transitions recorded"
             L.check(L.lib().gmcmc_read_diagnostics(self._h, None, None, None, None))
-        la = np.empty((n, self.n_chains), self.dtype)
+        la = np.empty((n, self.n_chains), np.float64 if getattr(self, "_discrete", False) else self.dtype)
         acc = np.empty((n, self.n_chains), np.uint8)
         hmc = isinstance(self, HMC)
         pq = np.empty((n, self.n_chains, self.dim), self.dtype) if hmc else None
@@ -507,22 +536,47 @@ class MetropolisHastings(_Sampler):
     core.rs:204-406) with an IsotropicGaussian proposal."""
 
     def __init__(self, target, proposal, initial_states, ctx=None, chain_offset=0, dtype=None):
+        self.ctx = ctx or default_context()
+        self._out_dtype = np.dtype(np.float64)   # Trace -> f64, core.rs:34-51
+        self.target, self.proposal = target, proposal
+        seed = int(np.random.SeedSequence().entropy & 0xFFFFFFFFFFFFFFFF)
+        h = C.c_void_p()
+        if hasattr(target, "int_kind"):
+            # integer-state chains (S = i32): Poisson / Binomial target with the +-1 random-walk proposal
+            if not isinstance(proposal, RandomWalkProposal):
+                raise TypeError("discrete targets run with RandomWalkProposal")
+            pos = np.ascontiguousarray(np.asarray(initial_states), dtype=np.int32)
+            if pos.ndim != 2:
+                raise ValueError("initial states must be [n_chains, dim]")
+            self.n_chains, self.dim = pos.shape
+            self.dtype = np.dtype(np.int32)
+            self._discrete = True
+            p = np.ascontiguousarray(target.params(), np.float64)
+            L.check(L.lib().gmcmc_mh_int_create(self.ctx._h, int(target.int_kind), L.ptr(p), C.c_size_t(p.size),
+                                                C.c_size_t(self.n_chains), C.c_int(self.dim), C.c_uint64(chain_offset),
+                                                L.ptr(pos), C.c_uint64(seed), C.byref(h)))
+            self._h = h
+            return
         if not isinstance(proposal, IsotropicGaussian):
             raise TypeError("the device path implements the IsotropicGaussian proposal")
-        self.ctx = ctx or default_context()
         pos = _as_positions(initial_states, dtype)
         self.n_chains, self.dim = pos.shape
         self.dtype = pos.dtype
-        self._out_dtype = np.dtype(np.float64)   # Trace -> f64, core.rs:34-51
         if target.dim is None:
             target.dim = self.dim
-        self.target, self.proposal = target, proposal
         self._th = target._create(self.ctx, self.dtype)
-        h = C.c_void_p()
-        seed = int(np.random.SeedSequence().entropy & 0xFFFFFFFFFFFFFFFF)
         L.check(L.lib().gmcmc_mh_create(self.ctx._h, self._th, C.c_double(proposal.std), C.c_size_t(self.n_chains),
                                         C.c_uint64(chain_offset), L.ptr(pos), C.c_uint64(seed), C.byref(h)))
         self._h = h
+
+    def inject_int(self, steps, ln_u):
+        """Test hook for integer-state chains: directions (+1 / -1) [n, chains, dim] and ln u [n, chains]."""
+        steps = np.ascontiguousarray(steps, np.int8)
+        ln_u = np.ascontiguousarray(ln_u, np.float64)
+        n = ln_u.shape[0]
+        assert steps.shape == (n, self.n_chains, self.dim) and ln_u.shape == (n, self.n_chains)
+        L.check(L.lib().gmcmc_mh_int_inject(self._h, L.ptr(steps), L.ptr(ln_u), C.c_size_t(n)))
+        self._n_inj = n
 
     def seed(self, seed):  # metropolis_hastings.rs:189-197
         return self.set_seed(seed)

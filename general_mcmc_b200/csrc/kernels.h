@@ -86,6 +86,24 @@ struct MhLaunch {
   float* diag_draws;        // [n, C, 3] draws used by the 2-D fast kernel (gmcmc_mh_record), or null
 };
 
+// integer-state MH (mh_int.cu): Poisson / Binomial targets, +-1 random-walk proposal (tests/metrohast_poisson_test.rs)
+struct MhIntLaunch {
+  int kind, dim, n;                 // 0 Poisson, 1 Binomial(n, p)
+  double lambda, ln_lambda, ln_p, ln_1mp, ln_half;   // logarithms evaluated on the host (glibc), like the CPU reference
+  const double* lnfact; int n_tab;  // device table of ln(k!), k < n_tab
+  size_t n_chains;
+  uint64_t chain_offset, seed;
+  uint32_t step_base, n_steps, n_skip;
+  int* state;                       // [C, d] int32 in/out
+  double* out; size_t out_n; uint32_t out_t0;
+  unsigned long long* accept_total;
+  const signed char* inj_steps;     // [n, C, d] +1 / -1, or null
+  const double* inj_lnu;            // [n, C], or null
+  double* diag_logratio; uint8_t* diag_acc;
+};
+cudaError_t launch_mh_int(const MhIntLaunch&, cudaStream_t);
+int mh_int_max_dim();
+
 // K3: dense-Gaussian HMC with the gradient GEMM on tcgen05 (dense_tc.cu)
 struct DenseTc;
 struct DenseTcStep {

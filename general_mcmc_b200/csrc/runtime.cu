@@ -128,7 +128,7 @@ struct gmcmc_target {
   void* plugin = nullptr;                       // dlopen handle
 };
 
-enum SamplerType { S_HMC = 0, S_MH = 1, S_NUTS = 2 };
+enum SamplerType { S_HMC = 0, S_MH = 1, S_NUTS = 2, S_MHINT = 3 };
 
 struct PooledDa {   // device-resident dual-averaging state of GMCMC_ADAPT_POOLED (all f64)
   double h_bar, log_eps_bar, mu, eps, m;
@@ -202,6 +202,11 @@ struct gmcmc_sampler {
   uint8_t* d_diag_acc = nullptr;
   void* d_diag_pq = nullptr;
   void* d_diag_pp = nullptr;
+  // integer-state MH (gmcmc_mh_int_create): Poisson / Binomial targets, +-1 random-walk proposal
+  int int_kind = 0, int_n = 0;
+  double int_lambda = 0.0, int_p = 0.0;
+  double* d_lnfact = nullptr; int n_lnfact = 0;
+  signed char* d_inj_isteps = nullptr;
   // gmcmc_mh_record: per-step record of the production 2-D fast MH kernel
   size_t rec_steps = 0;       // pending recorded transitions
   float* d_diag_draws = nullptr;
@@ -298,7 +303,7 @@ gmcmc_status ensure_samples(gmcmc_sampler* s, size_t bytes) {
   return GMCMC_OK;
 }
 
-inline int out_dtype_of(const gmcmc_sampler* s) { return s->type == S_MH ? (int)GMCMC_F64 : s->dtype; }
+inline int out_dtype_of(const gmcmc_sampler* s) { return (s->type == S_MH || s->type == S_MHINT) ? (int)GMCMC_F64 : s->dtype; }
 
 gmcmc_status set_eps_device(gmcmc_sampler* s, double eps) {
   if (s->dtype == GMCMC_F32) {
@@ -401,6 +406,36 @@ gmcmc_status mh_segment(gmcmc_sampler* s, size_t first, size_t count, size_t n_d
   cudaError_t e = s->tgt->custom ? s->tgt->custom->launch_mh(L, s->ctx->stream)
                   : (s->math == GMCMC_MATH_EXACT) ? launch_mh_exact(L, s->ctx->stream) : launch_mh_fast(L, s->ctx->stream);
   if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "MH kernel launch failed: %s", cudaGetErrorString(e));
+  s->launches += 1;
+  return GMCMC_OK;
+}
+
+gmcmc_status mh_int_segment(gmcmc_sampler* s, size_t first, size_t count, size_t n_discard, size_t n_collect, void* out,
+                            bool use_injection, size_t inj_first) {
+  if (count == 0) return GMCMC_OK;
+  MhIntLaunch L{};
+  L.kind = s->int_kind; L.dim = s->dim; L.n = s->int_n;
+  L.lambda = s->int_lambda;
+  L.ln_lambda = std::log(s->int_lambda); L.ln_p = std::log(s->int_p); L.ln_1mp = std::log(1.0 - s->int_p); L.ln_half = std::log(0.5);
+  L.lnfact = s->d_lnfact; L.n_tab = s->n_lnfact;
+  L.n_chains = s->n_chains; L.chain_offset = s->chain_offset; L.seed = s->seed;
+  L.step_base = s->step_index + (uint32_t)first;
+  L.n_steps = (uint32_t)count;
+  const size_t skip = first >= n_discard ? 0 : std::min(count, n_discard - first);
+  L.n_skip = (uint32_t)skip;
+  L.state = (int*)s->d_pos;
+  L.out = (out && skip < count) ? (double*)out : nullptr;
+  L.out_n = n_collect;
+  L.out_t0 = (uint32_t)(first >= n_discard ? first - n_discard : 0);
+  L.accept_total = s->d_counts + 0;
+  if (use_injection) {
+    L.inj_steps = s->d_inj_isteps + inj_first * s->n_chains * (size_t)s->dim;
+    L.inj_lnu = (const double*)s->d_inj_lnu + inj_first * s->n_chains;
+    L.diag_logratio = (double*)s->d_diag_logacc + inj_first * s->n_chains;
+    L.diag_acc = s->d_diag_acc + inj_first * s->n_chains;
+  }
+  cudaError_t e = launch_mh_int(L, s->ctx->stream);
+  if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "integer MH kernel launch failed: %s", cudaGetErrorString(e));
   s->launches += 1;
   return GMCMC_OK;
 }
@@ -581,7 +616,10 @@ gmcmc_status run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void
   const size_t inj = std::min(s->inj_steps, total);
   const size_t inj_first = s->diag_steps - s->inj_steps;  // offset of the first unconsumed injected transition
 
-  if (s->type == S_MH && s->rec_steps > 0) {
+  if (s->type == S_MHINT) {
+    GM_TRY(mh_int_segment(s, 0, inj, n_discard, n_collect, d_out, true, inj_first));
+    GM_TRY(mh_int_segment(s, inj, total - inj, n_discard, n_collect, d_out, false, 0));
+  } else if (s->type == S_MH && s->rec_steps > 0) {
     const size_t rec = std::min(s->rec_steps, total);
     GM_TRY(mh_segment(s, 0, rec, n_discard, n_collect, d_out, false, s->diag_steps - s->rec_steps, true));
     GM_TRY(mh_segment(s, rec, total - rec, n_discard, n_collect, d_out, false, 0));
@@ -1143,6 +1181,69 @@ gmcmc_status gmcmc_mh_create(gmcmc_ctx* ctx, gmcmc_target* tgt, double proposal_
   return GMCMC_OK;
 }
 
+gmcmc_status gmcmc_mh_int_create(gmcmc_ctx* ctx, gmcmc_int_target_kind kind, const double* params, size_t n_params,
+                                 size_t n_chains, int dim, uint64_t chain_offset, const int32_t* init_host, uint64_t seed,
+                                 gmcmc_sampler** out) {
+  GM_REQUIRE(ctx && out && init_host && params, "null argument");
+  GM_REQUIRE(n_chains >= 1 && dim >= 1 && dim <= mh_int_max_dim(), "integer MH supports 1 <= dim <= %d", mh_int_max_dim());
+  GM_REQUIRE(kind == GMCMC_ITARGET_POISSON || kind == GMCMC_ITARGET_BINOMIAL, "unknown integer target kind");
+  GM_REQUIRE(n_params == (kind == GMCMC_ITARGET_POISSON ? 1u : 2u), "Poisson takes [lambda], Binomial takes [n, p]");
+  GM_CU(cudaSetDevice(ctx->device));
+  gmcmc_sampler* s = new gmcmc_sampler();
+  s->type = S_MHINT; s->ctx = ctx; s->tgt = nullptr;
+  s->n_chains = n_chains; s->chain_offset = chain_offset; s->dim = dim; s->dtype = GMCMC_F32;   // 4-byte (int32) state elements
+  s->seed = seed; s->int_kind = (int)kind;
+  if (kind == GMCMC_ITARGET_POISSON) {
+    s->int_lambda = params[0]; s->int_p = 0.5;
+    if (!(s->int_lambda > 0.0)) { delete s; return fail(GMCMC_ERR_INVALID, "Poisson rate must be positive"); }
+  } else {
+    s->int_n = (int)params[0]; s->int_p = params[1]; s->int_lambda = 1.0;
+    if (s->int_n < 0 || !(s->int_p > 0.0 && s->int_p < 1.0)) { delete s; return fail(GMCMC_ERR_INVALID, "Binomial needs n >= 0 and 0 < p < 1"); }
+  }
+  // ln(k!) exactly as the CPU reference sums it (metrohast_poisson_test.rs:40-50): acc += ln(i), i = 1 .. k, in f64
+  const int n_tab = 4096;
+  std::vector<double> tab(n_tab, 0.0);
+  {
+    double acc = 0.0;
+    for (int k = 1; k < n_tab; ++k) { acc += std::log((double)k); tab[k] = k < 2 ? 0.0 : acc; }
+  }
+  const size_t bytes = n_chains * (size_t)dim * sizeof(int32_t);
+  bool ok = cudaMalloc(&s->d_pos, bytes) == cudaSuccess &&
+            cudaMemcpy(s->d_pos, init_host, bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMalloc(&s->d_counts, 8 * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMemset(s->d_counts, 0, 8 * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMalloc((void**)&s->d_lnfact, n_tab * sizeof(double)) == cudaSuccess &&
+            cudaMemcpy(s->d_lnfact, tab.data(), n_tab * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaEventCreate(&s->ev0) == cudaSuccess && cudaEventCreate(&s->ev1) == cudaSuccess;
+  if (!ok) {
+    gmcmc_status st = fail(GMCMC_ERR_CUDA, "sampler allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    gmcmc_sampler_destroy(s);
+    return st;
+  }
+  s->n_lnfact = n_tab;
+  *out = s;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_mh_int_inject(gmcmc_sampler* s, const int8_t* steps, const double* ln_u, size_t n_steps) {
+  GM_REQUIRE(s && s->type == S_MHINT && steps && ln_u && n_steps >= 1, "gmcmc_mh_int_inject: integer MH sampler, non-null streams");
+  GM_CU(cudaSetDevice(s->ctx->device));
+  GM_CU(cudaStreamSynchronize(s->ctx->stream));
+  cudaFree(s->d_inj_isteps); cudaFree(s->d_inj_lnu); cudaFree(s->d_diag_logacc); cudaFree(s->d_diag_acc);
+  s->d_inj_isteps = nullptr; s->d_inj_lnu = s->d_diag_logacc = nullptr; s->d_diag_acc = nullptr;
+  s->inj_steps = s->diag_steps = 0;
+  const size_t C = s->n_chains, d = (size_t)s->dim;
+  GM_CU(cudaMalloc((void**)&s->d_inj_isteps, n_steps * C * d));
+  GM_CU(cudaMalloc(&s->d_inj_lnu, n_steps * C * sizeof(double)));
+  GM_CU(cudaMalloc(&s->d_diag_logacc, n_steps * C * sizeof(double)));
+  GM_CU(cudaMalloc((void**)&s->d_diag_acc, n_steps * C));
+  GM_CU(cudaMemset(s->d_diag_acc, 0, n_steps * C));
+  GM_CU(cudaMemcpy(s->d_inj_isteps, steps, n_steps * C * d, cudaMemcpyHostToDevice));
+  GM_CU(cudaMemcpy(s->d_inj_lnu, ln_u, n_steps * C * sizeof(double), cudaMemcpyHostToDevice));
+  s->inj_steps = s->diag_steps = n_steps;
+  return GMCMC_OK;
+}
+
 gmcmc_status gmcmc_nuts_create(gmcmc_ctx* ctx, gmcmc_target* tgt, size_t n_chains, uint64_t chain_offset,
                                const void* init_host, double target_accept, uint32_t max_depth,
                                double init_step_size, uint64_t seed, gmcmc_sampler** out) {
@@ -1209,7 +1310,7 @@ gmcmc_status gmcmc_sampler_destroy(gmcmc_sampler* s) {
   cudaFree(s->d_mass_inv); cudaFree(s->d_mass_sqrt); cudaFree(s->d_run_mean); cudaFree(s->d_run_m2);
   cudaFree(s->d_inj_normals); cudaFree(s->d_inj_lnu);
   cudaFree(s->d_diag_logacc); cudaFree(s->d_diag_acc); cudaFree(s->d_diag_pq); cudaFree(s->d_diag_pp);
-  cudaFree(s->d_diag_draws);
+  cudaFree(s->d_diag_draws); cudaFree(s->d_lnfact); cudaFree(s->d_inj_isteps);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   for (cudaEvent_t e : s->ev_kern) if (e) cudaEventDestroy(e);
@@ -1421,7 +1522,7 @@ gmcmc_status gmcmc_read_diagnostics(gmcmc_sampler* s, void* log_accept, uint8_t*
   if (s->diag_steps == 0) return fail(GMCMC_ERR_STATE, "no injected transitions recorded");
   GM_CU(cudaSetDevice(s->ctx->device));
   GM_CU(cudaStreamSynchronize(s->ctx->stream));
-  const size_t es = esize(s->dtype), C = s->n_chains, d = (size_t)s->dim, n = s->diag_steps;
+  const size_t es = s->type == S_MHINT ? 8 : esize(s->dtype), C = s->n_chains, d = (size_t)s->dim, n = s->diag_steps;
   if (log_accept) GM_CU(cudaMemcpy(log_accept, s->d_diag_logacc, n * C * es, cudaMemcpyDeviceToHost));
   if (accepted) GM_CU(cudaMemcpy(accepted, s->d_diag_acc, n * C, cudaMemcpyDeviceToHost));
   if (prop_q) {

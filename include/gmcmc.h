@@ -158,6 +158,21 @@ gmcmc_status gmcmc_hmc_create(gmcmc_ctx*, gmcmc_target*, size_t n_chains, uint64
 gmcmc_status gmcmc_mh_create(gmcmc_ctx*, gmcmc_target*, double proposal_std, size_t n_chains,
                              uint64_t chain_offset, const void* init_host, uint64_t seed,
                              gmcmc_sampler** out);
+/* Integer-state Metropolis–Hastings: ≙ MetropolisHastings<S = i32, T = f64>::new + seed (metropolis_hastings.rs:151-197)
+ * with the discrete targets and the +-1 random-walk proposals of the reference's discrete-state tests
+ * (tests/metrohast_poisson_test.rs:18-86 Poisson(lambda), :195-252 Binomial(n, p)): unnorm_logp as written there (ln k!
+ * summed term by term), proposal k +- 1 with probability 1/2 clamped to the support, Proposal::logp = ln 0.5 both ways.
+ * State: int32 [n_chains, dim] (dim <= 8, coordinates independent); samples are f64 [C, n, dim] like every MH trace
+ * (core.rs:34-51).  Runs through gmcmc_run / gmcmc_run_device / gmcmc_run_stats / gmcmc_step / gmcmc_positions
+ * (int32) / gmcmc_counters_get like the other samplers.  RNG: stream 0 block 0, bit i of word 0 = direction of
+ * coordinate i (1: +1); stream 1 block 0 = accept uniform. */
+typedef enum { GMCMC_ITARGET_POISSON = 0 /* params [lambda] */, GMCMC_ITARGET_BINOMIAL = 1 /* params [n, p] */ } gmcmc_int_target_kind;
+gmcmc_status gmcmc_mh_int_create(gmcmc_ctx*, gmcmc_int_target_kind kind, const double* params, size_t n_params,
+                                 size_t n_chains, int dim, uint64_t chain_offset, const int32_t* init_host,
+                                 uint64_t seed, gmcmc_sampler** out);
+/* Test hook: the next n_steps transitions take these directions (int8 +1 / -1, [n_steps, n_chains, dim]) and
+ * ln u values (f64 [n_steps, n_chains]); log ratio (f64) and decisions through gmcmc_read_diagnostics. */
+gmcmc_status gmcmc_mh_int_inject(gmcmc_sampler*, const int8_t* steps, const double* ln_u, size_t n_steps);
 /* ≙ NUTS::new (nuts.rs:156-190) / GenericNUTS::new (generic_nuts.rs:370-398), identity mass.
  * max_depth 0 = uncapped like the reference up to an internal safety cap of 20.
  * init_step_size <= 0: find_reasonable_epsilon (generic_nuts.rs:1025-1102) per chain. */

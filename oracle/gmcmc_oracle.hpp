@@ -328,6 +328,69 @@ MhStepInfo<T> mh_step(const Target<T>& tgt, T prop_std, T* x, const T* normals, 
 }
 
 // ------------------------------------------------------------------------------------------
+// Integer-state Metropolis-Hastings: MetropolisHastings<S = i32, T = f64> with the discrete targets and the
+// +-1 random-walk proposals of /root/reference/tests/metrohast_poisson_test.rs:18-86 (Poisson) and :195-252
+// (Binomial).  The proposal's direction bits are injected (step = +1 / -1 per coordinate).
+// ------------------------------------------------------------------------------------------
+enum IntTargetKind { IT_POISSON = 0, IT_BINOMIAL = 1 };
+
+inline double ln_factorial(int k) {                 // metrohast_poisson_test.rs:40-50
+  if (k < 2) return 0.0;
+  double acc = 0.0;
+  for (int i = 1; i <= k; ++i) acc += std::log((double)i);
+  return acc;
+}
+
+struct IntTarget {
+  int kind = IT_POISSON;
+  int dim = 1;
+  double lambda = 1.0, p = 0.5;
+  int n = 0;
+  // unnorm_logp: metrohast_poisson_test.rs:24-36 (Poisson), :203-213 (Binomial); coordinates are independent and
+  // summed in order (the reference's examples are one-dimensional)
+  double logp(const int* k) const {
+    double total = 0.0;
+    for (int i = 0; i < dim; ++i) {
+      double lp;
+      if (kind == IT_POISSON) {
+        if (k[i] < 0) return -std::numeric_limits<double>::infinity();
+        const double kf = (double)k[i];
+        lp = kf * std::log(lambda) - lambda - ln_factorial(k[i]);
+      } else {
+        if (k[i] < 0 || k[i] > n) return -std::numeric_limits<double>::infinity();
+        const double kf = (double)k[i], nf = (double)n;
+        const double coeff = ln_factorial(n) - ln_factorial(k[i]) - ln_factorial(n - k[i]);
+        lp = coeff + kf * std::log(p) + (nf - kf) * std::log(1.0 - p);
+      }
+      total = (i == 0) ? lp : total + lp;
+    }
+    return total;
+  }
+  // PoissonRandomWalk::sample :67-78 (reflect below 0 = clamp at 0), BinomialRandomWalk::sample :236-241 (clamp to [0, n])
+  int propose(int cur, int step) const {
+    const int v = cur + step;
+    if (kind == IT_POISSON) return v < 0 ? 0 : v;
+    return std::min(std::max(v, 0), n);
+  }
+};
+
+struct MhIntStepInfo { double log_accept_ratio; int accepted; };
+
+// MHMarkovChain::step, metropolis_hastings.rs:306-318, with Proposal::logp == ln(0.5) in both directions (:80-83)
+inline MhIntStepInfo mh_int_step(const IntTarget& tgt, int* x, const signed char* steps, double ln_u) {
+  std::vector<int> proposed(tgt.dim);
+  for (int i = 0; i < tgt.dim; ++i) proposed[i] = tgt.propose(x[i], (int)steps[i]);
+  const double current_lp = tgt.logp(x);
+  const double proposed_lp = tgt.logp(proposed.data());
+  const double log_q = std::log(0.5);
+  MhIntStepInfo r;
+  r.log_accept_ratio = (proposed_lp + log_q) - (current_lp + log_q);
+  r.accepted = (r.log_accept_ratio > ln_u) ? 1 : 0;
+  if (r.accepted) std::copy(proposed.begin(), proposed.end(), x);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
 // NUTS (identity mass matrix).  generic_nuts.rs:755-925, 1025-1102, 1153-1418
 // ------------------------------------------------------------------------------------------
 // Injected random stream, consumed in the reference's draw order:

@@ -276,6 +276,32 @@ double orc_diag_mass_kinetic_inv_mul_f64(const double* var, int d, double jitter
   return nuts_kinetic<double>(p, d, &m);
 }
 
+// ---- integer-state MH (tests/metrohast_poisson_test.rs) ----
+// x [C,d] int32 in/out; steps [n,C,d] int8 (+1 / -1); ln_u [n,C]; samples f64 [C,n,d]; accepted [n,C]; log_ratio [n,C]
+void orc_mh_int_run(int kind, int dim, const double* params, size_t C, int* x, size_t n_steps, const signed char* steps,
+                    const double* ln_u, double* samples, uint8_t* accepted, double* log_ratio) {
+  IntTarget t;
+  t.kind = kind; t.dim = dim;
+  if (kind == IT_POISSON) t.lambda = params[0]; else { t.n = (int)params[0]; t.p = params[1]; }
+  const size_t d = (size_t)dim;
+#pragma omp parallel for schedule(static)
+  for (long long ci = 0; ci < (long long)C; ++ci) {
+    const size_t c = (size_t)ci;
+    for (size_t s = 0; s < n_steps; ++s) {
+      MhIntStepInfo r = mh_int_step(t, x + c * d, steps + (s * C + c) * d, ln_u[s * C + c]);
+      if (samples) for (size_t k = 0; k < d; ++k) samples[(c * n_steps + s) * d + k] = (double)x[c * d + k];
+      if (accepted) accepted[s * C + c] = (uint8_t)r.accepted;
+      if (log_ratio) log_ratio[s * C + c] = r.log_accept_ratio;
+    }
+  }
+}
+double orc_int_target_logp(int kind, int dim, const double* params, const int* k) {
+  IntTarget t;
+  t.kind = kind; t.dim = dim;
+  if (kind == IT_POISSON) t.lambda = params[0]; else { t.n = (int)params[0]; t.p = params[1]; }
+  return t.logp(k);
+}
+
 // ---- stats ----
 void orc_split_rhat_mean_ess(const float* sample, size_t c, size_t n, size_t p, float* rhat, float* ess_out) { split_rhat_mean_ess(sample, c, n, p, rhat, ess_out); }
 void orc_autocov_bf(const float* x, size_t n, size_t d, float* out) { autocov_bf(x, n, d, out); }

@@ -52,6 +52,7 @@ def lib(fast=False):
         L.orc_mh_bench_f64.restype = C.c_double
         L.orc_max_threads.restype = C.c_int
         L.orc_diag_mass_kinetic_inv_mul_f64.restype = C.c_double
+        L.orc_int_target_logp.restype = C.c_double
         _libs[key] = L
     return _libs[key]
 
@@ -195,6 +196,31 @@ def nuts_run(kind, params, q0, target_accept, max_depth, eps_init, n_collect, n_
         mass_inv = np.ones((Cn, d), dt)
         getattr(lib(fast), "orc_nuts_run_mass_" + _sfx(dt))(*args, _p(cfg), _p(mass_inv))
     return dict(q=q, samples=samples, eps=eps_f, leapfrogs=leap, used=used, exhausted=exh, mass_inv=mass_inv)
+
+
+POISSON, BINOMIAL = 0, 1
+
+
+def mh_int_run(kind, params, x0, steps, ln_u):
+    """Integer-state MH (tests/metrohast_poisson_test.rs): x0 [C,d] int32, steps [n,C,d] int8 (+-1), ln_u [n,C] f64."""
+    x = np.array(x0, dtype=np.int32, copy=True, order="C")
+    Cn, d = x.shape
+    steps = np.ascontiguousarray(steps, np.int8)
+    ln_u = np.ascontiguousarray(ln_u, np.float64)
+    n = steps.shape[0]
+    samples = np.zeros((Cn, n, d), np.float64)
+    acc = np.zeros((n, Cn), np.uint8)
+    lr = np.zeros((n, Cn), np.float64)
+    p = np.ascontiguousarray(params, np.float64)
+    lib().orc_mh_int_run(C.c_int(kind), C.c_int(d), _p(p), C.c_size_t(Cn), _p(x), C.c_size_t(n), _p(steps), _p(ln_u),
+                         _p(samples), _p(acc), _p(lr))
+    return dict(x=x, samples=samples, accepted=acc, log_ratio=lr)
+
+
+def int_target_logp(kind, params, k):
+    k = np.ascontiguousarray(k, np.int32)
+    p = np.ascontiguousarray(params, np.float64)
+    return lib().orc_int_target_logp(C.c_int(kind), C.c_int(k.size), _p(p), _p(k))
 
 
 def diag_mass_kinetic_inv_mul(var, p, jitter=1e-12):

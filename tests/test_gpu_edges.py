@@ -73,3 +73,59 @@ def test_pipelined_host_run_equals_device_run(ctx):
     b = np.concatenate([gm.HMC(gm.RosenbrockND(d), q0[i:i + 5000], 0.005, 4, seed=42, ctx=ctx, chain_offset=i).run(3, 1)
                         for i in range(0, Cn, 5000)])
     assert np.array_equal(a, b)
+
+
+# -------------------------------------------------------------------------------------------------
+# integer-state Metropolis-Hastings (tests/metrohast_poisson_test.rs)
+# -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,mk,kind,params,d,x0max", [
+    ("poisson", lambda: gm.PoissonTarget(4.0), 0, [4.0], 1, 9),
+    ("binomial", lambda: gm.BinomialTarget(10, 0.3), 1, [10, 0.3], 1, 10),
+    ("poisson3d", lambda: gm.PoissonTarget(2.5), 0, [2.5], 3, 6),
+])
+def test_mh_int_bit_exact_vs_oracle(ctx, oracle, name, mk, kind, params, d, x0max):
+    """MetropolisHastings<S = i32, T = f64> with injected proposal directions and ln u: decisions, log ratios, traces and
+    final states bit-identical to the oracle's restatement of metropolis_hastings.rs:306-318 on the reference's discrete
+    targets (ln k! summed term by term, clamped +-1 walk, ln 0.5 proposal terms kept in the ratio)."""
+    Cn, n, n_discard = 257, 60, 9
+    rng = np.random.default_rng(7)
+    x0 = rng.integers(0, x0max + 1, size=(Cn, d)).astype(np.int32)
+    steps = (rng.integers(0, 2, size=(n, Cn, d)) * 2 - 1).astype(np.int8)
+    ln_u = np.log(rng.random((n, Cn)))
+    ref = oracle.mh_int_run(kind, params, x0, steps, ln_u)
+    s = gm.MetropolisHastings(mk(), gm.RandomWalkProposal(), x0, ctx=ctx)
+    s.inject_int(steps, ln_u)
+    out = s.run(n - n_discard, n_discard)
+    diag = s.diagnostics()
+    assert out.dtype == np.float64
+    assert np.array_equal(diag["accepted"], ref["accepted"])
+    assert np.array_equal(diag["log_accept"], ref["log_ratio"])
+    assert np.array_equal(out, ref["samples"][:, n_discard:, :])
+    assert np.array_equal(s.positions(), ref["x"])
+    assert 0.2 < ref["accepted"].mean() < 0.98
+
+
+def test_mh_int_poisson_and_binomial_distributions(ctx):
+    """The reference's own acceptance test (tests/metrohast_poisson_test.rs:92-140, 254-290): 20,000 draws after 2,000
+    burn-in, empirical frequencies of k = 0..10 within 0.05 of the pmf — here over 4,096 chains, so within 0.005."""
+    from math import comb, exp, factorial
+    Cn = 4096
+    s = gm.MetropolisHastings(gm.PoissonTarget(4.0), gm.RandomWalkProposal(), np.zeros((Cn, 1), np.int32), ctx=ctx).seed(42)
+    out = s.run(2000, 2000)
+    assert np.array_equal(out, np.round(out)) and out.min() >= 0
+    freq = np.bincount(out.astype(np.int64).ravel(), minlength=11)[:11] / out.size
+    pmf = np.array([exp(-4.0) * 4.0 ** k / factorial(k) for k in range(11)])
+    assert np.abs(freq - pmf).max() < 0.005, (freq, pmf)
+    b = gm.MetropolisHastings(gm.BinomialTarget(10, 0.3), gm.RandomWalkProposal(), np.full((Cn, 1), 5, np.int32), ctx=ctx).seed(42)
+    out, st = b.run_progress(2000, 2000)
+    assert out.min() >= 0 and out.max() <= 10
+    freq = np.bincount(out.astype(np.int64).ravel(), minlength=11)[:11] / out.size
+    pmf = np.array([comb(10, k) * 0.3 ** k * 0.7 ** (10 - k) for k in range(11)])
+    assert np.abs(freq - pmf).max() < 0.005, (freq, pmf)
+    assert st.rhat_std.max < 1.01
+    # sharding and continuation invariance (Philox keyed by the global chain index)
+    x0 = np.arange(300, dtype=np.int32).reshape(300, 1) % 7
+    full = gm.MetropolisHastings(gm.PoissonTarget(4.0), gm.RandomWalkProposal(), x0, ctx=ctx).seed(9).run(30, 4)
+    lo = gm.MetropolisHastings(gm.PoissonTarget(4.0), gm.RandomWalkProposal(), x0[:100], ctx=ctx, chain_offset=0).seed(9).run(30, 4)
+    hi = gm.MetropolisHastings(gm.PoissonTarget(4.0), gm.RandomWalkProposal(), x0[100:], ctx=ctx, chain_offset=100).seed(9).run(30, 4)
+    assert np.array_equal(full, np.concatenate([lo, hi]))
