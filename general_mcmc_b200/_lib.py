@@ -24,7 +24,7 @@ SYMBOLS = [
     "gmcmc_host_free", "gmcmc_measure_fp32_peak", "gmcmc_target_create", "gmcmc_target_create_custom", "gmcmc_target_destroy", "gmcmc_target_logp_grad",
     "gmcmc_hmc_create", "gmcmc_mh_create", "gmcmc_mh_int_create", "gmcmc_mh_int_inject", "gmcmc_nuts_create", "gmcmc_sampler_destroy", "gmcmc_set_seed",
     "gmcmc_set_math_mode", "gmcmc_set_adaptation", "gmcmc_set_step_size", "gmcmc_inject", "gmcmc_mh_record", "gmcmc_mh_read_draws",
-    "gmcmc_nuts_inject", "gmcmc_nuts_state", "gmcmc_nuts_set_mass_adaptation", "gmcmc_nuts_mass_matrix", "gmcmc_read_diagnostics", "gmcmc_step", "gmcmc_run", "gmcmc_run_device", "gmcmc_reserve_samples",
+    "gmcmc_nuts_inject", "gmcmc_nuts_state", "gmcmc_nuts_set_mass_adaptation", "gmcmc_nuts_set_dense_max_dim", "gmcmc_nuts_mass_matrix", "gmcmc_read_diagnostics", "gmcmc_step", "gmcmc_run", "gmcmc_run_device", "gmcmc_reserve_samples",
     "gmcmc_run_stats", "gmcmc_positions", "gmcmc_set_positions", "gmcmc_counters_get",
     "gmcmc_sampler_info", "gmcmc_split_rhat_ess", "gmcmc_run_stats_from", "gmcmc_tracker_stats", "gmcmc_export_columns", "gmcmc_philox_blocks",
     "gmcmc_last_error", "gmcmc_version",

@@ -596,19 +596,20 @@ class MetropolisHastings(_Sampler):
 
 class NUTSMassMatrixConfig:
     """≙ NUTSMassMatrixConfig (generic_nuts.rs:40-78): warm-up mass-matrix adaptation of NUTS.  `adaptation` is
-    "none", "diagonal" (the reference default) or "dense" (not implemented: GMCMC_ERR_UNSUPPORTED)."""
+    "none", "diagonal" (the reference default) or "dense" (per-chain dense covariance up to dense_max_dim dimensions)."""
     _KINDS = {"none": 0, "diagonal": 1, "dense": 2}
 
     def __init__(self, adaptation="diagonal", start_buffer=75, end_buffer=50, initial_window=25, regularize=0.05,
-                 jitter=1e-6):
+                 jitter=1e-6, dense_max_dim=75):
         if adaptation not in self._KINDS:
             raise ValueError("adaptation must be one of %s" % sorted(self._KINDS))
         self.adaptation, self.start_buffer, self.end_buffer = adaptation, int(start_buffer), int(end_buffer)
         self.initial_window, self.regularize, self.jitter = int(initial_window), float(regularize), float(jitter)
+        self.dense_max_dim = int(dense_max_dim)
 
     @classmethod
     def disabled(cls):
-        return cls("none", 0, 0, 0, 0.0, 0.0)
+        return cls("none", 0, 0, 0, 0.0, 0.0, 0)
 
 
 class NUTS(_Sampler):
@@ -633,14 +634,18 @@ class NUTS(_Sampler):
         self._h = h
         if mass_matrix is not None and mass_matrix.adaptation != "none":
             m = mass_matrix
+            self._mass_kind = m.adaptation if not (m.adaptation == "dense" and self.dim > m.dense_max_dim) else "none"
+            L.check(L.lib().gmcmc_nuts_set_dense_max_dim(self._h, C.c_size_t(m.dense_max_dim)))
             L.check(L.lib().gmcmc_nuts_set_mass_adaptation(self._h, C.c_int(m._KINDS[m.adaptation]),
                                                            C.c_size_t(m.start_buffer), C.c_size_t(m.end_buffer),
                                                            C.c_size_t(m.initial_window), C.c_double(m.regularize),
                                                            C.c_double(m.jitter)))
 
     def mass_matrix(self):
-        """Per-chain diagonal inverse mass [chains, dim] and the number of warm-up updates applied so far."""
-        inv = np.empty((self.n_chains, self.dim), self.dtype)
+        """Per-chain inverse mass — [chains, dim] (diagonal) or [chains, dim, dim] (dense) — and the number of warm-up
+        updates applied so far."""
+        shape = (self.n_chains, self.dim, self.dim) if getattr(self, "_mass_kind", "") == "dense" else (self.n_chains, self.dim)
+        inv = np.empty(shape, self.dtype)
         n = C.c_uint64(0)
         L.check(L.lib().gmcmc_nuts_mass_matrix(self._h, L.ptr(inv), C.byref(n)))
         return inv, int(n.value)

@@ -154,7 +154,21 @@ struct NutsLaunch {
   uint32_t run_n_base;                                   // its sample count when the launch starts (same for every chain)
   uint32_t collect_after, collect_before;                // positions are collected for collect_after < m < collect_before
   int probe;              // with init_only: mass-matrix update probe (generic_nuts.rs:906-918) instead of init_chain_state
+  // dense mass matrix (MassMatrix::Dense): inverse mass [C, d, d], lower Cholesky factor [C, d, d], running outer-product
+  // sums [C, d, d]; dense_active = 0 until the first update (identity arithmetic)
+  void* mass_dinv; void* mass_chol; void* run_m2d; int dense_active;
 };
+
+// mass_dense.cu: maybe_update_mass_matrix, Dense branch (generic_nuts.rs:970-997) + dense_from_cov (:208-226) for every chain
+struct DenseMassUpdate {
+  int dtype; size_t n_chains; int d; unsigned int n;     // n = positions in the running covariance
+  void* run_mean; void* run_m2; void* run_m2d;           // reset on return
+  void* inv; void* chol;                                 // [C, d, d] out
+  void* scratch_l; void* scratch_invl;                   // [d, d, C] (chain fastest) work arrays
+  double regularize, jitter;
+  int* state;                                            // [C]: 0 identity, 1 all-ones diagonal (fallback), 2 dense
+};
+cudaError_t launch_dense_mass_update(const DenseMassUpdate&, cudaStream_t);
 
 struct StatsLaunch {
   const void* samples;   // [C, n, p] device, f32 (dtype 0) or f64 (dtype 1)

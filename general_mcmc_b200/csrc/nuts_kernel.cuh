@@ -73,6 +73,10 @@ struct NutsArgs {
   T* run_mean; T* run_m2;                         // [C, d], [C, d]
   uint32_t run_n_base;                            // positions already in the statistics when this launch starts (same for every chain)
   uint32_t collect_after, collect_before;
+  // dense mass matrix (MassMatrix::Dense, generic_nuts.rs:187-303): inverse mass = covariance estimate [C, d, d], lower
+  // Cholesky factor of it [C, d, d], running outer-product sums of the warm-up window [C, d, d] (upper triangle)
+  const T* mass_dinv; const T* mass_chol; T* run_m2d;
+  int dense_active;                               // 0 until the first update: identity arithmetic (MassMatrix::Identity)
 };
 
 enum NutsPhase : int { NP_START = 0, NP_LEAF = 1, NP_END = 2, NP_DONE = 3 };
@@ -218,10 +222,11 @@ __device__ __forceinline__ void load_slice_raw(T (&dst)[EPL], const T* src, cons
 // (level k >= 1: one per 2^(k+1) leaves) read their first leaf from the global workspace.
 enum NutsHot : int { H_QM = 0, H_PM = 1, H_QP = 2, H_PP = 3, H_LQ = 4, H_LP = 5, H_COUNT = 6 };
 
-// MASS: diagonal mass matrix + warm-up statistics compiled in (GenericNUTS::new_with_mass_matrix); the identity-mass
-// instantiation carries none of it (measured: the run-time test alone cost 16 % on BASELINE config 5).
+// MASS: 0 = identity mass; 1 = diagonal, 2 = dense mass matrix + warm-up statistics compiled in
+// (GenericNUTS::new_with_mass_matrix); the identity-mass instantiation carries none of it (measured: the run-time test
+// alone cost 16 % on BASELINE config 5).
 // LPC: lanes per chain as a compile-time constant (0 = run-time a.lpc): the shuffle trees unroll.
-template <class T, int EPL, class TAG, bool PADDED, bool MASS, int LPC>
+template <class T, int EPL, class TAG, bool PADDED, int MASS, int LPC>
 __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const NutsArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* smem = reinterpret_cast<T*>(smem_raw);
@@ -288,7 +293,34 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
   bool moved = false;      // the current transition accepted at least one subtree proposal
   // Diagonal mass matrix (MASS): its entries are re-read from global memory (L1-resident, coalesced) where they are
   // used instead of living in 2 x EPL registers.
-  constexpr bool has_mass = MASS;
+  constexpr bool has_mass = (MASS == 1);
+  constexpr bool dense_mass = (MASS == 2);
+  const bool dense_on = dense_mass && a.dense_active != 0;
+  // dense matrix-vector product for this chain: out_i = sum_j mat[i][j] in_j over j = 0 .. d-1 (or j <= i), summed left to
+  // right as MassMatrix::inv_mul / sample_momentum do (generic_nuts.rs:265-303); the vector is exchanged through the
+  // chain's scratch row.  Called warp-uniformly.
+  auto dense_mul = [&](const T* mat, const T (&in)[EPL], T (&out)[EPL], bool lower) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < EPL; ++j)
+      if (j < ln.nvalid) row[ln.lo + j] = in[j];
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      T acc = T(0);
+      if (e < ln.nvalid) {
+        const int i = ln.lo + e;
+        const T* mrow = mat + ((size_t)chain * d + (size_t)i) * d;
+        const int jmax = lower ? i : a.d - 1;
+        for (int jj = 0; jj <= jmax; ++jj) acc = acc + mrow[jj] * row[jj];
+      }
+      out[e] = acc;
+    }
+    __syncwarp();
+  };
+  T mp[EPL];     // M^-1 p of the current leaf (dense mass): shared by the kinetic energy and the whole-trajectory U-turn test
+#pragma unroll
+  for (int j = 0; j < EPL; ++j) mp[j] = T(0);
 
   // per-chain state in / out (each lane moves its own slice of the position row)
   auto load_chain = [&]() {
@@ -430,6 +462,16 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
             if (j < ln.nvalid) p[j] = pn[j] * a.mass_sqrt[chain * d + ln.lo + j];
         }
       }
+      if constexpr (dense_mass) {
+        if (dense_on) {      // sample_momentum, Dense: p = chol z (generic_nuts.rs:292-301)
+          T pc[EPL];
+          dense_mul(a.mass_chol, pn, pc, true);
+          if (is_start) {
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) p[j] = pc[j];
+          }
+        }
+      }
     }
 
     // ---- B. one gradient evaluation per chain: at the position (start) or after a leapfrog drift (leaf)
@@ -438,11 +480,18 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
     if (is_leaf) {
 #pragma unroll
       for (int j = 0; j < EPL; ++j) p[j] = p[j] + g[j] * he;
+    }
+    if constexpr (dense_mass) {
+      if (dense_on) dense_mul(a.mass_dinv, p, mp, false);                      // velocity = M^-1 p (apply_inv_mass)
+    }
+    if (is_leaf) {
 #pragma unroll
       for (int j = 0; j < EPL; ++j) {
         if constexpr (has_mass) {                                             // velocity = M^-1 p (apply_inv_mass)
           const T mi = (j < ln.nvalid) ? a.mass_inv[chain * d + ln.lo + j] : T(1);
           q[j] = q[j] + (mi * p[j]) * veps;
+        } else if constexpr (dense_mass) {
+          q[j] = q[j] + (dense_on ? mp[j] : p[j]) * veps;
         } else {
           q[j] = q[j] + p[j] * veps;
         }
@@ -455,10 +504,14 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
 #pragma unroll
       for (int j = 0; j < EPL; ++j) p[j] = p[j] + g[j] * he;
     }
+    if constexpr (dense_mass) {
+      if (dense_on) dense_mul(a.mass_dinv, p, mp, false);                      // row_dot of MassMatrix::kinetic, Dense
+    }
     T terms[EPL];
 #pragma unroll
     for (int j = 0; j < EPL; ++j) {                                              // MassMatrix::kinetic :228-263
       if constexpr (has_mass) terms[j] = p[j] * p[j] * ((j < ln.nvalid) ? a.mass_inv[chain * d + ln.lo + j] : T(1));
+      else if constexpr (dense_mass) terms[j] = dense_on ? p[j] * mp[j] : p[j] * p[j];
       else terms[j] = p[j] * p[j];
     }
     const T ke = T(0.5) * chain_sum<T, EPL>(terms, ln);
@@ -545,14 +598,20 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       //   backward (v = -1: f is the plus end):  (q+ - q-) = -diff: . v- = -r2, . v+ = -r1  -> both r <= 0
       // (negation is exact and commutes with rounding, so the sums are bit-identical to the reference's order)
       const bool fwd = (v == 1);
+      T vf[EPL];      // M^-1 p of the other trajectory end (dense mass, whole-trajectory test only: sub-tree tests use the identity, :1316)
+      if constexpr (dense_mass) {
+        if (dense_on && __any_sync(kFull, do_top)) dense_mul(a.mass_dinv, fp, vf, false);
+      }
       T r1, r2;
       chain_sum_fn2<T, EPL>(ln, [&](int j) {
         const T df = q[j] - fq[j];
         if (has_mass && do_top && j < ln.nvalid) return df * (a.mass_inv[chain * d + ln.lo + j] * fp[j]);
+        if (dense_mass && dense_on && do_top) return (j < ln.nvalid) ? df * vf[j] : T(0);
         return (!EP || j < ln.nvalid) ? df * fp[j] : T(0);
       }, [&](int j) {
         const T df = q[j] - fq[j];
         if (has_mass && do_top && j < ln.nvalid) return df * (a.mass_inv[chain * d + ln.lo + j] * p[j]);
+        if (dense_mass && dense_on && do_top) return (j < ln.nvalid) ? df * mp[j] : T(0);
         return (!EP || j < ln.nvalid) ? df * p[j] : T(0);
       }, r1, r2);
       const bool crit = fwd ? ((r1 >= T(0)) && (r2 >= T(0))) : ((r1 <= T(0)) && (r2 <= T(0)));
@@ -611,6 +670,8 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
     }
 
     // ---- D. end of the transition: dual averaging (generic_nuts.rs:882-924), write-out
+    bool did_collect = false;     // dense mass: this chain added its position to the running covariance in this pass
+    T dlt[dense_mass ? EPL : 1];
     if (phase == NP_END) {
       const uint32_t m = a.m_base + s + 1;
       my_depth += (unsigned long long)j_depth;
@@ -642,8 +703,10 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
             const T delta2 = x - mean;
             a.run_mean[idx] = mean;
             a.run_m2[idx] = a.run_m2[idx] + delta * delta2;
+            if constexpr (dense_mass) { dlt[j] = delta; row[ln.lo + j] = delta2; }
           }
         }
+        did_collect = true;
       }
       const long long slot = (long long)m - a.rec_off;
       if (a.out && slot >= 0 && slot < (long long)a.out_n) {
@@ -654,6 +717,24 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       ++s;
       if (s < a.n_steps) phase = NP_START;
       else { phase = NP_DONE; store_chain(); }
+    }
+    if constexpr (dense_mass) {
+      // RunningCov::update, dense part (generic_nuts.rs:115-126): m2[i][j] += delta_i * delta2_j for j >= i; the chain's
+      // delta2 vector was left in its scratch row above
+      if (a.run_m2d && __any_sync(kFull, did_collect)) {
+        __syncwarp();
+        if (did_collect) {
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) {
+            if (e < ln.nvalid) {
+              const int i = ln.lo + e;
+              T* mrow = a.run_m2d + ((size_t)chain * d + (size_t)i) * d;
+              for (int jj = i; jj < a.d; ++jj) mrow[jj] = mrow[jj] + dlt[e] * row[jj];
+            }
+          }
+        }
+        __syncwarp();
+      }
     }
   }
 
@@ -691,6 +772,7 @@ struct NutsInitArgs {
   // diagonal mass matrix: the momentum is z * sqrt(var) (sample_momentum, generic_nuts.rs:283-303); the step-size
   // search itself runs with the identity mass, as the reference's find_reasonable_epsilon does (:1009-1023)
   const T* mass_sqrt;
+  const T* mass_chol;     // dense mass: lower Cholesky factor [C, d, d], momentum = chol z (or null)
   // probe = 1: the step-size reset after a mass-matrix update (generic_nuts.rs:906-918): always search, from a fresh
   // momentum (Philox stream 3 of transition `step`), then mu = ln(10 eps), eps_bar = eps, h_bar = 0
   int probe;
@@ -741,6 +823,24 @@ __global__ void __launch_bounds__(kHmcBlock, 2) nuts_init_kernel(const NutsInitA
 #pragma unroll
     for (int j = 0; j < EPL; ++j)
       if (active && j < ln.nvalid) mom[j] = mom[j] * a.mass_sqrt[chain * d + ln.lo + j];
+  }
+  if (a.mass_chol) {      // sample_momentum, Dense (generic_nuts.rs:292-301): chol z, summed left to right
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < EPL; ++j)
+      if (j < ln.nvalid) row[ln.lo + j] = mom[j];
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      T acc = T(0);
+      if (active && e < ln.nvalid) {
+        const int i = ln.lo + e;
+        const T* mrow = a.mass_chol + (chain * d + (size_t)i) * d;
+        for (int jj = 0; jj <= i; ++jj) acc = acc + mrow[jj] * row[jj];
+      }
+      mom[e] = acc;
+    }
+    __syncwarp();
   }
   T eps = active ? a.eps[chain] : T(1);
   const bool need = active && (a.probe || fabs(eps + T(1)) <= (sizeof(T) == 4 ? T(1.1920929e-07) : T(2.220446049250313e-16)));
@@ -830,6 +930,8 @@ inline NutsArgs<T> make_nuts_args(const NutsLaunch& L) {
   a.mass_inv = (const T*)L.mass_inv; a.mass_sqrt = (const T*)L.mass_sqrt;
   a.run_mean = (T*)L.run_mean; a.run_m2 = (T*)L.run_m2; a.run_n_base = L.run_n_base;
   a.collect_after = L.collect_after; a.collect_before = L.collect_before;
+  a.mass_dinv = (const T*)L.mass_dinv; a.mass_chol = (const T*)L.mass_chol; a.run_m2d = (T*)L.run_m2d;
+  a.dense_active = L.dense_active;
   return a;
 }
 
@@ -848,6 +950,7 @@ inline cudaError_t nuts_launch_one(const NutsLaunch& L, cudaStream_t st) {
     a.eps = (T*)L.eps; a.mu = (T*)L.mu;
     a.inj_normals = L.inj_normals; a.n_norm = L.n_norm; a.inj_used = L.inj_used;
     a.mass_sqrt = (const T*)L.mass_sqrt; a.probe = L.probe; a.eps_bar = (T*)L.eps_bar; a.h_bar = (T*)L.h_bar;
+    a.mass_chol = (L.mass_chol && L.dense_active) ? (const T*)L.mass_chol : nullptr;
     const size_t smem = (size_t)(kHmcBlock / L.lpc) * d_pad * sizeof(T);
     auto kern = nuts_init_kernel<T, EPL, TAG>;
     if (smem > 48 * 1024) {
@@ -867,10 +970,13 @@ inline cudaError_t nuts_launch_one(const NutsLaunch& L, cudaStream_t st) {
   // lanes per chain as a compile-time constant for the wide 8-coordinate layout (d = 65 .. 128: BASELINE config 5)
   constexpr int kLpcFixed = (EPL == 8) ? 16 : 0;
   const bool fixed = kLpcFixed > 0 && L.lpc == kLpcFixed;
-  auto kern = fixed ? (L.mass_inv ? (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, true, kLpcFixed> : nuts_run_kernel<T, EPL, TAG, true, true, kLpcFixed>)
-                                  : (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, false, kLpcFixed> : nuts_run_kernel<T, EPL, TAG, true, false, kLpcFixed>))
-                    : (L.mass_inv ? (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, true, 0> : nuts_run_kernel<T, EPL, TAG, true, true, 0>)
-                                  : (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, false, 0> : nuts_run_kernel<T, EPL, TAG, true, false, 0>));
+  const int mass = L.mass_dinv ? 2 : (L.mass_inv ? 1 : 0);
+  void (*kern)(const NutsArgs<T>) = nullptr;
+  if (mass == 2) kern = exact_fit ? nuts_run_kernel<T, EPL, TAG, false, 2, 0> : nuts_run_kernel<T, EPL, TAG, true, 2, 0>;
+  else if (fixed) kern = mass ? (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, 1, kLpcFixed> : nuts_run_kernel<T, EPL, TAG, true, 1, kLpcFixed>)
+                              : (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, 0, kLpcFixed> : nuts_run_kernel<T, EPL, TAG, true, 0, kLpcFixed>);
+  else kern = mass ? (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, 1, 0> : nuts_run_kernel<T, EPL, TAG, true, 1, 0>)
+                   : (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, 0, 0> : nuts_run_kernel<T, EPL, TAG, true, 0, 0>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -183,6 +183,12 @@ struct gmcmc_sampler {
   uint64_t mass_updates = 0;
   void* d_mass_inv = nullptr; void* d_mass_sqrt = nullptr;          // [C, d] T
   void* d_run_mean = nullptr; void* d_run_m2 = nullptr;
+  // dense mass-matrix adaptation (MassMatrixAdaptation::Dense, generic_nuts.rs:36-39, 187-226, 970-997)
+  bool mass_dense = false;
+  size_t dense_max_dim = 75;
+  void* d_mass_dinv = nullptr; void* d_mass_chol = nullptr; void* d_run_m2d = nullptr;   // [C, d, d] T
+  void* d_scr_l = nullptr; void* d_scr_il = nullptr;                                      // [d, d, C] T work arrays of the update
+  int* d_mass_state = nullptr;                                                            // [C]
   // counters
   unsigned long long* d_counts = nullptr;  // [8]: accepts, divergences, grad_evals(NUTS), depth sum, NUTS chain queue, spare
   uint64_t transitions = 0;
@@ -465,7 +471,13 @@ gmcmc_status nuts_launch(gmcmc_sampler* s, NutsLaunch& L) {
   L.inj_used = s->d_nuts_used;
   L.queue = s->d_counts + 4;
   L.epl = s->epl; L.lpc = s->lpc;
-  if (s->mass_adapt) {
+  if (s->mass_adapt && s->mass_dense) {
+    L.mass_dinv = s->d_mass_dinv; L.mass_chol = s->d_mass_chol; L.run_m2d = s->d_run_m2d;
+    L.dense_active = s->mass_updates > 0 ? 1 : 0;
+    L.run_mean = s->d_run_mean; L.run_m2 = s->d_run_m2;
+    L.collect_after = (uint32_t)s->mass_start_buffer;
+    L.collect_before = (uint32_t)(L.n_discard > s->mass_end_buffer ? L.n_discard - s->mass_end_buffer : 0);
+  } else if (s->mass_adapt) {
     L.mass_inv = s->d_mass_inv; L.mass_sqrt = s->d_mass_sqrt;
     L.run_mean = s->d_run_mean; L.run_m2 = s->d_run_m2;
     L.collect_after = (uint32_t)s->mass_start_buffer;
@@ -552,7 +564,15 @@ gmcmc_status nuts_advance(gmcmc_sampler* s, const NutsLaunch& L0) {
     const size_t nd = s->n_chains * (size_t)s->dim;
     const unsigned blocks = (unsigned)((nd + 255) / 256);
     const double jit = std::max(s->mass_jitter, 1e-10);
-    if (s->dtype == GMCMC_F32)
+    if (s->mass_dense) {
+      DenseMassUpdate U{};
+      U.dtype = s->dtype; U.n_chains = s->n_chains; U.d = s->dim; U.n = (unsigned int)s->mass_run_n;
+      U.run_mean = s->d_run_mean; U.run_m2 = s->d_run_m2; U.run_m2d = s->d_run_m2d;
+      U.inv = s->d_mass_dinv; U.chol = s->d_mass_chol; U.scratch_l = s->d_scr_l; U.scratch_invl = s->d_scr_il;
+      U.regularize = s->mass_regularize; U.jitter = jit; U.state = s->d_mass_state;
+      cudaError_t eu = launch_dense_mass_update(U, s->ctx->stream);
+      if (eu != cudaSuccess) return fail(GMCMC_ERR_CUDA, "dense mass-matrix update failed: %s", cudaGetErrorString(eu));
+    } else if (s->dtype == GMCMC_F32)
       nuts_mass_update_kernel<float><<<blocks, 256, 0, s->ctx->stream>>>(nd, (unsigned int)s->mass_run_n, (float*)s->d_run_mean,
           (float*)s->d_run_m2, (float*)s->d_mass_inv, (float*)s->d_mass_sqrt, (float)s->mass_regularize, (float)jit);
     else
@@ -597,6 +617,7 @@ gmcmc_status nuts_run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard,
     const size_t es = esize(s->dtype), nd = s->n_chains * (size_t)s->dim;
     GM_CU(cudaMemsetAsync(s->d_run_mean, 0, nd * es, s->ctx->stream));
     GM_CU(cudaMemsetAsync(s->d_run_m2, 0, nd * es, s->ctx->stream));
+    if (s->mass_dense) GM_CU(cudaMemsetAsync(s->d_run_m2d, 0, nd * (size_t)s->dim * es, s->ctx->stream));
     s->mass_run_n = 0;
   }
   if (n_steps > 0 || L.write_init) GM_TRY(nuts_advance(s, L));
@@ -1308,6 +1329,8 @@ gmcmc_status gmcmc_sampler_destroy(gmcmc_sampler* s) {
   for (double* p : s->d_nuts_inj) cudaFree(p);
   cudaFree(s->d_nuts_used);
   cudaFree(s->d_mass_inv); cudaFree(s->d_mass_sqrt); cudaFree(s->d_run_mean); cudaFree(s->d_run_m2);
+  cudaFree(s->d_mass_dinv); cudaFree(s->d_mass_chol); cudaFree(s->d_run_m2d); cudaFree(s->d_scr_l); cudaFree(s->d_scr_il);
+  cudaFree(s->d_mass_state);
   cudaFree(s->d_inj_normals); cudaFree(s->d_inj_lnu);
   cudaFree(s->d_diag_logacc); cudaFree(s->d_diag_acc); cudaFree(s->d_diag_pq); cudaFree(s->d_diag_pp);
   cudaFree(s->d_diag_draws); cudaFree(s->d_lnfact); cudaFree(s->d_inj_isteps);
@@ -1457,14 +1480,47 @@ gmcmc_status gmcmc_nuts_inject(gmcmc_sampler* s, const double* normals, size_t n
 gmcmc_status gmcmc_nuts_set_mass_adaptation(gmcmc_sampler* s, gmcmc_mass_adaptation kind, size_t start_buffer,
                                             size_t end_buffer, size_t initial_window, double regularize, double jitter) {
   GM_REQUIRE(s && s->type == S_NUTS, "gmcmc_nuts_set_mass_adaptation applies to NUTS samplers");
-  if (kind == GMCMC_MASS_DENSE)
-    return fail(GMCMC_ERR_UNSUPPORTED, "dense mass-matrix adaptation is not implemented (diagonal and none are)");
-  GM_REQUIRE(kind == GMCMC_MASS_NONE || kind == GMCMC_MASS_DIAGONAL, "unknown mass-matrix adaptation kind");
+  GM_REQUIRE(kind == GMCMC_MASS_NONE || kind == GMCMC_MASS_DIAGONAL || kind == GMCMC_MASS_DENSE, "unknown mass-matrix adaptation kind");
   GM_REQUIRE(!s->tgt->custom, "mass-matrix adaptation is not available for plugin targets");
   GM_CU(cudaSetDevice(s->ctx->device));
   const size_t es = esize(s->dtype), C = s->n_chains, nd = C * (size_t)s->dim;
+  s->mass_dense = false;
   if (kind == GMCMC_MASS_NONE) {      // NUTSMassMatrixConfig::disabled(): identity mass, no warm-up statistics
     s->mass_adapt = false;
+    return GMCMC_OK;
+  }
+  if (kind == GMCMC_MASS_DENSE && (size_t)s->dim > s->dense_max_dim) {
+    // the reference falls back to diagonal STATISTICS above dense_max_dim (generic_nuts.rs:612-617) while
+    // maybe_update_mass_matrix still dispatches on the configured Dense adaptation and finds no dense sums (:972-974):
+    // the mass matrix is never updated.  Reproduced: identity mass for the whole run.
+    s->mass_adapt = false;
+    return GMCMC_OK;
+  }
+  if (kind == GMCMC_MASS_DENSE) {
+    const size_t ndd = nd * (size_t)s->dim;
+    if (!s->d_mass_dinv) {
+      bool ok = cudaMalloc(&s->d_mass_dinv, ndd * es) == cudaSuccess && cudaMalloc(&s->d_mass_chol, ndd * es) == cudaSuccess &&
+                cudaMalloc(&s->d_run_m2d, ndd * es) == cudaSuccess && cudaMalloc(&s->d_scr_l, ndd * es) == cudaSuccess &&
+                cudaMalloc(&s->d_scr_il, ndd * es) == cudaSuccess && cudaMalloc((void**)&s->d_mass_state, C * sizeof(int)) == cudaSuccess;
+      if (!ok) return fail(GMCMC_ERR_CUDA, "out of device memory for the dense mass-matrix state (%zu bytes per array)", ndd * es);
+    }
+    if (!s->d_run_mean) {
+      bool ok = cudaMalloc(&s->d_run_mean, nd * es) == cudaSuccess && cudaMalloc(&s->d_run_m2, nd * es) == cudaSuccess;
+      if (!ok) return fail(GMCMC_ERR_CUDA, "out of device memory for the mass-matrix state");
+    }
+    GM_CU(cudaMemsetAsync(s->d_mass_state, 0, C * sizeof(int), s->ctx->stream));
+    GM_CU(cudaMemsetAsync(s->d_run_m2d, 0, ndd * es, s->ctx->stream));
+    GM_CU(cudaMemsetAsync(s->d_mass_dinv, 0, ndd * es, s->ctx->stream));
+    GM_CU(cudaMemsetAsync(s->d_mass_chol, 0, ndd * es, s->ctx->stream));
+    GM_CU(cudaMemsetAsync(s->d_run_mean, 0, nd * es, s->ctx->stream));
+    GM_CU(cudaMemsetAsync(s->d_run_m2, 0, nd * es, s->ctx->stream));
+    s->mass_dense = true;
+    s->mass_adapt = true;
+    s->mass_start_buffer = start_buffer; s->mass_end_buffer = end_buffer; s->mass_initial_window = initial_window;
+    s->mass_regularize = regularize; s->mass_jitter = jitter;
+    s->mass_window_len = std::max<size_t>(initial_window, 10);
+    s->mass_next_window_end = std::max<size_t>(start_buffer, 1) + s->mass_window_len;
+    s->mass_run_n = 0; s->mass_updates = 0;
     return GMCMC_OK;
   }
   if (!s->d_mass_inv) {
@@ -1492,13 +1548,33 @@ gmcmc_status gmcmc_nuts_set_mass_adaptation(gmcmc_sampler* s, gmcmc_mass_adaptat
   return GMCMC_OK;
 }
 
+gmcmc_status gmcmc_nuts_set_dense_max_dim(gmcmc_sampler* s, size_t dense_max_dim) {
+  GM_REQUIRE(s && s->type == S_NUTS, "gmcmc_nuts_set_dense_max_dim applies to NUTS samplers");
+  s->dense_max_dim = dense_max_dim;
+  return GMCMC_OK;
+}
+
 gmcmc_status gmcmc_nuts_mass_matrix(gmcmc_sampler* s, void* inv_mass_out, uint64_t* n_updates_out) {
   GM_REQUIRE(s && s->type == S_NUTS, "gmcmc_nuts_mass_matrix applies to NUTS samplers");
   GM_REQUIRE(s->mass_adapt, "mass-matrix adaptation is not enabled on this sampler");
   GM_CU(cudaSetDevice(s->ctx->device));
   GM_CU(cudaStreamSynchronize(s->ctx->stream));
-  if (inv_mass_out)
+  if (inv_mass_out && s->mass_dense) {
+    // dense: [C, d, d]; the identity until the first update
+    const size_t d = (size_t)s->dim, ndd = s->n_chains * d * d, es = esize(s->dtype);
+    if (s->mass_updates > 0) {
+      GM_CU(cudaMemcpy(inv_mass_out, s->d_mass_dinv, ndd * es, cudaMemcpyDeviceToHost));
+    } else {
+      std::memset(inv_mass_out, 0, ndd * es);
+      for (size_t c = 0; c < s->n_chains; ++c)
+        for (size_t i = 0; i < d; ++i) {
+          if (s->dtype == GMCMC_F32) ((float*)inv_mass_out)[(c * d + i) * d + i] = 1.0f;
+          else ((double*)inv_mass_out)[(c * d + i) * d + i] = 1.0;
+        }
+    }
+  } else if (inv_mass_out) {
     GM_CU(cudaMemcpy(inv_mass_out, s->d_mass_inv, s->n_chains * (size_t)s->dim * esize(s->dtype), cudaMemcpyDeviceToHost));
+  }
   if (n_updates_out) *n_updates_out = s->mass_updates;
   return GMCMC_OK;
 }

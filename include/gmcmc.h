@@ -209,12 +209,20 @@ gmcmc_status gmcmc_nuts_inject(gmcmc_sampler*, const double* normals, size_t n_n
  * diagonal inverse mass from the running variance of its warm-up positions over doubling windows
  * (MassMatrixWarmup :134-175, RunningCov :81-132, maybe_update_mass_matrix :948-969); after every update a
  * fresh momentum (Philox stream 3 of the transition that ended the window) probes a new step size and dual
- * averaging restarts (:906-918).  GMCMC_MASS_DENSE returns GMCMC_ERR_UNSUPPORTED. */
+ * averaging restarts (:906-918).  GMCMC_MASS_DENSE ≙ MassMatrixAdaptation::Dense: the running covariance keeps the full
+ * outer-product sums (RunningCov :81-132), a window end turns them into the regularised covariance, its Cholesky factor
+ * and inverse per chain (dense_from_cov :208-226, cholesky_spd / invert_spd_from_cholesky :306-359, update :970-997), momenta
+ * are chol z, velocities and kinetic energy use the dense inverse, and — as in the reference — the step-size search and the
+ * sub-tree U-turn tests keep the identity.  Above dense_max_dim (default 75, gmcmc_nuts_set_dense_max_dim, call it first) the
+ * reference keeps diagonal statistics but still asks for a dense update and therefore never updates (:612-617, :972-974):
+ * the mass stays the identity, reproduced here.  Memory: 5 arrays of n_chains * dim^2 elements. */
 typedef enum { GMCMC_MASS_NONE = 0, GMCMC_MASS_DIAGONAL = 1, GMCMC_MASS_DENSE = 2 } gmcmc_mass_adaptation;
 gmcmc_status gmcmc_nuts_set_mass_adaptation(gmcmc_sampler*, gmcmc_mass_adaptation kind, size_t start_buffer,
                                             size_t end_buffer, size_t initial_window, double regularize,
                                             double jitter);
-/* Current diagonal inverse mass [C, dim] (sampler dtype; 1 = identity) and the number of updates so far. */
+gmcmc_status gmcmc_nuts_set_dense_max_dim(gmcmc_sampler*, size_t dense_max_dim);   /* NUTSMassMatrixConfig::dense_max_dim, :50,76 */
+/* Current inverse mass — diagonal adaptation: [C, dim]; dense adaptation: [C, dim, dim] (sampler dtype; identity before the
+ * first update) — and the number of updates so far. */
 gmcmc_status gmcmc_nuts_mass_matrix(gmcmc_sampler*, void* inv_mass_out, uint64_t* n_updates_out);
 /* NUTS per-chain state (tests / diagnostics): current step sizes [C] (sampler dtype), accumulated
  * leapfrogs [C], consumed injected draws [C][3] (normals, exp1, unif).  Any pointer may be NULL. */

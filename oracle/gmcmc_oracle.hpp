@@ -406,14 +406,64 @@ struct NutsStream {
   double next_unif()   { if (i_unif >= n_unif) { exhausted = true; return 0.75; } return unif[i_unif++]; }
 };
 
-// MassMatrix::{Identity, Diagonal}, generic_nuts.rs:177-304.  `inv` empty = Identity.  (Dense is out of scope.)
+// MassMatrix::{Identity, Diagonal, Dense}, generic_nuts.rs:177-304.  kind 0 = Identity, 1 = Diagonal, 2 = Dense.
+// cholesky_spd :306-331
+template <class T>
+inline bool cholesky_spd(const std::vector<T>& a, int dim, std::vector<T>& l) {
+  l.assign((size_t)dim * dim, T(0));
+  for (int i = 0; i < dim; ++i) {
+    for (int j = 0; j <= i; ++j) {
+      T sum = a[(size_t)i * dim + j];
+      for (int k = 0; k < j; ++k) sum = sum - l[(size_t)i * dim + k] * l[(size_t)j * dim + k];
+      if (i == j) {
+        if (sum <= T(0) || !std::isfinite(sum)) return false;
+        l[(size_t)i * dim + j] = std::sqrt(sum);
+      } else {
+        T dd = l[(size_t)j * dim + j];
+        if (dd <= T(0) || !std::isfinite(dd)) return false;
+        l[(size_t)i * dim + j] = sum / dd;
+      }
+    }
+  }
+  return true;
+}
+// invert_spd_from_cholesky :333-359
+template <class T>
+inline bool invert_spd_from_cholesky(const std::vector<T>& l, int dim, std::vector<T>& inv) {
+  std::vector<T> inv_l((size_t)dim * dim, T(0));
+  for (int i = 0; i < dim; ++i) {
+    T dd = l[(size_t)i * dim + i];
+    if (dd <= T(0) || !std::isfinite(dd)) return false;
+    inv_l[(size_t)i * dim + i] = T(1) / dd;
+    for (int j = i + 1; j < dim; ++j) {
+      T sum = T(0);
+      for (int k = i; k < j; ++k) sum = sum + l[(size_t)j * dim + k] * inv_l[(size_t)k * dim + i];
+      inv_l[(size_t)j * dim + i] = -sum / l[(size_t)j * dim + j];
+    }
+  }
+  inv.assign((size_t)dim * dim, T(0));
+  for (int i = 0; i < dim; ++i) {
+    for (int j = 0; j <= i; ++j) {
+      T sum = T(0);
+      for (int k = std::max(i, j); k < dim; ++k) sum = sum + inv_l[(size_t)k * dim + i] * inv_l[(size_t)k * dim + j];
+      inv[(size_t)i * dim + j] = sum;
+      inv[(size_t)j * dim + i] = sum;
+    }
+  }
+  return true;
+}
+
 template <class T>
 struct DiagMass {
-  std::vector<T> inv, sqrt_;
-  bool identity() const { return inv.empty(); }
+  int kind = 0;                 // 0 Identity, 1 Diagonal, 2 Dense
+  int dim = 0;
+  std::vector<T> inv, sqrt_;    // Diagonal: [d], [d];  Dense: inv [d*d]
+  std::vector<T> chol;          // Dense: lower Cholesky factor of the covariance [d*d]
+  bool identity() const { return kind == 0; }
   // diagonal_from_var, generic_nuts.rs:196-206
   static DiagMass from_var(std::vector<T> var, T jitter) {
     DiagMass m;
+    m.kind = 1; m.dim = (int)var.size();
     m.inv.resize(var.size()); m.sqrt_.resize(var.size());
     for (size_t i = 0; i < var.size(); ++i) {
       T v = std::max(var[i], jitter);
@@ -422,13 +472,59 @@ struct DiagMass {
     }
     return m;
   }
+  // dense_from_cov, generic_nuts.rs:208-226: up to 8 tries with the diagonal jitter growing tenfold
+  static bool dense_from_cov(const std::vector<T>& cov, int dim, T jitter, DiagMass* out) {
+    T j = std::max(jitter, (T)1e-10);
+    for (int t = 0; t < 8; ++t) {
+      std::vector<T> cov_try = cov;
+      for (int d = 0; d < dim; ++d) cov_try[(size_t)d * dim + d] = cov_try[(size_t)d * dim + d] + j;
+      std::vector<T> chol, inv;
+      if (cholesky_spd(cov_try, dim, chol) && invert_spd_from_cholesky(chol, dim, inv)) {
+        out->kind = 2; out->dim = dim; out->inv = inv; out->chol = chol; out->sqrt_.clear();
+        return true;
+      }
+      j = j * (T)10.0;
+    }
+    return false;
+  }
+  // inv_mul :265-281
+  void inv_mul(const T* in, T* out, int d) const {
+    if (kind == 0) { for (int i = 0; i < d; ++i) out[i] = in[i]; }
+    else if (kind == 1) { for (int i = 0; i < d; ++i) out[i] = inv[i] * in[i]; }
+    else {
+      for (int i = 0; i < d; ++i) {
+        T acc = T(0);
+        for (int jj = 0; jj < d; ++jj) acc = acc + inv[(size_t)i * d + jj] * in[jj];
+        out[i] = acc;
+      }
+    }
+  }
+  // sample_momentum :283-303 applied to already drawn standard normals
+  void scale_momentum(T* z, int d) const {
+    if (kind == 1) { for (int i = 0; i < d; ++i) z[i] = z[i] * sqrt_[i]; }
+    else if (kind == 2) {
+      std::vector<T> zz(z, z + d);
+      for (int i = 0; i < d; ++i) {
+        T acc = T(0);
+        for (int jj = 0; jj <= i; ++jj) acc = acc + chol[(size_t)i * d + jj] * zz[jj];
+        z[i] = acc;
+      }
+    }
+  }
 };
 
 template <class T>
 inline T nuts_kinetic(const T* p, int d, const DiagMass<T>* mass = nullptr) {  // generic_nuts.rs:228-263
   T q = 0;
-  if (!mass || mass->identity()) for (int i = 0; i < d; ++i) q = q + p[i] * p[i];
-  else for (int i = 0; i < d; ++i) q = q + p[i] * p[i] * mass->inv[i];
+  if (!mass || mass->kind == 0) for (int i = 0; i < d; ++i) q = q + p[i] * p[i];
+  else if (mass->kind == 1) for (int i = 0; i < d; ++i) q = q + p[i] * p[i] * mass->inv[i];
+  else {
+    for (int i = 0; i < d; ++i) {
+      T row_dot = T(0);
+      for (int j = 0; j < d; ++j) row_dot = row_dot + mass->inv[(size_t)i * d + j] * p[j];
+      q = q + p[i] * row_dot;
+    }
+  }
   return T(0.5) * q;
 }
 
@@ -441,7 +537,7 @@ inline T nuts_leapfrog(const Target<T>& tgt, T* q, T* p, T* g, T eps, const Diag
     add_scaled_assign(q, p, eps, d);  // identity mass: velocity = momentum
   } else {
     std::vector<T> vel(d);
-    for (int i = 0; i < d; ++i) vel[i] = mass->inv[i] * p[i];   // apply_inv_mass
+    mass->inv_mul(p, vel.data(), d);   // apply_inv_mass
     add_scaled_assign(q, vel.data(), eps, d);
   }
   T logp = tgt.logp_and_grad(q, g);
@@ -457,8 +553,11 @@ inline bool nuts_stop_criterion(const T* qm, const T* qp, const T* pm, const T* 
     for (int i = 0; i < d; ++i) { T df = qp[i] - qm[i]; dm = dm + df * pm[i]; }
     for (int i = 0; i < d; ++i) { T df = qp[i] - qm[i]; dp = dp + df * pp[i]; }
   } else {
-    for (int i = 0; i < d; ++i) { T df = qp[i] - qm[i]; dm = dm + df * (mass->inv[i] * pm[i]); }
-    for (int i = 0; i < d; ++i) { T df = qp[i] - qm[i]; dp = dp + df * (mass->inv[i] * pp[i]); }
+    std::vector<T> vm(d), vp(d);
+    mass->inv_mul(pm, vm.data(), d);
+    mass->inv_mul(pp, vp.data(), d);
+    for (int i = 0; i < d; ++i) { T df = qp[i] - qm[i]; dm = dm + df * vm[i]; }
+    for (int i = 0; i < d; ++i) { T df = qp[i] - qm[i]; dp = dp + df * vp[i]; }
   }
   return dm >= T(0) && dp >= T(0);
 }
@@ -572,13 +671,21 @@ struct NutsChain {
   DiagMass<T> mass;
   size_t next_window_end = 0, window_len = 0, run_n = 0;
   std::vector<T> run_mean, run_m2;
+  // dense adaptation (MassMatrixAdaptation::Dense): config_dense = what the config asks for; running_dense = whether the
+  // running covariance keeps the full matrix (new_shared falls back to diagonal statistics when dim > dense_max_dim, :612-628,
+  // while maybe_update_mass_matrix still dispatches on the CONFIG, :962-996: with the fallback the mass is never updated)
+  bool config_dense = false, running_dense = false;
+  std::vector<T> run_m2_dense;
   size_t mass_updates = 0;
-  void enable_mass_adaptation(size_t sb, size_t eb, size_t iw, double reg, double jit) {
+  void enable_mass_adaptation(size_t sb, size_t eb, size_t iw, double reg, double jit, bool dense = false, size_t dense_max_dim = 75) {
     mass_adapt = true; start_buffer = sb; end_buffer = eb; initial_window = iw; regularize = reg; jitter = jit;
     size_t sbm = std::max<size_t>(sb, 1);                 // MassMatrixWarmup::new, :141-150
     window_len = std::max<size_t>(iw, 10);
     next_window_end = sbm + window_len;
     run_mean.assign(tgt.dim, T(0)); run_m2.assign(tgt.dim, T(0)); run_n = 0;
+    config_dense = dense;
+    running_dense = dense && (size_t)tgt.dim <= dense_max_dim;
+    if (running_dense) run_m2_dense.assign((size_t)tgt.dim * tgt.dim, T(0));
   }
   bool should_collect(size_t mm, size_t n_warm) const {   // :152-160
     if (mm == 0 || mm > n_warm) return false;
@@ -606,8 +713,11 @@ struct NutsChain {
     n_collect = n_collect_; n_discard = n_discard_; m = 0;
     std::vector<T> mom0(d);
     for (int i = 0; i < d; ++i) mom0[i] = (T)rng.next_normal();
-    if (!mass.identity()) for (int i = 0; i < d; ++i) mom0[i] = mom0[i] * mass.sqrt_[i];   // sample_momentum :283-303
-    if (mass_adapt) { run_n = 0; std::fill(run_mean.begin(), run_mean.end(), T(0)); std::fill(run_m2.begin(), run_m2.end(), T(0)); }
+    mass.scale_momentum(mom0.data(), d);                                                     // sample_momentum :283-303
+    if (mass_adapt) {
+      run_n = 0; std::fill(run_mean.begin(), run_mean.end(), T(0)); std::fill(run_m2.begin(), run_m2.end(), T(0));
+      std::fill(run_m2_dense.begin(), run_m2_dense.end(), T(0));
+    }
     if (std::abs(epsilon + T(1)) <= std::numeric_limits<T>::epsilon())
       epsilon = nuts_find_reasonable_epsilon(tgt, position.data(), mom0.data());   // :745 — identity mass (find_reasonable_epsilon :1009-1023)
     mu = std::log(T(10) * epsilon);
@@ -618,7 +728,7 @@ struct NutsChain {
     m += 1;
     std::vector<T> mom0(d);
     for (int i = 0; i < d; ++i) mom0[i] = (T)rng.next_normal();                    // :761
-    if (!mass.identity()) for (int i = 0; i < d; ++i) mom0[i] = mom0[i] * mass.sqrt_[i];
+    mass.scale_momentum(mom0.data(), d);
     std::vector<T> grad(d, T(0));
     T logp = tgt.logp_and_grad(position.data(), grad.data());                     // :765
     T joint = logp - nuts_kinetic(mom0.data(), d, &mass);                         // :766
@@ -659,30 +769,56 @@ struct NutsChain {
       eta = std::pow(mm, -kappa);
       epsilon_bar = std::exp((T(1) - eta) * std::log(epsilon_bar) + eta * std::log(epsilon));
       if (mass_adapt && should_collect(m, n_discard)) {                             // :902-920
-        // RunningCov::update, :105-114
+        // RunningCov::update, :105-126
         run_n += 1;
         T n_s = (T)run_n;
+        std::vector<T> delta(d);
         for (int i = 0; i < d; ++i) {
-          T delta = position[i] - run_mean[i];
-          run_mean[i] = run_mean[i] + delta / n_s;
+          delta[i] = position[i] - run_mean[i];
+          run_mean[i] = run_mean[i] + delta[i] / n_s;
           T delta2 = position[i] - run_mean[i];
-          run_m2[i] = run_m2[i] + delta * delta2;
+          run_m2[i] = run_m2[i] + delta[i] * delta2;
         }
-        if (note_if_window_end(m, n_discard) && run_n >= 5) {                       // maybe_update_mass_matrix :948-969
+        if (running_dense) {
+          std::vector<T> delta2(d);
+          for (int i = 0; i < d; ++i) delta2[i] = position[i] - run_mean[i];
+          for (int i = 0; i < d; ++i)
+            for (int j = i; j < d; ++j) run_m2_dense[(size_t)i * d + j] = run_m2_dense[(size_t)i * d + j] + delta[i] * delta2[j];
+        }
+        if (note_if_window_end(m, n_discard) && run_n >= 5) {                       // maybe_update_mass_matrix :948-997
           T n_denom = (T)(run_n - 1);
           T reg = (T)regularize, omr = T(1) - reg;
           T jit = (T)std::max(jitter, 1e-10);
-          std::vector<T> var(d);
-          for (int i = 0; i < d; ++i) var[i] = std::max(omr * (run_m2[i] / n_denom) + reg, jit);
-          mass = DiagMass<T>::from_var(var, jit);
-          mass_updates += 1;
-          std::vector<T> probe(d);
-          for (int i = 0; i < d; ++i) probe[i] = (T)rng.next_normal() * mass.sqrt_[i];
-          epsilon = nuts_find_reasonable_epsilon(tgt, position.data(), probe.data());   // :911 — identity mass, as the reference
-          mu = std::log(T(10) * epsilon);
-          epsilon_bar = epsilon;
-          h_bar = T(0);
-          run_n = 0; std::fill(run_mean.begin(), run_mean.end(), T(0)); std::fill(run_m2.begin(), run_m2.end(), T(0));
+          bool updated = false;
+          if (!config_dense) {
+            std::vector<T> var(d);
+            for (int i = 0; i < d; ++i) var[i] = std::max(omr * (run_m2[i] / n_denom) + reg, jit);
+            mass = DiagMass<T>::from_var(var, jit);
+            updated = true;
+          } else if (running_dense) {
+            std::vector<T> cov((size_t)d * d, T(0));
+            for (int i = 0; i < d; ++i)
+              for (int j = i; j < d; ++j) {
+                T raw = run_m2_dense[(size_t)i * d + j] / n_denom;
+                T v = (i == j) ? std::max(omr * raw + reg, jit) : omr * raw;
+                cov[(size_t)i * d + j] = v; cov[(size_t)j * d + i] = v;
+              }
+            DiagMass<T> nm;
+            if (DiagMass<T>::dense_from_cov(cov, d, jit, &nm)) { mass = nm; updated = true; }
+            else if (mass.kind == 0) { mass = DiagMass<T>::from_var(std::vector<T>(d, T(1)), jit); updated = true; }   // :989-994
+          }                                                     // config Dense with diagonal statistics: None (:972-974)
+          if (updated) {
+            mass_updates += 1;
+            std::vector<T> probe(d);
+            for (int i = 0; i < d; ++i) probe[i] = (T)rng.next_normal();
+            mass.scale_momentum(probe.data(), d);
+            epsilon = nuts_find_reasonable_epsilon(tgt, position.data(), probe.data());   // :911 — identity mass, as the reference
+            mu = std::log(T(10) * epsilon);
+            epsilon_bar = epsilon;
+            h_bar = T(0);
+            run_n = 0; std::fill(run_mean.begin(), run_mean.end(), T(0)); std::fill(run_m2.begin(), run_m2.end(), T(0));
+            std::fill(run_m2_dense.begin(), run_m2_dense.end(), T(0));
+          }
         }
       }
     } else {

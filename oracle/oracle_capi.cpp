@@ -101,7 +101,8 @@ void nuts_run(int kind, int dim, const double* params, size_t np, size_t C, T* q
               size_t n_discard, const double* normals, size_t n_norm, const double* exp1, size_t n_exp,
               const double* unif, size_t n_unif, T* samples, T* eps_final, long long* leapfrogs,
               long long* used, int* exhausted, const double* mass_cfg /*null or [start_buffer, end_buffer, initial_window,
-              regularize, jitter]*/ = nullptr, T* mass_inv_out /*[C,d] or null*/ = nullptr, int n_runs = 1) {
+              regularize, jitter, dense (0 / 1), dense_max_dim]*/ = nullptr, T* mass_inv_out /*[C,d] (diagonal) / [C,d,d] (dense) or null*/ = nullptr,
+              int n_runs = 1, long long* mass_updates_out = nullptr) {
   const size_t d = (size_t)dim;
 #pragma omp parallel for schedule(dynamic, 1)
   for (long long ci = 0; ci < (long long)C; ++ci) {
@@ -116,7 +117,9 @@ void nuts_run(int kind, int dim, const double* params, size_t np, size_t C, T* q
     rng.normals = normals + c * n_norm; rng.n_normals = n_norm;
     rng.exp1 = exp1 + c * n_exp; rng.n_exp1 = n_exp;
     rng.unif = unif + c * n_unif; rng.n_unif = n_unif;
-    if (mass_cfg) ch.enable_mass_adaptation((size_t)mass_cfg[0], (size_t)mass_cfg[1], (size_t)mass_cfg[2], mass_cfg[3], mass_cfg[4]);
+    const bool want_dense = mass_cfg && mass_cfg[5] != 0.0;
+    if (mass_cfg) ch.enable_mass_adaptation((size_t)mass_cfg[0], (size_t)mass_cfg[1], (size_t)mass_cfg[2], mass_cfg[3], mass_cfg[4],
+                                            want_dense, (size_t)mass_cfg[6]);
     long long leap = 0;
     for (int run = 0; run < n_runs; ++run) {          // n_runs > 1: repeated run() calls on the same chain (state carries over)
       ch.init_chain_state(n_collect, n_discard, rng);
@@ -127,7 +130,16 @@ void nuts_run(int kind, int dim, const double* params, size_t np, size_t C, T* q
           std::memcpy(samples + (c * n_collect + (s - n_discard)) * d, ch.position.data(), d * sizeof(T));
       }
     }
-    if (mass_inv_out) for (size_t i = 0; i < d; ++i) mass_inv_out[c * d + i] = ch.mass.identity() ? T(1) : ch.mass.inv[i];
+    if (mass_inv_out) {
+      if (want_dense) {       // [C, d, d]: identity until the first update, diag(inv) for the all-ones fallback
+        for (size_t i = 0; i < d; ++i)
+          for (size_t j = 0; j < d; ++j)
+            mass_inv_out[(c * d + i) * d + j] = ch.mass.kind == 2 ? ch.mass.inv[i * d + j] : (i == j ? (ch.mass.kind == 1 ? ch.mass.inv[i] : T(1)) : T(0));
+      } else {
+        for (size_t i = 0; i < d; ++i) mass_inv_out[c * d + i] = ch.mass.identity() ? T(1) : ch.mass.inv[i];
+      }
+    }
+    if (mass_updates_out) mass_updates_out[c] = (long long)ch.mass_updates;
     std::memcpy(q + c * d, ch.position.data(), d * sizeof(T));
     if (eps_final) eps_final[c] = ch.epsilon;
     if (leapfrogs) leapfrogs[c] = leap;
@@ -261,15 +273,26 @@ void orc_nuts_run_f32(int kind, int dim, const double* params, size_t np, size_t
   nuts_run<float>(kind, dim, params, np, C, q, target_accept, max_depth, eps_init, n_collect, n_discard, normals, n_norm, exp1, n_exp, unif, n_unif, samples, eps_final, leapfrogs, used, exhausted);
 }
 // with diagonal mass-matrix adaptation (GenericNUTS::new_with_mass_matrix, generic_nuts.rs:379-398)
-void orc_nuts_run_mass_f64(int kind, int dim, const double* params, size_t np, size_t C, double* q, double target_accept, int max_depth, double eps_init, size_t n_collect, size_t n_discard, const double* normals, size_t n_norm, const double* exp1, size_t n_exp, const double* unif, size_t n_unif, double* samples, double* eps_final, long long* leapfrogs, long long* used, int* exhausted, const double* mass_cfg, double* mass_inv_out) {
-  nuts_run<double>(kind, dim, params, np, C, q, target_accept, max_depth, eps_init, n_collect, n_discard, normals, n_norm, exp1, n_exp, unif, n_unif, samples, eps_final, leapfrogs, used, exhausted, mass_cfg, mass_inv_out);
+void orc_nuts_run_mass_f64(int kind, int dim, const double* params, size_t np, size_t C, double* q, double target_accept, int max_depth, double eps_init, size_t n_collect, size_t n_discard, const double* normals, size_t n_norm, const double* exp1, size_t n_exp, const double* unif, size_t n_unif, double* samples, double* eps_final, long long* leapfrogs, long long* used, int* exhausted, const double* mass_cfg, double* mass_inv_out, long long* mass_updates_out) {
+  nuts_run<double>(kind, dim, params, np, C, q, target_accept, max_depth, eps_init, n_collect, n_discard, normals, n_norm, exp1, n_exp, unif, n_unif, samples, eps_final, leapfrogs, used, exhausted, mass_cfg, mass_inv_out, 1, mass_updates_out);
 }
-void orc_nuts_run_mass_f32(int kind, int dim, const double* params, size_t np, size_t C, float* q, float target_accept, int max_depth, float eps_init, size_t n_collect, size_t n_discard, const double* normals, size_t n_norm, const double* exp1, size_t n_exp, const double* unif, size_t n_unif, float* samples, float* eps_final, long long* leapfrogs, long long* used, int* exhausted, const double* mass_cfg, float* mass_inv_out) {
-  nuts_run<float>(kind, dim, params, np, C, q, target_accept, max_depth, eps_init, n_collect, n_discard, normals, n_norm, exp1, n_exp, unif, n_unif, samples, eps_final, leapfrogs, used, exhausted, mass_cfg, mass_inv_out);
+void orc_nuts_run_mass_f32(int kind, int dim, const double* params, size_t np, size_t C, float* q, float target_accept, int max_depth, float eps_init, size_t n_collect, size_t n_discard, const double* normals, size_t n_norm, const double* exp1, size_t n_exp, const double* unif, size_t n_unif, float* samples, float* eps_final, long long* leapfrogs, long long* used, int* exhausted, const double* mass_cfg, float* mass_inv_out, long long* mass_updates_out) {
+  nuts_run<float>(kind, dim, params, np, C, q, target_accept, max_depth, eps_init, n_collect, n_discard, normals, n_norm, exp1, n_exp, unif, n_unif, samples, eps_final, leapfrogs, used, exhausted, mass_cfg, mass_inv_out, 1, mass_updates_out);
 }
 
 // ---- mass matrix (MassMatrix::diagonal_from_var / kinetic / inv_mul, generic_nuts.rs:196-206, 228-281) ----
 // Reference KAT generic_nuts.rs:1427-1440: var = [4, 9], p = [2, 3] -> kinetic = 1.0, inv_mul = [0.5, 1/3].
+// Reference KAT generic_nuts.rs:1442-1457 (dense_mass_matrix_inverse_matches_identity_action): cov = [[2, .3], [.3, 1]], p = [.7, -1.1]:
+// MassMatrix::dense_from_cov -> inv_mul; returns 1 when the factorisation succeeded.  Also hands back inv and chol.
+int orc_dense_mass_inv_mul_f64(const double* cov, int d, double jitter, const double* p, double* inv_mul_out, double* inv_out, double* chol_out, double* ke_out) {
+  DiagMass<double> m;
+  if (!DiagMass<double>::dense_from_cov(std::vector<double>(cov, cov + (size_t)d * d), d, jitter, &m)) return 0;
+  m.inv_mul(p, inv_mul_out, d);
+  if (inv_out) std::copy(m.inv.begin(), m.inv.end(), inv_out);
+  if (chol_out) std::copy(m.chol.begin(), m.chol.end(), chol_out);
+  if (ke_out) *ke_out = nuts_kinetic<double>(p, d, &m);
+  return 1;
+}
 double orc_diag_mass_kinetic_inv_mul_f64(const double* var, int d, double jitter, const double* p, double* inv_mul_out) {
   DiagMass<double> m = DiagMass<double>::from_var(std::vector<double>(var, var + d), jitter);
   for (int i = 0; i < d; ++i) inv_mul_out[i] = m.inv[i] * p[i];   // inv_mul, :265-281

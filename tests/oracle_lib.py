@@ -189,13 +189,20 @@ def nuts_run(kind, params, q0, target_accept, max_depth, eps_init, n_collect, n_
             _p(exp1), C.c_size_t(exp1.shape[1]), _p(unif), C.c_size_t(unif.shape[1]), _p(samples), _p(eps_f),
             _p(leap), _p(used), _p(exh)]
     mass_inv = None
+    mass_updates = None
     if mass_cfg is None:
         getattr(lib(fast), "orc_nuts_run_" + _sfx(dt))(*args)
     else:
-        cfg = np.ascontiguousarray(mass_cfg, np.float64)
-        mass_inv = np.ones((Cn, d), dt)
-        getattr(lib(fast), "orc_nuts_run_mass_" + _sfx(dt))(*args, _p(cfg), _p(mass_inv))
-    return dict(q=q, samples=samples, eps=eps_f, leapfrogs=leap, used=used, exhausted=exh, mass_inv=mass_inv)
+        # (start_buffer, end_buffer, initial_window, regularize, jitter [, dense (0 / 1), dense_max_dim])
+        cfg = np.zeros(7, np.float64)
+        cfg[6] = 75
+        cfg[:len(mass_cfg)] = mass_cfg
+        dense = cfg[5] != 0.0
+        mass_inv = np.ones((Cn, d, d) if dense else (Cn, d), dt)
+        mass_updates = np.zeros(Cn, np.int64)
+        getattr(lib(fast), "orc_nuts_run_mass_" + _sfx(dt))(*args, _p(cfg), _p(mass_inv), _p(mass_updates))
+    return dict(q=q, samples=samples, eps=eps_f, leapfrogs=leap, used=used, exhausted=exh, mass_inv=mass_inv,
+                mass_updates=mass_updates)
 
 
 POISSON, BINOMIAL = 0, 1
@@ -221,6 +228,17 @@ def int_target_logp(kind, params, k):
     k = np.ascontiguousarray(k, np.int32)
     p = np.ascontiguousarray(params, np.float64)
     return lib().orc_int_target_logp(C.c_int(kind), C.c_int(k.size), _p(p), _p(k))
+
+
+def dense_mass(cov, p, jitter=1e-12):
+    """MassMatrix::dense_from_cov(cov, d, jitter) -> dict(inv_mul(p), inv, chol, kinetic(p)) or None (generic_nuts.rs:208-359)."""
+    cov = np.ascontiguousarray(cov, np.float64)
+    d = cov.shape[0]
+    p = np.ascontiguousarray(p, np.float64)
+    out, inv, chol = np.zeros(d), np.zeros((d, d)), np.zeros((d, d))
+    ke = C.c_double(0)
+    ok = lib().orc_dense_mass_inv_mul_f64(_p(cov), C.c_int(d), C.c_double(jitter), _p(p), _p(out), _p(inv), _p(chol), C.byref(ke))
+    return dict(inv_mul=out, inv=inv, chol=chol, kinetic=ke.value) if ok else None
 
 
 def diag_mass_kinetic_inv_mul(var, p, jitter=1e-12):

@@ -226,10 +226,107 @@ def test_nuts_mass_adaptation_philox_matches_oracle_distribution(ctx, oracle):
             assert np.allclose(got, want, rtol=0.25), (got, want)
 
 
-def test_nuts_dense_mass_adaptation_is_unsupported(ctx):
-    with pytest.raises(Exception):
-        gm.NUTS(gm.IsotropicGaussian(1.0, 3), np.zeros((4, 3), np.float32), 0.8, seed=1, ctx=ctx,
-                mass_matrix=gm.NUTSMassMatrixConfig("dense"))
+def _corr_gauss(d, seed=4):
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((d, d))
+    cov = a @ a.T / d + np.diag(np.linspace(0.3, 2.0, d))
+    return gm.DenseGaussian(np.zeros(d), cov=cov), cov
+
+
+@pytest.mark.parametrize("dtype,exact,n_discard,cfg,n_upd", [
+    (np.float64, True, 20, (1, 1, 10, 0.05, 1e-6), 2),
+    (np.float64, True, 40, (3, 2, 10, 0.05, 1e-6), 3),
+    (np.float32, True, 20, (1, 1, 10, 0.05, 1e-6), 2),
+    (np.float32, False, 20, (1, 1, 10, 0.05, 1e-6), 2),
+])
+def test_nuts_dense_mass_adaptation_matches_oracle(ctx, oracle, dtype, exact, n_discard, cfg, n_upd):
+    """MassMatrixAdaptation::Dense (generic_nuts.rs:36-39): running outer-product sums (RunningCov :81-132), regularised
+    covariance -> Cholesky -> inverse per chain at every window end (dense_from_cov :208-226, :306-359, :970-997), momenta
+    chol z, velocities / kinetic energy through the dense inverse, identity mass in the step-size search and the sub-tree
+    U-turn tests.  Same injected streams on both sides; bounds as for the diagonal case (per-chain medians, see there)."""
+    Cn, d, n_collect = 96, 5, 6
+    tgt, cov = _corr_gauss(d)
+    rng = np.random.default_rng(21)
+    q0 = (rng.standard_normal((Cn, d)) @ np.linalg.cholesky(cov).T).astype(dtype)
+    normals, exp1, unif = _streams(Cn, d, n_collect + n_discard + 4, seed=23, n_unif=20000)
+    ref = oracle.nuts_run(tgt.kind, tgt.params(), q0, 0.8, 8, -1.0, n_collect, n_discard, normals, exp1, unif,
+                          mass_cfg=cfg + (1, 75))
+    assert not ref["exhausted"].any() and (ref["mass_updates"] == n_upd).all()
+    s = gm.NUTS(tgt, q0, 0.8, seed=1, ctx=ctx, max_depth=8,
+                mass_matrix=gm.NUTSMassMatrixConfig("dense", *cfg)).set_math_mode(exact)
+    s.inject_streams(normals, exp1, unif)
+    out = s.run(n_collect, n_discard)
+    st = s.state()
+    inv, n_updates = s.mass_matrix()
+    assert inv.shape == (Cn, d, d) and n_updates == n_upd
+    assert np.array_equal(st["used"][:, 0].astype(np.int64), ref["used"][:, 0])
+    assert (ref["used"][:, 0] == d * (1 + n_collect + n_discard - 1 + n_upd)).all()
+    same = (st["leapfrogs"] == ref["leapfrogs"])
+    assert same.mean() > (0.9 if dtype == np.float64 else 0.6)
+    scale = np.abs(ref["mass_inv"][same]).reshape(same.sum(), -1).max(1)
+    err = np.abs(inv[same] - ref["mass_inv"][same]).reshape(same.sum(), -1).max(1) / scale
+    med_tol, max_tol = (1e-8, 1e-3) if dtype == np.float64 else (2e-3, 0.5)
+    print("dense mass %s %s: same trees %.3f, median inv err %.2e, max %.2e" % (dtype.__name__, "exact" if exact else "fast",
+                                                                                same.mean(), np.median(err), err.max()))
+    assert np.median(err) < med_tol and err.max() < max_tol
+    eps_err = np.abs(st["eps"][same] - ref["eps"][same]) / ref["eps"][same]
+    assert np.median(eps_err) < med_tol and eps_err.max() < max_tol
+    samp_err = np.abs(out[same] - ref["samples"][same]).reshape(same.sum(), -1).max(1)
+    assert np.median(samp_err) < 100 * med_tol
+    assert np.allclose(inv, np.swapaxes(inv, 1, 2), rtol=1e-5, atol=1e-6)           # symmetric
+    assert (np.linalg.eigvalsh(inv.astype(np.float64)) > 0).all()                   # positive definite
+    assert np.abs(inv[:, 0, 1]).max() > 1e-3                                        # the off-diagonal did move
+
+
+def test_nuts_dense_mass_above_dense_max_dim_keeps_identity(ctx, oracle):
+    """Reference quirk, reproduced: with dim > dense_max_dim the chain keeps diagonal statistics (generic_nuts.rs:612-617)
+    but maybe_update_mass_matrix still dispatches on the configured Dense adaptation, finds no dense sums and returns None
+    (:972-974): the mass matrix never leaves the identity.  Bit-identical to a run without adaptation (exact mode)."""
+    Cn, d, n_collect, n_discard = 64, 5, 5, 30
+    tgt, cov = _corr_gauss(d)
+    q0 = np.random.default_rng(2).standard_normal((Cn, d))
+    normals, exp1, unif = _streams(Cn, d, n_collect + n_discard + 4, seed=29, n_unif=20000)
+    ref = oracle.nuts_run(tgt.kind, tgt.params(), q0, 0.8, 8, -1.0, n_collect, n_discard, normals, exp1, unif,
+                          mass_cfg=(1, 1, 10, 0.05, 1e-6, 1, 3))
+    plain = oracle.nuts_run(tgt.kind, tgt.params(), q0, 0.8, 8, -1.0, n_collect, n_discard, normals, exp1, unif)
+    assert (ref["mass_updates"] == 0).all() and np.array_equal(ref["samples"], plain["samples"])
+    s = gm.NUTS(tgt, q0, 0.8, seed=1, ctx=ctx, max_depth=8,
+                mass_matrix=gm.NUTSMassMatrixConfig("dense", 1, 1, 10, 0.05, 1e-6, dense_max_dim=3)).set_math_mode(True)
+    s.inject_streams(normals, exp1, unif)
+    out = s.run(n_collect, n_discard)
+    p = gm.NUTS(tgt, q0, 0.8, seed=1, ctx=ctx, max_depth=8).set_math_mode(True)
+    p.inject_streams(normals, exp1, unif)
+    assert np.array_equal(out, p.run(n_collect, n_discard))
+    assert np.array_equal(s.state()["used"].astype(np.int64), ref["used"])
+
+
+def test_nuts_dense_mass_philox_recovers_correlated_gaussian(ctx, oracle):
+    """Philox path, reference default windows, 300 warm-up transitions on a correlated 6-D Gaussian: the adapted matrices
+    (`inv` = inverse of the regularised window covariance: the reference takes the mass to be the covariance, as its
+    diagonal variant takes it to be the variance) and the draws reproduce what the reference ALGORITHM produces (the
+    oracle on its own streams) — including its quirks (step-size search and sub-tree U-turn tests with the identity)."""
+    Cn, d = 1024, 6
+    tgt, cov = _corr_gauss(d, seed=9)
+    q0 = (np.random.default_rng(5).standard_normal((Cn, d)) @ np.linalg.cholesky(cov).T).astype(np.float32)
+    r2 = np.random.default_rng(1)
+    Co = 384
+    streams = (r2.standard_normal((Co, d * 412)), r2.exponential(size=(Co, 402)), r2.random((Co, 400000)))
+    ref = oracle.nuts_run(tgt.kind, tgt.params(), q0[:Co], 0.8, 10, -1.0, 100, 300, *streams, mass_cfg=(75, 50, 25, 0.05, 1e-6, 1, 75))
+    assert not ref["exhausted"].any()
+    s = gm.NUTS(tgt, q0, 0.8, seed=11, ctx=ctx, max_depth=10, mass_matrix=gm.NUTSMassMatrixConfig("dense"))
+    out = s.run(100, 300)
+    inv, n = s.mass_matrix()
+    assert n == 4 and np.isfinite(inv).all() and np.isfinite(out).all()
+    got = np.median(inv.astype(np.float64), axis=0)
+    want = np.median(ref["mass_inv"].astype(np.float64), axis=0)
+    print("dense mass philox: median inverse mass (GPU)\n", got.round(3), "\n(oracle)\n", want.round(3), "\n(target cov)\n", cov.round(3))
+    assert np.abs(got - want).max() < 0.25 * np.abs(want).max()
+    cov_gpu = np.cov(out.reshape(-1, d).astype(np.float64).T)
+    cov_ref = np.cov(ref["samples"].reshape(-1, d).astype(np.float64).T)
+    assert np.abs(cov_gpu - cov_ref).max() < 0.2 * np.abs(cov_ref).max()
+    leap_gpu = s.counters().grad_evals / (Cn * 399.0)
+    leap_ref = ref["leapfrogs"].mean() / 399.0
+    assert abs(leap_gpu / leap_ref - 1.0) < 0.2, (leap_gpu, leap_ref)
 
 
 # -------------------------------------------------------------------------------------------------

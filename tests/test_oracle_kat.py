@@ -63,6 +63,26 @@ def test_diagonal_mass_matrix_kat():
     assert abs(out[0] - 0.5) < 1e-12 and abs(out[1] - 1.0 / 3.0) < 1e-12
 
 
+def test_dense_mass_matrix_kat():
+    # /root/reference/src/generic_nuts.rs:1442-1457 (dense_mass_matrix_inverse_matches_identity_action): p' M^-1 p > 0;
+    # beyond the reference's assertion: inv is the inverse of cov + jitter I and chol its lower Cholesky factor
+    cov = np.array([[2.0, 0.3], [0.3, 1.0]])
+    p = np.array([0.7, -1.1])
+    m = O.dense_mass(cov, p, jitter=1e-12)
+    assert m is not None
+    assert p @ m["inv_mul"] > 0.0
+    covj = cov + 1e-10 * np.eye(2)          # dense_from_cov: jitter.max(1e-10) on the diagonal (:209-214)
+    assert np.allclose(m["inv"], np.linalg.inv(covj), rtol=1e-12)
+    assert np.allclose(m["chol"], np.linalg.cholesky(covj), rtol=1e-12)
+    assert np.isclose(m["kinetic"], 0.5 * p @ np.linalg.inv(covj) @ p, rtol=1e-12)
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((9, 9))
+    cov9 = a @ a.T + 0.1 * np.eye(9)
+    m9 = O.dense_mass(cov9, rng.standard_normal(9))
+    assert np.allclose(m9["inv"] @ (cov9 + 1e-10 * np.eye(9)), np.eye(9), atol=1e-9)
+    assert O.dense_mass(np.array([[1.0, 2.0], [2.0, 1.0]]) * np.nan, p) is None      # non-finite covariance: no factorisation
+
+
 def test_nuts_chain_runs_finite():
     # nuts.rs:603-665 (test_chain_2/3, test_run_1): finite, |x| < 100
     rng = np.random.default_rng(1)
