@@ -66,7 +66,7 @@ bool choose_nuts_decomposition(int dim, int dtype, int kind, int* epl, int* lpc)
     const char* l_env = std::getenv("GMCMC_NUTS_LPC");
     if (e_env && l_env) {
       const int e = std::atoi(e_env), l = std::atoi(l_env);
-      if ((e == 4 || e == 8 || e == 13 || e == big) && l >= 1 && l <= 32 && (l & (l - 1)) == 0 && e * l >= dim) {
+      if ((e == 4 || e == 8 || e == big) && l >= 1 && l <= 32 && (l & (l - 1)) == 0 && e * l >= dim) {
         *epl = e; *lpc = l;
         return true;
       }

@@ -474,91 +474,104 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       }
     }
 
-    // ---- B. one gradient evaluation per chain: at the position (start) or after a leapfrog drift (leaf)
-    const T veps = (T)v * eps;                 // generic_nuts.rs:1187
-    const T he = veps * T(0.5);                // leapfrog_with_mass :1396-1418
-    if (is_leaf) {
-#pragma unroll
-      for (int j = 0; j < EPL; ++j) p[j] = p[j] + g[j] * he;
-    }
-    if constexpr (dense_mass) {
-      if (dense_on) dense_mul(a.mass_dinv, p, mp, false);                      // velocity = M^-1 p (apply_inv_mass)
-    }
-    if (is_leaf) {
-#pragma unroll
-      for (int j = 0; j < EPL; ++j) {
-        if constexpr (has_mass) {                                             // velocity = M^-1 p (apply_inv_mass)
-          const T mi = (j < ln.nvalid) ? a.mass_inv[chain * d + ln.lo + j] : T(1);
-          q[j] = q[j] + (mi * p[j]) * veps;
-        } else if constexpr (dense_mass) {
-          q[j] = q[j] + (dense_on ? mp[j] : p[j]) * veps;
-        } else {
-          q[j] = q[j] + p[j] * veps;
-        }
-      }
-    }
-    // every chain is in the START, LEAF or DONE phase here, and a finished chain never reads g again: the
-    // gradient is written in place
-    const T logp = eval_target<T, EPL, EP, true>(TAG{}, q, g, ln, tp, row);
-    if (is_leaf) {
-#pragma unroll
-      for (int j = 0; j < EPL; ++j) p[j] = p[j] + g[j] * he;
-    }
-    if constexpr (dense_mass) {
-      if (dense_on) dense_mul(a.mass_dinv, p, mp, false);                      // row_dot of MassMatrix::kinetic, Dense
-    }
-    T terms[EPL];
-#pragma unroll
-    for (int j = 0; j < EPL; ++j) {                                              // MassMatrix::kinetic :228-263
-      if constexpr (has_mass) terms[j] = p[j] * p[j] * ((j < ln.nvalid) ? a.mass_inv[chain * d + ln.lo + j] : T(1));
-      else if constexpr (dense_mass) terms[j] = dense_on ? p[j] * mp[j] : p[j] * p[j];
-      else terms[j] = p[j] * p[j];
-    }
-    const T ke = T(0.5) * chain_sum<T, EPL>(terms, ln);
-    const T joint = logp - ke;
-
+    // ---- B. TWO gradient evaluations per chain and pass.  A chain that starts a transition evaluates the gradient at its
+    // position (slot 0), then takes the single leaf of the first doubling (slot 1); afterwards every doubling has an even
+    // number of leaves and a pass is one pair: leaf A (even index, slot 0: it becomes the pending left subtree of level 0) and
+    // leaf B (odd, slot 1: merged with A below).  The chains of a warp therefore stay aligned on pair boundaries, the even
+    // leaf never enters the merge loop, and the per-pass control (queue, momentum, phase tests) is paid once per two leaves.
     bool in_merge = false;
-    if (is_start) {
-      // generic_nuts.rs:765-781
-      joint0 = joint;
-      T e1;
-      if (inject) { e1 = (T)((i_exp < a.n_exp) ? a.inj_exp1[chain * a.n_exp + i_exp] : 1.0); ++i_exp; }
-      else {
-        const uint4 r = philox4x32_10(philox_ctr(gchain, a.step_base + s, 1u, 0u), a.key);
-        if constexpr (!kExact && sizeof(T) == 4) e1 = -__logf(u01(r.z));   // fast mode, f32: the 24 leading bits of word 2
-        else e1 = (T)(-log(u01d(r.z, r.w)));
-      }
-      logu = joint0 - e1;
-      store_slice<T, EPL>(hot + H_QM * wd, q, ln, true); store_slice<T, EPL>(hot + H_PM * wd, p, ln, true);
-      store_slice<T, EPL>(hot + H_QP * wd, q, ln, true); store_slice<T, EPL>(hot + H_PP * wd, p, ln, true);
-      store_slice<T, EPL>(e_gm, g, ln, true); store_slice<T, EPL>(e_gp, g, ln, true);
-      j_depth = 0; n_tot = 1; draw = 0; moved = false;
-      const T u1 = (T)next_unif();             // :783-784
-      v = (u1 < T(0.5)) ? 1 : -1;
-      leaf_i = 0; alpha_sum = T(0); n_alpha = 0;
-      phase = NP_LEAF;
-    } else if (is_leaf) {
-      // leaf of build_tree (j == 0 branch, generic_nuts.rs:1185-1222)
-      ++my_leapfrogs; ++chain_leaps;
-      nR = (logu < joint) ? 1 : 0;
-      sR = (logu - T(1000)) < joint;
-      if (!sR) ++my_diverge;
-      alpha_sum = alpha_sum + min(T(1), fast_exp<T>(joint - joint0));
-      ++n_alpha;
+    bool a_ok = true;        // leaf A kept its subtree alive (s'): leaf B is built (generic_nuts.rs:1251)
+#pragma unroll 1
+    for (int slot = 0; slot < 2; ++slot) {
+      const bool mv = (slot == 0) ? is_leaf : (is_start || (is_leaf && a_ok));   // this chain takes a leapfrog in this slot
+      const T veps = (T)v * eps;                 // generic_nuts.rs:1187
+      const T he = veps * T(0.5);                // leapfrog_with_mass :1396-1418
+      if (mv) {
 #pragma unroll
-      for (int j = 0; j < EPL; ++j) prime[j] = q[j];
-      if ((leaf_i & 1u) == 0u) {
-        // an even leaf is the first leaf of the left subtree of the next level-0 merge (shared memory) and, when its
-        // index is a multiple of 4, of later merges at levels >= 1 (global workspace, stack slot popcount(c >> 1))
-        store_slice<T, EPL>(hot + H_LQ * wd, q, ln, true);
-        store_slice<T, EPL>(hot + H_LP * wd, p, ln, true);
-        if ((leaf_i & 3u) == 0u) {
-          const int slot = __popc(leaf_i >> 1);
-          store_slice<T, EPL>(w_first + (unsigned)(slot * 2) * wd, q, ln, true);
-          store_slice<T, EPL>(w_first + (unsigned)(slot * 2 + 1) * wd, p, ln, true);
+        for (int j = 0; j < EPL; ++j) p[j] = p[j] + g[j] * he;
+      }
+      if constexpr (dense_mass) {
+        if (dense_on) dense_mul(a.mass_dinv, p, mp, false);                      // velocity = M^-1 p (apply_inv_mass)
+      }
+      if (mv) {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) {
+          if constexpr (has_mass) {                                             // velocity = M^-1 p (apply_inv_mass)
+            const T mi = (j < ln.nvalid) ? a.mass_inv[chain * d + ln.lo + j] : T(1);
+            q[j] = q[j] + (mi * p[j]) * veps;
+          } else if constexpr (dense_mass) {
+            q[j] = q[j] + (dense_on ? mp[j] : p[j]) * veps;
+          } else {
+            q[j] = q[j] + p[j] * veps;
+          }
         }
       }
-      in_merge = true;
+      // the gradient is written in place: a chain that does not move in this slot re-evaluates it at the same point (same
+      // value), a finished chain never reads it again
+      const T logp = eval_target<T, EPL, EP, true>(TAG{}, q, g, ln, tp, row);
+      if (mv) {
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) p[j] = p[j] + g[j] * he;
+      }
+      if constexpr (dense_mass) {
+        if (dense_on) dense_mul(a.mass_dinv, p, mp, false);                      // row_dot of MassMatrix::kinetic, Dense
+      }
+      T terms[EPL];
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) {                                              // MassMatrix::kinetic :228-263
+        if constexpr (has_mass) terms[j] = p[j] * p[j] * ((j < ln.nvalid) ? a.mass_inv[chain * d + ln.lo + j] : T(1));
+        else if constexpr (dense_mass) terms[j] = dense_on ? p[j] * mp[j] : p[j] * p[j];
+        else terms[j] = p[j] * p[j];
+      }
+      const T ke = T(0.5) * chain_sum<T, EPL>(terms, ln);
+      const T joint = logp - ke;
+
+      if (slot == 0 && is_start) {
+        // generic_nuts.rs:765-781
+        joint0 = joint;
+        T e1;
+        if (inject) { e1 = (T)((i_exp < a.n_exp) ? a.inj_exp1[chain * a.n_exp + i_exp] : 1.0); ++i_exp; }
+        else {
+          const uint4 r = philox4x32_10(philox_ctr(gchain, a.step_base + s, 1u, 0u), a.key);
+          if constexpr (!kExact && sizeof(T) == 4) e1 = -__logf(u01(r.z));   // fast mode, f32: the 24 leading bits of word 2
+          else e1 = (T)(-log(u01d(r.z, r.w)));
+        }
+        logu = joint0 - e1;
+        store_slice<T, EPL>(hot + H_QM * wd, q, ln, true); store_slice<T, EPL>(hot + H_PM * wd, p, ln, true);
+        store_slice<T, EPL>(hot + H_QP * wd, q, ln, true); store_slice<T, EPL>(hot + H_PP * wd, p, ln, true);
+        store_slice<T, EPL>(e_gm, g, ln, true); store_slice<T, EPL>(e_gp, g, ln, true);
+        j_depth = 0; n_tot = 1; draw = 0; moved = false;
+        const T u1 = (T)next_unif();             // :783-784
+        v = (u1 < T(0.5)) ? 1 : -1;
+        leaf_i = 0; alpha_sum = T(0); n_alpha = 0;
+        phase = NP_LEAF;
+      } else if (mv) {
+        // leaf of build_tree (j == 0 branch, generic_nuts.rs:1185-1222)
+        ++my_leapfrogs; ++chain_leaps;
+        nR = (logu < joint) ? 1 : 0;
+        sR = (logu - T(1000)) < joint;
+        if (!sR) ++my_diverge;
+        alpha_sum = alpha_sum + min(T(1), fast_exp<T>(joint - joint0));
+        ++n_alpha;
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) prime[j] = q[j];
+        if (slot == 0) {
+          // leaf A: the first leaf of the left subtree of the level-0 merge that follows in this pass (shared memory) and,
+          // when its index is a multiple of 4, of later merges at levels >= 1 (global workspace, stack slot popcount(c >> 1))
+          store_slice<T, EPL>(hot + H_LQ * wd, q, ln, true);
+          store_slice<T, EPL>(hot + H_LP * wd, p, ln, true);
+          if ((leaf_i & 3u) == 0u) {
+            const int slot_w = __popc(leaf_i >> 1);
+            store_slice<T, EPL>(w_first + (unsigned)(slot_w * 2) * wd, q, ln, true);
+            store_slice<T, EPL>(w_first + (unsigned)(slot_w * 2 + 1) * wd, p, ln, true);
+          }
+          a_ok = sR;
+          if (sR) { n_stack[0] = nR; ++leaf_i; }    // pending left subtree of level 0; leaf B follows
+          else in_merge = true;                     // failed subtree: passed up through the left children to the top
+        } else {
+          in_merge = true;                          // leaf B (level-0 merge first) or the single leaf of doubling 0 (top)
+        }
+      }
     }
     __syncwarp();     // the slices written above are read back (by the same lanes) through a different pointer type below
 
@@ -599,6 +612,8 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       // (negation is exact and commutes with rounding, so the sums are bit-identical to the reference's order)
       const bool fwd = (v == 1);
       T vf[EPL];      // M^-1 p of the other trajectory end (dense mass, whole-trajectory test only: sub-tree tests use the identity, :1316)
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) vf[j] = T(0);
       if constexpr (dense_mass) {
         if (dense_on && __any_sync(kFull, do_top)) dense_mul(a.mass_dinv, fp, vf, false);
       }
@@ -972,8 +987,11 @@ inline cudaError_t nuts_launch_one(const NutsLaunch& L, cudaStream_t st) {
   const bool fixed = kLpcFixed > 0 && L.lpc == kLpcFixed;
   const int mass = L.mass_dinv ? 2 : (L.mass_inv ? 1 : 0);
   void (*kern)(const NutsArgs<T>) = nullptr;
-  if (mass == 2) kern = exact_fit ? nuts_run_kernel<T, EPL, TAG, false, 2, 0> : nuts_run_kernel<T, EPL, TAG, true, 2, 0>;
-  else if (fixed) kern = mass ? (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, 1, kLpcFixed> : nuts_run_kernel<T, EPL, TAG, true, 1, kLpcFixed>)
+  if (mass == 2) {
+    // dense mass matrices are instantiated for the narrow slices only (d <= 128 covers dense_max_dim = 75 with room to spare)
+    if constexpr (EPL <= 8) kern = exact_fit ? nuts_run_kernel<T, EPL, TAG, false, 2, 0> : nuts_run_kernel<T, EPL, TAG, true, 2, 0>;
+    else return cudaErrorInvalidValue;
+  } else if (fixed) kern = mass ? (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, 1, kLpcFixed> : nuts_run_kernel<T, EPL, TAG, true, 1, kLpcFixed>)
                               : (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, 0, kLpcFixed> : nuts_run_kernel<T, EPL, TAG, true, 0, kLpcFixed>);
   else kern = mass ? (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, 1, 0> : nuts_run_kernel<T, EPL, TAG, true, 1, 0>)
                    : (exact_fit ? nuts_run_kernel<T, EPL, TAG, false, 0, 0> : nuts_run_kernel<T, EPL, TAG, true, 0, 0>);
@@ -998,13 +1016,15 @@ inline cudaError_t nuts_launch_one(const NutsLaunch& L, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-// EPL menu of the NUTS kernels: {2 (2-D targets), 4, 8, 13, 25 (f32 only)}
+// EPL menu of the NUTS kernels: {2 (2-D targets), 4, 8, 25 (f32 only), 13 (f64 only)}
 template <class T, class TAG>
 inline cudaError_t nuts_dispatch(const NutsLaunch& L, cudaStream_t st) {
   switch (L.epl) {
     case 4: return nuts_launch_one<T, 4, TAG>(L, st);
     case 8: return nuts_launch_one<T, 8, TAG>(L, st);
-    case 13: return nuts_launch_one<T, 13, TAG>(L, st);
+    case 13:
+      if constexpr (sizeof(T) == 8) return nuts_launch_one<T, 13, TAG>(L, st);
+      else return cudaErrorInvalidValue;
     case 25:
       if constexpr (sizeof(T) == 4) return nuts_launch_one<T, 25, TAG>(L, st);
       else return cudaErrorInvalidValue;

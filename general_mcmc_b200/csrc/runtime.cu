@@ -1497,6 +1497,8 @@ gmcmc_status gmcmc_nuts_set_mass_adaptation(gmcmc_sampler* s, gmcmc_mass_adaptat
     return GMCMC_OK;
   }
   if (kind == GMCMC_MASS_DENSE) {
+    if (s->epl > 8)
+      return fail(GMCMC_ERR_UNSUPPORTED, "dense mass matrices are built for dim <= 128 (got %d)", s->dim);
     const size_t ndd = nd * (size_t)s->dim;
     if (!s->d_mass_dinv) {
       bool ok = cudaMalloc(&s->d_mass_dinv, ndd * es) == cudaSuccess && cudaMalloc(&s->d_mass_chol, ndd * es) == cudaSuccess &&
