@@ -42,6 +42,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -221,9 +222,14 @@ struct GemmArgs {
   float norm_const;
   float zscale;           // the accumulator holds z / (zscale * dscale[1]): P is pre-scaled by a power of two in FP16 mode
   const float* dscale;    // device [2]: power-of-two scale applied to delta before the FP16 split, and its inverse
-  int persist;            // 1: the grid is a set of persistent clusters walking (row-tile group, column chunk) units (no row sums)
-  float* logp_out;        // [C] or null: logp = c - 1/2 sum z * delta
-  float* ke_out;          // [C] or null: 1/2 |p_new|^2
+  int persist;            // 1: the grid is a set of persistent clusters walking (row-tile group, column chunk) units
+  int row_base;           // first chain of this launch's chain block: row coordinate offset of the delta TMA loads (the other
+                          // pointers are pre-offset by the host)
+  // trajectory ends: per-unit partial row sums, one slot per (column chunk, epilogue warp of the quarter), summed in fixed
+  // order by the consumer (dense_accept_kernel) — every launch can then run the persistent unit schedule
+  float* quad_part;       // [n_chunks * kEpiWarps / 4][part_ld] or null: zs * sum_cols z * delta
+  float* ke_part;         // same shape or null: sum_cols p_new^2
+  size_t part_ld;
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -290,7 +296,7 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
         mbar_expect_tx(&raw_full[r], kRawBytes);
         int m0, n;
         unit_of(it / k_chunks, m0, n);
-        tma_load_2d(raw_base + (size_t)r * kRawBytes, &map_dl, &raw_full[r], (it % k_chunks) * kTileK, m0);
+        tma_load_2d(raw_base + (size_t)r * kRawBytes, &map_dl, &raw_full[r], (it % k_chunks) * kTileK, m0 + a.row_base);
       }
     }
   } else if (warp == 1) {
@@ -429,7 +435,7 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
       // current half is transposed, updated and stored — measured SLOWER, 17.9 vs 16.4 ms per transition: the registers it
       // takes spill, and the epilogue is not short of loads in flight: tensor pipe 57 %, L1 52 %, crossbar 40 %, DRAM 33 %, at
       // a power-limited 1.54 GHz, nothing saturated.)
-      const bool unit_fast = a.dl_next && !a.logp_out && !a.ke_out && nrows == 32 && (a.d & 3) == 0;
+      const bool unit_fast = a.dl_next && !a.quad_part && !a.ke_part && nrows == 32 && (a.d & 3) == 0;
       auto blk_fast = [&](int cb) { return unit_fast && cb < kTileN / 32 && n * kTileN + cb * 32 + 32 <= a.d; };
       const int sub = lane >> 3, ch = lane & 7;
       const uint32_t d4 = 4u * (uint32_t)a.d, k4 = 4u * (uint32_t)a.kpad;
@@ -551,7 +557,7 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
                 __stcs(p_blk + rr * d32, pn);
                 if (a.dl_next) a.dl_next[(row0 + r) * (size_t)a.kpad + col] = fmaf(a.drift_eps, pn, dv[rr]);
               }
-              if (a.logp_out || a.ke_out) {          // trajectory ends only: row sums over the 32 columns
+              if (a.quad_part || a.ke_part) {        // trajectory ends only: row sums over the 32 columns
                 float s1 = zv * dv[rr], s2 = pn * pn;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
@@ -561,23 +567,18 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
           }
         }
       }
+      if (a.quad_part || a.ke_part) {
+        // this warp's partial row sums of the unit (its column blocks of chunk n): one slot per (chunk, warp of the quarter)
+        const size_t slot = (size_t)(n * (kEpiWarps / 4) + cb_first);
+        if (lane < nrows) {
+          if (a.quad_part) a.quad_part[slot * a.part_ld + row0 + lane] = zs * quad;
+          if (a.ke_part) a.ke_part[slot * a.part_ld + row0 + lane] = ke;
+        }
+        quad = 0.f; ke = 0.f;
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-    }
-    // the warps of a quarter hold partial row sums (interleaved column blocks): combine through shared memory
-    if (a.logp_out || a.ke_out) {
-      __syncwarp();
-      tr[lane] = quad; tr[32 + lane] = ke;
-      asm volatile("bar.sync 1, %0;" ::"r"(32 * kEpiWarps) : "memory");   // epilogue warps only
-      if (cb_first == 0 && lane < nrows) {
-        float qsum = 0.f, ksum = 0.f;
-        for (int w = 0; w < kEpiWarps; ++w) {
-          if (((w + kFirstEpiWarp) & 3) == q4) { qsum += tr_base[(size_t)w * 16 * 33 + lane]; ksum += tr_base[(size_t)w * 16 * 33 + 32 + lane]; }
-        }
-        if (a.logp_out) a.logp_out[row0 + lane] = a.norm_const - 0.5f * (zs * qsum);
-        if (a.ke_out) a.ke_out[row0 + lane] = 0.5f * ksum;
-      }
     }
   }
   tc_fence_before();
@@ -659,7 +660,9 @@ struct AcceptArgs {
   size_t n_chains; int d, kpad;
   unsigned long long chain_offset; PhiloxKey key; uint32_t step;
   float* q; const float* dl; const float* mu; const float* p;
-  const float* logp0; const float* logp1; const float* ke0; const float* ke1;
+  // log densities / kinetic energy of the two trajectory ends as partial row sums [n_part][part_ld] of the GEMM epilogues
+  const float* quad0; const float* quad1; const float* ke0; const float* ke1_part;
+  int n_part; size_t part_ld; float norm_const;
   float* out; size_t out_n; long long slot;        // slot < 0: not recorded
   unsigned long long* accept_total; unsigned long long* diverge_total;
   const float* inj_lnu;      // [C] for this transition or null
@@ -671,7 +674,14 @@ __global__ void __launch_bounds__(256) dense_accept_kernel(const AcceptArgs a) {
   const size_t chain = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (chain >= a.n_chains) return;
-  const float log_accept = (a.logp1[chain] - a.logp0[chain]) + (a.ke0[chain] - a.ke1[chain]);
+  float q0 = 0.f, q1 = 0.f, k1 = 0.f;           // fixed summation order over the (chunk, warp) slots: deterministic
+  for (int i = 0; i < a.n_part; ++i) {
+    q0 += a.quad0[(size_t)i * a.part_ld + chain];
+    q1 += a.quad1[(size_t)i * a.part_ld + chain];
+    k1 += a.ke1_part[(size_t)i * a.part_ld + chain];
+  }
+  const float logp0 = a.norm_const - 0.5f * q0, logp1 = a.norm_const - 0.5f * q1, ke1 = 0.5f * k1;
+  const float log_accept = (logp1 - logp0) + (a.ke0[chain] - ke1);
   float ln_u;
   if (a.inj_lnu) ln_u = a.inj_lnu[chain];
   else ln_u = logf(u01(philox4x32_10(philox_ctr(a.chain_offset + chain, a.step, 1u, 0u), a.key).x));
@@ -746,7 +756,10 @@ struct DenseTc {
   float* dscale = nullptr;                 // device [2]: power-of-two scale of delta for this transition, and its inverse
   unsigned int* dmax_bits = nullptr;       // device [1]: max |delta| of the batch (float bits)
   int sms = 0;                             // SMs of the device (persistent grid size)
-  float *logp0 = nullptr, *logp1 = nullptr, *ke0 = nullptr, *ke1 = nullptr;
+  float *ke0 = nullptr;
+  float* part = nullptr;                   // [3][n_part][C]: partial row sums of the two trajectory-end GEMMs (quad0, quad1, ke1)
+  int n_part = 0;
+  size_t block_chains = 0;                 // chains per L2-resident block (0: all chains in one block)
   float norm_const = 0.f;
   CUtensorMap map_dl[2], map_bhi, map_blo;
   size_t smem = 0;
@@ -755,7 +768,7 @@ struct DenseTc {
 void dense_tc_destroy(DenseTc* t) {
   if (!t) return;
   cudaFree(t->p); cudaFree(t->dl[0]); cudaFree(t->dl[1]); cudaFree(t->b_hi); cudaFree(t->b_lo); cudaFree(t->mu);
-  cudaFree(t->logp0); cudaFree(t->logp1); cudaFree(t->ke0); cudaFree(t->ke1);
+  cudaFree(t->ke0); cudaFree(t->part);
   cudaFree(t->dscale); cudaFree(t->dmax_bits);
   delete t;
 }
@@ -770,13 +783,28 @@ DenseTc* dense_tc_create(size_t n_chains, int d, const double* params, const cha
   t->kpad = ((d + kKPadUnit - 1) / kKPadUnit) * kKPadUnit;
   t->npad = ((d + kTileN - 1) / kTileN) * kTileN;
   t->norm_const = (float)params[(size_t)d + (size_t)d * d];
+  t->n_part = (t->npad / kTileN) * (kEpiWarps / 4);
+  {
+    // Chain blocks (experiment, off by default): GMCMC_DENSE_WAVES = w > 0 walks the chains in blocks of w unit waves whose
+    // p / delta / delta' working set stays in the 126 MB L2 from one leapfrog to the next, so the epilogue's loads and stores
+    // hit L2 instead of HBM.  Measured SLOWER (65,536 chains, d = 1000: 21.1 / 20.2 / 18.9 / 18.2 ms per transition for w = 1 /
+    // 2 / 3 / 4 against 16.5 ms unblocked): the epilogue is not bound by HBM latency, and every extra launch pays its own
+    // pipeline fill and tail.
+    int waves = 0;
+    if (const char* w = std::getenv("GMCMC_DENSE_WAVES")) waves = std::atoi(w);
+    const int n_chunks = t->npad / kTileN, clusters = t->sms / kCluster;
+    if (waves > 0 && clusters > 0) {
+      const size_t groups = std::max<size_t>(1, (size_t)waves * clusters / n_chunks);
+      t->block_chains = groups * kTileM * kCluster;
+    }
+  }
   const size_t C = n_chains;
   bool ok = cudaMalloc(&t->p, C * d * 4) == cudaSuccess &&
             cudaMalloc(&t->dl[0], C * (size_t)t->kpad * 4) == cudaSuccess && cudaMalloc(&t->dl[1], C * (size_t)t->kpad * 4) == cudaSuccess &&
             cudaMemset(t->dl[1], 0, C * (size_t)t->kpad * 4) == cudaSuccess &&
             cudaMalloc(&t->b_hi, (size_t)t->npad * t->kpad * kOpElem) == cudaSuccess && cudaMalloc(&t->b_lo, (size_t)t->npad * t->kpad * kOpElem) == cudaSuccess &&
-            cudaMalloc(&t->mu, (size_t)d * 4) == cudaSuccess && cudaMalloc(&t->logp0, C * 4) == cudaSuccess &&
-            cudaMalloc(&t->logp1, C * 4) == cudaSuccess && cudaMalloc(&t->ke0, C * 4) == cudaSuccess && cudaMalloc(&t->ke1, C * 4) == cudaSuccess &&
+            cudaMalloc(&t->mu, (size_t)d * 4) == cudaSuccess && cudaMalloc(&t->ke0, C * 4) == cudaSuccess &&
+            cudaMalloc(&t->part, 3 * (size_t)(t->npad / kTileN) * (kEpiWarps / 4) * C * 4) == cudaSuccess &&
             cudaMalloc(&t->dscale, 8) == cudaSuccess && cudaMalloc(&t->dmax_bits, 4) == cudaSuccess &&
             cudaMemset(t->dmax_bits, 0, 4) == cudaSuccess;
   if (!ok) { *err = e_alloc; dense_tc_destroy(t); return nullptr; }
@@ -832,18 +860,23 @@ DenseTc* dense_tc_create(size_t n_chains, int d, const double* params, const cha
   return t;
 }
 
-// GEMM on delta buffer `buf` (0 / 1); drift_eps != 0 fuses the next leapfrog's drift and writes the other buffer
-static cudaError_t gemm_kick(DenseTc* t, int buf, float coef, float drift_eps, float* logp_out, float* ke_out, cudaStream_t st) {
+// GEMM on delta buffer `buf` (0 / 1) for the chain block [c0, c0 + nb); drift_eps != 0 fuses the next leapfrog's drift and
+// writes the other buffer; quad_part / ke_part (set of partial slots of this block's chains) at the trajectory ends
+static cudaError_t gemm_kick(DenseTc* t, size_t c0, size_t nb, int buf, float coef, float drift_eps, float* quad_part, float* ke_part,
+                             cudaStream_t st) {
   GemmArgs g;
-  g.d = t->d; g.kpad = t->kpad; g.npad = t->npad; g.n_chains = t->n_chains;
-  g.p = t->p; g.dl = t->dl[buf]; g.dl_next = drift_eps != 0.f ? t->dl[buf ^ 1] : nullptr;
+  g.d = t->d; g.kpad = t->kpad; g.npad = t->npad; g.n_chains = nb;
+  g.p = t->p + c0 * (size_t)t->d; g.dl = t->dl[buf] + c0 * (size_t)t->kpad;
+  g.dl_next = drift_eps != 0.f ? t->dl[buf ^ 1] + c0 * (size_t)t->kpad : nullptr;
   g.coef = coef; g.drift_eps = drift_eps; g.norm_const = t->norm_const; g.zscale = t->zscale; g.dscale = t->dscale;
-  g.logp_out = logp_out; g.ke_out = ke_out;
-  unsigned blocks = (unsigned)((t->n_chains + kTileM - 1) / kTileM);
-  blocks = (blocks + kCluster - 1) / kCluster * kCluster;   // whole clusters; a surplus CTA only feeds the multicast
-  // no row sums wanted (every launch but the two trajectory ends): persistent clusters over (row-tile group, chunk) units
-  g.persist = (!logp_out && !ke_out && t->sms > 0 && blocks > (unsigned)t->sms) ? 1 : 0;
-  if (g.persist) blocks = (unsigned)(t->sms / kCluster) * kCluster;
+  g.quad_part = quad_part ? quad_part + c0 : nullptr; g.ke_part = ke_part ? ke_part + c0 : nullptr; g.part_ld = t->n_chains;
+  g.row_base = (int)c0;
+  // persistent clusters over (row-tile group, column chunk) units, chunk fastest, for every launch
+  const size_t n_groups = (nb + (size_t)kTileM * kCluster - 1) / ((size_t)kTileM * kCluster);
+  const size_t n_units = n_groups * (size_t)(t->npad / kTileN);
+  const size_t clusters = std::min<size_t>(n_units, (size_t)std::max(1, t->sms / kCluster));
+  g.persist = 1;
+  const unsigned blocks = (unsigned)(clusters * kCluster);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = t->smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -855,46 +888,54 @@ static cudaError_t gemm_kick(DenseTc* t, int buf, float coef, float drift_eps, f
 
 // One HMC transition.  q: [C, d] current positions (in/out).  Returns the number of kernel launches (or -1).
 int dense_tc_transition(DenseTc* t, const DenseTcStep& S, cudaStream_t st) {
-  const size_t C = t->n_chains;
-  const unsigned wblocks = (unsigned)((C * 32 + 255) / 256);
-  int launches = 0;
-  BeginArgs b;
-  b.n_chains = C; b.d = t->d; b.kpad = t->kpad; b.chain_offset = S.chain_offset;
-  b.key = PhiloxKey{(uint32_t)S.seed, (uint32_t)(S.seed >> 32)}; b.step = S.step;
-  b.q = (const float*)S.q; b.p = t->p; b.mu = t->mu; b.dl = t->dl[0]; b.ke0 = t->ke0;
-  b.inj_normals = (const float*)S.inj_normals;
-  b.dmax_bits = t->dmax_bits;
-  dense_begin_kernel<<<wblocks, 256, 0, st>>>(b);
-  dense_scale_kernel<<<1, 1, 0, st>>>(t->dmax_bits, t->dscale);
-  launches += 2;
+  const size_t C = t->n_chains, d = (size_t)t->d;
+  const size_t blk = t->block_chains ? t->block_chains : C;
+  const size_t psz = (size_t)t->n_part * C;
+  float* quad0 = t->part; float* quad1 = t->part + psz; float* ke1 = t->part + 2 * psz;
   const float eps = (float)S.eps, half = 0.5f * eps;
-  // GEMM 0: gradient at the current point (log density, first half kick, drift of leapfrog 1);
-  // GEMM l (1 <= l < L): kick eps + drift of leapfrog l + 1;  GEMM L: last half kick, log density, kinetic energy
-  int final_buf = 0;
-  if (S.n_leapfrog == 0) {
-    if (gemm_kick(t, 0, 0.f, 0.f, t->logp0, t->ke1, st) != cudaSuccess) return -1;
-    ++launches;
-  } else {
-    if (gemm_kick(t, 0, half, eps, t->logp0, nullptr, st) != cudaSuccess) return -1;
-    ++launches;
-    for (uint32_t l = 1; l <= S.n_leapfrog; ++l) {
-      const bool last = (l == S.n_leapfrog);
-      if (gemm_kick(t, (int)(l & 1u), last ? half : eps, last ? 0.f : eps, last ? t->logp1 : nullptr, last ? t->ke1 : nullptr, st) != cudaSuccess)
-        return -1;
+  int launches = 0;
+  for (size_t c0 = 0; c0 < C; c0 += blk) {
+    const size_t nb = std::min(blk, C - c0);
+    const unsigned wblocks = (unsigned)((nb * 32 + 255) / 256);
+    BeginArgs b;
+    b.n_chains = nb; b.d = t->d; b.kpad = t->kpad; b.chain_offset = S.chain_offset + c0;
+    b.key = PhiloxKey{(uint32_t)S.seed, (uint32_t)(S.seed >> 32)}; b.step = S.step;
+    b.q = (const float*)S.q + c0 * d; b.p = t->p + c0 * d; b.mu = t->mu; b.dl = t->dl[0] + c0 * (size_t)t->kpad; b.ke0 = t->ke0 + c0;
+    b.inj_normals = S.inj_normals ? (const float*)S.inj_normals + c0 * d : nullptr;
+    b.dmax_bits = t->dmax_bits;
+    dense_begin_kernel<<<wblocks, 256, 0, st>>>(b);
+    dense_scale_kernel<<<1, 1, 0, st>>>(t->dmax_bits, t->dscale);
+    launches += 2;
+    // GEMM 0: gradient at the current point (log density, first half kick, drift of leapfrog 1);
+    // GEMM l (1 <= l < L): kick eps + drift of leapfrog l + 1;  GEMM L: last half kick, log density, kinetic energy
+    int final_buf = 0;
+    if (S.n_leapfrog == 0) {
+      if (gemm_kick(t, c0, nb, 0, 0.f, 0.f, quad0, ke1, st) != cudaSuccess) return -1;
       ++launches;
+    } else {
+      if (gemm_kick(t, c0, nb, 0, half, eps, quad0, nullptr, st) != cudaSuccess) return -1;
+      ++launches;
+      for (uint32_t l = 1; l <= S.n_leapfrog; ++l) {
+        const bool last = (l == S.n_leapfrog);
+        if (gemm_kick(t, c0, nb, (int)(l & 1u), last ? half : eps, last ? 0.f : eps, last ? quad1 : nullptr, last ? ke1 : nullptr, st) != cudaSuccess)
+          return -1;
+        ++launches;
+      }
+      final_buf = (int)(S.n_leapfrog & 1u);
     }
-    final_buf = (int)(S.n_leapfrog & 1u);
+    AcceptArgs a;
+    a.n_chains = nb; a.d = t->d; a.kpad = t->kpad; a.chain_offset = S.chain_offset + c0; a.key = b.key; a.step = S.step;
+    a.q = (float*)S.q + c0 * d; a.dl = t->dl[final_buf] + c0 * (size_t)t->kpad; a.mu = t->mu; a.p = t->p + c0 * d;
+    a.quad0 = quad0 + c0; a.quad1 = (S.n_leapfrog > 0 ? quad1 : quad0) + c0; a.ke0 = t->ke0 + c0; a.ke1_part = ke1 + c0;
+    a.n_part = t->n_part; a.part_ld = C; a.norm_const = t->norm_const;
+    a.out = S.out ? (float*)S.out + c0 * S.out_n * d : nullptr; a.out_n = S.out_n; a.slot = S.slot;
+    a.accept_total = S.accept_total; a.diverge_total = S.diverge_total;
+    a.inj_lnu = S.inj_lnu ? (const float*)S.inj_lnu + c0 : nullptr;
+    a.diag_logacc = S.diag_logacc ? (float*)S.diag_logacc + c0 : nullptr; a.diag_acc = S.diag_acc ? S.diag_acc + c0 : nullptr;
+    a.diag_pq = S.diag_pq ? (float*)S.diag_pq + c0 * d : nullptr; a.diag_pp = S.diag_pp ? (float*)S.diag_pp + c0 * d : nullptr;
+    dense_accept_kernel<<<wblocks, 256, 0, st>>>(a);
+    ++launches;
   }
-  AcceptArgs a;
-  a.n_chains = C; a.d = t->d; a.kpad = t->kpad; a.chain_offset = S.chain_offset; a.key = b.key; a.step = S.step;
-  a.q = (float*)S.q; a.dl = t->dl[final_buf]; a.mu = t->mu; a.p = t->p;
-  a.logp0 = t->logp0; a.logp1 = S.n_leapfrog > 0 ? t->logp1 : t->logp0; a.ke0 = t->ke0; a.ke1 = t->ke1;
-  a.out = (float*)S.out; a.out_n = S.out_n; a.slot = S.slot;
-  a.accept_total = S.accept_total; a.diverge_total = S.diverge_total;
-  a.inj_lnu = (const float*)S.inj_lnu;
-  a.diag_logacc = (float*)S.diag_logacc; a.diag_acc = S.diag_acc; a.diag_pq = (float*)S.diag_pq; a.diag_pp = (float*)S.diag_pp;
-  dense_accept_kernel<<<wblocks, 256, 0, st>>>(a);
-  ++launches;
   if (cudaGetLastError() != cudaSuccess) return -1;
   return launches;
 }

@@ -214,7 +214,7 @@ int stats_groups(size_t N, size_t p, size_t C, int sm_count);   // chain groups 
 void stats_fill_twiddles(size_t N, float* host_tw);
 cudaError_t launch_stats_accumulate(const StatsLaunch&, cudaStream_t);
 cudaError_t launch_stats_reduce(const StatsLaunch&, cudaStream_t);
-cudaError_t launch_stats_finalize(const StatsLaunch&, double total_chains, cudaStream_t);
+cudaError_t launch_stats_finalize(const StatsLaunch&, double total_chains, const double* total_chains_dev, cudaStream_t);
 
 // launchers (each returns the cudaError of the launch).  *_exact are compiled with --fmad=false.
 cudaError_t launch_hmc_fast(const HmcLaunch&, cudaStream_t);

@@ -113,6 +113,11 @@ struct gmcmc_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaStream_t aux_stream = nullptr;   // side stream of the pooled dual-averaging chain (reduce -> all-reduce -> update)
+  // work buffers of the device statistics (split R-hat / ESS), kept between calls: a call used to pay six cudaMalloc /
+  // cudaFree pairs, each an implicit device synchronisation
+  void* stats_arena = nullptr; size_t stats_arena_bytes = 0;
+  size_t stats_tw_n = 0;               // padded length whose twiddles sit at the head of the arena
+  float* stats_host = nullptr; size_t stats_host_n = 0;   // pinned result buffer
   int rank = 0, world = 1;
   void* comm = nullptr;
   int sm_count = 148;
@@ -756,14 +761,6 @@ gmcmc_status convert_on_device(gmcmc_ctx* ctx, const void* in, int in_dtype, voi
 
 // ---- statistics ---------------------------------------------------------------------------------
 constexpr size_t kStatsMaxPadded = 16384;   // longest padded series the in-kernel FFT takes (n <= 16385 draws)
-struct StatsBuffers {
-  void* tw = nullptr; float* part_spec = nullptr; double* part_mom = nullptr; float* spec = nullptr;
-  double* mom = nullptr; float* out = nullptr;
-  ~StatsBuffers() {
-    cudaFree(tw); cudaFree(part_spec); cudaFree(part_mom); cudaFree(spec); cudaFree(mom); cudaFree(out);
-  }
-};
-
 gmcmc_status device_split_rhat_ess(gmcmc_ctx* ctx, const void* d_samples, size_t C, size_t n, size_t p, int dtype,
                                    float* rhat, float* rhat_std, float* ess) {
   GM_REQUIRE(C >= 1 && n >= 4 && p >= 1, "split_rhat_ess needs C >= 1, n >= 4, p >= 1 (got %zu, %zu, %zu)", C, n, p);
@@ -778,40 +775,62 @@ gmcmc_status device_split_rhat_ess(gmcmc_ctx* ctx, const void* d_samples, size_t
   const int groups = stats_groups(S.N, p, C, ctx->sm_count);
   S.n_groups = groups;
   const size_t nk = S.N / 2 + 1;
-  StatsBuffers B;
-  std::vector<float> tw(S.N);   // N/2 (cos, sin) pairs
-  stats_fill_twiddles(S.N, tw.data());
-  GM_CU(cudaMalloc(&B.tw, std::max<size_t>(S.N, 2) * sizeof(float)));
-  GM_CU(cudaMemcpyAsync(B.tw, tw.data(), S.N * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-  GM_CU(cudaMalloc(&B.part_spec, (size_t)groups * p * nk * sizeof(float)));
-  GM_CU(cudaMalloc(&B.part_mom, (size_t)groups * p * 3 * sizeof(double)));
-  GM_CU(cudaMalloc(&B.spec, p * nk * sizeof(float)));
-  GM_CU(cudaMalloc(&B.mom, (p * 3 + 1) * sizeof(double)));
-  GM_CU(cudaMalloc(&B.out, 3 * p * sizeof(float)));
-  S.tw = B.tw; S.part_spec = B.part_spec; S.part_mom = B.part_mom; S.spec = B.spec; S.mom = B.mom;
-  S.rhat = B.out; S.rhat_std = B.out + p; S.ess = B.out + 2 * p; S.acov = nullptr;
+  // one arena, carved into 256-byte aligned pieces: twiddles | group spectra | group moments | spectrum | moments (+ chain count) | results
+  auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t b_tw = up(std::max<size_t>(S.N, 2) * sizeof(float)), b_ps = up((size_t)groups * p * nk * sizeof(float)),
+               b_pm = up((size_t)groups * p * 3 * sizeof(double)), b_sp = up(p * nk * sizeof(float)),
+               b_mo = up((p * 3 + 1) * sizeof(double)), b_out = up(3 * p * sizeof(float));
+  const size_t need = b_tw + b_ps + b_pm + b_sp + b_mo + b_out;
+  if (need > ctx->stats_arena_bytes) {
+    GM_CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->stats_arena);
+    ctx->stats_arena = nullptr; ctx->stats_arena_bytes = 0; ctx->stats_tw_n = 0;
+    GM_CU(cudaMalloc(&ctx->stats_arena, need));
+    ctx->stats_arena_bytes = need;
+  }
+  if (3 * p > ctx->stats_host_n) {
+    if (ctx->stats_host) cudaFreeHost(ctx->stats_host);
+    ctx->stats_host = nullptr; ctx->stats_host_n = 0;
+    GM_CU(cudaHostAlloc((void**)&ctx->stats_host, 3 * p * sizeof(float), cudaHostAllocDefault));
+    ctx->stats_host_n = 3 * p;
+  }
+  char* base = (char*)ctx->stats_arena;
+  void* tw_dev = base;
+  float* part_spec = (float*)(base + b_tw);
+  double* part_mom = (double*)(base + b_tw + b_ps);
+  float* spec = (float*)(base + b_tw + b_ps + b_pm);
+  double* mom = (double*)(base + b_tw + b_ps + b_pm + b_sp);
+  float* out = (float*)(base + b_tw + b_ps + b_pm + b_sp + b_mo);
+  if (ctx->stats_tw_n != S.N) {       // the twiddle table sits first: it survives while the padded length stays the same
+    std::vector<float> tw(S.N);       // N/2 (cos, sin) pairs
+    stats_fill_twiddles(S.N, tw.data());
+    GM_CU(cudaMemcpyAsync(tw_dev, tw.data(), S.N * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    GM_CU(cudaStreamSynchronize(ctx->stream));     // the source is a local vector
+    ctx->stats_tw_n = S.N;
+  }
+  S.tw = tw_dev; S.part_spec = part_spec; S.part_mom = part_mom; S.spec = spec; S.mom = mom;
+  S.rhat = out; S.rhat_std = out + p; S.ess = out + 2 * p; S.acov = nullptr;
   cudaError_t e = launch_stats_accumulate(S, ctx->stream);
   if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "stats_accumulate launch failed: %s", cudaGetErrorString(e));
   e = launch_stats_reduce(S, ctx->stream);
   if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "stats_reduce launch failed: %s", cudaGetErrorString(e));
-  double total_chains = (double)C;
+  const double* total_dev = nullptr;
   if (ctx->world > 1) {
-    // A2 + A3: moments (+ chain count) in f64, chain-summed power spectrum in f32
+    // A2 + A3: moments (+ chain count) in f64, chain-summed power spectrum in f32; the all-reduced chain count
+    // stays on the device (stats_finalize reads it there): no host round trip between the collectives and the finalize
     const double cc = (double)C;
-    GM_CU(cudaMemcpyAsync(B.mom + p * 3, &cc, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    GM_TRY(all_reduce(ctx, B.mom, p * 3 + 1, kNcclFloat64));
-    GM_TRY(all_reduce(ctx, B.spec, p * nk, kNcclFloat32));
-    GM_CU(cudaMemcpyAsync(&total_chains, B.mom + p * 3, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    GM_CU(cudaStreamSynchronize(ctx->stream));
+    GM_CU(cudaMemcpyAsync(mom + p * 3, &cc, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    GM_TRY(all_reduce(ctx, mom, p * 3 + 1, kNcclFloat64));
+    GM_TRY(all_reduce(ctx, spec, p * nk, kNcclFloat32));
+    total_dev = mom + p * 3;
   }
-  e = launch_stats_finalize(S, total_chains, ctx->stream);
+  e = launch_stats_finalize(S, (double)C, total_dev, ctx->stream);
   if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "stats_finalize launch failed: %s", cudaGetErrorString(e));
-  std::vector<float> host(3 * p);
-  GM_CU(cudaMemcpyAsync(host.data(), B.out, 3 * p * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CU(cudaMemcpyAsync(ctx->stats_host, out, 3 * p * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   GM_CU(cudaStreamSynchronize(ctx->stream));
-  if (rhat) std::memcpy(rhat, host.data(), p * sizeof(float));
-  if (rhat_std) std::memcpy(rhat_std, host.data() + p, p * sizeof(float));
-  if (ess) std::memcpy(ess, host.data() + 2 * p, p * sizeof(float));
+  if (rhat) std::memcpy(rhat, ctx->stats_host, p * sizeof(float));
+  if (rhat_std) std::memcpy(rhat_std, ctx->stats_host + p, p * sizeof(float));
+  if (ess) std::memcpy(ess, ctx->stats_host + 2 * p, p * sizeof(float));
   return GMCMC_OK;
 }
 
@@ -908,6 +927,8 @@ gmcmc_status gmcmc_ctx_destroy(gmcmc_ctx* c) {
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  cudaFree(c->stats_arena);
+  if (c->stats_host) cudaFreeHost(c->stats_host);
   delete c;
   return GMCMC_OK;
 }

@@ -204,6 +204,21 @@ __device__ __forceinline__ void dft8(float (&xr)[8], float (&xi)[8]) {
   for (int m = 0; m < 4; ++m) { xr[2 * m] = ur[m]; xi[2 * m] = ui[m]; xr[2 * m + 1] = vr[m]; xi[2 * m + 1] = vi[m]; }
 }
 
+// the same with x[4 .. 7] == 0 (zero padding): u_i = v_i = x_i
+__device__ __forceinline__ void dft8_upper_zero(float (&xr)[8], float (&xi)[8]) {
+  constexpr float c = 0.70710678118654752440f;
+  float ur[4], ui[4], vr[4], vi[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { ur[i] = xr[i]; ui[i] = xi[i]; vr[i] = xr[i]; vi[i] = xi[i]; }
+  { const float a = vr[1], b = vi[1]; vr[1] = (a + b) * c; vi[1] = (b - a) * c; }      // * w8
+  { const float a = vr[2], b = vi[2]; vr[2] = b; vi[2] = -a; }                          // * (-i)
+  { const float a = vr[3], b = vi[3]; vr[3] = (b - a) * c; vi[3] = -(a + b) * c; }     // * w8^3
+  dft4(ur[0], ui[0], ur[1], ui[1], ur[2], ui[2], ur[3], ui[3]);
+  dft4(vr[0], vi[0], vr[1], vi[1], vr[2], vi[2], vr[3], vi[3]);
+#pragma unroll
+  for (int m = 0; m < 4; ++m) { xr[2 * m] = ur[m]; xi[2 * m] = ui[m]; xr[2 * m + 1] = vr[m]; xi[2 * m + 1] = vi[m]; }
+}
+
 template <int LOG2N>
 struct WarpFft {
   static constexpr int N = 1 << LOG2N;
@@ -244,19 +259,23 @@ struct WarpFft {
         const int pb = padi(base);
         auto at = [&](int r) { return kLin ? pb + r * PSTR : padi(base + r * M); };
         float xr[8], xi[8];
+        if (FIRST) {
+          // inputs r = 4 .. 7 sit at indices >= N / 2 >= half: the zero padding.  Only four loads, and the first butterfly
+          // stage of the 8-point DFT (x_i +- x_{i+4}) degenerates to copies.
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          if (FIRST) {
+          for (int r = 0; r < 4; ++r) {
             const bool valid = base + r * M < half;
             const float vr = valid ? re[at(r)] - mean0 : 0.f;
             const float vi = valid ? im[at(r)] - mean1 : 0.f;
             sq0 += vr * vr; sq1 += vi * vi;
             xr[r] = vr; xi[r] = vi;
-          } else {
-            xr[r] = re[at(r)]; xi[r] = im[at(r)];
           }
+          dft8_upper_zero(xr, xi);
+        } else {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) { xr[r] = re[at(r)]; xi[r] = im[at(r)]; }
+          dft8(xr, xi);
         }
-        dft8(xr, xi);
         if (M > 1) {
           const float2 w1 = tw[j];
           float wr = w1.x, wi = w1.y;
@@ -490,7 +509,8 @@ __global__ void stats_reduce(const float* __restrict__ part_spec, const double* 
 
 // one CTA per parameter
 __global__ void __launch_bounds__(kStatsBlock)
-stats_finalize(const float* __restrict__ spec, const double* __restrict__ mom, double total_chains /*unsplit, all ranks*/,
+stats_finalize(const float* __restrict__ spec, const double* __restrict__ mom, double total_chains_host /*unsplit, all ranks*/,
+               const double* __restrict__ total_chains_dev /*same, device-resident (after an all-reduce), or null*/,
                size_t n, int p, int N, int log2n, const float2* __restrict__ tw, float* __restrict__ rhat,
                float* __restrict__ rhat_std, float* __restrict__ ess, float* __restrict__ acov_out /*[p][half] or null*/) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -500,6 +520,7 @@ stats_finalize(const float* __restrict__ spec, const double* __restrict__ mom, d
   const int k = blockIdx.x;
   const int nk = N / 2 + 1;
   const size_t half = n / 2;
+  const double total_chains = total_chains_dev ? *total_chains_dev : total_chains_host;
   const double c2 = 2.0 * total_chains;
 
   // symmetric real spectrum, bit-reversed slots; FFT of a real even sequence == N * inverse FFT
@@ -743,14 +764,14 @@ cudaError_t launch_stats_reduce(const StatsLaunch& S, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_stats_finalize(const StatsLaunch& S, double total_chains, cudaStream_t st) {
+cudaError_t launch_stats_finalize(const StatsLaunch& S, double total_chains, const double* total_chains_dev, cudaStream_t st) {
   const size_t smem = S.N * 8;
   auto kern = stats_finalize;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  kern<<<(unsigned)S.p, kStatsBlock, smem, st>>>(S.spec, S.mom, total_chains, S.n, S.p, (int)S.N, S.log2n,
+  kern<<<(unsigned)S.p, kStatsBlock, smem, st>>>(S.spec, S.mom, total_chains, total_chains_dev, S.n, S.p, (int)S.N, S.log2n,
                                                  (const float2*)S.tw, S.rhat, S.rhat_std, S.ess, S.acov);
   return cudaGetLastError();
 }
