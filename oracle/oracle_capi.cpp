@@ -164,6 +164,48 @@ inline void philox_normals(uint64_t seed, uint64_t chain, uint32_t step, uint32_
   }
 }
 
+// Tuned CPU transition for the timed baseline only (never used as the checker): the same HMC transition as hmc_step
+// (generic_hmc.rs:166-221) without per-call allocation (caller-owned scratch) and, for RosenbrockND, with the gradient in a
+// two-pass form the compiler vectorises (t_i = x_{i+1} - x_i^2 first, then g_i from t_i and t_{i-1}) instead of the scalar
+// recurrence of the checker.  Same operations per coordinate; summation order of the log density differs (vector lanes).
+template <class T>
+inline T rosenbrock_logp_grad_fast(const T* __restrict__ x, T* __restrict__ g, T* __restrict__ t, int d) {
+  T s = 0;
+  for (int i = 0; i < d - 1; ++i) {
+    const T ti = x[i + 1] - x[i] * x[i];
+    const T u = T(1) - x[i];
+    t[i] = ti;
+    s += T(100) * ti * ti + u * u;
+  }
+  g[0] = d > 1 ? T(400) * t[0] * x[0] + T(2) * (T(1) - x[0]) : T(0);
+  for (int i = 1; i < d - 1; ++i) g[i] = T(400) * t[i] * x[i] + T(2) * (T(1) - x[i]) - T(200) * t[i - 1];
+  if (d > 1) g[d - 1] = T(-200) * t[d - 2];
+  return -s;
+}
+
+template <class T>
+inline int hmc_step_fast(const Target<T>& tgt, T* q, const T* mom, T ln_u, T eps, int L, T* pq, T* pp, T* grad, T* scratch) {
+  const int d = tgt.dim;
+  const bool rosen = tgt.kind == T_ROSENBROCK_ND;
+  auto eval = [&](const T* x) -> T { return rosen ? rosenbrock_logp_grad_fast(x, grad, scratch, d) : tgt.logp_and_grad(x, grad); };
+  T ke0 = 0;
+  for (int i = 0; i < d; ++i) { pq[i] = q[i]; pp[i] = mom[i]; ke0 += mom[i] * mom[i]; }
+  const T logp0 = eval(q);
+  const T half = T(0.5) * eps;
+  T logp = logp0;
+  for (int l = 0; l < L; ++l) {
+    for (int i = 0; i < d; ++i) { pp[i] += grad[i] * half; pq[i] += pp[i] * eps; }
+    logp = eval(pq);
+    for (int i = 0; i < d; ++i) pp[i] += grad[i] * half;
+  }
+  T ke1 = 0;
+  for (int i = 0; i < d; ++i) ke1 += pp[i] * pp[i];
+  const T log_accept = (logp - logp0) + (T(0.5) * ke0 - T(0.5) * ke1);
+  const int acc = ln_u <= log_accept;
+  if (acc) for (int i = 0; i < d; ++i) q[i] = pq[i];
+  return acc;
+}
+
 template <class T>
 double hmc_bench(int kind, int dim, const double* params, size_t np, size_t C, T* q, T eps, int L,
                  size_t n_steps, uint64_t seed, int threads, T* samples) {
@@ -175,7 +217,7 @@ double hmc_bench(int kind, int dim, const double* params, size_t np, size_t C, T
   auto t0 = std::chrono::steady_clock::now();
 #pragma omp parallel
   {
-    std::vector<T> mom(d);
+    std::vector<T> mom(d), pq(d), pp(d), grad(d), scratch(d);
 #pragma omp for schedule(static)
     for (long long ci = 0; ci < (long long)C; ++ci) {
       size_t c = (size_t)ci;
@@ -186,7 +228,7 @@ double hmc_bench(int kind, int dim, const double* params, size_t np, size_t C, T
         uint32_t r[4];
         Philox::block(ctr, key, r);
         T ln_u = (T)std::log(u01_f32(r[0]));
-        hmc_step(t, q + c * d, mom.data(), ln_u, eps, L, (T*)nullptr, (T*)nullptr);
+        hmc_step_fast(t, q + c * d, mom.data(), ln_u, eps, L, pq.data(), pp.data(), grad.data(), scratch.data());
         if (samples) std::memcpy(samples + (c * n_steps + s) * d, q + c * d, d * sizeof(T));
       }
     }
