@@ -692,12 +692,15 @@ def leg_cfg4_strong(env, total_chains=STRONG_CHAINS, n_collect=1000, n_discard=2
     c = s.counters()
     value = total_chains * (n_collect + n_discard) * N_LEAPFROG / (ms * 1e-3)
     st = L.RunStatsC()
-    ctx.synchronize()
-    t0 = time.perf_counter()
-    L.check(lib.gmcmc_run_stats_from(ctx._h, C.c_void_p(holder["p"]), C.c_size_t(chains), C.c_size_t(n_collect), C.c_size_t(DIM),
-                                     L.F32, 1, C.byref(st)))
-    ctx.synchronize()
-    stats_ms = env.max_over_ranks((time.perf_counter() - t0) * 1e3)
+    stats_times = []
+    for _ in range(2):       # the first call pays one-time costs (kernel loading, work-buffer allocation); the second is reported
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        L.check(lib.gmcmc_run_stats_from(ctx._h, C.c_void_p(holder["p"]), C.c_size_t(chains), C.c_size_t(n_collect), C.c_size_t(DIM),
+                                         L.F32, 1, C.byref(st)))
+        ctx.synchronize()
+        stats_times.append(env.max_over_ranks((time.perf_counter() - t0) * 1e3))
+    stats_ms = stats_times[-1]
     converged = st.rhat_std.max < 1.01
     tfl = value / world * FLOP_PER_GRAD_EVAL / 1e12
     peak = env.fp32_peak()
@@ -709,7 +712,8 @@ def leg_cfg4_strong(env, total_chains=STRONG_CHAINS, n_collect=1000, n_discard=2
            "step_size": c.step_size, "roofline_frac_fp32": tfl / peak if peak else None,
            "collectives_in_timed_region": "A1: %d NCCL all-reduces of 2 doubles (one per warm-up transition, on a side stream, "
                                           "one transition lagged)" % (n_discard if world > 1 else 0),
-           "device_stats_ms": stats_ms, "stats_read_gbs": chains * n_collect * DIM * 4 / (stats_ms * 1e-3) / 1e9,
+           "device_stats_ms": stats_ms, "device_stats_first_call_ms": stats_times[0],
+           "stats_read_gbs": chains * n_collect * DIM * 4 / (stats_ms * 1e-3) / 1e9,
            "min_ess": st.ess.min, "median_ess": st.ess.median, "split_rhat_max": st.rhat_std.max, "converged": bool(converged),
            "min_ess_per_sec": st.ess.min / (ms * 1e-3) if converged else None, "clocks": clk,
            "note": "value = total chains x (warm-up + collected) transitions x L / device time of the whole run (max over "
