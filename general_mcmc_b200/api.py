@@ -280,6 +280,11 @@ def build_custom_target(source, out=None, extra_flags=()):
     return out
 
 
+def build_custom_conditional(source, out=None, extra_flags=()):
+    """nvcc-compiles a Gibbs conditional source (see csrc/gmcmc_custom_conditional.cuh) into a plugin .so for sm_100a."""
+    return build_custom_target(source, out, ("--fmad=false",) + tuple(extra_flags))
+
+
 # ------------------------------------------------------------------------------------------------
 # statistics (stats.rs)
 # ------------------------------------------------------------------------------------------------
@@ -592,6 +597,73 @@ class MetropolisHastings(_Sampler):
         out = np.empty((self._n_inj, self.n_chains, 3), np.float32)
         L.check(L.lib().gmcmc_mh_read_draws(self._h, L.ptr(out)))
         return out
+
+
+class ConstantConditional:
+    """≙ the ConstantConditional of the reference's Gibbs tests (gibbs.rs:177-186): every coordinate becomes c."""
+    cond_kind = 0
+
+    def __init__(self, c):
+        self.c = float(c)
+
+    def params(self):
+        return [self.c]
+
+
+class MixtureConditional:
+    """≙ MixtureConditional (gibbs.rs:188-245) on the state [x, z]: x | z ~ N(mu_z, sigma_z^2), z | x Bernoulli with
+    the posterior weight of mode 1."""
+    cond_kind = 1
+
+    def __init__(self, mu0, sigma0, mu1, sigma1, pi0):
+        self.mu0, self.sigma0, self.mu1, self.sigma1, self.pi0 = (float(v) for v in (mu0, sigma0, mu1, sigma1, pi0))
+
+    def params(self):
+        return [self.mu0, self.sigma0, self.mu1, self.sigma1, self.pi0]
+
+
+class CustomConditional:
+    """A conditional compiled ahead of time into a plugin (csrc/gmcmc_custom_conditional.cuh); the plugin fixes dim."""
+
+    def __init__(self, plugin_path, params=()):
+        self.plugin_path = str(plugin_path)
+        self._params = [float(v) for v in params]
+
+    def params(self):
+        return self._params
+
+
+class GibbsSampler(_Sampler):
+    """≙ gibbs::GibbsSampler (gibbs.rs:107-162) + ChainRunner (core.rs:204-406): `run(n_collect, n_discard)` returns f64
+    [n_chains, n_collect, dim]; one transition is one full sweep over the coordinates (gibbs.rs:89-105)."""
+
+    def __init__(self, target, initial_states, ctx=None, chain_offset=0):
+        self.ctx = ctx or default_context()
+        self._out_dtype = np.dtype(np.float64)
+        self.dtype = np.dtype(np.float64)
+        self.target = target
+        pos = _as_positions(initial_states, np.float64)
+        self.n_chains, self.dim = pos.shape
+        seed = int(np.random.SeedSequence().entropy & 0xFFFFFFFFFFFFFFFF)
+        p = np.ascontiguousarray(target.params(), np.float64)
+        h = C.c_void_p()
+        if isinstance(target, CustomConditional):
+            L.check(L.lib().gmcmc_gibbs_create_custom(self.ctx._h, target.plugin_path.encode(), L.ptr(p) if p.size else None,
+                                                      C.c_size_t(p.size), C.c_size_t(self.n_chains), C.c_uint64(chain_offset),
+                                                      L.ptr(pos), C.c_uint64(seed), C.byref(h)))
+        else:
+            L.check(L.lib().gmcmc_gibbs_create(self.ctx._h, int(target.cond_kind), L.ptr(p), C.c_size_t(p.size),
+                                               C.c_size_t(self.n_chains), C.c_int(self.dim), C.c_uint64(chain_offset),
+                                               L.ptr(pos), C.c_uint64(seed), C.byref(h)))
+        self._h = h
+
+    def inject(self, normals, uniforms):
+        """Test hook: the first normal / uniform of every (sweep, coordinate), f64 [n, chains, dim] each."""
+        normals = np.ascontiguousarray(normals, np.float64)
+        uniforms = np.ascontiguousarray(uniforms, np.float64)
+        n = normals.shape[0]
+        assert normals.shape == (n, self.n_chains, self.dim) and uniforms.shape == normals.shape
+        L.check(L.lib().gmcmc_gibbs_inject(self._h, L.ptr(normals), L.ptr(uniforms), C.c_size_t(n)))
 
 
 class NUTSMassMatrixConfig:

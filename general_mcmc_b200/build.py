@@ -47,6 +47,7 @@ def _units():
     units.append(("mh_exact.cu", "mh_exact.o", ["--fmad=false"]))
     units.append(("mh_int.cu", "mh_int.o", ["--fmad=false"]))
     units.append(("mass_dense.cu", "mass_dense.o", ["--fmad=false"]))
+    units.append(("gibbs.cu", "gibbs.o", ["--fmad=false"]))
     for extra in ("dense_tc.cu",):
         if os.path.exists(os.path.join(CSRC, extra)):
             flags = ["--fmad=false"] if extra.endswith("_exact.cu") else []

@@ -104,6 +104,26 @@ struct MhIntLaunch {
 cudaError_t launch_mh_int(const MhIntLaunch&, cudaStream_t);
 int mh_int_max_dim();
 
+// Gibbs sweeps (gibbs_kernel.cuh / gibbs.cu): built-in conditionals of the reference's tests, or a plugin's
+struct GibbsLaunch {
+  int kind, dim;                    // 0 ConstantConditional [c], 1 MixtureConditional [mu0, sigma0, mu1, sigma1, pi0] on [x, z]
+  const double* params;             // device
+  size_t n_chains;
+  uint64_t chain_offset, seed;
+  uint32_t step_base, n_steps, n_skip;
+  double* state;                    // [C, d] in/out
+  double* out; size_t out_n; uint32_t out_t0;
+  const double* inj_normals;        // [n, C, d] first normal of each (transition, coordinate), or null
+  const double* inj_uniforms;       // [n, C, d] first uniform, or null
+};
+cudaError_t launch_gibbs(const GibbsLaunch&, cudaStream_t);
+int gibbs_max_dim();
+struct CustomConditionalVTable {
+  int abi_version;
+  int dim;
+  cudaError_t (*launch_gibbs)(const GibbsLaunch&, cudaStream_t);
+};
+
 // K3: dense-Gaussian HMC with the gradient GEMM on tcgen05 (dense_tc.cu)
 struct DenseTc;
 struct DenseTcStep {

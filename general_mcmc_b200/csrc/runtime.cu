@@ -133,7 +133,7 @@ struct gmcmc_target {
   void* plugin = nullptr;                       // dlopen handle
 };
 
-enum SamplerType { S_HMC = 0, S_MH = 1, S_NUTS = 2, S_MHINT = 3 };
+enum SamplerType { S_HMC = 0, S_MH = 1, S_NUTS = 2, S_MHINT = 3, S_GIBBS = 4 };
 
 struct PooledDa {   // device-resident dual-averaging state of GMCMC_ADAPT_POOLED (all f64)
   double h_bar, log_eps_bar, mu, eps, m;
@@ -218,6 +218,12 @@ struct gmcmc_sampler {
   double int_lambda = 0.0, int_p = 0.0;
   double* d_lnfact = nullptr; int n_lnfact = 0;
   signed char* d_inj_isteps = nullptr;
+  // Gibbs (gmcmc_gibbs_create[_custom]): conditional kind / plugin, device parameter block, injected uniforms
+  int gibbs_kind = 0;
+  const CustomConditionalVTable* gibbs_custom = nullptr;
+  void* gibbs_plugin = nullptr;
+  double* d_gibbs_params = nullptr;
+  double* d_inj_unif = nullptr;
   // gmcmc_mh_record: per-step record of the production 2-D fast MH kernel
   size_t rec_steps = 0;       // pending recorded transitions
   float* d_diag_draws = nullptr;
@@ -314,7 +320,9 @@ gmcmc_status ensure_samples(gmcmc_sampler* s, size_t bytes) {
   return GMCMC_OK;
 }
 
-inline int out_dtype_of(const gmcmc_sampler* s) { return (s->type == S_MH || s->type == S_MHINT) ? (int)GMCMC_F64 : s->dtype; }
+inline int out_dtype_of(const gmcmc_sampler* s) {
+  return (s->type == S_MH || s->type == S_MHINT || s->type == S_GIBBS) ? (int)GMCMC_F64 : s->dtype;
+}
 
 gmcmc_status set_eps_device(gmcmc_sampler* s, double eps) {
   if (s->dtype == GMCMC_F32) {
@@ -447,6 +455,30 @@ gmcmc_status mh_int_segment(gmcmc_sampler* s, size_t first, size_t count, size_t
   }
   cudaError_t e = launch_mh_int(L, s->ctx->stream);
   if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "integer MH kernel launch failed: %s", cudaGetErrorString(e));
+  s->launches += 1;
+  return GMCMC_OK;
+}
+
+gmcmc_status gibbs_segment(gmcmc_sampler* s, size_t first, size_t count, size_t n_discard, size_t n_collect, void* out,
+                           bool use_injection, size_t inj_first) {
+  if (count == 0) return GMCMC_OK;
+  GibbsLaunch L{};
+  L.kind = s->gibbs_kind; L.dim = s->dim; L.params = s->d_gibbs_params;
+  L.n_chains = s->n_chains; L.chain_offset = s->chain_offset; L.seed = s->seed;
+  L.step_base = s->step_index + (uint32_t)first;
+  L.n_steps = (uint32_t)count;
+  const size_t skip = first >= n_discard ? 0 : std::min(count, n_discard - first);
+  L.n_skip = (uint32_t)skip;
+  L.state = (double*)s->d_pos;
+  L.out = (out && skip < count) ? (double*)out : nullptr;
+  L.out_n = n_collect;
+  L.out_t0 = (uint32_t)(first >= n_discard ? first - n_discard : 0);
+  if (use_injection) {
+    L.inj_normals = (const double*)s->d_inj_normals + inj_first * s->n_chains * (size_t)s->dim;
+    L.inj_uniforms = s->d_inj_unif + inj_first * s->n_chains * (size_t)s->dim;
+  }
+  cudaError_t e = s->gibbs_custom ? s->gibbs_custom->launch_gibbs(L, s->ctx->stream) : launch_gibbs(L, s->ctx->stream);
+  if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "Gibbs kernel launch failed: %s", cudaGetErrorString(e));
   s->launches += 1;
   return GMCMC_OK;
 }
@@ -645,6 +677,9 @@ gmcmc_status run_into(gmcmc_sampler* s, size_t n_collect, size_t n_discard, void
   if (s->type == S_MHINT) {
     GM_TRY(mh_int_segment(s, 0, inj, n_discard, n_collect, d_out, true, inj_first));
     GM_TRY(mh_int_segment(s, inj, total - inj, n_discard, n_collect, d_out, false, 0));
+  } else if (s->type == S_GIBBS) {
+    GM_TRY(gibbs_segment(s, 0, inj, n_discard, n_collect, d_out, true, inj_first));
+    GM_TRY(gibbs_segment(s, inj, total - inj, n_discard, n_collect, d_out, false, 0));
   } else if (s->type == S_MH && s->rec_steps > 0) {
     const size_t rec = std::min(s->rec_steps, total);
     GM_TRY(mh_segment(s, 0, rec, n_discard, n_collect, d_out, false, s->diag_steps - s->rec_steps, true));
@@ -1286,6 +1321,93 @@ gmcmc_status gmcmc_mh_int_inject(gmcmc_sampler* s, const int8_t* steps, const do
   return GMCMC_OK;
 }
 
+namespace {
+gmcmc_status gibbs_common(gmcmc_ctx* ctx, const double* params, size_t n_params, size_t n_chains, int dim, uint64_t chain_offset,
+                          const double* init_host, uint64_t seed, gmcmc_sampler** out) {
+  gmcmc_sampler* s = new gmcmc_sampler();
+  s->type = S_GIBBS; s->ctx = ctx; s->tgt = nullptr;
+  s->n_chains = n_chains; s->chain_offset = chain_offset; s->dim = dim; s->dtype = GMCMC_F64;
+  s->seed = seed;
+  const size_t bytes = n_chains * (size_t)dim * sizeof(double);
+  const size_t pbytes = std::max<size_t>(n_params, 1) * sizeof(double);
+  bool ok = cudaMalloc(&s->d_pos, bytes) == cudaSuccess &&
+            cudaMemcpy(s->d_pos, init_host, bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMalloc(&s->d_counts, 8 * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMemset(s->d_counts, 0, 8 * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMalloc((void**)&s->d_gibbs_params, pbytes) == cudaSuccess &&
+            cudaMemset(s->d_gibbs_params, 0, pbytes) == cudaSuccess &&
+            (n_params == 0 || cudaMemcpy(s->d_gibbs_params, params, n_params * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess) &&
+            cudaEventCreate(&s->ev0) == cudaSuccess && cudaEventCreate(&s->ev1) == cudaSuccess;
+  if (!ok) {
+    gmcmc_status st = fail(GMCMC_ERR_CUDA, "sampler allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    gmcmc_sampler_destroy(s);
+    return st;
+  }
+  *out = s;
+  return GMCMC_OK;
+}
+}  // namespace
+
+gmcmc_status gmcmc_gibbs_create(gmcmc_ctx* ctx, gmcmc_conditional_kind kind, const double* params, size_t n_params,
+                                size_t n_chains, int dim, uint64_t chain_offset, const double* init_host, uint64_t seed,
+                                gmcmc_sampler** out) {
+  GM_REQUIRE(ctx && out && init_host && params, "null argument");
+  GM_REQUIRE(kind == GMCMC_COND_CONSTANT || kind == GMCMC_COND_MIXTURE_XZ, "unknown conditional kind");
+  GM_REQUIRE(n_chains >= 1 && dim >= 1 && dim <= gibbs_max_dim(), "built-in conditionals support 1 <= dim <= %d", gibbs_max_dim());
+  if (kind == GMCMC_COND_CONSTANT) GM_REQUIRE(n_params == 1, "ConstantConditional takes [c]");
+  if (kind == GMCMC_COND_MIXTURE_XZ) {
+    GM_REQUIRE(n_params == 5 && dim == 2, "MixtureConditional takes [mu0, sigma0, mu1, sigma1, pi0] and the state [x, z]");
+    GM_REQUIRE(params[1] > 0.0 && params[3] > 0.0 && params[4] > 0.0 && params[4] < 1.0, "MixtureConditional needs sigma > 0 and 0 < pi0 < 1");
+  }
+  GM_CU(cudaSetDevice(ctx->device));
+  gmcmc_sampler* s = nullptr;
+  GM_TRY(gibbs_common(ctx, params, n_params, n_chains, dim, chain_offset, init_host, seed, &s));
+  s->gibbs_kind = (int)kind;
+  *out = s;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_gibbs_create_custom(gmcmc_ctx* ctx, const char* plugin_path, const double* params, size_t n_params,
+                                       size_t n_chains, uint64_t chain_offset, const double* init_host, uint64_t seed,
+                                       gmcmc_sampler** out) {
+  GM_REQUIRE(ctx && out && init_host && plugin_path, "null argument");
+  GM_REQUIRE(n_params == 0 || params, "null parameter block");
+  GM_REQUIRE(n_chains >= 1, "n_chains must be >= 1");
+  GM_CU(cudaSetDevice(ctx->device));
+  void* h = dlopen(plugin_path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) return fail(GMCMC_ERR_INVALID, "cannot load conditional plugin %s: %s", plugin_path, dlerror());
+  using EntryFn = const CustomConditionalVTable* (*)(void);
+  EntryFn entry = (EntryFn)dlsym(h, "gmcmc_conditional_entry");
+  if (!entry) { dlclose(h); return fail(GMCMC_ERR_INVALID, "%s does not export gmcmc_conditional_entry (GMCMC_REGISTER_CONDITIONAL)", plugin_path); }
+  const CustomConditionalVTable* vt = entry();
+  if (!vt || vt->abi_version != kCustomAbiVersion || vt->dim < 1 || !vt->launch_gibbs) {
+    dlclose(h);
+    return fail(GMCMC_ERR_INVALID, "conditional plugin %s has an incompatible ABI version or dimension", plugin_path);
+  }
+  gmcmc_sampler* s = nullptr;
+  gmcmc_status st = gibbs_common(ctx, params, n_params, n_chains, vt->dim, chain_offset, init_host, seed, &s);
+  if (st != GMCMC_OK) { dlclose(h); return st; }
+  s->gibbs_kind = -1; s->gibbs_custom = vt; s->gibbs_plugin = h;
+  *out = s;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_gibbs_inject(gmcmc_sampler* s, const double* normals, const double* uniforms, size_t n_steps) {
+  GM_REQUIRE(s && s->type == S_GIBBS && normals && uniforms && n_steps >= 1, "gmcmc_gibbs_inject: Gibbs sampler, non-null streams");
+  GM_CU(cudaSetDevice(s->ctx->device));
+  GM_CU(cudaStreamSynchronize(s->ctx->stream));
+  cudaFree(s->d_inj_normals); cudaFree(s->d_inj_unif);
+  s->d_inj_normals = nullptr; s->d_inj_unif = nullptr;
+  s->inj_steps = s->diag_steps = 0;
+  const size_t bytes = n_steps * s->n_chains * (size_t)s->dim * sizeof(double);
+  GM_CU(cudaMalloc(&s->d_inj_normals, bytes));
+  GM_CU(cudaMalloc((void**)&s->d_inj_unif, bytes));
+  GM_CU(cudaMemcpy(s->d_inj_normals, normals, bytes, cudaMemcpyHostToDevice));
+  GM_CU(cudaMemcpy(s->d_inj_unif, uniforms, bytes, cudaMemcpyHostToDevice));
+  s->inj_steps = s->diag_steps = n_steps;
+  return GMCMC_OK;
+}
+
 gmcmc_status gmcmc_nuts_create(gmcmc_ctx* ctx, gmcmc_target* tgt, size_t n_chains, uint64_t chain_offset,
                                const void* init_host, double target_accept, uint32_t max_depth,
                                double init_step_size, uint64_t seed, gmcmc_sampler** out) {
@@ -1355,6 +1477,8 @@ gmcmc_status gmcmc_sampler_destroy(gmcmc_sampler* s) {
   cudaFree(s->d_inj_normals); cudaFree(s->d_inj_lnu);
   cudaFree(s->d_diag_logacc); cudaFree(s->d_diag_acc); cudaFree(s->d_diag_pq); cudaFree(s->d_diag_pp);
   cudaFree(s->d_diag_draws); cudaFree(s->d_lnfact); cudaFree(s->d_inj_isteps);
+  cudaFree(s->d_gibbs_params); cudaFree(s->d_inj_unif);
+  if (s->gibbs_plugin) dlclose(s->gibbs_plugin);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   for (cudaEvent_t e : s->ev_kern) if (e) cudaEventDestroy(e);
@@ -1618,6 +1742,7 @@ gmcmc_status gmcmc_nuts_state(gmcmc_sampler* s, void* eps_out, long long* leapfr
 
 gmcmc_status gmcmc_read_diagnostics(gmcmc_sampler* s, void* log_accept, uint8_t* accepted, void* prop_q, void* prop_p) {
   GM_REQUIRE(s, "null sampler");
+  GM_REQUIRE(s->type != S_GIBBS, "Gibbs sweeps have no accept / reject diagnostics");
   if (s->diag_steps == 0) return fail(GMCMC_ERR_STATE, "no injected transitions recorded");
   GM_CU(cudaSetDevice(s->ctx->device));
   GM_CU(cudaStreamSynchronize(s->ctx->stream));

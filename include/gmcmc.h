@@ -173,6 +173,27 @@ gmcmc_status gmcmc_mh_int_create(gmcmc_ctx*, gmcmc_int_target_kind kind, const d
 /* Test hook: the next n_steps transitions take these directions (int8 +1 / -1, [n_steps, n_chains, dim]) and
  * ln u values (f64 [n_steps, n_chains]); log ratio (f64) and decisions through gmcmc_read_diagnostics. */
 gmcmc_status gmcmc_mh_int_inject(gmcmc_sampler*, const int8_t* steps, const double* ln_u, size_t n_steps);
+/* Gibbs sampling: ≙ GibbsSampler::new + set_seed (gibbs.rs:139-162); one transition = one full sweep
+ * (GibbsMarkovChain::step, gibbs.rs:89-105: for i in 0 .. dim, state[i] = conditional.sample(i, &state)).  The
+ * reference's `Conditional<S>` is a host closure; here it is one of the conditionals of the reference's own tests
+ * (gibbs.rs:177-245: ConstantConditional { c }, any dim <= 8; MixtureConditional { mu0, sigma0, mu1, sigma1, pi0 } on the
+ * state [x, z]) or a device function compiled ahead of time into a plugin (general_mcmc_b200/csrc/
+ * gmcmc_custom_conditional.cuh, GMCMC_REGISTER_CONDITIONAL; the plugin fixes dim).  State and samples: f64
+ * [n_chains, dim] / [C, n, dim] (core.rs:34-51).  Runs through gmcmc_run / gmcmc_run_device / gmcmc_run_stats /
+ * gmcmc_step / gmcmc_positions like the other samplers.  RNG: draw k (< 4) of coordinate i at transition s comes from
+ * Philox block (chain, s, stream 0, block 4 i + k): words (0, 1) -> the normal, words (2, 3) -> the uniform.  Unlike the
+ * reference, whose per-chain clones of a conditional share one RNG state (every chain then draws the same numbers,
+ * gibbs.rs:145-148), chains here are independent. */
+typedef enum { GMCMC_COND_CONSTANT = 0 /* params [c] */, GMCMC_COND_MIXTURE_XZ = 1 /* params [mu0, sigma0, mu1, sigma1, pi0] */ } gmcmc_conditional_kind;
+gmcmc_status gmcmc_gibbs_create(gmcmc_ctx*, gmcmc_conditional_kind kind, const double* params, size_t n_params,
+                                size_t n_chains, int dim, uint64_t chain_offset, const double* init_host,
+                                uint64_t seed, gmcmc_sampler** out);
+gmcmc_status gmcmc_gibbs_create_custom(gmcmc_ctx*, const char* plugin_path, const double* params, size_t n_params,
+                                       size_t n_chains, uint64_t chain_offset, const double* init_host,
+                                       uint64_t seed, gmcmc_sampler** out);
+/* Test hook: the next n_steps sweeps take the first normal and the first uniform of every (sweep, coordinate) from
+ * these f64 arrays [n_steps, n_chains, dim]. */
+gmcmc_status gmcmc_gibbs_inject(gmcmc_sampler*, const double* normals, const double* uniforms, size_t n_steps);
 /* ≙ NUTS::new (nuts.rs:156-190) / GenericNUTS::new (generic_nuts.rs:370-398), identity mass.
  * max_depth 0 = uncapped like the reference up to an internal safety cap of 20.
  * init_step_size <= 0: find_reasonable_epsilon (generic_nuts.rs:1025-1102) per chain. */

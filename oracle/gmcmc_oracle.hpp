@@ -391,6 +391,45 @@ inline MhIntStepInfo mh_int_step(const IntTarget& tgt, int* x, const signed char
 }
 
 // ------------------------------------------------------------------------------------------
+// Gibbs sweeps.  GibbsMarkovChain::step gibbs.rs:89-105 with the conditionals of the reference's own tests
+// (gibbs.rs:177-245).  Randomness is injected: normals[i] / uniforms[i] are the draws coordinate i's conditional takes.
+// ------------------------------------------------------------------------------------------
+enum GibbsCondKind { GC_CONSTANT = 0, GC_MIXTURE_XZ = 1 };
+
+struct GibbsConditional {
+  int kind = GC_CONSTANT;
+  double c = 0.0;                                         // ConstantConditional :177-186
+  double mu0 = 0, sigma0 = 1, mu1 = 0, sigma1 = 1, pi0 = 0.5;   // MixtureConditional :188-197
+  // MixtureConditional::normal_pdf :200-205
+  static double normal_pdf(double x, double mu, double sigma) {
+    const double var = sigma * sigma;
+    const double coeff = 1.0 / std::sqrt(2.0 * 3.14159265358979323846 * var);
+    const double dx = x - mu;
+    const double exp_val = std::exp(-(dx * dx) / (2.0 * var));
+    return coeff * exp_val;
+  }
+  // Conditional::sample :208-243
+  double sample(int i, const double* given, double normal, double uniform) const {
+    if (kind == GC_CONSTANT) return c;
+    if (i == 0) {
+      const double z = given[1];
+      return z < 0.5 ? mu0 + sigma0 * normal : mu1 + sigma1 * normal;
+    }
+    const double x = given[0];
+    const double p0 = pi0 * normal_pdf(x, mu0, sigma0);
+    const double p1 = (1.0 - pi0) * normal_pdf(x, mu1, sigma1);
+    const double total = p0 + p1;
+    const double prob_z1 = total > 0.0 ? p1 / total : 0.5;
+    return uniform < prob_z1 ? 1.0 : 0.0;
+  }
+};
+
+// one full sweep, gibbs.rs:96-99: coordinate i sees the already-updated coordinates 0 .. i - 1
+inline void gibbs_step(const GibbsConditional& cond, double* state, int dim, const double* normals, const double* uniforms) {
+  for (int i = 0; i < dim; ++i) state[i] = cond.sample(i, state, normals[i], uniforms[i]);
+}
+
+// ------------------------------------------------------------------------------------------
 // NUTS (identity mass matrix).  generic_nuts.rs:755-925, 1025-1102, 1153-1418
 // ------------------------------------------------------------------------------------------
 // Injected random stream, consumed in the reference's draw order:

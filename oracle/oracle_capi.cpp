@@ -367,6 +367,25 @@ double orc_int_target_logp(int kind, int dim, const double* params, const int* k
   return t.logp(k);
 }
 
+// ---- Gibbs sweeps (gibbs.rs:89-105) ----
+// x [C,d] f64 in/out; normals, uniforms [n,C,d]; samples f64 [C,n,d]
+void orc_gibbs_run(int kind, int dim, const double* params, size_t C, double* x, size_t n_steps, const double* normals,
+                   const double* uniforms, double* samples) {
+  GibbsConditional g;
+  g.kind = kind;
+  if (kind == GC_CONSTANT) g.c = params[0];
+  else { g.mu0 = params[0]; g.sigma0 = params[1]; g.mu1 = params[2]; g.sigma1 = params[3]; g.pi0 = params[4]; }
+  const size_t d = (size_t)dim;
+#pragma omp parallel for schedule(static)
+  for (long long ci = 0; ci < (long long)C; ++ci) {
+    const size_t c = (size_t)ci;
+    for (size_t s = 0; s < n_steps; ++s) {
+      gibbs_step(g, x + c * d, dim, normals + (s * C + c) * d, uniforms + (s * C + c) * d);
+      if (samples) for (size_t k = 0; k < d; ++k) samples[(c * n_steps + s) * d + k] = x[c * d + k];
+    }
+  }
+}
+
 // ---- stats ----
 void orc_split_rhat_mean_ess(const float* sample, size_t c, size_t n, size_t p, float* rhat, float* ess_out) { split_rhat_mean_ess(sample, c, n, p, rhat, ess_out); }
 void orc_autocov_bf(const float* x, size_t n, size_t d, float* out) { autocov_bf(x, n, d, out); }

@@ -224,6 +224,19 @@ def mh_int_run(kind, params, x0, steps, ln_u):
     return dict(x=x, samples=samples, accepted=acc, log_ratio=lr)
 
 
+def gibbs_run(kind, params, x0, normals, uniforms):
+    """Gibbs sweeps (gibbs.rs:89-105) with the reference tests' conditionals: x0 [C,d] f64, normals / uniforms [n,C,d]."""
+    x = np.array(x0, dtype=np.float64, copy=True, order="C")
+    Cn, d = x.shape
+    normals = np.ascontiguousarray(normals, np.float64)
+    uniforms = np.ascontiguousarray(uniforms, np.float64)
+    n = normals.shape[0]
+    samples = np.zeros((Cn, n, d), np.float64)
+    p = np.ascontiguousarray(params, np.float64)
+    lib().orc_gibbs_run(C.c_int(kind), C.c_int(d), _p(p), C.c_size_t(Cn), _p(x), C.c_size_t(n), _p(normals), _p(uniforms), _p(samples))
+    return dict(x=x, samples=samples)
+
+
 def int_target_logp(kind, params, k):
     k = np.ascontiguousarray(k, np.int32)
     p = np.ascontiguousarray(params, np.float64)

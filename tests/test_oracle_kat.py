@@ -287,3 +287,18 @@ def test_committed_golden_fixtures_match_oracle():
         r = O.hmc_run(O.ROSENBROCK_ND, [], np.asarray(cfg1["start"], dt), 0.01, 10, mom, ln_u)
         assert np.array_equal(r["q"].astype(np.float64), np.asarray(cfg1[name]["final_positions"]))
         assert r["accepted"].sum(0).tolist() == cfg1[name]["accepted_per_chain"]
+
+
+def test_gibbs_oracle_matches_reference_tests():
+    """gibbs.rs:248-262 (constant conditional: one sweep sets every coordinate) and :291-383 (mixture moments within 10 %)."""
+    x0 = np.zeros((2, 3))
+    r = O.gibbs_run(0, [7.0], x0, np.zeros((1, 2, 3)), np.zeros((1, 2, 3)))
+    assert np.array_equal(r["x"], np.full((2, 3), 7.0))
+    rng = np.random.default_rng(0)
+    for mu0, s0, mu1, s1, pi0 in ((-2.0, 1.0, 3.0, 1.5, 0.5), (-42.0, 69.0, 1.0, 2.0, 0.123)):
+        n, Cn = 20000, 8
+        r = O.gibbs_run(1, [mu0, s0, mu1, s1, pi0], np.zeros((Cn, 2)), rng.standard_normal((n, Cn, 2)), rng.random((n, Cn, 2)))
+        x = r["samples"][:, 1000:, 0].ravel()
+        mean = pi0 * mu0 + (1 - pi0) * mu1
+        var = pi0 * (s0 ** 2 + (mu0 - mean) ** 2) + (1 - pi0) * (s1 ** 2 + (mu1 - mean) ** 2)
+        assert abs(x.mean() - mean) < abs(mean) / 10 and abs(x.var(ddof=1) - var) < var / 10
