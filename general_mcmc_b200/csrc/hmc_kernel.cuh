@@ -543,6 +543,104 @@ __device__ __forceinline__ T eval_kick(TagRosenbrockND, const T (&x)[EPL], T (&p
   return T(0);
 }
 
+// ------------------------------------------------------------------------------------------------
+// RosenbrockND, f32, fast mode, exact-fit decomposition: the (L - 1) inner leapfrogs on PACKED pairs — an experiment,
+// OFF by default because it measured slower.
+// The scalar loop above is bound by the instruction issue rate (FFMA is 77 % of the issued instructions, issue slots
+// 84 % busy, FMA pipe 73 %: profiles/r2_hmc_run_kernel_full.txt).  Blackwell's fma.rn.f32x2 (SASS FFMA2) does two FMAs
+// per issued instruction, so the same six FMAs per coordinate need half the issue slots: 108 instead of 160 instructions
+// per leapfrog (72 FFMA2 with immediate / broadcast operands, 22 MOV, 6 FFMA).  Coordinates j and j + H (H = EPL / 2) of a
+// lane form pair j: the "next coordinate" of a pair is then simply the next pair, and the stencil needs no re-packing
+// except at the lane's two ends.  The loop tracks y = -q: with s_j = y_j^2 + y_{j+1} (= -t_j), a' = 400 s + 2,
+// low = y a' + 2, g = 200 s_{j-1} + low every operation is a plain a * b + c (f32x2 has no operand negation), and each
+// result is the exact negative / equal of the scalar formulation's (round-to-nearest is symmetric), so the trajectory is
+// bit-identical to the scalar loop's (the whole GPU suite passes with it on).
+// Measured on B200 (65,536 chains, d = 100, L = 32): 57.0 us per transition against 53.4 us for the scalar loop
+// (3.62e10 vs 3.85e10 grad-evals/s): FFMA2 does not issue at the rate of two FFMAs (tools/microbench_fp32.cu: the
+// packed form sustains 47 TFLOP/s where scalar FFMA with constant operands sustains 72), so halving the instruction
+// count buys nothing.
+// ------------------------------------------------------------------------------------------------
+#ifndef GM_K1_PACKED
+#define GM_K1_PACKED 0
+#endif
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ float lo2(unsigned long long v) { float lo, hi; upk2(v, lo, hi); return lo; }
+__device__ __forceinline__ float hi2(unsigned long long v) { float lo, hi; upk2(v, lo, hi); return hi; }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// n_iter times: q += eps p ; p += eps grad(q)   (the merged-kick inner loop of the fast mode)
+template <int EPL>
+__device__ __forceinline__ void rosen_leapfrogs_packed(float (&q)[EPL], float (&p)[EPL], const float eps, const uint32_t n_iter,
+                                                       const Lane& ln) {
+  constexpr int H = EPL / 2;
+  constexpr bool ODD = (EPL & 1) != 0;
+  unsigned long long y2[H], p2[H];
+  float ys = 0.f, ps = 0.f;          // the odd coordinate 2H
+#pragma unroll
+  for (int k = 0; k < H; ++k) { y2[k] = pk2(-q[k], -q[k + H]); p2[k] = pk2(p[k], p[k + H]); }
+  if constexpr (ODD) { ys = -q[2 * H]; ps = p[2 * H]; }
+  const float neps = -eps;
+  const unsigned long long c_neps = pk2(neps, neps), c_eps = pk2(eps, eps);
+  const unsigned long long c400 = pk2(400.f, 400.f), c200 = pk2(200.f, 200.f), c2 = pk2(2.f, 2.f);
+  for (uint32_t it = 0; it < n_iter; ++it) {
+    // drift: y -= eps p
+#pragma unroll
+    for (int k = 0; k < H; ++k) y2[k] = fma2(p2[k], c_neps, y2[k]);
+    if constexpr (ODD) ys = fmaf(ps, neps, ys);
+    const float y_next_lane = __shfl_down_sync(kFull, lo2(y2[0]), 1);
+    // s_j = y_j^2 + y_{j+1}; the last coordinate of the chain has no such term
+    unsigned long long s2[H];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k + 1 < H; ++k) s2[k] = fma2(y2[k], y2[k], y2[k + 1]);
+    if constexpr (ODD) {
+      s2[H - 1] = fma2(y2[H - 1], y2[H - 1], pk2(hi2(y2[0]), ys));
+      ss = fmaf(ys, ys, y_next_lane);
+      if (ln.last) ss = 0.f;
+    } else {
+      s2[H - 1] = fma2(y2[H - 1], y2[H - 1], pk2(hi2(y2[0]), y_next_lane));
+      if (ln.last) s2[H - 1] = pk2(lo2(s2[H - 1]), 0.f);
+    }
+    float prev = __shfl_up_sync(kFull, ODD ? ss : hi2(s2[H - 1]), 1);
+    if (ln.first) prev = 0.f;
+    // gradient straight into the momentum: a' = 400 s + 2, low = y a' + 2, g = 200 s_{j-1} + low, p += eps g
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      const unsigned long long a2 = fma2(s2[k], c400, c2);
+      unsigned long long low = fma2(y2[k], a2, c2);
+      if constexpr (!ODD) { if (k == H - 1 && ln.last) low = pk2(lo2(low), 0.f); }
+      const unsigned long long sp = (k == 0) ? pk2(prev, lo2(s2[H - 1])) : s2[k - 1];
+      const unsigned long long g2 = fma2(sp, c200, low);
+      p2[k] = fma2(g2, c_eps, p2[k]);
+    }
+    if constexpr (ODD) {
+      const float a1 = fmaf(ss, 400.f, 2.f);
+      float low = fmaf(ys, a1, 2.f);
+      if (ln.last) low = 0.f;
+      const float g1 = fmaf(hi2(s2[H - 1]), 200.f, low);
+      ps = fmaf(g1, eps, ps);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < H; ++k) {
+    float a, b;
+    upk2(y2[k], a, b); q[k] = -a; q[k + H] = -b;
+    upk2(p2[k], a, b); p[k] = a; p[k + H] = b;
+  }
+  if constexpr (ODD) { q[2 * H] = -ys; p[2 * H] = ps; }
+}
+
 template <class T>
 __host__ inline TParams<T> make_tparams(const TargetDesc& td) {
   TParams<T> tp;
@@ -803,10 +901,14 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
       // merged kicks: p += eps/2 g ; (q += eps p ; p += eps grad(q)) x (L-1) ; q += eps p ; p += eps/2 grad(q)
       if (have_logp_cur) { eval_kick<T, EPL, PADDED, false, 1>(TAG{}, q, p, half, ln, a.tp, row); logp0 = logp_cur; }
       else logp0 = eval_kick<T, EPL, PADDED, true, 1>(TAG{}, q, p, half, ln, a.tp, row);
-      for (uint32_t l = 0; l + 1 < a.L; ++l) {
+      if constexpr (GM_K1_PACKED && std::is_same<TAG, TagRosenbrockND>::value && sizeof(T) == 4 && !PADDED && EPL >= 4) {
+        rosen_leapfrogs_packed<EPL>(q, p, eps, a.L - 1, ln);
+      } else {
+        for (uint32_t l = 0; l + 1 < a.L; ++l) {
 #pragma unroll
-        for (int j = 0; j < EPL; ++j) q[j] += eps * p[j];
-        eval_kick<T, EPL, PADDED, false, 1>(TAG{}, q, p, eps, ln, a.tp, row);
+          for (int j = 0; j < EPL; ++j) q[j] += eps * p[j];
+          eval_kick<T, EPL, PADDED, false, 1>(TAG{}, q, p, eps, ln, a.tp, row);
+        }
       }
 #pragma unroll
       for (int j = 0; j < EPL; ++j) q[j] += eps * p[j];
