@@ -904,11 +904,17 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
       if constexpr (GM_K1_PACKED && std::is_same<TAG, TagRosenbrockND>::value && sizeof(T) == 4 && !PADDED && EPL >= 4) {
         rosen_leapfrogs_packed<EPL>(q, p, eps, a.L - 1, ln);
       } else {
-        for (uint32_t l = 0; l + 1 < a.L; ++l) {
+        // The loop is bound by register-file reads (a three-register FFMA sustains 47 of the 72 TFLOP/s a constant-operand
+        // FFMA does, tools/microbench_fp32.cu).  When the step size is the launch-wide value the host passed by value, the
+        // drift and the kick take it as a constant-bank operand: 53.3 -> 51.0 us per transition at config 4's shape.
+        auto inner = [&](const T eps_l) {
+          for (uint32_t l = 0; l + 1 < a.L; ++l) {
 #pragma unroll
-          for (int j = 0; j < EPL; ++j) q[j] += eps * p[j];
-          eval_kick<T, EPL, PADDED, false, 1>(TAG{}, q, p, eps, ln, a.tp, row);
-        }
+            for (int j = 0; j < EPL; ++j) q[j] += eps_l * p[j];
+            eval_kick<T, EPL, PADDED, false, 1>(TAG{}, q, p, eps_l, ln, a.tp, row);
+          }
+        };
+        if (a.eps == nullptr && !per_chain_da) inner(a.eps_val); else inner(eps);
       }
 #pragma unroll
       for (int j = 0; j < EPL; ++j) q[j] += eps * p[j];
