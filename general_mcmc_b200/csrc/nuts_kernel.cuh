@@ -181,6 +181,9 @@ __device__ __forceinline__ void chain_sum_fn2(const Lane& ln, F1 f1, F2 f2, T& o
   }
 }
 
+#ifndef GM_NUTS_PIN_TID
+#define GM_NUTS_PIN_TID 0   // measured: 1.00e9 vs 1.02e9 leapfrogs/s with the index pinned — the rematerialisation is the cheaper choice
+#endif
 #ifndef GM_NUTS_MINB
 #define GM_NUTS_MINB 4   // 128 registers per thread: no spills, one more CTA per SM to hide the serial per-pass latency (+6 %)
 #endif
@@ -238,16 +241,23 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
   // all its transitions, takes the next chain from a global queue — tree sizes are heavy-tailed (a few chains build
   // 20x larger trees), so a static chain -> lane-group assignment would leave most of the GPU waiting for them.
   const int lpc = LPC > 0 ? LPC : a.lpc;
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  // At 125 registers the compiler rematerialises the addresses derived from the thread index inside the loop (11 % of the
+  // issued instructions: profiles/r2_nuts_run_kernel_full.txt); pinning the index in a register (GM_NUTS_PIN_TID) was
+  // measured 2 % slower.
+  unsigned tix = threadIdx.x;
+#if GM_NUTS_PIN_TID
+  asm volatile("mov.b32 %0, %0;" : "+r"(tix));
+#endif
+  const int tid = blockIdx.x * blockDim.x + (int)tix;
   const Lane ln = make_lane<EPL>(tid, lpc, a.d);
   const size_t slot_id = (size_t)(tid / lpc);      // workspace row of this lane group
   size_t chain = slot_id;
   bool active = chain < a.n_chains;
-  const int lane = threadIdx.x & 31;
+  const int lane = (int)(tix & 31u);
   const int chains_in_warp = 32 / lpc;
   const int chain_in_warp = lane / lpc;
   const size_t warp_elems = (size_t)chains_in_warp * a.d_pad;
-  T* warp_pos = smem + (size_t)(threadIdx.x >> 5) * 2 * warp_elems;
+  T* warp_pos = smem + (size_t)(tix >> 5) * 2 * warp_elems;
   T* pos_row = warp_pos + (size_t)chain_in_warp * a.d_pad;
   T* row = warp_pos + warp_elems + (size_t)chain_in_warp * a.d_pad;
   unsigned long long gchain = a.chain_offset + chain;
@@ -268,21 +278,21 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
     T* smu = smem + smem_off;
     const int K = a.tp.n_comp;
     const T* gmu = a.tp.dp + K;
-    for (int i = threadIdx.x; i < K * lpc * EPLP; i += blockDim.x) {
+    for (int i = (int)tix; i < K * lpc * EPLP; i += blockDim.x) {
       const int k = i / (lpc * EPLP), rem = i - k * (lpc * EPLP);
       const int part = rem / EPLP, j = rem - part * EPLP;
       const int col = part * EPL + j;
       smu[i] = (j < EPL && col < a.d) ? gmu[(size_t)k * a.d + col] : T(0);
     }
     T* slw = smu + (size_t)K * lpc * EPLP;
-    if ((int)threadIdx.x < K) slw[threadIdx.x] = a.tp.dp[K + (size_t)K * a.d + threadIdx.x];
+    if ((int)tix < K) slw[tix] = a.tp.dp[K + (size_t)K * a.d + tix];
     tp.smem_mu = smu;
     tp.smem_logw = slw;
     smem_off += ((size_t)K * lpc * EPLP + kMaxComp + 3) / 4 * 4;
   }
-  T* hot = smem + smem_off + (size_t)(threadIdx.x / lpc) * H_COUNT * wd;
+  T* hot = smem + smem_off + (size_t)(tix / (unsigned)lpc) * H_COUNT * wd;
   // uniform ring of this chain: 2 lpc doubles (kHmcBlock * 2 doubles per CTA), after the hot vectors
-  double* s_unif = reinterpret_cast<double*>(smem + smem_off + (size_t)kHmcBlock * H_COUNT * EPLP) + (size_t)(threadIdx.x / lpc) * 2 * lpc;
+  double* s_unif = reinterpret_cast<double*>(smem + smem_off + (size_t)kHmcBlock * H_COUNT * EPLP) + (size_t)(tix / (unsigned)lpc) * 2 * lpc;
   __syncthreads();
 
   T eps = T(1), eps_bar = T(1), h_bar = T(0), mu = T(0);

@@ -224,7 +224,10 @@ struct WarpFft {
   static constexpr int N = 1 << LOG2N;
   static constexpr int NP8 = LOG2N / 3;                 // radix-8 passes
   static constexpr int RL = 1 << (LOG2N % 3);           // radix of the final short pass (1: none)
-  static constexpr int PADN = N + N / 8;
+  // plane length: one pad float per 8 (the passes' strides) plus 2, so that a parameter's plane pair starts 4 banks after
+  // its neighbour's: the tile loader's stores (8 parameters x 4 consecutive draws per warp instruction) then hit 32 different
+  // banks — with N + N / 8 every plane started on bank 0 and those stores were 8-way conflicts.
+  static constexpr int PADN = N + N / 8 + 2;
   static constexpr int LASTR = RL > 1 ? RL : 8;
   static constexpr int NB_LAST = (N / LASTR + 31) / 32;
   static constexpr int ACC = LASTR * NB_LAST;           // |Z|^2 accumulators per lane
@@ -466,7 +469,7 @@ stats_accumulate_warp(const TIN* __restrict__ samples, size_t C, size_t n, int p
   }
 }
 
-static size_t warp_fft_smem(size_t N) { return (size_t)kWarpFftWarps * 2 * (N + N / 8) * sizeof(float); }
+static size_t warp_fft_smem(size_t N) { return (size_t)kWarpFftWarps * 2 * (N + N / 8 + 2) * sizeof(float); }
 
 template <class TIN>
 cudaError_t launch_accumulate_warp(const StatsLaunch& S, cudaStream_t st) {
