@@ -400,24 +400,33 @@ stats_accumulate_warp(const TIN* __restrict__ samples, size_t C, size_t n, int p
   constexpr int NLD = (N / 2 + 31) / 32;
   const int lj = lane & 7, lt0 = threadIdx.x >> 3;
   float pa[NLD], pb[NLD];
+  // addresses: one uniform base per (chain, half) and a 32-bit element offset per thread that advances by 32 draws per
+  // load (a chain's [n, p] block is far below 2^32 elements) — the 64-bit multiply per load of the first version was a
+  // fifth of the kernel's instructions
+  const unsigned row_step = 32u * (unsigned)p;
+  const unsigned off0 = (unsigned)lt0 * (unsigned)p + (unsigned)lj;
+  const bool lane_on = lj < np;
   auto prefetch = [&](size_t c) {
-    const TIN* src0 = samples + c * n * (size_t)p + k0 + lj;
-    const TIN* src1 = src0 + off2 * (size_t)p;
+    const TIN* base0 = samples + c * n * (size_t)p + k0;
+    const TIN* base1 = base0 + off2 * (size_t)p;
+    unsigned off = off0;
 #pragma unroll
     for (int m = 0; m < NLD; ++m) {
-      const int t = lt0 + 32 * m;
-      const bool on = lj < np && t < half;
-      pa[m] = on ? (float)src0[(size_t)t * p] : 0.f;
-      pb[m] = on ? (float)src1[(size_t)t * p] : 0.f;
+      const bool on = lane_on && (lt0 + 32 * m) < half;
+      pa[m] = on ? (float)base0[off] : 0.f;
+      pb[m] = on ? (float)base1[off] : 0.f;
+      off += row_step;
     }
   };
   auto commit = [&]() {
     float* pr = planes + (size_t)lj * 2 * PADN;
     float ls0 = 0.f, ls1 = 0.f;
+    // draws at or beyond `half` are stored too (as the zeros prefetch left): t <= 32 NLD - 1 < N, inside the plane, and the
+    // first pass masks them anyway — no branch per store
 #pragma unroll
     for (int m = 0; m < NLD; ++m) {
-      const int t = lt0 + 32 * m;
-      if (t < half) { const int pt = padi(t); pr[pt] = pa[m]; pr[PADN + pt] = pb[m]; }
+      const int pt = padi(lt0 + 32 * m);
+      pr[pt] = pa[m]; pr[PADN + pt] = pb[m];
       ls0 += pa[m]; ls1 += pb[m];
     }
     ls0 += __shfl_xor_sync(0xffffffffu, ls0, 8); ls1 += __shfl_xor_sync(0xffffffffu, ls1, 8);
