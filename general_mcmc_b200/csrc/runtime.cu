@@ -116,6 +116,7 @@ struct gmcmc_ctx {
   // work buffers of the device statistics (split R-hat / ESS), kept between calls: a call used to pay six cudaMalloc /
   // cudaFree pairs, each an implicit device synchronisation
   void* stats_arena = nullptr; size_t stats_arena_bytes = 0;
+  void* tracker_arena = nullptr; size_t tracker_arena_bytes = 0;   // K6 work buffers (per-chain means, results), cached
   size_t stats_tw_n = 0;               // padded length whose twiddles sit at the head of the arena
   float* stats_host = nullptr; size_t stats_host_n = 0;   // pinned result buffer
   int rank = 0, world = 1;
@@ -963,6 +964,7 @@ gmcmc_status gmcmc_ctx_destroy(gmcmc_ctx* c) {
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   cudaFree(c->stats_arena);
+  cudaFree(c->tracker_arena);
   if (c->stats_host) cudaFreeHost(c->stats_host);
   delete c;
   return GMCMC_OK;
@@ -2007,17 +2009,29 @@ gmcmc_status gmcmc_tracker_stats(gmcmc_ctx* ctx, const void* samples, size_t C, 
                                  int on_device, float* rhat, float* max_rhat, float* p_accept) {
   GM_REQUIRE(ctx && samples, "null argument");
   GM_REQUIRE(C >= 2 && n >= 2 && p >= 1, "the tracker R-hat needs C >= 2 chains and n >= 2 draws (got %zu, %zu)", C, n);
-  TempDevice tmp, mean, mean_sq, out;
+  GM_CU(cudaSetDevice(ctx->device));
+  TempDevice tmp;
   const void* d = nullptr;
   GM_TRY(stage_samples(ctx, samples, C * n * p * esize(dtype), on_device, &tmp, &d));
-  GM_CU(cudaMalloc(&mean.p, C * p * sizeof(float)));
-  GM_CU(cudaMalloc(&mean_sq.p, C * p * sizeof(float)));
-  GM_CU(cudaMalloc(&out.p, (p + 1) * sizeof(float)));
-  cudaError_t e = launch_tracker(d, dtype, C, n, (int)p, (float*)mean.p, (float*)mean_sq.p, (float*)out.p, (float*)out.p + p,
-                                 ctx->stream);
+  // work buffers live in a cached arena (a progress display polls this entry point; three cudaMalloc / cudaFree pairs per
+  // call cost more than the kernels): per-chain mean | mean of squares | results
+  auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t b_mean = up(C * p * sizeof(float)), b_out = up((p + 1) * sizeof(float));
+  const size_t need = 2 * b_mean + b_out;
+  if (need > ctx->tracker_arena_bytes) {
+    GM_CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->tracker_arena);
+    ctx->tracker_arena = nullptr; ctx->tracker_arena_bytes = 0;
+    GM_CU(cudaMalloc(&ctx->tracker_arena, need));
+    ctx->tracker_arena_bytes = need;
+  }
+  float* mean = (float*)ctx->tracker_arena;
+  float* mean_sq = (float*)((char*)ctx->tracker_arena + b_mean);
+  float* out = (float*)((char*)ctx->tracker_arena + 2 * b_mean);
+  cudaError_t e = launch_tracker(d, dtype, C, n, (int)p, mean, mean_sq, out, out + p, ctx->stream);
   if (e != cudaSuccess) return fail(GMCMC_ERR_CUDA, "tracker launch failed: %s", cudaGetErrorString(e));
   std::vector<float> host(p + 1);
-  GM_CU(cudaMemcpyAsync(host.data(), out.p, (p + 1) * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  GM_CU(cudaMemcpyAsync(host.data(), out, (p + 1) * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   GM_CU(cudaStreamSynchronize(ctx->stream));
   if (rhat) std::memcpy(rhat, host.data(), p * sizeof(float));
   if (max_rhat) {   // MultiChainTracker::max_rhat: reduce(f32::max), which skips NaN operands
