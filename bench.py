@@ -648,12 +648,40 @@ def leg_nuts(env, steps, warmup, chains, want_cpu=True):
     roof.update(traffic_fields("nuts_mixture", chains))
     e2e, _ = e2e_leg(env, s, chains, DIM, np.float32, 4, 3, counter_units=True)
     e2e["unit"] = "grad-evals/s"
+    # ---- min-ESS/sec (BASELINE metric, second half) on config 5 as stated: a fresh sampler, 200 warm-up + 200 collected
+    # transitions inside the events, ESS / R-hat of the 200 draws reduced on the device over all ranks' chains
+    L, lib = env.L, env.lib
+    s2 = gm.NUTS(tgt, q0, 0.8, seed=43, ctx=ctx, chain_offset=rank * chains, max_depth=10)
+    n_ess = 200
+    s2.reserve(n_ess)
+    holder = {}
+    c_a = s2.counters()
+    run_ms = env.timed(lambda: holder.setdefault("p", s2.run_device(n_ess, 200)))
+    c_b = s2.counters()
+    st = L.RunStatsC()
+    for _ in range(2):
+        ctx.synchronize()
+        t_s0 = time.perf_counter()
+        L.check(lib.gmcmc_run_stats_from(ctx._h, C.c_void_p(holder["p"]), C.c_size_t(chains), C.c_size_t(n_ess), C.c_size_t(DIM),
+                                         L.F32, 1, C.byref(st)))
+        ctx.synchronize()
+        t_s1 = time.perf_counter()
+    stats_ms = env.max_over_ranks((t_s1 - t_s0) * 1e3)
+    converged = st.rhat_std.max < 1.01
+    ess = {"min_ess": st.ess.min, "median_ess": st.ess.median,
+           "min_ess_per_sec": st.ess.min / (run_ms * 1e-3) if converged else None,
+           "draws_per_chain": n_ess, "warmup_transitions": 200, "chains_total": chains * world, "run_ms": run_ms,
+           "leapfrogs_per_sec_incl_warmup": env.sum_over_ranks(c_b.grad_evals - c_a.grad_evals) / (run_ms * 1e-3),
+           "split_rhat_max": st.rhat_std.max, "converged": bool(converged), "device_stats_ms": stats_ms,
+           "note": "config 5 as stated (200 warm-up + 200 collected transitions, both inside the timed region); ESS per "
+                   "stats.rs:523-573 over all ranks' chains; seconds = the whole run, burn-in included, stats excluded (SURVEY 8d)"}
+    s2.close()
     cpu = None
     if rank == 0 and world == 1 and want_cpu:
         r, th, sample = cpu_nuts_rate(10.0)
         cpu = {"value": r, "unit": "grad-evals/s", "cores": th, "kind": "port", "sample": sample}
     out = {"metric": "leapfrog_grad_evals_per_sec", "value": value, "unit": "grad-evals/s", "ms_per_step": ms / steps, "dtype": "f32",
-           "steps": steps,
+           "steps": steps, "ess": ess,
            "config": {"workload": WORKLOAD_NAMES["nuts_mixture"] % (DIM, chains), "chains_per_gpu": chains,
                       "transitions_per_launch": per_launch, "step_size": c1.step_size,
                       "accept_rate": (c1.accepts - c0.accepts) / max(1, c1.transitions - c0.transitions),
