@@ -116,7 +116,7 @@ template <class T>
 struct TParams {          // per-launch target parameters in T
   T sp[kMaxScalarParams];
   const T* dp;            // device block (dense Gaussian: mu[d], P[d*d], nc; mixture: w[K], mu[K*d], ln w[K])
-  const T* smem_mu;       // mixture means staged in shared memory, lane-padded [K][lpc][roundup(EPL, 4)], or null
+  const T* smem_mu;       // mixture means staged in shared memory, lane-padded [K][roundup(EPL, 4) / VN][lpc][VN] (16-byte units), or null
   const T* smem_logw;     // mixture log weights staged in shared memory [K], or null
   int n_comp;
   // derived for DiffableGaussian2D (distributions.rs:229-253)
@@ -276,11 +276,11 @@ __device__ __forceinline__ void mixture_mean_slice(T (&m)[EPL], const TParams<T>
     using V = typename VecOf<T>::type;
     constexpr int VN = VecOf<T>::n;
     constexpr int EPLP = (EPL + 3) / 4 * 4;
-    const V* s = reinterpret_cast<const V*>(tp.smem_mu + ((size_t)k * ln.lpc + ln.part) * EPLP);
+    const V* s = reinterpret_cast<const V*>(tp.smem_mu + (size_t)k * ln.lpc * EPLP) + ln.part;   // unit i of lane `part` at i * lpc + part
 #pragma unroll
     for (int i = 0; i < EPLP / VN; ++i) {
       if (i * VN < EPL) {
-        const V v = s[i];
+        const V v = s[i * ln.lpc];
         if constexpr (VN == 4) {
           m[i * 4] = v.x;
           if (i * 4 + 1 < EPL) m[i * 4 + 1 < EPL ? i * 4 + 1 : 0] = v.y;

@@ -81,9 +81,11 @@ struct NutsArgs {
 
 enum NutsPhase : int { NP_START = 0, NP_LEAF = 1, NP_END = 2, NP_DONE = 3 };
 
-// Workspace vectors are stored lane-padded: lane `part` owns EPLP = roundup(EPL, 4) consecutive elements at
-// part * EPLP, so every slice is 16-byte aligned and moves as float4 / double2 (3.5x fewer LSU instructions than
-// element-wise accesses at EPL = 25).
+// Workspace vectors are stored lane-padded in 16-byte units (float4 / double2): lane `part` owns EPLP = roundup(EPL, 4)
+// elements, unit i of lane `part` at unit index i * lpc + part — consecutive lanes are 16 bytes apart, so a quarter-warp's
+// LDS.128 / STS.128 covers every bank once and the global copies are fully coalesced (3.5x fewer LSU instructions than
+// element-wise accesses at EPL = 25; with the first layout, part * EPLP + i, lanes were 32 bytes apart and every shared
+// access was a 2-way bank conflict: 7e8 conflict cycles per launch in profiles/r2_nuts_run_kernel_full.txt).
 template <int EPL> struct Eplp { static constexpr int value = (EPL + 3) / 4 * 4; };
 
 template <class T, int EPL>
@@ -91,13 +93,13 @@ __device__ __forceinline__ void load_slice(T (&dst)[EPL], const T* src, const La
   using V = typename VecOf<T>::type;
   constexpr int VN = VecOf<T>::n;
   constexpr int EPLP = Eplp<EPL>::value;
-  const V* s = reinterpret_cast<const V*>(src + (size_t)ln.part * EPLP);
+  const V* s = reinterpret_cast<const V*>(src) + ln.part;
 #pragma unroll
   for (int i = 0; i < EPLP / VN; ++i) {
     if (i * VN < EPL) {
       T e[VN];
       if (on) {
-        const V v = s[i];
+        const V v = s[i * ln.lpc];
         if constexpr (VN == 4) { e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w; }
         else { e[0] = v.x; e[1] = v.y; }
       }
@@ -112,7 +114,7 @@ __device__ __forceinline__ void store_slice(T* dst, const T (&src)[EPL], const L
   using V = typename VecOf<T>::type;
   constexpr int VN = VecOf<T>::n;
   constexpr int EPLP = Eplp<EPL>::value;
-  V* d = reinterpret_cast<V*>(dst + (size_t)ln.part * EPLP);
+  V* d = reinterpret_cast<V*>(dst) + ln.part;
   if (!on) return;
 #pragma unroll
   for (int i = 0; i < EPLP / VN; ++i) {
@@ -125,7 +127,7 @@ __device__ __forceinline__ void store_slice(T* dst, const T (&src)[EPL], const L
       } else {
         v.x = src[i * 2]; v.y = (i * 2 + 1 < EPL) ? src[i * 2 + 1 < EPL ? i * 2 + 1 : 0] : T(0);
       }
-      d[i] = v;
+      d[i * ln.lpc] = v;
     }
   }
 }
@@ -201,11 +203,11 @@ __device__ __forceinline__ void load_slice_raw(T (&dst)[EPL], const T* src, cons
   using V = typename VecOf<T>::type;
   constexpr int VN = VecOf<T>::n;
   constexpr int EPLP = Eplp<EPL>::value;
-  const V* s = reinterpret_cast<const V*>(src + (size_t)ln.part * EPLP);
+  const V* s = reinterpret_cast<const V*>(src) + ln.part;
 #pragma unroll
   for (int i = 0; i < EPLP / VN; ++i) {
     if (i * VN < EPL) {
-      const V v = s[i];
+      const V v = s[i * ln.lpc];
       if constexpr (VN == 4) {
         dst[i * 4] = v.x;
         if (i * 4 + 1 < EPL) dst[i * 4 + 1 < EPL ? i * 4 + 1 : 0] = v.y;
@@ -282,7 +284,8 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       const int k = i / (lpc * EPLP), rem = i - k * (lpc * EPLP);
       const int part = rem / EPLP, j = rem - part * EPLP;
       const int col = part * EPL + j;
-      smu[i] = (j < EPL && col < a.d) ? gmu[(size_t)k * a.d + col] : T(0);
+      constexpr int VN = VecOf<T>::n;      // unit layout of the lane-padded vectors: unit (j / VN) of lane `part` at (j / VN) * lpc + part
+      smu[(size_t)k * lpc * EPLP + ((j / VN) * lpc + part) * VN + (j % VN)] = (j < EPL && col < a.d) ? gmu[(size_t)k * a.d + col] : T(0);
     }
     T* slw = smu + (size_t)K * lpc * EPLP;
     if ((int)tix < K) slw[tix] = a.tp.dp[K + (size_t)K * a.d + tix];
