@@ -46,6 +46,7 @@ N_LEAPFROG = 32
 STEP_SIZE = 0.01
 TRANSITIONS_PER_LAUNCH = 100
 E2E_TRANSITIONS = 16
+E2E_VARIANT_TRANSITIONS = 128   # draws per call of the stats-only / device-resident end-to-end contracts
 # Algorithmic FP32 work per gradient evaluation per chain: 6 FMAs per coordinate (t_i, 400 t_i - 2, x_i(.) + 2,
 # - 200 t_{i-1} + (.), p += eps g, q += eps p) = 12 flop x d.  SURVEY 8(d)'s 21 d counted mul and add separately and a
 # log-density per leapfrog; the log density is only needed at the two trajectory ends (kernel K1).
@@ -418,6 +419,15 @@ def e2e_leg(env, s, chains, dim, out_dtype, e2e_T, calls, units_per_call=None, c
             units = units_per_call * calls * env.world
         return units / secs, secs
 
+    def measure_units(call, n_calls, units_call):
+        nonlocal calls, units_per_call
+        keep = (calls, units_per_call)
+        calls, units_per_call = n_calls, units_call
+        try:
+            return measure(call)
+        finally:
+            calls, units_per_call = keep
+
     value, secs = measure(lambda: s.run(e2e_T, 0, out=host_out))
     h2d = init_host.nbytes / e2e_T
     d2h = host_out.nbytes / e2e_T
@@ -427,19 +437,26 @@ def e2e_leg(env, s, chains, dim, out_dtype, e2e_T, calls, units_per_call=None, c
                    "call, which bounds this figure"}
     extra = {}
     if variants:
+        # the two contracts that do not move the sample tensor are measured at a call length a progress display or a
+        # run_positions user would use (E2E_VARIANT_TRANSITIONS draws per call; RunStats of 16 draws is not a use case)
+        vT = E2E_VARIANT_TRANSITIONS
+        v_units = units_per_call / e2e_T * vT
+        s.reserve(vT)
         st = L.RunStatsC()
-        v2, _ = measure(lambda: L.check(lib.gmcmc_run_stats(s._h, C.c_size_t(e2e_T), C.c_size_t(0), None, L.dtype_code(out_dtype),
-                                                             C.byref(st))))
-        extra["e2e_stats_only"] = {"value": v2, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 60.0 / e2e_T,
+        v2, _ = measure_units(lambda: L.check(lib.gmcmc_run_stats(s._h, C.c_size_t(vT), C.c_size_t(0), None, L.dtype_code(out_dtype),
+                                                                   C.byref(st))), 3, v_units)
+        extra["e2e_stats_only"] = {"value": v2, "h2d_bytes_per_step": init_host.nbytes / vT, "d2h_bytes_per_step": 60.0 / vT,
+                                   "transitions_per_call": vT, "calls": 3,
                                    "api": "gmcmc_set_positions + gmcmc_run_stats(out = NULL) ≙ run_progress: RunStats only "
                                           "(device ESS / split R-hat over all ranks' chains) crosses PCIe"}
         pos = np.empty((chains, dim), s.dtype)
 
         def dev_call():
-            s.run_device(e2e_T, 0)
+            s.run_device(vT, 0)
             L.check(lib.gmcmc_positions(s._h, L.ptr(pos)))
-        v3, _ = measure(dev_call)
-        extra["e2e_device"] = {"value": v3, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": pos.nbytes / e2e_T,
+        v3, _ = measure_units(dev_call, 3, v_units)
+        extra["e2e_device"] = {"value": v3, "h2d_bytes_per_step": init_host.nbytes / vT, "d2h_bytes_per_step": pos.nbytes / vT,
+                               "transitions_per_call": vT, "calls": 3,
                                "api": "gmcmc_set_positions + gmcmc_run_device + gmcmc_positions ≙ run_positions "
                                       "(batched_hmc.rs:115-123): samples stay on the GPU, final positions come back"}
     env.free_pinned(host_ptr)
