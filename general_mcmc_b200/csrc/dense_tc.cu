@@ -79,10 +79,16 @@ constexpr int kCluster = GM_TC_CLUSTER;
 #ifndef GM_TC_EPI_PREFETCH
 #define GM_TC_EPI_PREFETCH 0
 #endif
+#ifndef GM_TC_EPI_PIPE
+#define GM_TC_EPI_PIPE 0      // 1: fast epilogue blocks keep the p / delta loads of both 16-row halves in flight across the TMEM read and
+                              // refill them block to block (see the epilogue) — measured SLOWER (19.1 vs 16.4 ms per transition): at the 128
+                              // registers a 480-thread CTA allows, the 64 load registers spill and the spill stores wait for the loads
+#endif
 #ifndef GM_TC_EPI_WARPS
 #define GM_TC_EPI_WARPS 8
 #endif
 constexpr int kEpiWarps = GM_TC_EPI_WARPS;   // multiple of 4: kEpiWarps / 4 warps per TMEM lane quarter, interleaved over the 32-column blocks
+constexpr int kTrFloats = GM_TC_EPI_PIPE ? 32 * 32 : 16 * 33;   // per epilogue warp: the accumulator rows in transit (a 32 x 32 block, or 16 rows of 33)
 constexpr int kCvtWarps = 4;
 constexpr int kFirstCvtWarp = 3, kFirstEpiWarp = kFirstCvtWarp + kCvtWarps;
 constexpr int kGemmThreads = 32 * (kFirstEpiWarp + kEpiWarps);
@@ -185,6 +191,21 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 16 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // shared-memory matrix descriptor: K-major operand tile, rows of kTileK floats, swizzle width = row width (8-row atoms)
@@ -416,7 +437,7 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
     const int q4 = warp & 3;                     // TMEM lane quarter this warp may access
     const float zs = kF16 ? a.zscale * a.dscale[1] : a.zscale;   // z = zs * accumulator
     const float coef = a.coef * zs;
-    float* tr = tr_base + (size_t)ew * 16 * 33;
+    float* tr = tr_base + (size_t)ew * kTrFloats;
     // the kEpiWarps / 4 warps that share a quarter interleave over the 32-column blocks
     int cb_first = 0;
     for (int w = kFirstEpiWarp; w < warp; ++w) cb_first += ((w & 3) == q4) ? 1 : 0;
@@ -461,10 +482,70 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
 #else
       bool preA = false;
 #endif
+#if GM_TC_EPI_PIPE
+      // The epilogue is what the tensor pipe waits for (both accumulator buffers full), and its time was the global-load
+      // latency of p / delta, exposed twice per 32 x 32 block (long_scoreboard 63 % of the kernel's stall samples).  Pipelined
+      // form: the loads of BOTH 16-row halves of a block are issued before the accumulator is complete / read from TMEM, the
+      // block goes to shared memory in two 16-column reads (so the accumulator registers never coexist with more than the 64
+      // load registers), and each half's registers are refilled with the next block's loads as soon as the half is stored.
+      // this warp's blocks are cb_first, cb_first + step, ...; the leading n_fast of them take the pipelined path
+      constexpr int kStep = kEpiWarps / 4;
+      int n_fast = 0;
+      for (int cb = cb_first; cb < kTileN / 32 && blk_fast(cb); cb += kStep) ++n_fast;
+      if (n_fast > 0) { issue(cb_first, 0, pA, dA); issue(cb_first, 16, pB, dB); }
+      auto process = [&](int cb, int rb, const float4 (&pv4)[4], const float4 (&dv4)[4]) {
+        const int c0 = n * kTileN + cb * 32;
+        const size_t r_first = row0 + rb + sub;
+        float* p_ptr = a.p + r_first * (size_t)a.d + c0 + 4 * ch;
+        float* dn_ptr = a.dl_next + r_first * (size_t)a.kpad + c0 + 4 * ch;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int r = rb + 4 * jj + sub;
+          const float4 zv = *reinterpret_cast<const float4*>(tr + r * 32 + ((ch ^ (r & 7)) << 2));
+          float4 pn, dn;
+          pn.x = fmaf(-coef, zv.x, pv4[jj].x); pn.y = fmaf(-coef, zv.y, pv4[jj].y);
+          pn.z = fmaf(-coef, zv.z, pv4[jj].z); pn.w = fmaf(-coef, zv.w, pv4[jj].w);
+          dn.x = fmaf(a.drift_eps, pn.x, dv4[jj].x); dn.y = fmaf(a.drift_eps, pn.y, dv4[jj].y);
+          dn.z = fmaf(a.drift_eps, pn.z, dv4[jj].z); dn.w = fmaf(a.drift_eps, pn.w, dv4[jj].w);
+          __stcs(reinterpret_cast<float4*>(p_ptr + jj * d4), pn);
+          *reinterpret_cast<float4*>(dn_ptr + jj * k4) = dn;
+        }
+      };
+#endif
       mbar_wait(&tfull[acc], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
 #pragma unroll 1
       for (int cb = cb_first; cb < kTileN / 32; cb += kEpiWarps / 4) {
+#if GM_TC_EPI_PIPE
+        if ((cb - cb_first) / kStep < n_fast) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * kTileN + cb * 32);
+          // row `lane` of the block as eight 16-byte chunks, chunk i at position i ^ (lane & 7): conflict-free for these
+          // row-wise writes and for the 4-rows-by-8-chunks reads of process()
+          float4* trow = reinterpret_cast<float4*>(tr + lane * 32);
+          __syncwarp();                          // the previous block's reads of the staging buffer are done
+          {
+            float z[16];
+            tc_ld16(taddr, z);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) trow[i ^ (lane & 7)] = make_float4(z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]);
+          }
+          {
+            float z[16];
+            tc_ld16(taddr + 16u, z);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) trow[(4 + i) ^ (lane & 7)] = make_float4(z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]);
+          }
+          __syncwarp();
+          process(cb, 0, pA, dA);
+          // the next fast block's loads refill each half's registers as soon as the half is stored; after the last one the
+          // same block is loaded once more (unused) so that the loads stay unconditional and the 64 values stay in registers
+          const int cbn = ((cb - cb_first) / kStep + 1 < n_fast) ? cb + kStep : cb;
+          issue(cbn, 0, pA, dA);
+          process(cb, 16, pB, dB);
+          issue(cbn, 16, pB, dB);
+          continue;
+        }
+#endif
         float z[32];
         tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * kTileN + cb * 32), z);
         const int c0 = n * kTileN + cb * 32;
@@ -474,6 +555,7 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
 #endif
         const int col = c0 + lane;
         const bool col_ok = col < a.d;
+#if !GM_TC_EPI_PIPE
         if (blk_fast(cb)) {
           // one 16-row half: transpose staging (row L of the half as eight 16-byte chunks, chunk i at position i ^ (L & 7):
           // conflict-free for the row-wise writes and for the 4-rows-by-8-chunks reads), kick, next drift, stores
@@ -523,6 +605,7 @@ dense_gemm_kick_kernel(const __grid_constant__ CUtensorMap map_dl, const __grid_
 #endif
           continue;
         }
+#endif
         preA = false;
 #pragma unroll 1
         for (int rb = 0; rb < 32; rb += 16) {
@@ -851,7 +934,7 @@ DenseTc* dense_tc_create(size_t n_chains, int d, const double* params, const cha
        make_map(&t->map_blo, t->b_lo, (uint64_t)t->npad, (uint64_t)t->kpad, kTileN / kCluster, kOpElem);
   if (!ok) { *err = e_map; dense_tc_destroy(t); return nullptr; }
   t->smem = (size_t)kStages * kStageBytes + (size_t)kRawStages * kRawBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ +
-            (size_t)kEpiWarps * 16 * 33 * 4 /*epilogue transpose*/;
+            (size_t)kEpiWarps * kTrFloats * 4 /*epilogue transpose*/;
   if (cudaFuncSetAttribute(dense_gemm_kick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->smem) != cudaSuccess) {
     *err = "dense tensor-core path: shared-memory opt-in failed";
     dense_tc_destroy(t);

@@ -255,7 +255,10 @@ gmcmc_status gmcmc_nuts_state(gmcmc_sampler*, void* eps_out, long long* leapfrog
 gmcmc_status gmcmc_read_diagnostics(gmcmc_sampler*, void* log_accept, uint8_t* accepted, void* prop_q,
                                     void* prop_p);
 
-gmcmc_status gmcmc_step(gmcmc_sampler*); /* ≙ HMC::step (hmc.rs:308), MarkovChain::step (core.rs:79-85) */
+/* ≙ HMC::step (hmc.rs:308), MarkovChain::step (core.rs:79-85): one transition, nothing recorded.  For an HMC sampler with
+ * step-size adaptation enabled (gmcmc_set_adaptation, an extension the reference's HMC does not have) the step counts as a
+ * warm-up transition and advances dual averaging; call gmcmc_set_adaptation(s, GMCMC_ADAPT_NONE, ...) first for a plain step. */
+gmcmc_status gmcmc_step(gmcmc_sampler*);
 /* ≙ HMC::run (hmc.rs:164-181), BatchedGenericHMC::run (batched_hmc.rs:93-112), ChainRunner::run
  * (core.rs:219-229), NUTS::run (nuts.rs:214-257).  out_host: [C, n_collect, dim] of out_dtype. */
 gmcmc_status gmcmc_run(gmcmc_sampler*, size_t n_collect, size_t n_discard, void* out_host,
