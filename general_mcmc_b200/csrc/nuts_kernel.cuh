@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
     for (int j = 0; j < EPL; ++j)
       if (j < ln.nvalid) pos_row[ln.lo + j] = a.positions[chain * d + ln.lo + j];
     eps = a.eps[chain]; eps_bar = a.eps_bar[chain]; h_bar = a.h_bar[chain]; mu = a.mu[chain];
-    if (inject) { i_norm = a.inj_used[chain * 3]; i_exp = a.inj_used[chain * 3 + 1]; i_unif = a.inj_used[chain * 3 + 2]; }
+    if (__builtin_expect(inject, 0)) { i_norm = a.inj_used[chain * 3]; i_exp = a.inj_used[chain * 3 + 1]; i_unif = a.inj_used[chain * 3 + 2]; }
     if (a.write_init && a.out) {
 #pragma unroll
       for (int j = 0; j < EPL; ++j)
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
       if (j < ln.nvalid) a.positions[chain * d + ln.lo + j] = pos_row[ln.lo + j];
     if (ln.part == 0) {
       a.eps[chain] = eps; a.eps_bar[chain] = eps_bar; a.h_bar[chain] = h_bar;
-      if (inject) { a.inj_used[chain * 3] = i_norm; a.inj_used[chain * 3 + 1] = i_exp; a.inj_used[chain * 3 + 2] = i_unif; }
+      if (__builtin_expect(inject, 0)) { a.inj_used[chain * 3] = i_norm; a.inj_used[chain * 3 + 1] = i_exp; a.inj_used[chain * 3 + 2] = i_unif; }
       if (a.chain_leapfrogs) a.chain_leapfrogs[chain] += (long long)chain_leaps;
     }
   };
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
   const unsigned chain_mask = (lpc >= 32) ? kFull : (((1u << lpc) - 1u) << ln.gbase);
   const uint32_t u_per = 2u * (uint32_t)lpc;
   auto next_unif = [&]() -> double {
-    if (inject) {
+    if (__builtin_expect(inject, 0)) {
       const double u = (i_unif < a.n_unif) ? a.inj_unif[chain * a.n_unif + i_unif] : 0.75;
       ++i_unif;
       return u;
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
     const bool is_leaf = (phase == NP_LEAF);
     if (__any_sync(kFull, is_start)) {
       T pn[EPL];
-      if (inject) {
+      if (__builtin_expect(inject, 0)) {
 #pragma unroll
         for (int j = 0; j < EPL; ++j) {
           const unsigned long long idx = i_norm + (unsigned long long)(ln.lo + j);
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_NUTS_MINB) nuts_run_kernel(const
         // generic_nuts.rs:765-781
         joint0 = joint;
         T e1;
-        if (inject) { e1 = (T)((i_exp < a.n_exp) ? a.inj_exp1[chain * a.n_exp + i_exp] : 1.0); ++i_exp; }
+        if (__builtin_expect(inject, 0)) { e1 = (T)((i_exp < a.n_exp) ? a.inj_exp1[chain * a.n_exp + i_exp] : 1.0); ++i_exp; }
         else {
           const uint4 r = philox4x32_10(philox_ctr(gchain, a.step_base + s, 1u, 0u), a.key);
           if constexpr (!kExact && sizeof(T) == 4) e1 = -__logf(u01(r.z));   // fast mode, f32: the 24 leading bits of word 2
