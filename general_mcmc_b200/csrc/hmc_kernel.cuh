@@ -555,9 +555,9 @@ __device__ __forceinline__ T eval_kick(TagRosenbrockND, const T (&x)[EPL], T (&p
 // result is the exact negative / equal of the scalar formulation's (round-to-nearest is symmetric), so the trajectory is
 // bit-identical to the scalar loop's (the whole GPU suite passes with it on).
 // Measured on B200 (65,536 chains, d = 100, L = 32): 57.0 us per transition against 53.4 us for the scalar loop
-// (3.62e10 vs 3.85e10 grad-evals/s): FFMA2 does not issue at the rate of two FFMAs (tools/microbench_fp32.cu: the
-// packed form sustains 47 TFLOP/s where scalar FFMA with constant operands sustains 72), so halving the instruction
-// count buys nothing.
+// (3.62e10 vs 3.85e10 grad-evals/s): the packed form reads the same registers per FMA, and register-file reads are
+// the limit (tools/microbench_fp32.cu: FFMA2 with three distinct register pairs sustains 47 TFLOP/s like scalar
+// three-register FFMA, against 72 for constant operands), so halving the instruction count buys nothing.
 // ------------------------------------------------------------------------------------------------
 #ifndef GM_K1_PACKED
 #define GM_K1_PACKED 0
