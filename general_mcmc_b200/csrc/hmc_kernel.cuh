@@ -559,6 +559,14 @@ __device__ __forceinline__ T eval_kick(TagRosenbrockND, const T (&x)[EPL], T (&p
 // the limit (tools/microbench_fp32.cu: FFMA2 with three distinct register pairs sustains 47 TFLOP/s like scalar
 // three-register FFMA, against 72 for constant operands), so halving the instruction count buys nothing.
 // ------------------------------------------------------------------------------------------------
+// tuning knob: unroll factor of the inner leapfrog loop (default: the compiler's choice, 2)
+#define GM_PRAGMA_(x) _Pragma(#x)
+#define GM_PRAGMA(x) GM_PRAGMA_(x)
+#ifdef GM_K1_LOOP_UNROLL
+#define GM_K1_UNROLL_PRAGMA GM_PRAGMA(unroll GM_K1_LOOP_UNROLL)
+#else
+#define GM_K1_UNROLL_PRAGMA
+#endif
 #ifndef GM_K1_PACKED
 #define GM_K1_PACKED 0
 #endif
@@ -907,6 +915,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
         // FFMA does, tools/microbench_fp32.cu).  When the step size is the launch-wide value the host passed by value, the
         // drift and the kick take it as a constant-bank operand: 53.3 -> 51.0 us per transition at config 4's shape.
         auto inner = [&](const T eps_l) {
+          GM_K1_UNROLL_PRAGMA
           for (uint32_t l = 0; l + 1 < a.L; ++l) {
 #pragma unroll
             for (int j = 0; j < EPL; ++j) q[j] += eps_l * p[j];
