@@ -464,6 +464,20 @@ __device__ __forceinline__ T eval_target(TagGauss2D, const T (&x)[EPL], T (&g)[E
 // reference's two consecutive half-kicks with the same gradient, batched_hmc.rs:187 + :175).  Returns
 // the log density when WANT_LOGP.  Generic version: gradient slice in registers, then the kick.
 // ----------------------------------------------------------------------------------------------
+// Gradient cache (fast mode, RosenbrockND): a transition of L leapfrogs needs L + 1 gradients, and the first of them is at
+// the current point — the gradient the previous transition already evaluated at its trajectory end (accepted) or start
+// (rejected).  The kernel keeps both in two shared-memory rows per chain and swaps them on acceptance, so a transition
+// evaluates L gradients; the cached value is the same function of the same position, hence the same bits.
+// An experiment, OFF by default: measured on B200 (65,536 chains, d = 100, L = 32, all parity tests green) it is 0.6 % SLOWER
+// (51.97 vs 51.68 us per transition, profiles/r2_k1_gradcache_experiment.txt) although it issues 2.5 % fewer instructions:
+// 168 instead of 162 registers and 25 LDS + 25 STS per transition on the trajectory's critical path cost what the
+// 125 saved FFMAs bought.
+#ifndef GM_K1_GRADCACHE
+#define GM_K1_GRADCACHE 0
+#endif
+template <class TAG> struct GradCache { static constexpr bool on = false; };
+template <> struct GradCache<TagRosenbrockND> { static constexpr bool on = GM_K1_GRADCACHE && !kExact; };
+
 template <class T, int EPL, bool PADDED, bool WANT_LOGP, int NK, class TAG>
 __device__ __forceinline__ T eval_kick(TAG, const T (&x)[EPL], T (&p)[EPL], const T coef, const Lane& ln,
                                        const TParams<T>& tp, T* row) {
@@ -479,9 +493,9 @@ __device__ __forceinline__ T eval_kick(TAG, const T (&x)[EPL], T (&p)[EPL], cons
 
 // RosenbrockND: the gradient never materialises — each coordinate's stencil value goes straight into
 // its momentum (6 FMAs per coordinate per leapfrog in fast mode: drift 1, t 1, gradient 3, kick 1).
-template <class T, int EPL, bool PADDED, bool WANT_LOGP, int NK>
+template <class T, int EPL, bool PADDED, bool WANT_LOGP, int NK, bool SAVE = false>
 __device__ __forceinline__ T eval_kick(TagRosenbrockND, const T (&x)[EPL], T (&p)[EPL], const T coef, const Lane& ln,
-                                       const TParams<T>&, T*) {
+                                       const TParams<T>&, T*, T* gsave = nullptr /* SAVE: the lane's slice of a gradient row */) {
   const T x_next_lane = __shfl_down_sync(kFull, x[0], 1);
   T gt[EPL];     // fast: t_j ; exact: gt_j = -200 t_j
   T terms[EPL];
@@ -533,6 +547,7 @@ __device__ __forceinline__ T eval_kick(TagRosenbrockND, const T (&x)[EPL], T (&p
     }
     p[j] = p[j] + gi * coef;
     if constexpr (NK == 2) p[j] = p[j] + gi * coef;
+    if constexpr (SAVE) { if (!PADDED || j < ln.nvalid) gsave[j] = gi; }
   }
   if constexpr (WANT_LOGP) {
     int nl = ln.d - 1 - ln.lo;
@@ -791,8 +806,12 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
   const int warp_in_block = threadIdx.x >> 5;
   const int chain_in_warp = lane / a.lpc;
   const size_t warp_elems = (size_t)chains_in_warp * a.d_pad;
-  T* warp_pos = smem + (size_t)warp_in_block * 2 * warp_elems;
+  constexpr bool kGC = GradCache<TAG>::on;
+  T* warp_pos = smem + (size_t)warp_in_block * (kGC ? 4 : 2) * warp_elems;
   T* warp_scr = warp_pos + warp_elems;
+  // gradient cache: two more rows per chain, the lane's slice of row `g_sel` = gradient at the current point
+  T* const g_rows = warp_scr + warp_elems + (size_t)chain_in_warp * a.d_pad + ln.lo;
+  int g_sel = 0;
   T* pos_row = warp_pos + (size_t)chain_in_warp * a.d_pad;
   T* row = warp_scr + (size_t)chain_in_warp * a.d_pad;
   const size_t warp_first_chain = (size_t)((tid & ~31) / a.lpc);
@@ -906,8 +925,20 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
       logp1 = eval_kick<T, EPL, PADDED, true, 1>(TAG{}, q, p, half, ln, a.tp, row);
     } else {
       // merged kicks: p += eps/2 g ; (q += eps p ; p += eps grad(q)) x (L-1) ; q += eps p ; p += eps/2 grad(q)
-      if (have_logp_cur) { eval_kick<T, EPL, PADDED, false, 1>(TAG{}, q, p, half, ln, a.tp, row); logp0 = logp_cur; }
-      else logp0 = eval_kick<T, EPL, PADDED, true, 1>(TAG{}, q, p, half, ln, a.tp, row);
+      if constexpr (kGC) {
+        T* g_cur = g_rows + (g_sel ? warp_elems : 0);
+        if (have_logp_cur) {
+#pragma unroll
+          for (int j = 0; j < EPL; ++j)
+            if (!PADDED || j < ln.nvalid) p[j] = p[j] + g_cur[j] * half;
+          logp0 = logp_cur;
+        } else {
+          logp0 = eval_kick<T, EPL, PADDED, true, 1, true>(TAG{}, q, p, half, ln, a.tp, row, g_cur);
+        }
+      } else {
+        if (have_logp_cur) { eval_kick<T, EPL, PADDED, false, 1>(TAG{}, q, p, half, ln, a.tp, row); logp0 = logp_cur; }
+        else logp0 = eval_kick<T, EPL, PADDED, true, 1>(TAG{}, q, p, half, ln, a.tp, row);
+      }
       if constexpr (GM_K1_PACKED && std::is_same<TAG, TagRosenbrockND>::value && sizeof(T) == 4 && !PADDED && EPL >= 4) {
         rosen_leapfrogs_packed<EPL>(q, p, eps, a.L - 1, ln);
       } else {
@@ -926,7 +957,8 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
       }
 #pragma unroll
       for (int j = 0; j < EPL; ++j) q[j] += eps * p[j];
-      logp1 = eval_kick<T, EPL, PADDED, true, 1>(TAG{}, q, p, half, ln, a.tp, row);
+      if constexpr (kGC) logp1 = eval_kick<T, EPL, PADDED, true, 1, true>(TAG{}, q, p, half, ln, a.tp, row, g_rows + (g_sel ? 0 : warp_elems));
+      else logp1 = eval_kick<T, EPL, PADDED, true, 1>(TAG{}, q, p, half, ln, a.tp, row);
     }
 
     // ---- 4. Hamiltonian + Metropolis accept (batched_hmc.rs:148-162 / generic_hmc.rs:195-200)
@@ -948,6 +980,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
     }
     logp_cur = accept ? logp1 : logp0;
     have_logp_cur = true;
+    if constexpr (kGC) g_sel ^= accept ? 1 : 0;   // the trajectory end's gradient row becomes the current point's
     const bool finite = (log_accept == log_accept) && (fabs(log_accept) < T(INFINITY));
     const T alpha = finite ? min(T(1), exp(log_accept)) : (log_accept > T(0) ? T(1) : T(0));
     if (active && ln.part == 0) {
@@ -1081,7 +1114,7 @@ inline cudaError_t launch_one(const HmcLaunch& L, cudaStream_t st) {
   HmcArgs<T> a = make_args<T>(L);
   const size_t threads = L.n_chains * (size_t)L.lpc;
   const unsigned blocks = (unsigned)((threads + kHmcBlock - 1) / kHmcBlock);
-  const size_t smem = 2 * (size_t)(kHmcBlock / L.lpc) * a.d_pad * sizeof(T);
+  const size_t smem = (GradCache<TAG>::on ? 4 : 2) * (size_t)(kHmcBlock / L.lpc) * a.d_pad * sizeof(T);
   auto kern = hmc_run_kernel<T, EPL, TAG, PADDED>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
