@@ -544,10 +544,11 @@ def leg_hmc_rosenbrock(env, steps, warmup, chains, want_ess=True, want_cpu=True,
     out = {"metric": "leapfrog_grad_evals_per_sec", "value": value, "unit": "grad-evals/s", "ms_per_step": ms / steps,
            "dtype": "f32", "steps": steps,
            "config": {"workload": WORKLOAD_NAMES["hmc_rosenbrock"] % (DIM, chains, N_LEAPFROG), "chains_per_gpu": chains,
-                      "transitions_per_launch": per_launch, "step_size": step_size, "accept_rate": c.accept_rate,
+                      "transitions_per_launch": max(plan), "launch_plan": plan, "step_size": step_size,
+                      "accept_rate": c.accept_rate,
                       "l2": "256 MB L2 flush before the timed region; chain state is register-resident within a launch and "
                             "each launch streams %.0f MB of samples (> 126 MB L2), so nothing is reused from L2 between "
-                            "launches" % (chains * BYTES_PER_STEP_PER_CHAIN * per_launch / 1e6)},
+                            "launches" % (chains * BYTES_PER_STEP_PER_CHAIN * max(plan) / 1e6)},
            "e2e": e2e, "gpu_launches": len(plan), "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "ess": ess}
     out.update(extra)
     s.close()
