@@ -585,6 +585,9 @@ __device__ __forceinline__ T eval_kick(TagRosenbrockND, const T (&x)[EPL], T (&p
 #ifndef GM_K1_PACKED
 #define GM_K1_PACKED 0
 #endif
+#ifndef GM_K1_LOAD_UN
+#define GM_K1_LOAD_UN 8    // loads in flight per lane of the launch-head state load (padded rows; 8 and 32 measure the same)
+#endif
 __device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
   unsigned long long r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -818,7 +821,7 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
   const unsigned long long gchain = a.chain_offset + chain;
 
   // current positions -> shared rows.  The warp's chains are one contiguous run of the [C, d] array: it is read as a flat
-  // list with 8 loads in flight per lane (a dependent load -> store loop over the rows cost ~15 us of HBM latency per CTA,
+  // list with all loads in flight per lane (a dependent load -> store loop over the rows cost ~15 us of HBM latency per CTA,
   // more than a whole transition, which is what made short launches 2.3x as expensive per transition); rows of chains past
   // the end and padding columns get a harmless point.
   {
@@ -829,20 +832,45 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
     if (a.d_pad != a.d || nch < chains_in_warp)
       for (int i = lane; i < (int)warp_elems; i += 32) warp_pos[i] = T(1);
     __syncwarp();
-    constexpr int UN = 8;
-    for (int base = 0; base < total; base += 32 * UN) {
-      T v[UN];
+    using V = typename VecOf<T>::type;
+    constexpr int VN = VecOf<T>::n;
+    if (a.d_pad == a.d && (a.d % VN) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      // unpadded rows (config 4: d = 100): the shared rows ARE the flat list, moved in 16-byte units.  (The general path
+      // below divides every index by d: those divisions were 11 % of a one-transition launch's instructions,
+      // profiles/r2_hmc_single_transition_launch_after.txt.)
+      const V* src_v = reinterpret_cast<const V*>(src);
+      V* dst_v = reinterpret_cast<V*>(warp_pos);
+      const int nv = total / VN;
+      constexpr int UV = 8;
+      for (int base = 0; base < nv; base += 32 * UV) {
+        V v[UV];
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int idx = base + lane + 32 * u;
-        v[u] = idx < total ? __ldg(src + idx) : T(1);
+        for (int u = 0; u < UV; ++u) {
+          const int idx = base + lane + 32 * u;
+          if (idx < nv) v[u] = __ldg(src_v + idx);
+        }
+#pragma unroll
+        for (int u = 0; u < UV; ++u) {
+          const int idx = base + lane + 32 * u;
+          if (idx < nv) dst_v[idx] = v[u];
+        }
       }
+    } else {
+      constexpr int UN = GM_K1_LOAD_UN;
+      for (int base = 0; base < total; base += 32 * UN) {
+        T v[UN];
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int idx = base + lane + 32 * u;
-        if (idx < total) {
-          const int c = idx / a.d;
-          warp_pos[(size_t)c * a.d_pad + (idx - c * a.d)] = v[u];
+        for (int u = 0; u < UN; ++u) {
+          const int idx = base + lane + 32 * u;
+          v[u] = idx < total ? __ldg(src + idx) : T(1);
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const int idx = base + lane + 32 * u;
+          if (idx < total) {
+            const int c = idx / a.d;
+            warp_pos[(size_t)c * a.d_pad + (idx - c * a.d)] = v[u];
+          }
         }
       }
     }
@@ -1034,10 +1062,20 @@ __global__ void __launch_bounds__(kHmcBlock, GM_MINB) hmc_run_kernel(const HmcAr
     const int nch = live_chains < (size_t)chains_in_warp ? (int)live_chains : chains_in_warp;
     const int total = nch * a.d;
     T* dst = a.positions + warp_first_chain * (size_t)a.d;
+    using V = typename VecOf<T>::type;
+    constexpr int VN = VecOf<T>::n;
+    if (a.d_pad == a.d && (a.d % VN) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      const V* src_v = reinterpret_cast<const V*>(warp_pos);
+      V* dst_v = reinterpret_cast<V*>(dst);
+      const int nv = total / VN;
 #pragma unroll 4
-    for (int idx = lane; idx < total; idx += 32) {
-      const int c = idx / a.d;
-      dst[idx] = warp_pos[(size_t)c * a.d_pad + (idx - c * a.d)];
+      for (int idx = lane; idx < nv; idx += 32) dst_v[idx] = src_v[idx];
+    } else {
+#pragma unroll 4
+      for (int idx = lane; idx < total; idx += 32) {
+        const int c = idx / a.d;
+        dst[idx] = warp_pos[(size_t)c * a.d_pad + (idx - c * a.d)];
+      }
     }
   }
   if (active && per_chain_da && ln.part == 0) {
