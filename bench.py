@@ -360,10 +360,14 @@ class Env:
             evs[used[0]].record(self.stream)
         t0 = time.time()
         with torch.cuda.stream(self.stream):
-            # a short device-side delay ahead of the first event: the host enqueues the event and the first launch while the
-            # GPU is still busy, so the timed region starts with the kernel already queued (otherwise the few microseconds
-            # the host needs to issue the first launch are charged to a region that may only last a millisecond)
-            torch.cuda._sleep(400000)
+            # device-side pre-roll ahead of the first event, on the library's stream: ~4 ms of all-SM FP32 FMA work
+            # (gmcmc_ctx_warm_fp32, no synchronisation).  (1) The host enqueues the event and the first launch while the
+            # GPU is still working, so the region starts with the kernel already queued.  (2) The barrier above leaves the
+            # GPU idle, and a B200 runs the first millisecond after an idle gap 3 % slow: a 20-transition K1 launch takes
+            # 1,087 us after a gap (or after a one-thread spin, or after memory-only work), 1,052 us after all-SM compute
+            # (tools/k1_cold_launch.py, profiles/r2_k1_cold_launch.txt) — the state W warm-up steps are meant to establish
+            # and the barrier undoes.  The L2 flush above stands: the pre-roll touches no memory.
+            self.L.check(self.lib.gmcmc_ctx_warm_fp32(self.ctx._h, C.c_double(4.0)))
             evs[0].record(self.stream)
             if marks:
                 fn(mark)
@@ -548,7 +552,8 @@ def leg_hmc_rosenbrock(env, steps, warmup, chains, want_ess=True, want_cpu=True,
                       "accept_rate": c.accept_rate,
                       "l2": "256 MB L2 flush before the timed region; chain state is register-resident within a launch and "
                             "each launch streams %.0f MB of samples (> 126 MB L2), so nothing is reused from L2 between "
-                            "launches" % (chains * BYTES_PER_STEP_PER_CHAIN * max(plan) / 1e6)},
+                            "launches; ~4 ms of all-SM FP32 work (gmcmc_ctx_warm_fp32) is queued, untimed, ahead of the first event so the "
+                            "region does not start from the idle state the barrier leaves" % (chains * BYTES_PER_STEP_PER_CHAIN * max(plan) / 1e6)},
            "e2e": e2e, "gpu_launches": len(plan), "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "ess": ess}
     out.update(extra)
     s.close()

@@ -21,7 +21,7 @@ ADAPT_NONE, ADAPT_PER_CHAIN, ADAPT_POOLED = 0, 1, 2
 SYMBOLS = [
     "gmcmc_ctx_create", "gmcmc_nccl_unique_id", "gmcmc_ctx_create_dist", "gmcmc_ctx_destroy",
     "gmcmc_ctx_synchronize", "gmcmc_ctx_stream", "gmcmc_ctx_all_reduce_f64", "gmcmc_host_alloc",
-    "gmcmc_host_free", "gmcmc_measure_fp32_peak", "gmcmc_target_create", "gmcmc_target_create_custom", "gmcmc_target_destroy", "gmcmc_target_logp_grad",
+    "gmcmc_host_free", "gmcmc_measure_fp32_peak", "gmcmc_ctx_warm_fp32", "gmcmc_target_create", "gmcmc_target_create_custom", "gmcmc_target_destroy", "gmcmc_target_logp_grad",
     "gmcmc_hmc_create", "gmcmc_mh_create", "gmcmc_mh_int_create", "gmcmc_mh_int_inject", "gmcmc_gibbs_create", "gmcmc_gibbs_create_custom", "gmcmc_gibbs_inject", "gmcmc_nuts_create", "gmcmc_sampler_destroy", "gmcmc_set_seed",
     "gmcmc_set_math_mode", "gmcmc_set_adaptation", "gmcmc_set_step_size", "gmcmc_inject", "gmcmc_mh_record", "gmcmc_mh_read_draws",
     "gmcmc_nuts_inject", "gmcmc_nuts_state", "gmcmc_nuts_set_mass_adaptation", "gmcmc_nuts_set_dense_max_dim", "gmcmc_nuts_mass_matrix", "gmcmc_read_diagnostics", "gmcmc_step", "gmcmc_run", "gmcmc_run_device", "gmcmc_reserve_samples",

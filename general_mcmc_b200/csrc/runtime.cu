@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, f
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) s += acc[i];
-  if (s == 123.456f) out[0] = s;   // never true in practice; keeps the loop alive
+  if (out && s == 123.456f) out[0] = s;   // never true in practice; keeps the loop alive
 }
 
 gmcmc_status make_target_desc(const gmcmc_target* t, TargetDesc* out) {
@@ -1029,6 +1029,17 @@ gmcmc_status gmcmc_measure_fp32_peak(gmcmc_ctx* c, double* tflops) {
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   *tflops = best;
+  return GMCMC_OK;
+}
+
+gmcmc_status gmcmc_ctx_warm_fp32(gmcmc_ctx* c, double approx_ms) {
+  GM_REQUIRE(c, "null argument");
+  GM_REQUIRE(approx_ms >= 0.0 && approx_ms <= 100.0, "approx_ms must be in [0, 100]");
+  GM_CU(cudaSetDevice(c->device));
+  // one launch is 2 * 16 * 8192 * 256 * (8 blocks per SM) flop: about 1.1 ms at the FFMA peak of a B200
+  const int launches = (int)std::ceil(approx_ms / 1.1);
+  for (int i = 0; i < launches; ++i) ffma_peak_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(nullptr, 8192, 0.999f, 0.001f);
+  GM_CU(cudaGetLastError());
   return GMCMC_OK;
 }
 

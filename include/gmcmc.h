@@ -130,6 +130,10 @@ gmcmc_status gmcmc_host_free(void* p);
 /* measured FP32 FMA-pipe peak of this GPU in TFLOP/s (roofline denominator of the register-resident
  * trajectory kernels; the driver's MEASURED_PEAKS.json only holds HBM and bf16 tensor peaks) */
 gmcmc_status gmcmc_measure_fp32_peak(gmcmc_ctx*, double* tflops);
+/* queues about `approx_ms` (0 .. 100) milliseconds of all-SM FP32 FMA work on the context's stream and returns without
+ * synchronising.  Benchmark plumbing: a B200 runs the first millisecond after an idle gap (a host synchronisation)
+ * about 3 % slow, so a timed region that follows a barrier is preceded by this (bench.py; no reference counterpart). */
+gmcmc_status gmcmc_ctx_warm_fp32(gmcmc_ctx*, double approx_ms);
 
 /* ---- targets (distributions.rs traits Target / BatchedGradientTarget / GradientTarget :67-110) */
 gmcmc_status gmcmc_target_create(gmcmc_ctx*, gmcmc_target_kind kind, gmcmc_dtype dtype, int dim,
