@@ -40,15 +40,26 @@ def test_single_chain_single_dim_and_empty_runs(ctx, oracle, dtype):
 
 def test_ragged_grids_match_oracle(ctx, oracle):
     """Chain counts that are not multiples of the warp / CTA / staging sizes, dims that need padding lanes."""
-    for Cn, d in [(1, 7), (33, 5), (129, 37), (1000, 3)]:
+    # the last three shapes have unpadded rows (d a multiple of the 16-byte unit): the flat state load / store of K1 with a
+    # ragged last warp, in both dtypes
+    for Cn, d, dtype in [(1, 7, np.float32), (33, 5, np.float32), (129, 37, np.float32), (1000, 3, np.float32),
+                         (13, 8, np.float32), (77, 100, np.float32), (5, 16, np.float32), (77, 100, np.float64), (13, 6, np.float64)]:
         rng = np.random.default_rng(Cn * 100 + d)
-        q0 = (1.0 + 0.2 * rng.standard_normal((Cn, d))).astype(np.float32)
-        mom = rng.standard_normal((2, Cn, d)).astype(np.float32)
-        ln_u = np.log(rng.random((2, Cn))).astype(np.float32)
+        q0 = (1.0 + 0.2 * rng.standard_normal((Cn, d))).astype(dtype)
+        mom = rng.standard_normal((2, Cn, d)).astype(dtype)
+        ln_u = np.log(rng.random((2, Cn))).astype(dtype)
         ref = oracle.hmc_run(oracle.ROSENBROCK_ND, [], q0, 0.01, 4, mom, ln_u)
         s = gm.HMC(gm.RosenbrockND(d), q0, 0.01, 4, seed=1, ctx=ctx).set_math_mode(True)
         s.inject(mom, ln_u)
-        assert np.array_equal(s.run(2, 0), ref["samples"]), (Cn, d)
+        assert np.array_equal(s.run(2, 0), ref["samples"]), (Cn, d, dtype)
+        assert np.array_equal(s.positions(), ref["samples"][:, -1]), (Cn, d, dtype)      # the state written back at the launch end
+        # fast mode (the production instantiation) takes the same load / store path
+        f = gm.HMC(gm.RosenbrockND(d), q0, 0.01, 4, seed=1, ctx=ctx)
+        f.inject(mom[:1], ln_u[:1])
+        out = f.run(1, 0)
+        tol = 1e-5 if dtype == np.float32 else 1e-10
+        assert np.allclose(out[:, 0], ref["samples"][:, 0], rtol=tol, atol=tol), (Cn, d, dtype)
+        assert np.array_equal(f.positions(), out[:, 0]), (Cn, d, dtype)
 
 
 def test_stats_minimal_and_unsupported_are_reported(ctx):
