@@ -10,7 +10,13 @@
 namespace gm {
 
 constexpr int kMaxScalarParams = 8;
-constexpr int kHmcBlock = 128;  // threads per CTA of the trajectory kernels
+#ifndef GM_HMC_BLOCK
+// tuning knob.  Measured on B200: 64-thread CTAs run K1 exactly as fast as 128-thread ones (profiles/r2_k1_cta_size_experiment.txt),
+// and a 13th resident warp cannot be had from smaller CTAs: registers are granted per SM sub-partition, so 13 or 18 warps per SM
+// get the register budget of 16 or 20 (ptxas: 128 / 96 registers with spills where 12 / 16 warps get 168 / 128)
+#define GM_HMC_BLOCK 128
+#endif
+constexpr int kHmcBlock = GM_HMC_BLOCK;  // threads per CTA of the trajectory kernels
 
 struct TargetDesc {
   int kind;                          // gmcmc_target_kind
