@@ -508,7 +508,7 @@ def leg_hmc_rosenbrock(env, steps, warmup, chains, want_ess=True, want_cpu=True,
                     "note": "state is register-resident for all L steps; HBM carries only the sample write-out, so this "
                             "kernel is FP32-pipe bound, not HBM bound (north_star: FP32-pipe utilisation)"}}
     roof.update(traffic_fields("hmc_rosenbrock", chains))
-    e2e_calls = max(3, min(20, steps // E2E_TRANSITIONS))
+    e2e_calls = max(8, min(20, steps // E2E_TRANSITIONS))     # >= 8 calls (~70 ms): PCIe rates wobble by several % between short bursts
     e2e, extra = e2e_leg(env, s, chains, DIM, np.float32, E2E_TRANSITIONS, e2e_calls,
                          units_per_call=unit_per_step * E2E_TRANSITIONS, variants=variants)
     e2e["unit"] = "grad-evals/s"
