@@ -187,7 +187,11 @@ __device__ __forceinline__ void chain_sum_fn2(const Lane& ln, F1 f1, F2 f2, T& o
 #define GM_NUTS_PIN_TID 0   // measured: 1.00e9 vs 1.02e9 leapfrogs/s with the index pinned — the rematerialisation is the cheaper choice
 #endif
 #ifndef GM_NUTS_MINB
-#define GM_NUTS_MINB 4   // 128 registers per thread: no spills, one more CTA per SM to hide the serial per-pass latency (+6 %)
+// Resident CTAs per SM the kernel is register-budgeted for.  Round 1's layout gained 6 % from 4 CTAs (128 registers); with the
+// hot vectors in shared memory and two leaves per pass, 3 CTAs (146 registers: the addresses and target parameters the
+// 128-register build rematerialised in the loop stay in registers) are 4 % faster: 1.18e9 against 1.13e9 leapfrogs/s on
+// config 5 (profiles/r2_nuts_occupancy_3_vs_4.txt).
+#define GM_NUTS_MINB 3
 #endif
 
 // Targets whose padded slots (coordinates past the end of the chain in a non exact-fit decomposition) may simply hold
