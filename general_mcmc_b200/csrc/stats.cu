@@ -163,6 +163,8 @@ stats_accumulate(const TIN* __restrict__ samples, size_t C, size_t n, int p, int
 //   * twiddles: one table entry w_L^j per butterfly, its powers by complex multiplication.
 // ------------------------------------------------------------------------------------------------
 constexpr int kWarpFftWarps = 8;   // warps per CTA = parameters per CTA
+// resident CTAs per SM of the warp-FFT kernel for N <= 512.  Measured at 65,536 x 500 x 100: 2 CTAs (125 registers, no spills)
+// 10.8 ms, 3 CTAs (80 registers) 9.6 ms, 4 CTAs (64 registers, spills) 10.5 ms (profiles/r2_k4_occupancy_scan.txt)
 #ifndef GM_STATS_MINB
 #define GM_STATS_MINB 3
 #endif
